@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- traversed edges/sec (mxm TEPS) for FalkorDB's CondTraverse hot path on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input: a batch of `--sources` source vertices
+F (|batch| x n, one entry per row -- cond_traverse.rs:600-601) pushed through a 3-hop GrB_mxm chain F*A*A*A over
+GxB_ANY_PAIR_BOOL (cond_traverse.rs:602-605) on a Graph500 RMAT graph, then materialised as sorted CSR (the form
+the reference's row iterator walks, cond_traverse.rs:608,644).  TEPS = sum over hops of
+flops_h = sum_{(i,k) in F_h} deg_A(k)  divided by the step time  (SURVEY.md 8d).
+
+  value : device-resident -- F already in HBM when the timed region starts; CUDA-event timed on the library's stream
+  e2e   : the same step through the public C ABI with HOST buffers: GxB_Matrix_build_Scalar from host index arrays
+          (H2D inside), 3x GrB_mxm, GrB_Matrix_wait, B200_Matrix_export_CSR of the result into host memory (D2H inside)
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on a bounded
+sample of the same workload.  Multi-GPU: the batch rows are independent, so ranks shard the sources with A replicated
+and no data-path collective (weak scaling: fixed sources per rank).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=24)
+    ap.add_argument("--edge-factor", type=int, default=16)
+    ap.add_argument("--sources", type=int, default=64, help="frontier rows per batch (per GPU)")
+    ap.add_argument("--hops", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-sources", type=int, default=0, help="sources per CPU sample (0 = auto: ~5 s of CPU work)")
+    ap.add_argument("--bits-mode", type=int, default=-1)
+    ap.add_argument("--pull-mode", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pick_sources(deg, nbatches, nsrc, seed, rank):
+    """Seeded batches of distinct source vertices with non-zero out-degree."""
+    rng = np.random.default_rng(seed * 1000003 + rank)
+    cand = np.nonzero(deg > 0)[0]
+    return [rng.choice(cand, size=nsrc, replace=False).astype(np.uint64) for _ in range(nbatches)]
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_chain(orc, A, src, hops):
+    F = orc.build_matrix(len(src), A.nrows, np.arange(len(src)), src)
+    flops = 0
+    for _ in range(hops):
+        F, fl = orc.mxm(F, A, return_flops=True)
+        flops += fl
+    return F, flops
+
+
+def run_reference(a):
+    """The reference's CPU implementation of the path.  SuiteSparse:GraphBLAS is not vendored under /root/reference and
+    cannot be built here (cmake + generated code), so this arm times the oracle port (kind="port") with every host
+    thread OpenMP gives it.  Each step = a bounded sample (--cpu-sources sources) of the b200 arm's workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as orc
+    t0 = time.time()
+    A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
+    gen_s = time.time() - t0
+    deg = np.diff(A.p)
+    cores = orc.num_threads()
+    S = a.cpu_sources
+    if S <= 0:  # calibrate: one untimed chain with one source per thread, then size a step to ~5 s of CPU work
+        probe = pick_sources(deg, 1, max(8, cores), a.seed + 17, 0)[0]
+        t0 = time.perf_counter()
+        cpu_chain(orc, A, probe, a.hops)
+        per_src = (time.perf_counter() - t0) / len(probe)
+        S = int(min(256, max(cores, round(5.0 / max(per_src, 1e-6)))))
+    a.cpu_sources = S
+    batches = pick_sources(deg, a.steps + a.warmup, a.cpu_sources, a.seed, 0)
+    for b in batches[:a.warmup]:
+        cpu_chain(orc, A, b, a.hops)
+    flops, t = 0, 0.0
+    for b in batches[a.warmup:]:
+        t0 = time.perf_counter()
+        _, fl = cpu_chain(orc, A, b, a.hops)
+        t += time.perf_counter() - t0
+        flops += fl
+    teps = flops / t
+    sample = f"{a.hops}-hop chain, {a.cpu_sources} sources/step, RMAT-{a.scale} ef{a.edge_factor}, {a.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": teps,
+        "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
+        "config": {"workload": f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}",
+                   "sources_per_step": a.cpu_sources, "graph_build_s": round(gen_s, 1)},
+        "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": teps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import falkordb_b200 as fb
+    from falkordb_b200._lib import lib
+    from falkordb_b200.grb import Matrix
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = lib()
+    fb.init()
+    fb.set_option("bits_mode", a.bits_mode)
+    fb.set_option("pull_mode", a.pull_mode)
+    n = 1 << a.scale
+
+    # ---- setup (untimed): graph on device, transpose mirror, source batches ----
+    t0 = time.time()
+    A = fb.rmat(a.scale, a.edge_factor, a.seed)
+    A.prepare(True)
+    setup_s = time.time() - t0
+    nnzA = A.nvals()
+    p, _, _ = (np.empty(n + 1, np.uint64), None, None)
+    fb.check(L.B200_Matrix_export_CSR(A.h, p.ctypes.data, None, None, 0))
+    deg = np.diff(p.astype(np.int64))
+    nb = a.steps + a.warmup
+    batches = pick_sources(deg, nb, a.sources, a.seed, rank)
+    rows = np.arange(a.sources, dtype=np.uint64)
+    stream = torch.cuda.ExternalStream(L.B200_stream())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def chain(F):
+        fl = 0
+        for _ in range(a.hops):
+            F.lmxm(A)
+            fl += fb.get_stat("last_flops")
+        F.wait()                      # materialise sorted CSR on the device
+        return fl
+
+    # ---- device-resident arm: F0 handles pre-built in HBM, dup'ed inside the step ----
+    F0 = []
+    for b in batches:
+        F = Matrix(a.sources, n, bool)
+        F.build(rows, b)
+        F.wait()
+        F0.append(F)
+    for i in range(a.warmup):
+        chain(F0[i].dup())
+    fb.set_option("timing", 1)
+    fb.reset_stats()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    flops = 0
+    nnz_out = 0
+    for i in range(a.warmup, nb):
+        F = F0[i].dup()
+        flops += chain(F)
+        nnz_out += F.nvals()
+        del F
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = fb.get_stat("launches")
+    kstats = {}
+    for name in ("bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "bits_fill", "bits_count"):
+        m, nl, by = C.c_double(), C.c_uint64(), C.c_uint64()
+        if L.B200_kernel_stats(name.encode(), C.byref(m), C.byref(nl), C.byref(by)) == 0 and nl.value:
+            kstats[name] = {"ms": m.value, "launches": nl.value, "bytes": by.value}
+    fb.set_option("timing", 0)
+
+    # ---- e2e arm: host buffers in, host CSR out, through the public C ABI ----
+    max_out = int(max(1, nnz_out // max(1, a.steps)) * 1.5) + 1024
+    out_p = torch.empty(a.sources + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    out_j = torch.empty(max_out, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    src_pin = [torch.from_numpy(b.astype(np.int64)).pin_memory().numpy().view(np.uint64) for b in batches]
+    rows_pin = torch.from_numpy(rows.astype(np.int64)).pin_memory().numpy().view(np.uint64)
+
+    def e2e_step(i):
+        F = Matrix(a.sources, n, bool)
+        F.build(rows_pin, src_pin[i])          # H2D of the step's inputs inside GxB_Matrix_build_Scalar
+        fl = chain(F)
+        nv = F.nvals()
+        nonlocal out_j
+        if nv > len(out_j):
+            out_j = torch.empty(int(nv * 1.2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        fb.check(L.B200_Matrix_export_CSR(F.h, out_p.ctypes.data, out_j.ctypes.data, None, 0))  # D2H of the result
+        return fl, nv
+
+    for i in range(a.warmup):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    f0.record(stream)
+    e2e_flops, e2e_nnz = 0, 0
+    for i in range(a.warmup, nb):
+        fl, nv = e2e_step(i)
+        e2e_flops += fl
+        e2e_nnz += nv
+    f1.record(stream)
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)  # device clock on the library stream; spans the host-side gaps between calls too
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    # sortedness + checksum property of the last result (size-independent parity property, cheap)
+    lastp = out_p.astype(np.int64)
+    assert lastp[0] == 0 and np.all(np.diff(lastp) >= 0)
+    r0 = out_j[lastp[0]:lastp[1]]
+    assert np.all(np.diff(r0.astype(np.int64)) > 0), "row 0 of the result is not strictly ascending"
+
+    # ---- reduce over ranks: time = max, work = sum ----
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = torch.tensor([flops, e2e_flops, launches, nnz_out], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = t.tolist()
+        flops, e2e_flops, launches, nnz_out = [int(x) for x in w.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    # dominant kernel = the family with the largest accumulated device time
+    roof = None
+    if kstats:
+        dom = max(kstats, key=lambda k: kstats[k]["ms"])
+        ks = kstats[dom]
+        per_launch_bytes = ks["bytes"] / ks["launches"]
+        per_launch_ms = ks["ms"] / ks["launches"]
+        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": None, "launch_ms": per_launch_ms, "launches": ks["launches"],
+                "share_of_step": ks["ms"] / ms,
+                "algorithmic_bytes_per_launch": per_launch_bytes}
+    # SURVEY 8d's row-wise formula (4 B per flop dominant) for the whole step, for reference: a frontier kernel that
+    # serves 64*W rows per pass over A reads far fewer bytes than this, so this fraction may exceed 1.
+    survey_bytes = 4 * flops + 4 * nnz_out
+    survey = {"bytes_mxm_formula": survey_bytes, "achieved": survey_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+              "frac_of_peak": survey_bytes / (ms * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            import oracle as orc
+            from oracle import CSR
+            pj = np.empty(nnzA, np.uint32)
+            fb.check(L.B200_Matrix_export_CSR(A.h, p.ctypes.data, pj.ctypes.data, None, 0))
+            Ao = CSR(n, n, p.astype(np.int64), pj)
+            ncpu = a.cpu_sources if a.cpu_sources > 0 else min(a.sources, max(8, orc.num_threads()))
+            b = batches[a.warmup][:ncpu]
+            t0 = time.perf_counter()
+            Fo, cfl = cpu_chain(orc, Ao, b, a.hops)
+            ct = time.perf_counter() - t0
+            # parity spot-check at FULL size: the same sources through the GPU path must give identical rows
+            G = Matrix(len(b), n, bool)
+            G.build(np.arange(len(b), dtype=np.uint64), b)
+            chain(G)
+            gp, gj, _ = G.export_csr()
+            parity = bool(np.array_equal(gp, Fo.p) and np.array_equal(gj, Fo.j))
+            cpu = {"value": cfl / ct, "unit": "edges/s", "cores": orc.num_threads(), "kind": "port",
+                   "sample": f"{a.hops}-hop chain for the first {len(b)} sources of the first timed batch ({cfl} flops, {ct:.1f} s)",
+                   "full_size_parity_bit_exact": parity}
+        except Exception as ex:  # the baseline must never take the bench line down
+            cpu = {"value": None, "error": repr(ex)}
+
+    h2d = 16 * a.sources
+    d2h = int(4 * e2e_nnz / a.steps + 8 * (a.sources + 1))
+    line = {
+        "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": flops / (ms * 1e-3), "unit": "edges/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
+        "config": {"workload": f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}",
+                   "n": n, "nnz_A": nnzA, "sources_per_gpu_per_step": a.sources, "parallelism": f"replicated A, sources sharded x{world}",
+                   "l2_policy": "inputs larger than L2 (A col_idx %.2f GB) and a fresh random source batch every step" % (4 * nnzA / 1e9),
+                   "bits_mode": a.bits_mode, "pull_mode": a.pull_mode, "setup_s": round(setup_s, 2)},
+        "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz_out / a.steps,
+        "e2e": {"value": e2e_flops / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": e2e_wall_ms / a.steps},
+        "gpu_launches": int(launches), "kernels": kstats, "roofline": roof, "roofline_survey_formula": survey,
+        "cpu_baseline": cpu, "clocks": clk}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,171 @@
+// common.cuh -- device-memory, stream, launch-accounting and error plumbing shared by every
+// translation unit of libb200grb.so (the B200-native GraphBLAS traversal backend).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cstdio>
+
+namespace b200 {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+struct CudaError : std::runtime_error {
+    cudaError_t code;
+    CudaError(cudaError_t c, const char *file, int line)
+        : std::runtime_error(std::string(cudaGetErrorName(c)) + ": " + cudaGetErrorString(c) + " at " + file + ":" +
+                             std::to_string(line)),
+          code(c) {}
+};
+struct GrbError : std::runtime_error {
+    int info;
+    GrbError(int i, const std::string &m) : std::runtime_error(m), info(i) {}
+};
+
+#define CUDA_TRY(expr)                                                    \
+    do {                                                                  \
+        cudaError_t e__ = (expr);                                         \
+        if (e__ != cudaSuccess) throw ::b200::CudaError(e__, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- global context (one process per GPU; one library stream) -------------------------------
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::atomic<u64> launches{0};     // kernels of THIS library launched (bench.py gpu_launches)
+    std::atomic<u64> lib_launches{0}; // CUB primitives launched on our behalf (sort / scan)
+    // last-op statistics (read through B200_get_stat)
+    std::atomic<u64> last_flops{0}, total_flops{0}, last_path{0};
+    std::atomic<u64> h2d_bytes{0}, d2h_bytes{0};
+    // tunables (B200_set_option)
+    i64 opt_bits_mode = -1;        // -1 auto, 0 never use the bit-frontier path, 1 always when legal
+    i64 opt_pull_mode = -1;        // -1 auto, 0 push only, 1 pull only
+    i64 opt_small_cap = 4096;      // rows with <= this many flops use the shared-memory sort path
+    i64 opt_bitmap_budget = (i64)2 << 30; // bytes of global bitmap scratch per heavy-row wave
+    i64 opt_bits_min_flops = 1 << 22;     // auto mode: use bit-frontier when flops >= this
+    i64 opt_sync_after_op = 0;
+    i64 opt_timing = 0;
+};
+Context &ctx();
+void ensure_init();
+
+inline cudaStream_t stream() { return ctx().stream; }
+
+// ---- optional per-kernel timing (CUDA events on the launch stream; B200_set_option("timing",1)) ----
+enum TimedId { TK_BITS_PULL = 0, TK_BITS_PULL_LONG, TK_BITS_PUSH, TK_HEAVY_ACC, TK_SMALL_ROWS, TK_BITS_FILL, TK_BITS_COUNT,
+               TK_BITMAP_EXPAND, TK_BFS_EXPAND, TK_UNION, TK_FILTER, TK_COUNT_ };
+const char *timed_name(int id);
+void timed_begin(int id);
+void timed_end(int id, u64 algorithmic_bytes);
+struct TimedScope {
+    int id; u64 bytes;
+    TimedScope(int i, u64 b) : id(i), bytes(b) { timed_begin(id); }
+    ~TimedScope() { timed_end(id, bytes); }
+};
+// drains recorded events: total ms / launches / bytes per id
+void timed_collect(double *ms, u64 *launches, u64 *bytes);
+void timed_reset();
+
+// ---- stream-ordered device buffers ----------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : ptr(o.ptr), n(o.n) { o.ptr = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); ptr = o.ptr; n = o.n; o.ptr = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) { ptr = nullptr; return; }
+        CUDA_TRY(cudaMallocAsync((void **)&ptr, count * sizeof(T), stream()));
+    }
+    void release() {
+        if (ptr) { cudaFreeAsync(ptr, stream()); ptr = nullptr; }
+        n = 0;
+    }
+    void zero() { if (n) CUDA_TRY(cudaMemsetAsync(ptr, 0, n * sizeof(T), stream())); }
+    T *release_ownership() { T *p = ptr; ptr = nullptr; n = 0; return p; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline void sync_stream() { CUDA_TRY(cudaStreamSynchronize(stream())); }
+
+template <typename T>
+inline T read_scalar(const T *dptr) {
+    T v;
+    CUDA_TRY(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, stream()));
+    sync_stream();
+    return v;
+}
+template <typename T>
+inline void h2d(T *dst, const T *src, size_t n) {
+    if (n) { CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream())); ctx().h2d_bytes += n * sizeof(T); }
+}
+template <typename T>
+inline void d2h(T *dst, const T *src, size_t n) {
+    if (n) { CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream())); ctx().d2h_bytes += n * sizeof(T); }
+}
+template <typename T>
+inline void d2d(T *dst, const T *src, size_t n) {
+    if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, stream()));
+}
+
+// Kernel launch with accounting.  Usage: LAUNCH(kernel, grid, block, smem, args...)
+#define LAUNCH(kern, grid, block, smem, ...)                                   \
+    do {                                                                       \
+        ::b200::ctx().launches.fetch_add(1, std::memory_order_relaxed);        \
+        kern<<<(grid), (block), (smem), ::b200::stream()>>>(__VA_ARGS__);      \
+        CUDA_TRY(cudaGetLastError());                                          \
+    } while (0)
+
+inline u32 grid_for(u64 items, u32 per_block, u64 cap = 0x7fffffffULL) {
+    u64 g = (items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (u32)g;
+}
+
+// ---- device CSR -----------------------------------------------------------------------------
+// rowptr u64[nrows+1], col u32[nnz] ascending within a row, val u64[nnz] or null (iso/pattern).
+struct DevCSR {
+    u64 nrows = 0, ncols = 0, nnz = 0;
+    DevBuf<u64> p;
+    DevBuf<u32> j;
+    DevBuf<u64> x; // empty => pattern-only (every stored value is true / 1)
+    bool has_values() const { return x.ptr != nullptr; }
+    void clear() { p.release(); j.release(); x.release(); nnz = 0; }
+};
+
+// frontier bit-matrix: an r x n boolean matrix (r <= 64*W) stored vertex-major:
+// word[v*W + w] bit b  <=>  entry (row 64*w+b, col v).
+struct DevBits {
+    u64 nrows = 0, ncols = 0;
+    u32 W = 0;
+    DevBuf<u64> w;
+    bool valid() const { return w.ptr != nullptr; }
+    void clear() { w.release(); W = 0; }
+};
+
+// ---- primitive wrappers implemented in prims.cu (CUB scan / sort) ----------------------------
+void exclusive_scan_u64(const u64 *in, u64 *out, size_t n);           // out[i] = sum in[0..i)
+void exclusive_scan_u32_to_u64(const u32 *in, u64 *out, size_t n);
+void sort_keys_u64(u64 *keys_in_out, size_t n, int end_bit);            // ascending, in place (uses temp)
+void sort_pairs_u64(u64 *keys_in_out, u64 *vals_in_out, size_t n, int end_bit); // stable
+u64 reduce_sum_u64(const u64 *in, size_t n);
+
+} // namespace b200

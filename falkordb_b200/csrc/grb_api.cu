@@ -1,0 +1,1411 @@
+// grb_api.cu -- the C ABI (include/b200grb.h): opaque handles, GraphBLAS write-back semantics
+// (mask / complement / structural / replace / accum) and dispatch onto the CUDA kernel layer.
+//
+// Handle model.  A GrB_Matrix owns up to three interchangeable forms of the same content:
+//   host  : hypersparse sorted tuples (element access, iterators, pending setElement/removeElement)
+//   dev   : device CSR (every bulk operation)
+//   bits  : device frontier bit-matrix (short-fat mxm results between hops, bits.cu)
+// plus a cached transpose mirror of `dev` for the pull direction.  Bulk results are produced on the
+// device and only travel to the host when something observes them (GraphBLAS non-blocking mode:
+// matrix.rs:116-131 initialises GrB_NONBLOCKING).  There is NO CPU implementation of any bulk
+// operation in this file: without a GPU they fail with GxB_GPU_ERROR.
+#include "../../include/b200grb.h"
+#include "common.cuh"
+#include "ops.cuh"
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------ opaque types
+struct GB_Type_opaque { int code; size_t size; const char *name; };
+struct GB_UnaryOp_opaque { int code; };
+struct GB_BinaryOp_opaque { int code; };
+struct GB_Semiring_opaque { int code; };
+struct GB_Global_opaque { int x; };
+struct GB_Descriptor_opaque { bool t0, t1, comp, structure, replace; };
+struct GB_Scalar_opaque { int type; bool has; uint64_t val; };
+
+enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3 };
+enum { OP_ANY_BOOL = 1, OP_SECOND_UINT64 = 2, OP_ANY_UINT64 = 3 };
+
+static GB_Type_opaque t_bool = {T_BOOL, 1, "bool"}, t_u64 = {T_UINT64, 8, "uint64_t"}, t_i64 = {T_INT64, 8, "int64_t"};
+static GB_Semiring_opaque s_any_pair = {1};
+static GB_BinaryOp_opaque b_any_bool = {OP_ANY_BOOL}, b_second_u64 = {OP_SECOND_UINT64}, b_any_u64 = {OP_ANY_UINT64};
+static GB_UnaryOp_opaque u_one_bool = {1};
+static GB_Global_opaque g_global = {0};
+
+extern "C" {
+GrB_Type GrB_BOOL = &t_bool, GrB_UINT64 = &t_u64, GrB_INT64 = &t_i64;
+GrB_Semiring GxB_ANY_PAIR_BOOL = &s_any_pair;
+GrB_BinaryOp GxB_ANY_BOOL = &b_any_bool, GrB_SECOND_UINT64 = &b_second_u64, GxB_ANY_UINT64 = &b_any_u64;
+GrB_UnaryOp GxB_ONE_BOOL = &u_one_bool;
+const GrB_Global GrB_GLOBAL = &g_global;
+}
+
+#define DESC(name, R, S, C, T0, T1) \
+    static GB_Descriptor_opaque d_##name = {T0, T1, C, S, R}; \
+    extern "C" { GrB_Descriptor GrB_DESC_##name = &d_##name; }
+DESC(T1, 0, 0, 0, 0, 1) DESC(T0, 0, 0, 0, 1, 0) DESC(T0T1, 0, 0, 0, 1, 1)
+DESC(C, 0, 0, 1, 0, 0) DESC(CT1, 0, 0, 1, 0, 1) DESC(CT0, 0, 0, 1, 1, 0) DESC(CT0T1, 0, 0, 1, 1, 1)
+DESC(S, 0, 1, 0, 0, 0) DESC(ST1, 0, 1, 0, 0, 1) DESC(ST0, 0, 1, 0, 1, 0) DESC(ST0T1, 0, 1, 0, 1, 1)
+DESC(SC, 0, 1, 1, 0, 0) DESC(SCT1, 0, 1, 1, 0, 1) DESC(SCT0, 0, 1, 1, 1, 0) DESC(SCT0T1, 0, 1, 1, 1, 1)
+DESC(R, 1, 0, 0, 0, 0) DESC(RT1, 1, 0, 0, 0, 1) DESC(RT0, 1, 0, 0, 1, 0) DESC(RT0T1, 1, 0, 0, 1, 1)
+DESC(RC, 1, 0, 1, 0, 0) DESC(RCT1, 1, 0, 1, 0, 1) DESC(RCT0, 1, 0, 1, 1, 0) DESC(RCT0T1, 1, 0, 1, 1, 1)
+DESC(RS, 1, 1, 0, 0, 0) DESC(RST1, 1, 1, 0, 0, 1) DESC(RST0, 1, 1, 0, 1, 0) DESC(RST0T1, 1, 1, 0, 1, 1)
+DESC(RSC, 1, 1, 1, 0, 0) DESC(RSCT1, 1, 1, 1, 0, 1) DESC(RSCT0, 1, 1, 1, 1, 0) DESC(RSCT0T1, 1, 1, 1, 1, 1)
+
+struct HostStore {
+    std::vector<u64> hrow; // ascending ids of the non-empty rows
+    std::vector<u64> hptr; // hrow.size()+1
+    std::vector<u64> hcol; // ascending inside a row
+    std::vector<u64> hval; // empty for pattern-only (BOOL)
+    void clear() { hrow.clear(); hptr.assign(1, 0); hcol.clear(); hval.clear(); }
+    u64 nnz() const { return hcol.size(); }
+};
+struct PendingOp { u64 i, j, v; u64 seq; bool del; };
+
+static const u32 MAGIC = 0xB200A7u;
+
+struct GB_Matrix_opaque {
+    u32 magic = MAGIC;
+    int type = T_BOOL;
+    u64 nrows = 0, ncols = 0;
+    std::mutex mu;
+    bool host_valid = true;
+    HostStore host;
+    std::vector<PendingOp> pending;
+    bool dev_valid = false;
+    DevCSR dev;
+    bool bits_valid = false;
+    DevBits bits;
+    bool devT_valid = false;
+    DevCSR devT;
+    LongRows lr;
+    int sparsity_control = GxB_HYPERSPARSE | GxB_SPARSE | GxB_BITMAP | GxB_FULL;
+    int hyper_hash = 1;
+    int orientation = GrB_ROWMAJOR;
+    GB_Matrix_opaque() { host.clear(); }
+    bool valued() const { return type != T_BOOL; }
+};
+
+struct GB_Vector_opaque {
+    u32 magic = MAGIC;
+    int type = T_BOOL;
+    u64 n = 0;
+    std::vector<u64> idx; // ascending
+    std::vector<i64> val; // same length (bool: 1)
+};
+
+struct GB_Iterator_opaque {
+    GrB_Matrix A = nullptr;
+    u64 k = 0; // vector (non-empty row) position
+    u64 q = 0; // entry position
+    bool exhausted = true;
+};
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string tl_error;
+static std::mutex g_gpu_mu; // serialises GPU submission across caller threads
+static bool g_initialised = false;
+
+template <class F>
+static GrB_Info guarded(F &&f) {
+    try {
+        return f();
+    } catch (const GrbError &e) {
+        tl_error = e.what();
+        return (GrB_Info)e.info;
+    } catch (const CudaError &e) {
+        tl_error = e.what();
+        if (e.code == cudaErrorMemoryAllocation) return GrB_OUT_OF_MEMORY;
+        return GxB_GPU_ERROR;
+    } catch (const std::bad_alloc &) {
+        tl_error = "host allocation failed";
+        return GrB_OUT_OF_MEMORY;
+    } catch (const std::exception &e) {
+        tl_error = e.what();
+        return GrB_PANIC;
+    }
+}
+#define CHECK_PTR(p) do { if (!(p)) { tl_error = "null pointer: " #p; return GrB_NULL_POINTER; } } while (0)
+#define CHECK_MAT(m) do { if (!(m)) { tl_error = "null matrix: " #m; return GrB_NULL_POINTER; } \
+                          if ((m)->magic != MAGIC) { tl_error = "invalid matrix: " #m; return GrB_INVALID_OBJECT; } } while (0)
+
+struct MultiLock {
+    std::vector<std::unique_lock<std::mutex>> locks;
+    MultiLock(std::initializer_list<GrB_Matrix> ms) {
+        std::vector<GrB_Matrix> v;
+        for (GrB_Matrix m : ms) if (m) v.push_back(m);
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        for (GrB_Matrix m : v) locks.emplace_back(m->mu);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ form management
+static void invalidate_aux(GrB_Matrix A) {
+    A->devT_valid = false;
+    A->devT.clear();
+    A->lr.rows.release();
+    A->lr.built = false;
+    A->lr.n = 0;
+}
+
+static void set_dev(GrB_Matrix A, DevCSR &&d) {
+    A->dev = std::move(d);
+    A->dev.nrows = A->nrows; A->dev.ncols = A->ncols;
+    // type discipline: BOOL is pattern-only, UINT64/INT64 always carry a value array
+    if (!A->valued()) A->dev.x.release();
+    else if (!A->dev.has_values()) {
+        A->dev.x.alloc(A->dev.nnz);
+        fill_u64(A->dev.x.ptr, 1, A->dev.nnz); // typecast of `true`
+    }
+    A->dev_valid = true;
+    A->host_valid = false;
+    A->host.clear();
+    A->pending.clear();
+    A->bits_valid = false;
+    A->bits.clear();
+    invalidate_aux(A);
+}
+
+static void set_bits(GrB_Matrix A, DevBits &&b) {
+    A->bits = std::move(b);
+    A->bits_valid = true;
+    A->dev_valid = false;
+    A->dev.clear();
+    A->host_valid = false;
+    A->host.clear();
+    A->pending.clear();
+    invalidate_aux(A);
+}
+
+static void set_empty(GrB_Matrix A) {
+    A->host.clear();
+    A->host_valid = true;
+    A->pending.clear();
+    A->dev_valid = false; A->dev.clear();
+    A->bits_valid = false; A->bits.clear();
+    invalidate_aux(A);
+}
+
+static void download_to_host(GrB_Matrix A); // fwd
+
+// apply queued setElement / removeElement onto the host store (GrB_Matrix_wait, matrix.rs:781-796)
+static void finish_pending(GrB_Matrix A) {
+    if (A->pending.empty()) return;
+    if (!A->host_valid) download_to_host(A);
+    std::vector<PendingOp> &p = A->pending;
+    std::sort(p.begin(), p.end(), [](const PendingOp &a, const PendingOp &b) {
+        if (a.i != b.i) return a.i < b.i;
+        if (a.j != b.j) return a.j < b.j;
+        return a.seq < b.seq;
+    });
+    // keep the last op per coordinate
+    std::vector<PendingOp> last;
+    last.reserve(p.size());
+    for (size_t t = 0; t < p.size(); t++)
+        if (t + 1 == p.size() || p[t + 1].i != p[t].i || p[t + 1].j != p[t].j) last.push_back(p[t]);
+    HostStore &h = A->host;
+    HostStore out;
+    out.hptr.clear();
+    bool valued = A->valued();
+    size_t pi = 0;
+    u64 k = 0, nvec = h.hrow.size();
+    auto emit = [&](u64 row, u64 col, u64 val) {
+        if (out.hrow.empty() || out.hrow.back() != row) { out.hrow.push_back(row); out.hptr.push_back(out.hcol.size()); }
+        out.hcol.push_back(col);
+        if (valued) out.hval.push_back(val);
+    };
+    while (k < nvec || pi < last.size()) {
+        u64 row;
+        if (k >= nvec) row = last[pi].i;
+        else if (pi >= last.size()) row = h.hrow[k];
+        else row = std::min(h.hrow[k], last[pi].i);
+        u64 q = 0, qe = 0;
+        if (k < nvec && h.hrow[k] == row) { q = h.hptr[k]; qe = h.hptr[k + 1]; k++; }
+        while (q < qe || (pi < last.size() && last[pi].i == row)) {
+            bool hp = pi < last.size() && last[pi].i == row;
+            if (q < qe && (!hp || h.hcol[q] < last[pi].j)) {
+                emit(row, h.hcol[q], valued ? h.hval[q] : 1);
+                q++;
+            } else {
+                const PendingOp &op = last[pi];
+                if (q < qe && h.hcol[q] == op.j) q++; // overwritten or deleted
+                if (!op.del) emit(row, op.j, op.v);
+                pi++;
+            }
+        }
+    }
+    out.hptr.push_back(out.hcol.size());
+    A->host = std::move(out);
+    A->pending.clear();
+    A->dev_valid = false; A->dev.clear();
+    A->bits_valid = false; A->bits.clear();
+    invalidate_aux(A);
+}
+
+static void upload_to_dev(GrB_Matrix A) {
+    if (A->nrows >= ((u64)1 << 32) || A->ncols >= ((u64)1 << 32))
+        throw GrbError(GrB_NOT_IMPLEMENTED, "bulk GPU operations need dimensions < 2^32 (host-only hypersparse matrix)");
+    ensure_init();
+    HostStore &h = A->host;
+    u64 nvec = h.hrow.size(), nnz = h.nnz();
+    DevCSR d;
+    d.nrows = A->nrows; d.ncols = A->ncols; d.nnz = nnz;
+    d.p.alloc(A->nrows + 1);
+    if (nnz == 0) {
+        d.p.zero();
+    } else {
+        DevBuf<u64> dh(nvec), dp(nvec + 1), dc(nnz);
+        h2d(dh.ptr, h.hrow.data(), nvec);
+        h2d(dp.ptr, h.hptr.data(), nvec + 1);
+        h2d(dc.ptr, h.hcol.data(), nnz);
+        rowptr_from_hyper(dh.ptr, dp.ptr, nvec, A->nrows, d.p.ptr);
+        d.j.alloc(nnz);
+        narrow_u64(dc.ptr, d.j.ptr, nnz);
+        if (A->valued()) { d.x.alloc(nnz); h2d(d.x.ptr, h.hval.data(), nnz); }
+        sync_stream(); // host vectors are pageable: make sure staging copies are done before they can change
+    }
+    A->dev = std::move(d);
+    A->dev_valid = true;
+}
+
+static void ensure_dev(GrB_Matrix A) {
+    finish_pending(A);
+    if (A->dev_valid) return;
+    if (A->bits_valid) {
+        DevCSR d;
+        bits_to_csr(A->bits, d);
+        A->dev = std::move(d);
+        if (A->valued()) { A->dev.x.alloc(A->dev.nnz); fill_u64(A->dev.x.ptr, 1, A->dev.nnz); }
+        A->dev_valid = true;
+        return;
+    }
+    upload_to_dev(A);
+}
+
+static void download_to_host(GrB_Matrix A) {
+    if (A->host_valid) return;
+    if (!A->dev_valid) ensure_dev(A);
+    const DevCSR &d = A->dev;
+    HostStore h;
+    h.clear();
+    if (d.nnz) {
+        DevBuf<u64> dh, dp, dc(d.nnz);
+        u64 nvec = hyper_from_rowptr(d.p.ptr, d.nrows, d.nnz, dh, dp);
+        widen_u32(d.j.ptr, dc.ptr, d.nnz);
+        h.hrow.resize(nvec);
+        h.hptr.resize(nvec + 1);
+        h.hcol.resize(d.nnz);
+        d2h(h.hrow.data(), dh.ptr, nvec);
+        d2h(h.hptr.data(), dp.ptr, nvec + 1);
+        d2h(h.hcol.data(), dc.ptr, d.nnz);
+        if (A->valued()) { h.hval.resize(d.nnz); d2h(h.hval.data(), d.x.ptr, d.nnz); }
+        sync_stream();
+    }
+    A->host = std::move(h);
+    A->host_valid = true;
+}
+
+static void ensure_host(GrB_Matrix A) {
+    if (!A->host_valid) download_to_host(A);
+    finish_pending(A);
+}
+
+static void ensure_bits(GrB_Matrix A) {
+    finish_pending(A);
+    if (A->bits_valid) return;
+    ensure_dev(A);
+    DevBits b;
+    bits_from_csr(A->dev, b);
+    A->bits = std::move(b);
+    A->bits_valid = true;
+}
+
+static void ensure_devT(GrB_Matrix A) {
+    ensure_dev(A);
+    if (!A->devT_valid) {
+        DevCSR t;
+        transpose_csr(A->dev, t, false); // pattern-only mirror
+        A->devT = std::move(t);
+        A->devT_valid = true;
+    }
+    if (!A->lr.built) build_long_rows(A->devT, A->lr);
+}
+
+static u64 matrix_nvals(GrB_Matrix A) {
+    finish_pending(A);
+    if (A->host_valid) return A->host.nnz();
+    if (A->dev_valid) return A->dev.nnz;
+    return bits_nvals(A->bits);
+}
+
+// ------------------------------------------------------------------------------------------------ write-back
+struct Desc { bool t0 = false, t1 = false, comp = false, structure = false, replace = false; };
+static Desc get_desc(GrB_Descriptor d) {
+    Desc r;
+    if (d) { r.t0 = d->t0; r.t1 = d->t1; r.comp = d->comp; r.structure = d->structure; r.replace = d->replace; }
+    return r;
+}
+
+// C<M,desc> = accum ? (C (+) T) : T       (GraphBLAS C API 2.1 write-back; accum is ANY or absent)
+static void write_back(GrB_Matrix C, DevCSR &&T, GrB_Matrix M, const Desc &d, bool accum) {
+    bool valued = C->valued();
+    DevCSR Z;
+    if (accum) {
+        ensure_dev(C);
+        ewise_union(C->dev, T, valued, Z);
+    } else {
+        Z = std::move(T);
+    }
+    if (!M) {
+        if (d.comp) { // complement of "no mask" admits nothing
+            if (d.replace) set_empty(C);
+            return;
+        }
+        set_dev(C, std::move(Z));
+        return;
+    }
+    ensure_dev(M);
+    DevCSR Zm;
+    filter_by_mask(Z, M->dev, d.comp, d.structure, Zm);
+    if (d.replace) { set_dev(C, std::move(Zm)); return; }
+    ensure_dev(C);
+    DevCSR Ck, U;
+    filter_by_mask(C->dev, M->dev, !d.comp, d.structure, Ck);
+    ewise_union(Ck, Zm, valued, U);
+    set_dev(C, std::move(U));
+}
+
+static void check_mask_dims(GrB_Matrix C, GrB_Matrix M) {
+    if (M && (M->nrows != C->nrows || M->ncols != C->ncols)) throw GrbError(GrB_DIMENSION_MISMATCH, "mask dimensions differ from C");
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char *B200_last_error(void) { return tl_error.c_str(); }
+
+GrB_Info GxB_init(int mode, void *(*)(size_t), void *(*)(size_t, size_t), void *(*)(void *, size_t), void (*)(void *)) {
+    (void)mode;
+    // Host containers use the C++ allocator; the user allocator hooks only matter for Redis memory
+    // accounting in the reference (matrix.rs:104-107) and are accepted for signature compatibility.
+    g_initialised = true;
+    return GrB_SUCCESS; // the CUDA context is created lazily by the first bulk operation
+}
+GrB_Info GrB_init(int mode) { return GxB_init(mode, nullptr, nullptr, nullptr, nullptr); }
+GrB_Info GrB_finalize(void) { g_initialised = false; return GrB_SUCCESS; }
+GrB_Info GrB_Global_set_INT32(GrB_Global, int32_t, int field) {
+    if (field == GxB_JIT_C_CONTROL || field == GxB_BURBLE) return GrB_SUCCESS;
+    return GrB_INVALID_VALUE;
+}
+GrB_Info GxB_Global_Option_set_INT32(int field, int32_t) {
+    if (field == GxB_NTHREADS) return GrB_SUCCESS; // host thread count is irrelevant to the GPU path
+    return GrB_INVALID_VALUE;
+}
+
+// ---------------------------------------------------------------------------------------------- objects
+GrB_Info GrB_Matrix_new(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols) {
+    CHECK_PTR(A); CHECK_PTR(type);
+    if (nrows > ((u64)1 << 60) || ncols > ((u64)1 << 60)) { tl_error = "dimension > 2^60"; return GrB_INVALID_VALUE; }
+    return guarded([&]() {
+        GrB_Matrix m = new GB_Matrix_opaque();
+        m->type = type->code;
+        m->nrows = nrows; m->ncols = ncols;
+        *A = m;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_free(GrB_Matrix *A) {
+    if (!A || !*A) return GrB_SUCCESS;
+    if ((*A)->magic != MAGIC) return GrB_INVALID_OBJECT;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        (*A)->magic = 0;
+        delete *A;
+        *A = nullptr;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A) {
+    CHECK_PTR(C); CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        GrB_Matrix m = new GB_Matrix_opaque();
+        m->type = A->type; m->nrows = A->nrows; m->ncols = A->ncols;
+        m->sparsity_control = A->sparsity_control; m->orientation = A->orientation;
+        // pending work is copied, not finished (GB_dup; relied on by Matrix::grown, matrix.rs:691-698)
+        m->pending = A->pending;
+        m->host_valid = A->host_valid;
+        if (A->host_valid) m->host = A->host;
+        if (A->dev_valid) { csr_copy(A->dev, m->dev, true); m->dev_valid = true; }
+        if (A->bits_valid && !A->dev_valid) { bits_copy(A->bits, m->bits); m->bits_valid = true; }
+        *C = m;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_clear(GrB_Matrix A) {
+    CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        set_empty(A);
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_resize(GrB_Matrix C, GrB_Index nr, GrB_Index nc) {
+    CHECK_MAT(C);
+    if (nr > ((u64)1 << 60) || nc > ((u64)1 << 60)) return GrB_INVALID_VALUE;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C};
+        bool shrink = nr < C->nrows || nc < C->ncols;
+        finish_pending(C);
+        if (C->host_valid) {
+            if (shrink) {
+                HostStore &h = C->host, out;
+                out.hptr.clear();
+                bool valued = C->valued();
+                for (u64 k = 0; k < h.hrow.size(); k++) {
+                    if (h.hrow[k] >= nr) break;
+                    size_t before = out.hcol.size();
+                    for (u64 q = h.hptr[k]; q < h.hptr[k + 1]; q++) {
+                        if (h.hcol[q] >= nc) break;
+                        out.hcol.push_back(h.hcol[q]);
+                        if (valued) out.hval.push_back(h.hval[q]);
+                    }
+                    if (out.hcol.size() > before) { out.hrow.push_back(h.hrow[k]); out.hptr.push_back(before); }
+                }
+                out.hptr.push_back(out.hcol.size());
+                C->host = std::move(out);
+            }
+            C->nrows = nr; C->ncols = nc;
+            C->dev_valid = false; C->dev.clear();
+            C->bits_valid = false; C->bits.clear();
+            invalidate_aux(C);
+            return GrB_SUCCESS;
+        }
+        ensure_dev(C);
+        if (nr >= ((u64)1 << 32) || nc >= ((u64)1 << 32)) { // leaves the device-capable range
+            download_to_host(C);
+            C->nrows = nr; C->ncols = nc;
+            C->dev_valid = false; C->dev.clear();
+            C->bits_valid = false; C->bits.clear();
+            invalidate_aux(C);
+            return GrB_SUCCESS;
+        }
+        DevCSR out;
+        csr_resize(C->dev, nr, nc, out);
+        C->nrows = nr; C->ncols = nc;
+        set_dev(C, std::move(out));
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_nrows(GrB_Index *n, GrB_Matrix A) { CHECK_PTR(n); CHECK_MAT(A); *n = A->nrows; return GrB_SUCCESS; }
+GrB_Info GrB_Matrix_ncols(GrB_Index *n, GrB_Matrix A) { CHECK_PTR(n); CHECK_MAT(A); *n = A->ncols; return GrB_SUCCESS; }
+GrB_Info GrB_Matrix_nvals(GrB_Index *n, GrB_Matrix A) {
+    CHECK_PTR(n); CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        *n = matrix_nvals(A);
+        return GrB_SUCCESS;
+    });
+}
+
+static u64 nonempty_rows(GrB_Matrix A) { return A->host.hrow.size(); }
+
+GrB_Info GrB_Matrix_set_INT32(GrB_Matrix A, int32_t value, int field) {
+    CHECK_MAT(A);
+    switch (field) {
+    case GxB_SPARSITY_CONTROL: A->sparsity_control = value; return GrB_SUCCESS;
+    case GrB_STORAGE_ORIENTATION_HINT: A->orientation = value; return GrB_SUCCESS;
+    case GxB_HYPER_HASH: A->hyper_hash = value; return GrB_SUCCESS;
+    default: return GrB_INVALID_VALUE;
+    }
+}
+
+GrB_Info GrB_Matrix_get_INT32(GrB_Matrix A, int32_t *value, int field) {
+    CHECK_MAT(A); CHECK_PTR(value);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        switch (field) {
+        case GxB_SPARSITY_CONTROL: *value = A->sparsity_control; return GrB_SUCCESS;
+        case GrB_STORAGE_ORIENTATION_HINT: *value = A->orientation; return GrB_SUCCESS;
+        case GxB_HYPER_HASH: *value = A->hyper_hash; return GrB_SUCCESS;
+        case GxB_WILL_WAIT: *value = (!A->pending.empty() || (A->bits_valid && !A->dev_valid && !A->host_valid)) ? 1 : 0; return GrB_SUCCESS;
+        case GxB_SPARSITY_STATUS: {
+            // never bitmap/full on this path (matrix.rs:401-426, 558-575).  Hypersparse when pinned so,
+            // or when allowed and fewer than 1/16 of the rows are non-empty (SuiteSparse hyper_switch).
+            bool hyper = false;
+            if (A->sparsity_control == GxB_HYPERSPARSE) hyper = true;
+            else if ((A->sparsity_control & GxB_HYPERSPARSE) && A->host_valid && A->pending.empty()) {
+                hyper = A->nrows > 1 && nonempty_rows(A) * 16 < A->nrows;
+            }
+            if (!(A->sparsity_control & GxB_SPARSE) && (A->sparsity_control & GxB_HYPERSPARSE)) hyper = true;
+            *value = hyper ? GxB_HYPERSPARSE : GxB_SPARSE;
+            return GrB_SUCCESS;
+        }
+        default: return GrB_INVALID_VALUE;
+        }
+    });
+}
+
+GrB_Info GxB_Matrix_type(GrB_Type *type, GrB_Matrix A) {
+    CHECK_PTR(type); CHECK_MAT(A);
+    *type = A->type == T_BOOL ? GrB_BOOL : (A->type == T_UINT64 ? GrB_UINT64 : GrB_INT64);
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_Matrix_iso(bool *iso, GrB_Matrix A) { CHECK_PTR(iso); CHECK_MAT(A); *iso = (A->type == T_BOOL); return GrB_SUCCESS; }
+GrB_Info GxB_Matrix_memoryUsage(size_t *size, GrB_Matrix A) {
+    CHECK_PTR(size); CHECK_MAT(A);
+    size_t s = sizeof(GB_Matrix_opaque);
+    s += (A->host.hrow.size() + A->host.hptr.size() + A->host.hcol.size() + A->host.hval.size()) * 8;
+    s += A->pending.size() * sizeof(PendingOp);
+    s += A->dev.p.bytes() + A->dev.j.bytes() + A->dev.x.bytes() + A->bits.w.bytes();
+    s += A->devT.p.bytes() + A->devT.j.bytes() + A->devT.x.bytes();
+    *size = s;
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_Matrix_fprint(GrB_Matrix A, const char *name, int pr, FILE *f) {
+    CHECK_MAT(A);
+    if (pr <= 0) return GrB_SUCCESS;
+    if (!f) f = stdout;
+    fprintf(f, "b200grb matrix %s: %llu x %llu, type %d, forms host=%d dev=%d bits=%d pending=%zu\n", name ? name : "",
+            (unsigned long long)A->nrows, (unsigned long long)A->ncols, A->type, A->host_valid, A->dev_valid, A->bits_valid,
+            A->pending.size());
+    return GrB_SUCCESS;
+}
+
+GrB_Info GrB_Matrix_wait(GrB_Matrix A, int waitmode) {
+    CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        finish_pending(A);
+        if (waitmode == GrB_MATERIALIZE && !A->host_valid && !A->dev_valid && A->bits_valid) ensure_dev(A);
+        if (A->dev_valid || A->bits_valid) sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- element access
+static GrB_Info set_element(GrB_Matrix C, u64 v, u64 i, u64 j) {
+    if (i >= C->nrows || j >= C->ncols) { tl_error = "setElement index out of bounds"; return GrB_INVALID_INDEX; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C};
+        if (!C->host_valid) download_to_host(C);
+        PendingOp op{i, j, v, (u64)C->pending.size(), false};
+        C->pending.push_back(op);
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GrB_Matrix_setElement_BOOL(GrB_Matrix C, bool x, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(C);
+    if (C->type == T_BOOL && !x) {
+        tl_error = "BOOL matrices are pattern-only on this backend (stored false is never used on the path: versioned_matrix.rs:413-416)";
+        return GrB_NOT_IMPLEMENTED;
+    }
+    return set_element(C, x ? 1 : 0, i, j);
+}
+GrB_Info GrB_Matrix_setElement_UINT64(GrB_Matrix C, uint64_t x, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(C);
+    if (C->type == T_BOOL && x == 0) { tl_error = "typecast of 0 into a pattern-only BOOL matrix"; return GrB_NOT_IMPLEMENTED; }
+    return set_element(C, C->type == T_BOOL ? 1 : x, i, j);
+}
+GrB_Info GrB_Matrix_removeElement(GrB_Matrix C, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(C);
+    if (i >= C->nrows || j >= C->ncols) return GrB_INVALID_INDEX;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C};
+        if (!C->host_valid) download_to_host(C);
+        PendingOp op{i, j, 0, (u64)C->pending.size(), true};
+        C->pending.push_back(op);
+        return GrB_SUCCESS;
+    });
+}
+
+// returns entry position or ~0
+static u64 host_find(const HostStore &h, u64 i, u64 j) {
+    auto it = std::lower_bound(h.hrow.begin(), h.hrow.end(), i);
+    if (it == h.hrow.end() || *it != i) return ~0ULL;
+    u64 k = (u64)(it - h.hrow.begin());
+    auto b = h.hcol.begin() + h.hptr[k], e = h.hcol.begin() + h.hptr[k + 1];
+    auto c = std::lower_bound(b, e, j);
+    if (c == e || *c != j) return ~0ULL;
+    return (u64)(c - h.hcol.begin());
+}
+
+static GrB_Info extract_element(u64 *x, GrB_Matrix A, u64 i, u64 j) {
+    if (i >= A->nrows || j >= A->ncols) return GrB_INVALID_INDEX;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        if (!A->host_valid || !A->pending.empty()) ensure_host(A);
+        u64 q = host_find(A->host, i, j);
+        if (q == ~0ULL) return GrB_NO_VALUE;
+        if (x) *x = A->valued() ? A->host.hval[q] : 1;
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GrB_Matrix_extractElement_BOOL(bool *x, GrB_Matrix A, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(A); CHECK_PTR(x);
+    u64 v = 0;
+    GrB_Info r = extract_element(&v, A, i, j);
+    if (r == GrB_SUCCESS) *x = (v != 0);
+    return r;
+}
+GrB_Info GrB_Matrix_extractElement_UINT64(uint64_t *x, GrB_Matrix A, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(A); CHECK_PTR(x);
+    return extract_element(x, A, i, j);
+}
+GrB_Info GxB_Matrix_isStoredElement(GrB_Matrix A, GrB_Index i, GrB_Index j) {
+    CHECK_MAT(A);
+    return extract_element(nullptr, A, i, j);
+}
+
+static GrB_Info extract_tuples(GrB_Index *I, GrB_Index *J, void *X, int xkind, GrB_Index *nvals, GrB_Matrix A) {
+    CHECK_MAT(A); CHECK_PTR(nvals);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_host(A);
+        const HostStore &h = A->host;
+        if (*nvals < h.nnz()) { tl_error = "extractTuples: output arrays too small"; return GrB_INSUFFICIENT_SPACE; }
+        for (u64 k = 0; k < h.hrow.size(); k++)
+            for (u64 q = h.hptr[k]; q < h.hptr[k + 1]; q++) {
+                if (I) I[q] = h.hrow[k];
+                if (J) J[q] = h.hcol[q];
+                if (X) {
+                    u64 v = A->valued() ? h.hval[q] : 1;
+                    if (xkind == 1) ((bool *)X)[q] = v != 0; else ((uint64_t *)X)[q] = v;
+                }
+            }
+        *nvals = h.nnz();
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GrB_Matrix_extractTuples_BOOL(GrB_Index *I, GrB_Index *J, bool *X, GrB_Index *nvals, GrB_Matrix A) {
+    return extract_tuples(I, J, X, 1, nvals, A);
+}
+GrB_Info GrB_Matrix_extractTuples_UINT64(GrB_Index *I, GrB_Index *J, uint64_t *X, GrB_Index *nvals, GrB_Matrix A) {
+    return extract_tuples(I, J, X, 2, nvals, A);
+}
+
+// ---------------------------------------------------------------------------------------------- build
+GrB_Info GrB_Scalar_new(GrB_Scalar *s, GrB_Type type) {
+    CHECK_PTR(s); CHECK_PTR(type);
+    *s = new GB_Scalar_opaque{type->code, false, 0};
+    return GrB_SUCCESS;
+}
+GrB_Info GrB_Scalar_setElement_BOOL(GrB_Scalar s, bool x) { CHECK_PTR(s); s->has = true; s->val = x ? 1 : 0; return GrB_SUCCESS; }
+GrB_Info GrB_Scalar_free(GrB_Scalar *s) { if (s && *s) { delete *s; *s = nullptr; } return GrB_SUCCESS; }
+
+static bool matrix_is_empty(GrB_Matrix C) {
+    if (!C->pending.empty()) return false;
+    if (C->host_valid) return C->host.nnz() == 0;
+    if (C->dev_valid) return C->dev.nnz == 0;
+    return bits_nvals(C->bits) == 0;
+}
+
+// host-side build for matrices outside the device-capable range (e.g. Tensor's 2^60 x 2^60 `me`)
+static GrB_Info build_host(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const u64 *X, u64 n) {
+    struct T { u64 i, j, v, s; };
+    std::vector<T> t(n);
+    for (u64 k = 0; k < n; k++) {
+        if (I[k] >= C->nrows || J[k] >= C->ncols) { tl_error = "build: index out of bounds"; return GrB_INDEX_OUT_OF_BOUNDS; }
+        t[k] = T{I[k], J[k], X ? X[k] : 1, k};
+    }
+    std::sort(t.begin(), t.end(), [](const T &a, const T &b) {
+        if (a.i != b.i) return a.i < b.i;
+        if (a.j != b.j) return a.j < b.j;
+        return a.s < b.s;
+    });
+    HostStore h;
+    h.hptr.clear();
+    for (u64 k = 0; k < n; k++) {
+        if (k && t[k].i == t[k - 1].i && t[k].j == t[k - 1].j) continue;
+        if (h.hrow.empty() || h.hrow.back() != t[k].i) { h.hrow.push_back(t[k].i); h.hptr.push_back(h.hcol.size()); }
+        h.hcol.push_back(t[k].j);
+        if (C->valued()) h.hval.push_back(t[k].v);
+    }
+    h.hptr.push_back(h.hcol.size());
+    set_empty(C);
+    C->host = std::move(h);
+    return GrB_SUCCESS;
+}
+
+static GrB_Info build_common(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const u64 *X, u64 n) {
+    CHECK_MAT(C);
+    if (n) { CHECK_PTR(I); CHECK_PTR(J); }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C};
+        if (!matrix_is_empty(C)) { tl_error = "build: output matrix not empty"; return GrB_OUTPUT_NOT_EMPTY; }
+        if (n == 0) return GrB_SUCCESS;
+        if (C->nrows >= ((u64)1 << 32) || C->ncols >= ((u64)1 << 32)) return build_host(C, I, J, X, n);
+        ensure_init();
+        DevBuf<u64> dI(n), dJ(n), dX;
+        h2d(dI.ptr, (const u64 *)I, n);
+        h2d(dJ.ptr, (const u64 *)J, n);
+        if (X && C->valued()) { dX.alloc(n); h2d(dX.ptr, X, n); }
+        DevCSR out;
+        bool err = false;
+        build_from_device_coo(dI.ptr, dJ.ptr, dX.ptr, n, C->nrows, C->ncols, out, &err);
+        sync_stream();
+        if (err) { tl_error = "build: index out of bounds"; return GrB_INDEX_OUT_OF_BOUNDS; }
+        set_dev(C, std::move(out));
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GxB_Matrix_build_Scalar(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, GrB_Scalar scalar, GrB_Index nvals) {
+    CHECK_PTR(scalar);
+    if (!scalar->has) { tl_error = "build_Scalar: empty scalar"; return GrB_EMPTY_OBJECT; }
+    if (C && C->magic == MAGIC && C->type == T_BOOL && scalar->val == 0) {
+        tl_error = "build_Scalar(false) into a pattern-only BOOL matrix"; return GrB_NOT_IMPLEMENTED;
+    }
+    if (C && C->magic == MAGIC && C->valued()) {
+        std::vector<u64> X(nvals, scalar->val);
+        return build_common(C, I, J, X.data(), nvals);
+    }
+    return build_common(C, I, J, nullptr, nvals);
+}
+GrB_Info GrB_Matrix_build_UINT64(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const uint64_t *X, GrB_Index nvals,
+                                 GrB_BinaryOp dup) {
+    (void)dup; // ANY (or any dup): the first tuple of a duplicate run wins, deterministically
+    if (nvals) CHECK_PTR(X);
+    if (C && C->magic == MAGIC && C->type == T_BOOL) {
+        for (u64 k = 0; k < nvals; k++) if (X[k] == 0) { tl_error = "typecast of 0 into pattern-only BOOL"; return GrB_NOT_IMPLEMENTED; }
+        return build_common(C, I, J, nullptr, nvals);
+    }
+    return build_common(C, I, J, X, nvals);
+}
+GrB_Info GrB_Matrix_build_BOOL(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const bool *X, GrB_Index nvals,
+                               GrB_BinaryOp dup) {
+    (void)dup;
+    if (nvals) CHECK_PTR(X);
+    CHECK_MAT(C);
+    if (C->type == T_BOOL) {
+        for (u64 k = 0; k < nvals; k++) if (!X[k]) { tl_error = "stored false in pattern-only BOOL"; return GrB_NOT_IMPLEMENTED; }
+        return build_common(C, I, J, nullptr, nvals);
+    }
+    std::vector<u64> V(nvals);
+    for (u64 k = 0; k < nvals; k++) V[k] = X[k] ? 1 : 0;
+    return build_common(C, I, J, V.data(), nvals);
+}
+
+// ---------------------------------------------------------------------------------------------- mxm
+static bool bits_legal(GrB_Matrix C, GrB_Matrix M, GrB_Matrix A, GrB_Matrix B, const Desc &d) {
+    if (C->type != T_BOOL) return false;
+    if (bits_words_for(A->nrows) == 0) return false;
+    if (A->ncols >= ((u64)1 << 32) || B->ncols >= ((u64)1 << 32)) return false;
+    if (M && !(d.comp && d.structure && d.replace)) return false; // the delta_lmxm form (matrix.rs:1383-1394)
+    if (!M && d.comp) return false;
+    return true;
+}
+
+GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Matrix B,
+                 GrB_Descriptor desc) {
+    CHECK_MAT(C); CHECK_MAT(A); CHECK_MAT(B); CHECK_PTR(semiring);
+    if (Mask) CHECK_MAT(Mask);
+    if (semiring != GxB_ANY_PAIR_BOOL) { tl_error = "mxm: only GxB_ANY_PAIR_BOOL is on the traversal path"; return GrB_NOT_IMPLEMENTED; }
+    if (accum && accum != GxB_ANY_BOOL) { tl_error = "mxm: accum must be NULL or GxB_ANY_BOOL"; return GrB_NOT_IMPLEMENTED; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C, Mask, A, B};
+        ensure_init();
+        Context &cx = ctx();
+        Desc d = get_desc(desc);
+        u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
+        u64 br = d.t1 ? B->ncols : B->nrows, bc = d.t1 ? B->nrows : B->ncols;
+        if (ac != br || C->nrows != ar || C->ncols != bc) throw GrbError(GrB_DIMENSION_MISMATCH, "mxm: dimension mismatch");
+        check_mask_dims(C, Mask);
+
+        // ---- frontier bit-matrix path (short-fat A, CondTraverse's F*A) ----
+        if (!accum && !d.t0 && !d.t1 && cx.opt_bits_mode != 0 && bits_legal(C, Mask, A, B, d)) {
+            bool use_bits = (cx.opt_bits_mode == 1);
+            finish_pending(A);
+            if (!use_bits) {
+                if (A->bits_valid && !A->dev_valid && !A->host_valid) use_bits = true; // stay in frontier form mid-chain
+                else {
+                    ensure_dev(A); ensure_dev(B);
+                    u64 fl = spgemm_flops(A->dev, B->dev);
+                    use_bits = fl >= (u64)cx.opt_bits_min_flops;
+                }
+            }
+            if (use_bits) {
+                ensure_bits(A);
+                ensure_dev(B);
+                if (cx.opt_pull_mode != 0) ensure_devT(B);
+                DevBits Y;
+                u64 fl = 0;
+                int path = 0;
+                bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : nullptr, Y, &fl, &path);
+                if (Mask) {
+                    ensure_bits(Mask);
+                    bits_andnot(Y, Mask->bits);
+                }
+                cx.last_flops = fl; cx.total_flops += fl; cx.last_path = (u64)path;
+                set_bits(C, std::move(Y));
+                if (cx.opt_sync_after_op) sync_stream();
+                return GrB_SUCCESS;
+            }
+        }
+
+        // ---- general row-wise path ----
+        ensure_dev(A); ensure_dev(B);
+        const DevCSR *Ad = &A->dev, *Bd = &B->dev;
+        if (d.t0) { ensure_devT(A); Ad = &A->devT; }
+        if (d.t1) { ensure_devT(B); Bd = &B->devT; }
+        DevCSR T;
+        u64 fl = 0;
+        spgemm_anypair(*Ad, *Bd, T, &fl);
+        cx.last_flops = fl; cx.total_flops += fl; cx.last_path = 1;
+        write_back(C, std::move(T), Mask, d, accum != nullptr);
+        if (cx.opt_sync_after_op) sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- eWise / transpose / apply
+static void check_same_dims(GrB_Matrix C, u64 r, u64 c, const char *what) {
+    if (C->nrows != r || C->ncols != c) throw GrbError(GrB_DIMENSION_MISMATCH, std::string(what) + ": dimension mismatch");
+}
+static const DevCSR *operand(GrB_Matrix A, bool transposed) {
+    ensure_dev(A);
+    if (!transposed) return &A->dev;
+    ensure_devT(A);
+    return &A->devT;
+}
+
+GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_BinaryOp add, GrB_Matrix A,
+                                      GrB_Matrix B, GrB_Descriptor desc) {
+    CHECK_MAT(C); CHECK_MAT(A); CHECK_MAT(B); CHECK_PTR(add);
+    if (Mask) CHECK_MAT(Mask);
+    if (accum) { tl_error = "eWiseAdd: accum not on the path"; return GrB_NOT_IMPLEMENTED; }
+    if (add != GxB_ANY_BOOL && add != GrB_SECOND_UINT64 && add != GxB_ANY_UINT64) {
+        tl_error = "eWiseAdd: op must be GxB_ANY_BOOL / GrB_SECOND_UINT64 / GxB_ANY_UINT64"; return GrB_NOT_IMPLEMENTED;
+    }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C, Mask, A, B};
+        ensure_init();
+        Desc d = get_desc(desc);
+        u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
+        u64 br = d.t1 ? B->ncols : B->nrows, bc = d.t1 ? B->nrows : B->ncols;
+        if (ar != br || ac != bc) throw GrbError(GrB_DIMENSION_MISMATCH, "eWiseAdd: operand dimensions differ");
+        check_same_dims(C, ar, ac, "eWiseAdd");
+        check_mask_dims(C, Mask);
+        if (!C->valued() && (A->valued() || B->valued()))
+            throw GrbError(GrB_NOT_IMPLEMENTED, "eWiseAdd: valued -> BOOL typecast is not on the path (use apply(ONE): matrix.rs:898-905)");
+        // frontier form: C = A u B with no mask is a word-wise OR (delta_lmxm's accum step, matrix.rs:1398-1400)
+        if (!Mask && !d.comp && !d.t0 && !d.t1 && !C->valued() && (A->bits_valid || B->bits_valid) &&
+            A->pending.empty() && B->pending.empty() && bits_words_for(A->nrows) != 0 &&
+            ((A->bits_valid && !A->dev_valid && !A->host_valid) || (B->bits_valid && !B->dev_valid && !B->host_valid))) {
+            ensure_bits(A); ensure_bits(B);
+            DevBits Y;
+            bits_copy(A->bits, Y);
+            bits_or(Y, B->bits);
+            set_bits(C, std::move(Y));
+            return GrB_SUCCESS;
+        }
+        if (C->valued() && (d.t0 || d.t1))
+            throw GrbError(GrB_NOT_IMPLEMENTED, "eWiseAdd: transposed valued operands are not on the path");
+        const DevCSR *Ad = operand(A, d.t0), *Bd = operand(B, d.t1);
+        DevCSR T;
+        ewise_union(*Ad, *Bd, C->valued(), T);
+        write_back(C, std::move(T), Mask, d, false);
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_eWiseMult_Semiring(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring semiring,
+                                       GrB_Matrix A, GrB_Matrix B, GrB_Descriptor desc) {
+    CHECK_MAT(C); CHECK_MAT(A); CHECK_MAT(B); CHECK_PTR(semiring);
+    if (Mask) CHECK_MAT(Mask);
+    if (accum) { tl_error = "eWiseMult: accum not on the path"; return GrB_NOT_IMPLEMENTED; }
+    if (semiring != GxB_ANY_PAIR_BOOL) { tl_error = "eWiseMult: only GxB_ANY_PAIR_BOOL"; return GrB_NOT_IMPLEMENTED; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C, Mask, A, B};
+        ensure_init();
+        Desc d = get_desc(desc);
+        u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
+        u64 br = d.t1 ? B->ncols : B->nrows, bc = d.t1 ? B->nrows : B->ncols;
+        if (ar != br || ac != bc) throw GrbError(GrB_DIMENSION_MISMATCH, "eWiseMult: operand dimensions differ");
+        check_same_dims(C, ar, ac, "eWiseMult");
+        check_mask_dims(C, Mask);
+        const DevCSR *Ad = operand(A, d.t0), *Bd = operand(B, d.t1);
+        DevCSR T;
+        ewise_intersect(*Ad, *Bd, T);
+        write_back(C, std::move(T), Mask, d, false);
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Matrix A, GrB_Descriptor desc) {
+    CHECK_MAT(C); CHECK_MAT(A);
+    if (Mask) CHECK_MAT(Mask);
+    if (accum) { tl_error = "transpose: accum not on the path"; return GrB_NOT_IMPLEMENTED; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C, Mask, A};
+        ensure_init();
+        Desc d = get_desc(desc);
+        // T = (A^T0)' : with T0 set the double transpose is the identity (masked copy, matrix.rs:824-845)
+        bool eff_transpose = !d.t0;
+        u64 tr = eff_transpose ? A->ncols : A->nrows, tc = eff_transpose ? A->nrows : A->ncols;
+        check_same_dims(C, tr, tc, "transpose");
+        check_mask_dims(C, Mask);
+        if (!C->valued() && A->valued())
+            throw GrbError(GrB_NOT_IMPLEMENTED, "transpose: valued -> BOOL typecast is not on the path");
+        ensure_dev(A);
+        DevCSR T;
+        if (eff_transpose) transpose_csr(A->dev, T, C->valued());
+        else csr_copy(A->dev, T, C->valued());
+        write_back(C, std::move(T), Mask, d, false);
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Matrix_apply(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_UnaryOp op, GrB_Matrix A, GrB_Descriptor desc) {
+    CHECK_MAT(C); CHECK_MAT(A); CHECK_PTR(op);
+    if (Mask) CHECK_MAT(Mask);
+    if (op != GxB_ONE_BOOL) { tl_error = "apply: only GxB_ONE_BOOL (set_pattern, matrix.rs:906-924)"; return GrB_NOT_IMPLEMENTED; }
+    if (accum && accum != GxB_ANY_BOOL) { tl_error = "apply: accum must be NULL or GxB_ANY_BOOL"; return GrB_NOT_IMPLEMENTED; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{C, Mask, A};
+        ensure_init();
+        Desc d = get_desc(desc);
+        u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
+        check_same_dims(C, ar, ac, "apply");
+        check_mask_dims(C, Mask);
+        const DevCSR *Ad = operand(A, d.t0);
+        DevCSR T;
+        csr_copy(*Ad, T, false); // ONE: pattern of A, every value true -- A's values are never read
+        write_back(C, std::move(T), Mask, d, accum != nullptr);
+        return GrB_SUCCESS;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- iterator
+GrB_Info GxB_Iterator_new(GxB_Iterator *it) { CHECK_PTR(it); *it = new GB_Iterator_opaque(); return GrB_SUCCESS; }
+GrB_Info GxB_Iterator_free(GxB_Iterator *it) { if (it && *it) { delete *it; *it = nullptr; } return GrB_SUCCESS; }
+
+GrB_Info GxB_rowIterator_attach(GxB_Iterator it, GrB_Matrix A, GrB_Descriptor) {
+    CHECK_PTR(it); CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        if (!A->host_valid || !A->pending.empty()) ensure_host(A);
+        it->A = A; it->k = 0; it->q = 0; it->exhausted = true;
+        return GrB_SUCCESS;
+    });
+}
+GrB_Index GxB_rowIterator_kount(GxB_Iterator it) {
+    if (!it || !it->A) return 0;
+    GrB_Matrix A = it->A;
+    int32_t st = GxB_SPARSE;
+    GrB_Matrix_get_INT32(A, &st, GxB_SPARSITY_STATUS);
+    return st == GxB_HYPERSPARSE ? (GrB_Index)A->host.hrow.size() : A->nrows;
+}
+// positions at the first stored row >= `row`; empty rows are skipped (hypersparse behaviour; the
+// reference loops over GrB_NO_VALUE rows anyway, matrix.rs:1523-1531)
+GrB_Info GxB_rowIterator_seekRow(GxB_Iterator it, GrB_Index row) {
+    CHECK_PTR(it); CHECK_PTR(it->A);
+    const HostStore &h = it->A->host;
+    u64 k = (u64)(std::lower_bound(h.hrow.begin(), h.hrow.end(), row) - h.hrow.begin());
+    it->k = k;
+    if (k >= h.hrow.size()) { it->exhausted = true; return GxB_EXHAUSTED; }
+    it->q = h.hptr[k];
+    it->exhausted = false;
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_rowIterator_nextRow(GxB_Iterator it) {
+    CHECK_PTR(it); CHECK_PTR(it->A);
+    const HostStore &h = it->A->host;
+    if (it->exhausted) return GxB_EXHAUSTED;
+    it->k++;
+    if (it->k >= h.hrow.size()) { it->exhausted = true; return GxB_EXHAUSTED; }
+    it->q = h.hptr[it->k];
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_rowIterator_nextCol(GxB_Iterator it) {
+    CHECK_PTR(it); CHECK_PTR(it->A);
+    const HostStore &h = it->A->host;
+    if (it->exhausted) return GxB_EXHAUSTED;
+    if (it->q + 1 < h.hptr[it->k + 1]) { it->q++; return GrB_SUCCESS; }
+    return GrB_NO_VALUE; // end of this row; position unchanged
+}
+GrB_Index GxB_rowIterator_getRowIndex(GxB_Iterator it) {
+    if (!it || !it->A) return 0;
+    const HostStore &h = it->A->host;
+    if (it->exhausted || it->k >= h.hrow.size()) return it->A->nrows; // SuiteSparse returns nrows when exhausted
+    return h.hrow[it->k];
+}
+GrB_Index GxB_rowIterator_getColIndex(GxB_Iterator it) {
+    if (!it || !it->A || it->exhausted) return 0;
+    return it->A->host.hcol[it->q];
+}
+uint64_t GxB_Iterator_get_UINT64(GxB_Iterator it) {
+    if (!it || !it->A || it->exhausted) return 0;
+    return it->A->valued() ? it->A->host.hval[it->q] : 1;
+}
+bool GxB_Iterator_get_BOOL(GxB_Iterator it) { return GxB_Iterator_get_UINT64(it) != 0; }
+
+// ---------------------------------------------------------------------------------------------- vectors
+GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n) {
+    CHECK_PTR(v); CHECK_PTR(type);
+    GrB_Vector x = new GB_Vector_opaque();
+    x->type = type->code; x->n = n;
+    *v = x;
+    return GrB_SUCCESS;
+}
+GrB_Info GrB_Vector_free(GrB_Vector *v) { if (v && *v) { delete *v; *v = nullptr; } return GrB_SUCCESS; }
+GrB_Info GrB_Vector_size(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->n; return GrB_SUCCESS; }
+GrB_Info GrB_Vector_nvals(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->idx.size(); return GrB_SUCCESS; }
+GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i) {
+    CHECK_PTR(v);
+    if (i >= v->n) return GrB_INVALID_INDEX;
+    auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
+    size_t pos = it - v->idx.begin();
+    if (it != v->idx.end() && *it == i) v->val[pos] = x;
+    else { v->idx.insert(it, i); v->val.insert(v->val.begin() + pos, x ? 1 : 0); }
+    return GrB_SUCCESS;
+}
+GrB_Info GrB_Vector_extractElement_INT64(int64_t *x, GrB_Vector v, GrB_Index i) {
+    CHECK_PTR(x); CHECK_PTR(v);
+    if (i >= v->n) return GrB_INVALID_INDEX;
+    auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
+    if (it == v->idx.end() || *it != i) return GrB_NO_VALUE;
+    *x = v->val[it - v->idx.begin()];
+    return GrB_SUCCESS;
+}
+GrB_Info GrB_Vector_extractElement_BOOL(bool *x, GrB_Vector v, GrB_Index i) {
+    int64_t t = 0;
+    CHECK_PTR(x);
+    GrB_Info r = GrB_Vector_extractElement_INT64(&t, v, i);
+    if (r == GrB_SUCCESS) *x = t != 0;
+    return r;
+}
+GrB_Info GrB_Vector_extractTuples_INT64(GrB_Index *I, int64_t *X, GrB_Index *nvals, GrB_Vector v) {
+    CHECK_PTR(nvals); CHECK_PTR(v);
+    if (*nvals < v->idx.size()) return GrB_INSUFFICIENT_SPACE;
+    for (size_t k = 0; k < v->idx.size(); k++) { if (I) I[k] = v->idx[k]; if (X) X[k] = v->val[k]; }
+    *nvals = v->idx.size();
+    return GrB_SUCCESS;
+}
+GrB_Info GrB_Vector_extractTuples_BOOL(GrB_Index *I, bool *X, GrB_Index *nvals, GrB_Vector v) {
+    CHECK_PTR(nvals); CHECK_PTR(v);
+    if (*nvals < v->idx.size()) return GrB_INSUFFICIENT_SPACE;
+    for (size_t k = 0; k < v->idx.size(); k++) { if (I) I[k] = v->idx[k]; if (X) X[k] = v->val[k] != 0; }
+    *nvals = v->idx.size();
+    return GrB_SUCCESS;
+}
+
+// one frontier step w<mask> = u*A (vxm) or A*u (mxv) over ANY_PAIR, run as a 1-row mxm
+static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u,
+                              GrB_Matrix A, GrB_Descriptor desc, bool is_mxv) {
+    CHECK_PTR(w); CHECK_PTR(u); CHECK_MAT(A);
+    if (semiring != GxB_ANY_PAIR_BOOL || accum) { tl_error = "vxm/mxv: ANY_PAIR, no accum"; return GrB_NOT_IMPLEMENTED; }
+    Desc d = get_desc(desc);
+    // vxm: w' = u' * A (T1 transposes A).  mxv: w = A*u <=> w' = u' * A' (T0 transposes A).
+    bool a_transposed = is_mxv ? !d.t0 : d.t1;
+    u64 inner = a_transposed ? A->ncols : A->nrows, outer = a_transposed ? A->nrows : A->ncols;
+    if (u->n != inner || w->n != outer || (mask && mask->n != outer)) return GrB_DIMENSION_MISMATCH;
+    GrB_Matrix F = nullptr, Mm = nullptr, Cm = nullptr;
+    GrB_Info info = GrB_Matrix_new(&F, GrB_BOOL, 1, inner);
+    if (info) return info;
+    GrB_Matrix_new(&Cm, GrB_BOOL, 1, outer);
+    std::vector<u64> zeros(std::max(u->idx.size(), mask ? mask->idx.size() : (size_t)0), 0);
+    GrB_Scalar s; GrB_Scalar_new(&s, GrB_BOOL); GrB_Scalar_setElement_BOOL(s, true);
+    std::vector<u64> uidx;
+    for (size_t k = 0; k < u->idx.size(); k++) if (u->val[k] != 0 || u->type != T_BOOL) uidx.push_back(u->idx[k]);
+    info = GxB_Matrix_build_Scalar(F, zeros.data(), uidx.data(), s, uidx.size());
+    if (!info && mask) {
+        GrB_Matrix_new(&Mm, GrB_BOOL, 1, outer);
+        std::vector<u64> midx;
+        for (size_t k = 0; k < mask->idx.size(); k++) if (d.structure || mask->val[k] != 0) midx.push_back(mask->idx[k]);
+        info = GxB_Matrix_build_Scalar(Mm, zeros.data(), midx.data(), s, midx.size());
+    }
+    if (!info) {
+        // existing w content matters only without replace; seed C with it
+        if (mask && !d.replace && !w->idx.empty()) {
+            std::vector<u64> z2(w->idx.size(), 0);
+            info = GxB_Matrix_build_Scalar(Cm, z2.data(), w->idx.data(), s, w->idx.size());
+        }
+    }
+    if (!info) {
+        GB_Descriptor_opaque dd = {false, a_transposed, d.comp, true, d.replace};
+        info = GrB_mxm(Cm, Mm, nullptr, GxB_ANY_PAIR_BOOL, F, A, &dd);
+    }
+    if (!info) {
+        GrB_Index nv = 0;
+        GrB_Matrix_nvals(&nv, Cm);
+        std::vector<u64> I(nv), J(nv);
+        GrB_Index cap = nv;
+        info = GrB_Matrix_extractTuples_BOOL(I.data(), J.data(), nullptr, &cap, Cm);
+        if (!info) {
+            w->idx.assign(J.begin(), J.end());
+            w->val.assign(nv, 1);
+        }
+    }
+    GrB_Scalar_free(&s);
+    GrB_Matrix_free(&F); GrB_Matrix_free(&Mm); GrB_Matrix_free(&Cm);
+    return info;
+}
+GrB_Info GrB_vxm(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u, GrB_Matrix A,
+                 GrB_Descriptor desc) {
+    return frontier_step(w, mask, accum, semiring, u, A, desc, false);
+}
+GrB_Info GrB_mxv(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Vector u,
+                 GrB_Descriptor desc) {
+    return frontier_step(w, mask, accum, semiring, u, A, desc, true);
+}
+
+// ---------------------------------------------------------------------------------------------- LAGraph subset
+int LAGraph_Init(char *msg) { if (msg) msg[0] = 0; return 0; }
+int LAGraph_Finalize(char *msg) { if (msg) msg[0] = 0; return 0; }
+int LAGraph_New(LAGraph_Graph *G, GrB_Matrix *A, LAGraph_Kind kind, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G) return GrB_NULL_POINTER;
+    LAGraph_Graph g = (LAGraph_Graph)calloc(1, sizeof(struct LAGraph_Graph_struct));
+    if (!g) return GrB_OUT_OF_MEMORY;
+    g->kind = kind;
+    if (A) { g->A = *A; *A = nullptr; } // the matrix MOVES into the graph (lagraph_bindings.rs:175)
+    g->is_symmetric_structure = -1; g->nself_edges = -1;
+    *G = g;
+    return 0;
+}
+int LAGraph_Delete(LAGraph_Graph *G, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G || !*G) return 0;
+    GrB_Matrix_free(&(*G)->A);
+    GrB_Matrix_free(&(*G)->AT);
+    GrB_Vector_free(&(*G)->out_degree);
+    GrB_Vector_free(&(*G)->in_degree);
+    free(*G);
+    *G = nullptr;
+    return 0;
+}
+
+GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level, int64_t *parent, int location,
+                  uint64_t *edges_traversed) {
+    CHECK_MAT(A); CHECK_PTR(level);
+    if (A->nrows != A->ncols) { tl_error = "BFS needs a square adjacency matrix"; return GrB_DIMENSION_MISMATCH; }
+    if (src >= A->nrows) return GrB_INVALID_INDEX;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        u64 n = A->nrows, edges = 0;
+        if (location == B200_LOC_DEVICE) {
+            bfs_run(A->dev, src, max_level, level, parent, &edges);
+            sync_stream();
+        } else {
+            DevBuf<i64> dl(n), dp;
+            if (parent) dp.alloc(n);
+            bfs_run(A->dev, src, max_level, dl.ptr, parent ? dp.ptr : nullptr, &edges);
+            d2h(level, dl.ptr, n);
+            if (parent) d2h(parent, dp.ptr, n);
+            sync_stream();
+        }
+        if (edges_traversed) *edges_traversed = edges;
+        return GrB_SUCCESS;
+    });
+}
+
+int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGraph_Graph G, GrB_Index src, int64_t max_level,
+                                     int64_t dest, bool many_expected, char *msg) {
+    (void)many_expected;
+    if (msg) msg[0] = 0;
+    if (!G || !G->A) return GrB_NULL_POINTER;
+    if (dest >= 0) { if (msg) snprintf(msg, 256, "dest early-exit is not supported"); return GrB_NOT_IMPLEMENTED; }
+    u64 n = G->A->nrows;
+    std::vector<i64> lv(n), pr;
+    if (parent) pr.resize(n);
+    GrB_Info info = B200_bfs(G->A, src, max_level < 0 ? -1 : max_level, lv.data(), parent ? pr.data() : nullptr, B200_LOC_HOST, nullptr);
+    if (info) { if (msg) snprintf(msg, 256, "%s", tl_error.c_str()); return info; }
+    auto fill = [&](GrB_Vector *out, const std::vector<i64> &src_v) {
+        GrB_Vector v = new GB_Vector_opaque();
+        v->type = T_INT64; v->n = n;
+        for (u64 i = 0; i < n; i++) if (src_v[i] >= 0) { v->idx.push_back(i); v->val.push_back(src_v[i]); }
+        *out = v;
+    };
+    if (level) fill(level, lv);
+    if (parent) fill(parent, pr);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- B200 extensions
+GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols, const uint64_t *Ap,
+                                const uint32_t *Aj, const uint64_t *Ax, int location) {
+    CHECK_PTR(A); CHECK_PTR(type); CHECK_PTR(Ap);
+    if (nrows >= ((u64)1 << 32) || ncols >= ((u64)1 << 32)) return GrB_NOT_IMPLEMENTED;
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        ensure_init();
+        GrB_Matrix m = new GB_Matrix_opaque();
+        m->type = type->code; m->nrows = nrows; m->ncols = ncols;
+        DevCSR d;
+        d.nrows = nrows; d.ncols = ncols;
+        d.p.alloc(nrows + 1);
+        u64 nnz;
+        if (location == B200_LOC_DEVICE) {
+            d2d(d.p.ptr, (const u64 *)Ap, nrows + 1);
+            nnz = read_scalar(d.p.ptr + nrows);
+        } else {
+            nnz = Ap[nrows];
+            h2d(d.p.ptr, (const u64 *)Ap, nrows + 1);
+        }
+        d.nnz = nnz;
+        d.j.alloc(nnz);
+        bool vals = m->valued() && Ax;
+        if (vals) d.x.alloc(nnz);
+        if (location == B200_LOC_DEVICE) { d2d(d.j.ptr, (const u32 *)Aj, nnz); if (vals) d2d(d.x.ptr, (const u64 *)Ax, nnz); }
+        else { h2d(d.j.ptr, (const u32 *)Aj, nnz); if (vals) h2d(d.x.ptr, (const u64 *)Ax, nnz); }
+        sync_stream();
+        set_dev(m, std::move(d));
+        *A = m;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64_t *Ax, int location) {
+    CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        const DevCSR &d = A->dev;
+        if (location == B200_LOC_DEVICE) {
+            if (Ap) d2d((u64 *)Ap, d.p.ptr, d.nrows + 1);
+            if (Aj) d2d((u32 *)Aj, d.j.ptr, d.nnz);
+            if (Ax && d.has_values()) d2d((u64 *)Ax, d.x.ptr, d.nnz);
+        } else {
+            if (Ap) d2h((u64 *)Ap, d.p.ptr, d.nrows + 1);
+            if (Aj) d2h((u32 *)Aj, d.j.ptr, d.nnz);
+            if (Ax && d.has_values()) d2h((u64 *)Ax, d.x.ptr, d.nnz);
+        }
+        sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax) {
+    CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        sync_stream();
+        if (Ap) *Ap = A->dev.p.ptr;
+        if (Aj) *Aj = A->dev.j.ptr;
+        if (Ax) *Ax = A->dev.x.ptr;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose) {
+    CHECK_MAT(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        if (want_transpose) ensure_devT(A);
+        sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed) {
+    CHECK_PTR(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        ensure_init();
+        GrB_Matrix m = new GB_Matrix_opaque();
+        m->type = T_BOOL; m->nrows = m->ncols = (u64)1 << scale;
+        DevCSR d;
+        rmat_csr(scale, edge_factor, seed, d);
+        sync_stream();
+        set_dev(m, std::move(d));
+        *A = m;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info B200_sync(void) {
+    return guarded([&]() {
+        if (ctx().ready) sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+void *B200_stream(void) {
+    try { ensure_init(); } catch (...) { return nullptr; }
+    return (void *)ctx().stream;
+}
+uint64_t B200_get_stat(const char *name) {
+    Context &c = ctx();
+    std::string n = name ? name : "";
+    if (n == "launches") return c.launches.load();
+    if (n == "lib_launches") return c.lib_launches.load();
+    if (n == "last_flops") return c.last_flops.load();
+    if (n == "total_flops") return c.total_flops.load();
+    if (n == "last_path") return c.last_path.load();
+    if (n == "h2d_bytes") return c.h2d_bytes.load();
+    if (n == "d2h_bytes") return c.d2h_bytes.load();
+    if (n == "num_sms") return (uint64_t)c.num_sms;
+    return ~0ULL;
+}
+int B200_kernel_stats(const char *name, double *ms, uint64_t *launches, uint64_t *bytes) {
+    double m[TK_COUNT_]; u64 n[TK_COUNT_], b[TK_COUNT_];
+    try { timed_collect(m, n, b); } catch (...) { return -1; }
+    for (int i = 0; i < TK_COUNT_; i++)
+        if (name && std::string(name) == timed_name(i)) {
+            if (ms) *ms = m[i];
+            if (launches) *launches = n[i];
+            if (bytes) *bytes = b[i];
+            return 0;
+        }
+    return -3;
+}
+void B200_reset_stats(void) {
+    Context &c = ctx();
+    if (c.ready) { try { timed_reset(); } catch (...) {} }
+    c.launches = 0; c.lib_launches = 0; c.last_flops = 0; c.total_flops = 0; c.h2d_bytes = 0; c.d2h_bytes = 0;
+}
+GrB_Info B200_set_option(const char *name, int64_t value) {
+    Context &c = ctx();
+    std::string n = name ? name : "";
+    if (n == "bits_mode") c.opt_bits_mode = value;
+    else if (n == "pull_mode") c.opt_pull_mode = value;
+    else if (n == "small_cap") c.opt_small_cap = value;
+    else if (n == "bitmap_budget") c.opt_bitmap_budget = value;
+    else if (n == "bits_min_flops") c.opt_bits_min_flops = value;
+    else if (n == "sync_after_op") c.opt_sync_after_op = value;
+    else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
+    else return GrB_INVALID_VALUE;
+    return GrB_SUCCESS;
+}
+
+} // extern "C"

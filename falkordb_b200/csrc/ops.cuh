@@ -1,0 +1,52 @@
+// ops.cuh -- host-callable entry points of the kernel layer (all enqueue on b200::stream()).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// build.cu
+void build_from_device_coo(const u64 *dI, const u64 *dJ, const u64 *dX, u64 n, u64 nrows, u64 ncols, DevCSR &out,
+                           bool *index_error);
+void transpose_csr(const DevCSR &A, DevCSR &out, bool keep_values);
+void rmat_csr(int scale, u64 edge_factor, u64 seed, DevCSR &out);
+
+// spgemm.cu : C = pattern(A*B) over ANY_PAIR, row-wise push (Gustavson family)
+void spgemm_anypair(const DevCSR &A, const DevCSR &B, DevCSR &C, u64 *flops_out);
+u64 spgemm_flops(const DevCSR &A, const DevCSR &B);
+
+// bits.cu : frontier bit-matrix path for short-fat left operands (<= 1024 rows)
+u32 bits_words_for(u64 nrows);
+void bits_from_csr(const DevCSR &F, DevBits &X);
+void bits_to_csr(const DevBits &X, DevCSR &C);
+u64 bits_nvals(const DevBits &X);
+struct LongRows { DevBuf<u32> rows; u64 n = 0; u64 maxdeg = 0; bool built = false; };
+void build_long_rows(const DevCSR &AT, LongRows &lr);
+// Y = X * A.  AT (= A') + its long-row list enable the pull direction; may be null (push only).
+void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, const LongRows *lr, DevBits &Y, u64 *flops_out,
+              int *path_out);
+void bits_andnot(DevBits &Y, const DevBits &M); // Y &= ~M
+void bits_or(DevBits &Y, const DevBits &Z);     // Y |= Z
+void bits_copy(const DevBits &X, DevBits &Y);
+
+// ewise.cu : search-based set algebra on sorted CSR rows
+void csr_copy(const DevCSR &A, DevCSR &out, bool keep_values);
+void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out); // overlap: B's value (SECOND)
+void ewise_intersect(const DevCSR &A, const DevCSR &B, DevCSR &out);               // pattern only
+// keep t in T iff (t in M [and M's value != 0 unless structural]) XOR comp
+void filter_by_mask(const DevCSR &T, const DevCSR &M, bool comp, bool structural, DevCSR &out);
+void csr_resize(const DevCSR &A, u64 nrows, u64 ncols, DevCSR &out); // grow/shrink dims (drops out-of-range)
+
+// bfs.cu
+void bfs_run(const DevCSR &A, u64 src, i64 max_level, i64 *d_level, i64 *d_parent, u64 *edges_traversed);
+
+// hypersparse host form <-> dense device rowptr (ewise.cu)
+void rowptr_from_hyper(const u64 *d_hrow, const u64 *d_hptr, u64 nvec, u64 nrows, u64 *d_p);
+u64 hyper_from_rowptr(const u64 *d_p, u64 nrows, u64 nnz, DevBuf<u64> &d_hrow, DevBuf<u64> &d_hptr);
+void widen_u32(const u32 *in, u64 *out, u64 n);
+void narrow_u64(const u64 *in, u32 *out, u64 n);
+
+// generic tiny helpers (ewise.cu)
+void fill_u64(u64 *p, u64 v, u64 n);
+void fill_i64(i64 *p, i64 v, u64 n);
+
+} // namespace b200

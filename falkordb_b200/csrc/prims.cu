@@ -1,0 +1,161 @@
+// prims.cu -- context bring-up and the CUB-backed scan / radix-sort primitives.
+// CUB (shipped with the CUDA toolkit) is used for the utility primitives only -- exclusive
+// scans of row counts and the radix sort inside COO->CSR build / transpose; every kernel on the
+// traversal hot path (mxm, frontier hops, materialise, eWise, BFS) is hand-written.
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#include <mutex>
+
+namespace b200 {
+
+Context &ctx() {
+    static Context c;
+    return c;
+}
+
+void ensure_init() {
+    static std::mutex mu;
+    Context &c = ctx();
+    if (c.ready) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (c.ready) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw GrbError(-7002, "libb200grb: no CUDA device visible -- this backend has no CPU fallback");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    c.device = dev;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    c.num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    // keep freed blocks cached in the stream-ordered pool: no cudaMalloc in steady state
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    u64 thresh = ~0ULL;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    c.ready = true;
+}
+
+// ---- per-kernel timing registry ------------------------------------------------------------------
+struct TimedRec { int id; cudaEvent_t e0, e1; u64 bytes; };
+static std::vector<TimedRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_timed_mu;
+static cudaEvent_t g_open[TK_COUNT_];
+static double g_ms[TK_COUNT_];
+static u64 g_n[TK_COUNT_], g_bytes[TK_COUNT_];
+
+const char *timed_name(int id) {
+    static const char *names[] = {"bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "small_rows", "bits_fill",
+                                  "bits_count", "bitmap_expand", "bfs_expand", "union", "filter"};
+    return (id >= 0 && id < TK_COUNT_) ? names[id] : "?";
+}
+static cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    return e;
+}
+void timed_begin(int id) {
+    if (!ctx().opt_timing) return;
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    cudaEvent_t e = get_event();
+    CUDA_TRY(cudaEventRecord(e, stream()));
+    g_open[id] = e;
+}
+void timed_end(int id, u64 bytes) {
+    if (!ctx().opt_timing) return;
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    if (!g_open[id]) return;
+    cudaEvent_t e = get_event();
+    CUDA_TRY(cudaEventRecord(e, stream()));
+    g_recs.push_back(TimedRec{id, g_open[id], e, bytes});
+    g_open[id] = nullptr;
+}
+static void drain_locked() {
+    if (g_recs.empty()) return;
+    CUDA_TRY(cudaStreamSynchronize(stream()));
+    for (TimedRec &r : g_recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { g_ms[r.id] += ms; g_n[r.id]++; g_bytes[r.id] += r.bytes; }
+        g_event_pool.push_back(r.e0);
+        g_event_pool.push_back(r.e1);
+    }
+    g_recs.clear();
+}
+void timed_collect(double *ms, u64 *launches, u64 *bytes) {
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    drain_locked();
+    for (int i = 0; i < TK_COUNT_; i++) { ms[i] = g_ms[i]; launches[i] = g_n[i]; bytes[i] = g_bytes[i]; }
+}
+void timed_reset() {
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    drain_locked();
+    for (int i = 0; i < TK_COUNT_; i++) { g_ms[i] = 0; g_n[i] = 0; g_bytes[i] = 0; }
+}
+
+void exclusive_scan_u64(const u64 *in, u64 *out, size_t n) {
+    if (n == 0) return;
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, stream()));
+    DevBuf<char> tmp(tb);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.ptr, tb, in, out, n, stream()));
+    ctx().lib_launches += 2;
+}
+
+struct U32ToU64 {
+    __host__ __device__ u64 operator()(u32 v) const { return (u64)v; }
+};
+
+void exclusive_scan_u32_to_u64(const u32 *in, u64 *out, size_t n) {
+    if (n == 0) return;
+    auto it = thrust::make_transform_iterator(in, U32ToU64());
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, out, n, stream()));
+    DevBuf<char> tmp(tb);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.ptr, tb, it, out, n, stream()));
+    ctx().lib_launches += 2;
+}
+
+void sort_keys_u64(u64 *keys, size_t n, int end_bit) {
+    if (n <= 1) return;
+    DevBuf<u64> alt(n);
+    cub::DoubleBuffer<u64> db(keys, alt.ptr);
+    if ((u64)n > 0x7fffffffULL) throw GrbError(-8, "sort_keys_u64: more than 2^31-1 keys not supported yet");
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int)n, 0, end_bit, stream()));
+    DevBuf<char> tmp(tb);
+    CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp.ptr, tb, db, (int)n, 0, end_bit, stream()));
+    if (db.Current() != keys) d2d(keys, db.Current(), n);
+    ctx().lib_launches += 8;
+}
+
+void sort_pairs_u64(u64 *keys, u64 *vals, size_t n, int end_bit) {
+    if (n <= 1) return;
+    if ((u64)n > 0x7fffffffULL) throw GrbError(-8, "sort_pairs_u64: more than 2^31-1 keys not supported yet");
+    DevBuf<u64> altk(n), altv(n);
+    cub::DoubleBuffer<u64> dk(keys, altk.ptr), dv(vals, altv.ptr);
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n, 0, end_bit, stream()));
+    DevBuf<char> tmp(tb);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.ptr, tb, dk, dv, (int)n, 0, end_bit, stream()));
+    if (dk.Current() != keys) d2d(keys, dk.Current(), n);
+    if (dv.Current() != vals) d2d(vals, dv.Current(), n);
+    ctx().lib_launches += 8;
+}
+
+u64 reduce_sum_u64(const u64 *in, size_t n) {
+    if (n == 0) return 0;
+    DevBuf<u64> out(1);
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceReduce::Sum(nullptr, tb, in, out.ptr, n, stream()));
+    DevBuf<char> tmp(tb);
+    CUDA_TRY(cub::DeviceReduce::Sum(tmp.ptr, tb, in, out.ptr, n, stream()));
+    ctx().lib_launches += 2;
+    return read_scalar(out.ptr);
+}
+
+} // namespace b200

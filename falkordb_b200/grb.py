@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's GraphBLAS wrapper, method for method:
+``Matrix<T>`` in graph/src/graph/graphblas/matrix.rs (new :1119/:1214, build :1186/:1281, set/get
+:1143-1172/:1248-1275, lmxm/rmxm :930-968, delta_lmxm :1317-1402, element_wise_add :852, element_wise_multiply
+:876, set_pattern :906, transpose :633, remove_all/select :824-845, wait :781, dup :1062, grown :700, iter :1471).
+Everything is a direct call into libb200grb.so through the GraphBLAS C ABI (include/b200grb.h)."""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from ._lib import lib, obj, check, GrbError, P, U64
+
+GxB_SPARSITY_STATUS, GxB_SPARSITY_CONTROL, GxB_HYPER_HASH, GxB_WILL_WAIT = 7034, 7036, 7048, 7076
+GrB_STORAGE_ORIENTATION_HINT = 100
+GxB_HYPERSPARSE, GxB_SPARSE = 1, 2
+GrB_MATERIALIZE = 1
+U64_MAX = (1 << 64) - 1
+
+
+class Descriptor(enum.Enum):
+    """matrix.rs:223-255"""
+    T0 = "T0"; T1 = "T1"; T0T1 = "T0T1"; C = "C"; CT0 = "CT0"; CT1 = "CT1"; CT0T1 = "CT0T1"
+    S = "S"; ST0 = "ST0"; ST1 = "ST1"; ST0T1 = "ST0T1"; SC = "SC"; SCT0 = "SCT0"; SCT1 = "SCT1"; SCT0T1 = "SCT0T1"
+    R = "R"; RT0 = "RT0"; RT1 = "RT1"; RT0T1 = "RT0T1"; RC = "RC"; RCT0 = "RCT0"; RCT1 = "RCT1"; RCT0T1 = "RCT0T1"
+    RS = "RS"; RST0 = "RST0"; RST1 = "RST1"; RST0T1 = "RST0T1"; RSC = "RSC"; RSCT0 = "RSCT0"; RSCT1 = "RSCT1"
+    RSCT0T1 = "RSCT0T1"
+
+
+def _desc(d):
+    if d is None:
+        return None
+    return obj("GrB_DESC_" + d.value)
+
+
+def init():
+    """matrix.rs:116-185 (GxB_init NONBLOCKING + JIT control + LAGraph_Init)"""
+    L = lib()
+    check(L.GxB_init(0, None, None, None, None))
+    check(L.GrB_Global_set_INT32(obj("GrB_GLOBAL"), 2, 7029))
+    assert L.LAGraph_Init(None) == 0
+
+
+def _u64arr(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Matrix:
+    """``Matrix<bool>`` (dtype=bool) or ``Matrix<u64>`` (dtype='u64')."""
+
+    def __init__(self, nrows, ncols, dtype=bool, _handle=None):
+        self.dtype = bool if dtype in (bool, "bool") else "u64"
+        if _handle is not None:
+            self.h = _handle
+            return
+        h = P()
+        check(lib().GrB_Matrix_new(C.byref(h), obj("GrB_BOOL" if self.dtype is bool else "GrB_UINT64"), nrows, ncols))
+        self.h = h
+        # pin_sparse, matrix.rs:405-426
+        check(lib().GrB_Matrix_set_INT32(self.h, GxB_SPARSE | GxB_HYPERSPARSE, GxB_SPARSITY_CONTROL))
+        check(lib().GrB_Matrix_set_INT32(self.h, 0, GrB_STORAGE_ORIENTATION_HINT))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                lib().GrB_Matrix_free(C.byref(self.h))
+        except Exception:
+            pass
+
+    # ---- constructors -------------------------------------------------------------------------
+    @staticmethod
+    def import_csr(nrows, ncols, p, j, x=None, dtype=bool):
+        p = np.ascontiguousarray(p, dtype=np.uint64)
+        j = np.ascontiguousarray(j, dtype=np.uint32)
+        xx = None if x is None else np.ascontiguousarray(x, dtype=np.uint64)
+        h = P()
+        dt = bool if dtype in (bool, "bool") else "u64"
+        check(lib().B200_Matrix_import_CSR(C.byref(h), obj("GrB_BOOL" if dt is bool else "GrB_UINT64"), nrows, ncols,
+                                           p.ctypes.data, j.ctypes.data if len(j) else None,
+                                           None if xx is None else xx.ctypes.data, 0))
+        return Matrix(nrows, ncols, dt, _handle=h)
+
+    def export_csr(self):
+        n, nnz = self.nrows(), self.nvals()
+        p = np.empty(n + 1, np.uint64)
+        j = np.empty(nnz, np.uint32)
+        x = np.empty(nnz, np.uint64) if self.dtype != bool else None
+        check(lib().B200_Matrix_export_CSR(self.h, p.ctypes.data, j.ctypes.data if nnz else None,
+                                           None if x is None else x.ctypes.data, 0))
+        return p.astype(np.int64), j, x
+
+    def into_hyper(self):
+        """matrix.rs:558-575"""
+        check(lib().GrB_Matrix_set_INT32(self.h, GxB_HYPERSPARSE, GxB_SPARSITY_CONTROL))
+        check(lib().GrB_Matrix_set_INT32(self.h, 0, GxB_HYPER_HASH))
+        return self
+
+    # ---- shape / status -----------------------------------------------------------------------
+    def nrows(self):
+        v = U64()
+        check(lib().GrB_Matrix_nrows(C.byref(v), self.h))
+        return v.value
+
+    def ncols(self):
+        v = U64()
+        check(lib().GrB_Matrix_ncols(C.byref(v), self.h))
+        return v.value
+
+    def nvals(self):
+        v = U64()
+        check(lib().GrB_Matrix_nvals(C.byref(v), self.h))
+        return v.value
+
+    def pending(self):
+        v = C.c_int32()
+        check(lib().GrB_Matrix_get_INT32(self.h, C.byref(v), GxB_WILL_WAIT))
+        return v.value == 1
+
+    def sparsity_status(self):
+        v = C.c_int32()
+        check(lib().GrB_Matrix_get_INT32(self.h, C.byref(v), GxB_SPARSITY_STATUS))
+        return {1: "hypersparse", 2: "sparse", 4: "bitmap", 8: "full"}.get(v.value, "unknown")
+
+    def is_iso(self):
+        v = C.c_bool()
+        check(lib().GxB_Matrix_iso(C.byref(v), self.h))
+        return v.value
+
+    def memory_usage(self):
+        v = C.c_size_t()
+        check(lib().GxB_Matrix_memoryUsage(C.byref(v), self.h))
+        return v.value
+
+    def wait(self):
+        check(lib().GrB_Matrix_wait(self.h, GrB_MATERIALIZE))
+
+    def clear(self):
+        check(lib().GrB_Matrix_clear(self.h))
+
+    def resize(self, nrows, ncols):
+        check(lib().GrB_Matrix_resize(self.h, nrows, ncols))
+
+    def dup(self):
+        h = P()
+        check(lib().GrB_Matrix_dup(C.byref(h), self.h))
+        return Matrix(0, 0, self.dtype, _handle=h)
+
+    def grown(self, nrows, ncols):
+        r0, c0 = self.nrows(), self.ncols()
+        assert nrows >= r0 and ncols >= c0, f"grown must not shrink: {r0}x{c0} -> {nrows}x{ncols}"
+        out = self.dup()
+        if nrows != r0 or ncols != c0:
+            out.resize(nrows, ncols)
+        return out
+
+    # ---- element access -----------------------------------------------------------------------
+    def set(self, i, j, value=True):
+        if self.dtype is bool:
+            check(lib().GrB_Matrix_setElement_BOOL(self.h, bool(value), i, j))
+        else:
+            check(lib().GrB_Matrix_setElement_UINT64(self.h, int(value), i, j))
+
+    def get(self, i, j):
+        if self.dtype is bool:
+            v = C.c_bool()
+            info = lib().GrB_Matrix_extractElement_BOOL(C.byref(v), self.h, i, j)
+        else:
+            v = U64()
+            info = lib().GrB_Matrix_extractElement_UINT64(C.byref(v), self.h, i, j)
+        if info == 0:
+            return v.value
+        if info == 1:
+            return None
+        check(info)
+
+    def contains(self, i, j):
+        return lib().GxB_Matrix_isStoredElement(self.h, i, j) == 0
+
+    def remove(self, i, j):
+        check(lib().GrB_Matrix_removeElement(self.h, i, j))
+
+    def build(self, rows, cols, vals=None):
+        rows, cols = _u64arr(rows), _u64arr(cols)
+        assert len(rows) == len(cols)
+        if len(rows) == 0:
+            return
+        if self.dtype is bool:
+            s = P()
+            check(lib().GrB_Scalar_new(C.byref(s), obj("GrB_BOOL")))
+            check(lib().GrB_Scalar_setElement_BOOL(s, True))
+            try:
+                check(lib().GxB_Matrix_build_Scalar(self.h, rows.ctypes.data, cols.ctypes.data, s, len(rows)))
+            finally:
+                lib().GrB_Scalar_free(C.byref(s))
+        else:
+            vals = _u64arr(vals)
+            check(lib().GrB_Matrix_build_UINT64(self.h, rows.ctypes.data, cols.ctypes.data, vals.ctypes.data, len(rows),
+                                                obj("GxB_ANY_UINT64")))
+
+    # ---- bulk algebra -------------------------------------------------------------------------
+    def lmxm(self, b):
+        check(lib().GrB_mxm(self.h, None, None, obj("GxB_ANY_PAIR_BOOL"), self.h, b.h, None))
+
+    def rmxm(self, b):
+        check(lib().GrB_mxm(self.h, None, None, obj("GxB_ANY_PAIR_BOOL"), b.h, self.h, None))
+
+    def mxm(self, a, b, mask=None, descriptor=None):
+        check(lib().GrB_mxm(self.h, mask.h if mask is not None else None, None, obj("GxB_ANY_PAIR_BOOL"), a.h, b.h,
+                            _desc(descriptor)))
+
+    def delta_lmxm(self, m, dp, dm):
+        """matrix.rs:1317-1402, statement for statement."""
+        dp.wait()
+        dm.wait()
+        dp_nvals, dm_nvals = dp.nvals(), dm.nvals()
+        if dp_nvals == 0 and dm_nvals == 0:
+            self.lmxm(m)
+            return
+        nrows, ncols = self.nrows(), m.ncols()
+        mask = None
+        if dm_nvals > 0:
+            mk = Matrix(nrows, ncols, bool)
+            mk.mxm(self, dm)
+            if mk.nvals() > 0:
+                mask = mk
+        accum = None
+        if dp_nvals > 0:
+            ac = Matrix(nrows, ncols, bool)
+            ac.mxm(self, dp)
+            if ac.nvals() > 0:
+                accum = ac
+        if mask is not None:
+            self.mxm(self, m, mask, Descriptor.RSC)
+        else:
+            self.mxm(self, m)
+        if accum is not None:
+            self.element_wise_add(None, None, accum, None)
+
+    def element_wise_add(self, mask=None, a=None, b=None, descriptor=None):
+        op = obj("GxB_ANY_BOOL") if self.dtype is bool else obj("GrB_SECOND_UINT64")
+        check(lib().GrB_Matrix_eWiseAdd_BinaryOp(self.h, mask.h if mask is not None else None, None, op,
+                                                 (a or self).h, (b or self).h, _desc(descriptor)))
+
+    def element_wise_multiply(self, mask=None, a=None, b=None, descriptor=None):
+        check(lib().GrB_Matrix_eWiseMult_Semiring(self.h, mask.h if mask is not None else None, None,
+                                                  obj("GxB_ANY_PAIR_BOOL"), (a or self).h, (b or self).h, _desc(descriptor)))
+
+    def intersection_nvals(self, b):
+        t = Matrix(self.nrows(), self.ncols(), bool)
+        check(lib().GrB_Matrix_eWiseMult_Semiring(t.h, None, None, obj("GxB_ANY_PAIR_BOOL"), self.h, b.h, None))
+        return t.nvals()
+
+    def set_pattern(self, mask, a, descriptor=None):
+        check(lib().GrB_Matrix_apply(self.h, mask.h if mask is not None else None, obj("GxB_ANY_BOOL"), obj("GxB_ONE_BOOL"),
+                                     a.h, _desc(descriptor)))
+
+    def transpose(self):
+        t = Matrix(self.ncols(), self.nrows(), self.dtype)
+        check(lib().GrB_transpose(t.h, None, None, self.h, None))
+        return t
+
+    def remove_all(self, b):
+        check(lib().GrB_transpose(self.h, b.h, None, self.h, obj("GrB_DESC_RCT0")))
+
+    def select(self, mask, a):
+        check(lib().GrB_transpose(self.h, mask.h, None, a.h, obj("GrB_DESC_RCT0")))
+
+    # ---- iteration (matrix.rs:1471-1605: the reference's loop over the C iterator, verbatim) ----
+    def iter(self, min_row=0, max_row=U64_MAX):
+        L = lib()
+        it = P()
+        check(L.GxB_Iterator_new(C.byref(it)))
+        try:
+            check(L.GxB_rowIterator_attach(it, self.h, None))
+            info = L.GxB_rowIterator_seekRow(it, min_row)
+            while info == 1 and L.GxB_rowIterator_getRowIndex(it) < max_row:
+                info = L.GxB_rowIterator_nextRow(it)
+            depleted = info != 0 or L.GxB_rowIterator_getRowIndex(it) > max_row
+            while not depleted:
+                row, col = L.GxB_rowIterator_getRowIndex(it), L.GxB_rowIterator_getColIndex(it)
+                item = (row, col) if self.dtype is bool else (row, col, L.GxB_Iterator_get_UINT64(it))
+                if L.GxB_rowIterator_nextCol(it) != 0:
+                    info = L.GxB_rowIterator_nextRow(it)
+                    while info == 1 and L.GxB_rowIterator_getRowIndex(it) < max_row:
+                        info = L.GxB_rowIterator_nextRow(it)
+                    depleted = info != 0 or L.GxB_rowIterator_getRowIndex(it) > max_row
+                yield item
+        finally:
+            L.GxB_Iterator_free(C.byref(it))
+
+    def hyper_vector_count(self):
+        if self.sparsity_status() != "hypersparse":
+            return None
+        L = lib()
+        it = P()
+        check(L.GxB_Iterator_new(C.byref(it)))
+        check(L.GxB_rowIterator_attach(it, self.h, None))
+        k = L.GxB_rowIterator_kount(it)
+        L.GxB_Iterator_free(C.byref(it))
+        return k
+
+    def tuple_set(self):
+        return set(self.iter())
+
+    def extract_tuples(self):
+        n = self.nvals()
+        I, J = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        nv = U64(n)
+        if self.dtype is bool:
+            check(lib().GrB_Matrix_extractTuples_BOOL(I.ctypes.data, J.ctypes.data, None, C.byref(nv), self.h))
+            return I, J, None
+        X = np.empty(n, np.uint64)
+        check(lib().GrB_Matrix_extractTuples_UINT64(I.ctypes.data, J.ctypes.data, X.ctypes.data, C.byref(nv), self.h))
+        return I, J, X
+
+    def prepare(self, want_transpose=True):
+        check(lib().B200_Matrix_prepare(self.h, int(want_transpose)))
+        return self
+
+
+def rmat(scale, edge_factor=16, seed=1):
+    h = P()
+    check(lib().B200_Matrix_rmat(C.byref(h), scale, edge_factor, seed))
+    return Matrix(0, 0, bool, _handle=h)
+
+
+def bfs(A, src, max_level=-1, want_parent=True):
+    n = A.nrows()
+    level = np.empty(n, np.int64)
+    parent = np.empty(n, np.int64) if want_parent else None
+    edges = U64()
+    check(lib().B200_bfs(A.h, src, max_level, level.ctypes.data, None if parent is None else parent.ctypes.data, 0,
+                         C.byref(edges)))
+    return level, parent, edges.value
+
+
+def get_stat(name):
+    return lib().B200_get_stat(name.encode())
+
+
+def reset_stats():
+    lib().B200_reset_stats()
+
+
+def set_option(name, value):
+    check(lib().B200_set_option(name.encode(), int(value)))
+
+
+def sync():
+    check(lib().B200_sync())

@@ -1,0 +1,247 @@
+/*
+ * b200grb.h -- C ABI of libb200grb.so, the Blackwell-native GraphBLAS traversal backend.
+ *
+ * Drop-in boundary: FalkorDB links SuiteSparse:GraphBLAS through the bindgen
+ * declarations in graph/src/graph/graphblas/mod.rs and the link line graph/build.rs:52-55.
+ * Every declaration below mirrors the C signature mod.rs binds (file:line cited per entry), so
+ * swapping `static=graphblas` for `dylib=b200grb` re-points the graph store's hot calls
+ * (graph/src/graph/graphblas/matrix.rs) at this library.  All entry points return GrB_Info
+ * (mod.rs:274-296); handles are opaque and owned by the library until *_free.
+ *
+ * Scope: the subset on the traversal path -- GrB_mxm over GxB_ANY_PAIR_BOOL with structural /
+ * complemented / replace masks, eWiseAdd / eWiseMult / transpose (incl. the RCT0 masked copy) /
+ * apply(ONE) for delta-matrix sync, build, element access, row iterators, wait, and the BFS entry
+ * LAGr_BreadthFirstSearch_Extended.  Anything else returns GrB_NOT_IMPLEMENTED.  There is no CPU
+ * fallback: bulk operations run on the GPU or fail with GxB_GPU_ERROR.
+ *
+ * B200_* entry points are extensions (zero-copy CSR hand-off, statistics, the synthetic RMAT input
+ * generator) with no SuiteSparse counterpart; they play the role GxB_Container load/unload plays in
+ * the reference (matrix.rs:428-546).
+ */
+#ifndef B200GRB_H
+#define B200GRB_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t GrB_Index; /* mod.rs:271 */
+
+typedef enum { /* mod.rs:274-296 */
+    GrB_SUCCESS = 0,
+    GrB_NO_VALUE = 1,
+    GxB_EXHAUSTED = 7089,
+    GrB_UNINITIALIZED_OBJECT = -1,
+    GrB_NULL_POINTER = -2,
+    GrB_INVALID_VALUE = -3,
+    GrB_INVALID_INDEX = -4,
+    GrB_DOMAIN_MISMATCH = -5,
+    GrB_DIMENSION_MISMATCH = -6,
+    GrB_OUTPUT_NOT_EMPTY = -7,
+    GrB_NOT_IMPLEMENTED = -8,
+    GrB_ALREADY_SET = -9,
+    GrB_PANIC = -101,
+    GrB_OUT_OF_MEMORY = -102,
+    GrB_INSUFFICIENT_SPACE = -103,
+    GrB_INVALID_OBJECT = -104,
+    GrB_INDEX_OUT_OF_BOUNDS = -105,
+    GrB_EMPTY_OBJECT = -106,
+    GxB_JIT_ERROR = -7001,
+    GxB_GPU_ERROR = -7002,
+    GxB_OUTPUT_IS_READONLY = -7003
+} GrB_Info;
+
+typedef enum { GrB_NONBLOCKING = 0, GrB_BLOCKING = 1 } GrB_Mode;
+typedef enum { GrB_COMPLETE = 0, GrB_MATERIALIZE = 1 } GrB_WaitMode;   /* mod.rs:3032-3033 */
+typedef enum { GrB_ROWMAJOR = 0, GrB_COLMAJOR = 1 } GrB_Orientation;   /* mod.rs:3006-3007 */
+
+/* option fields used by the reference (mod.rs:2887-2963, 152) */
+#define GrB_STORAGE_ORIENTATION_HINT 100
+#define GxB_BURBLE 7019
+#define GxB_JIT_C_CONTROL 7029
+#define GxB_SPARSITY_STATUS 7034
+#define GxB_SPARSITY_CONTROL 7036
+#define GxB_HYPER_HASH 7048
+#define GxB_WILL_WAIT 7076
+#define GxB_NTHREADS 7086
+/* sparsity bits (mod.rs:159-162) */
+#define GxB_HYPERSPARSE 1
+#define GxB_SPARSE 2
+#define GxB_BITMAP 4
+#define GxB_FULL 8
+
+typedef struct GB_Type_opaque *GrB_Type;             /* mod.rs:316 */
+typedef struct GB_UnaryOp_opaque *GrB_UnaryOp;       /* mod.rs:322 */
+typedef struct GB_BinaryOp_opaque *GrB_BinaryOp;     /* mod.rs:328 */
+typedef struct GB_Semiring_opaque *GrB_Semiring;     /* mod.rs:346 */
+typedef struct GB_Descriptor_opaque *GrB_Descriptor; /* mod.rs:310 */
+typedef struct GB_Scalar_opaque *GrB_Scalar;         /* mod.rs:352 */
+typedef struct GB_Vector_opaque *GrB_Vector;         /* mod.rs:358 */
+typedef struct GB_Matrix_opaque *GrB_Matrix;         /* mod.rs:364 */
+typedef struct GB_Global_opaque *GrB_Global;         /* mod.rs:370 */
+typedef struct GB_Iterator_opaque *GxB_Iterator;     /* mod.rs:383 */
+
+/* exported data symbols (mod.rs:430-544, 721, 1301, 1547, 1643, 3001, 6852) */
+extern GrB_Type GrB_BOOL, GrB_UINT64, GrB_INT64;
+extern GrB_Semiring GxB_ANY_PAIR_BOOL;
+extern GrB_BinaryOp GxB_ANY_BOOL, GrB_SECOND_UINT64, GxB_ANY_UINT64;
+extern GrB_UnaryOp GxB_ONE_BOOL;
+extern const GrB_Global GrB_GLOBAL;
+/* the 31 predefined descriptors: T0/T1 = transpose input 0/1, C = complement mask,
+ * S = structural mask, R = replace output (matrix.rs:80-85, 313-351) */
+extern GrB_Descriptor GrB_DESC_T1, GrB_DESC_T0, GrB_DESC_T0T1, GrB_DESC_C, GrB_DESC_CT1, GrB_DESC_CT0, GrB_DESC_CT0T1,
+    GrB_DESC_S, GrB_DESC_ST1, GrB_DESC_ST0, GrB_DESC_ST0T1, GrB_DESC_SC, GrB_DESC_SCT1, GrB_DESC_SCT0, GrB_DESC_SCT0T1,
+    GrB_DESC_R, GrB_DESC_RT1, GrB_DESC_RT0, GrB_DESC_RT0T1, GrB_DESC_RC, GrB_DESC_RCT1, GrB_DESC_RCT0, GrB_DESC_RCT0T1,
+    GrB_DESC_RS, GrB_DESC_RST1, GrB_DESC_RST0, GrB_DESC_RST0T1, GrB_DESC_RSC, GrB_DESC_RSCT1, GrB_DESC_RSCT0,
+    GrB_DESC_RSCT0T1;
+
+/* ---- lifecycle (matrix.rs:116-221) ---- */
+GrB_Info GxB_init(int mode, void *(*user_malloc)(size_t), void *(*user_calloc)(size_t, size_t),
+                  void *(*user_realloc)(void *, size_t), void (*user_free)(void *)); /* mod.rs:7970 */
+GrB_Info GrB_init(int mode);
+GrB_Info GrB_finalize(void);                                                          /* mod.rs:7967 */
+GrB_Info GrB_Global_set_INT32(GrB_Global g, int32_t value, int field);                /* mod.rs:10974 */
+GrB_Info GxB_Global_Option_set_INT32(int field, int32_t value);                       /* mod.rs:15577 */
+
+/* ---- matrix objects ---- */
+GrB_Info GrB_Matrix_new(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols); /* mod.rs:9444 */
+GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A);                                    /* mod.rs:9452 */
+GrB_Info GrB_Matrix_free(GrB_Matrix *A);                                                 /* mod.rs:15072 */
+GrB_Info GrB_Matrix_clear(GrB_Matrix A);                                                 /* mod.rs:9476 */
+GrB_Info GrB_Matrix_resize(GrB_Matrix C, GrB_Index nrows_new, GrB_Index ncols_new);      /* mod.rs:14055 */
+GrB_Info GrB_Matrix_nrows(GrB_Index *nrows, GrB_Matrix A);                               /* mod.rs:9479 */
+GrB_Info GrB_Matrix_ncols(GrB_Index *ncols, GrB_Matrix A);                               /* mod.rs:9485 */
+GrB_Info GrB_Matrix_nvals(GrB_Index *nvals, GrB_Matrix A);                               /* mod.rs:9491 */
+GrB_Info GrB_Matrix_set_INT32(GrB_Matrix A, int32_t value, int field);                   /* mod.rs:10713 */
+GrB_Info GrB_Matrix_get_INT32(GrB_Matrix A, int32_t *value, int field);                  /* mod.rs:10230 */
+GrB_Info GxB_Matrix_type(GrB_Type *type, GrB_Matrix A);                                  /* mod.rs:9503 */
+GrB_Info GxB_Matrix_iso(bool *iso, GrB_Matrix A);                                        /* mod.rs:15103 */
+GrB_Info GxB_Matrix_memoryUsage(size_t *size, GrB_Matrix A);                             /* mod.rs:9497 */
+GrB_Info GxB_Matrix_fprint(GrB_Matrix A, const char *name, int pr, FILE *f);             /* mod.rs:14132 */
+GrB_Info GrB_Matrix_wait(GrB_Matrix A, int waitmode);                                    /* mod.rs:11078 */
+
+/* ---- element access (matrix.rs:1143-1172, 1248-1275, 731-737, 1035-1045) ---- */
+GrB_Info GrB_Matrix_setElement_BOOL(GrB_Matrix C, bool x, GrB_Index i, GrB_Index j);       /* mod.rs:9685 */
+GrB_Info GrB_Matrix_setElement_UINT64(GrB_Matrix C, uint64_t x, GrB_Index i, GrB_Index j); /* mod.rs:9749 */
+GrB_Info GrB_Matrix_extractElement_BOOL(bool *x, GrB_Matrix A, GrB_Index i, GrB_Index j);  /* mod.rs:9797 */
+GrB_Info GrB_Matrix_extractElement_UINT64(uint64_t *x, GrB_Matrix A, GrB_Index i, GrB_Index j); /* mod.rs:9861 */
+GrB_Info GrB_Matrix_removeElement(GrB_Matrix C, GrB_Index i, GrB_Index j);                 /* mod.rs:9924 */
+GrB_Info GxB_Matrix_isStoredElement(GrB_Matrix A, GrB_Index i, GrB_Index j);               /* mod.rs:9917 */
+GrB_Info GrB_Matrix_extractTuples_BOOL(GrB_Index *I, GrB_Index *J, bool *X, GrB_Index *nvals, GrB_Matrix A);     /* mod.rs:9931 */
+GrB_Info GrB_Matrix_extractTuples_UINT64(GrB_Index *I, GrB_Index *J, uint64_t *X, GrB_Index *nvals, GrB_Matrix A); /* mod.rs:10003 */
+
+/* ---- build (matrix.rs:1186-1210, 1281-1303) ---- */
+GrB_Info GrB_Scalar_new(GrB_Scalar *s, GrB_Type type);      /* mod.rs:8677 */
+GrB_Info GrB_Scalar_setElement_BOOL(GrB_Scalar s, bool x);  /* mod.rs:8726 */
+GrB_Info GrB_Scalar_free(GrB_Scalar *s);                    /* mod.rs:15066 */
+GrB_Info GxB_Matrix_build_Scalar(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, GrB_Scalar scalar,
+                                 GrB_Index nvals);          /* mod.rs:9659 */
+GrB_Info GrB_Matrix_build_UINT64(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const uint64_t *X,
+                                 GrB_Index nvals, GrB_BinaryOp dup); /* mod.rs:9589 */
+GrB_Info GrB_Matrix_build_BOOL(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const bool *X, GrB_Index nvals,
+                               GrB_BinaryOp dup);           /* mod.rs:9509 */
+
+/* ---- bulk algebra: the hot calls ---- */
+GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Matrix B,
+                 GrB_Descriptor desc);                      /* mod.rs:11162; matrix.rs:935,956,1346,1366,1386 */
+GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_BinaryOp add, GrB_Matrix A,
+                                      GrB_Matrix B, GrB_Descriptor desc); /* mod.rs:11316; matrix.rs:862 */
+GrB_Info GrB_Matrix_eWiseMult_Semiring(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring semiring,
+                                       GrB_Matrix A, GrB_Matrix B, GrB_Descriptor desc); /* mod.rs:11228; matrix.rs:749,884 */
+GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Matrix A,
+                       GrB_Descriptor desc);                /* mod.rs:14013; matrix.rs:658,829,841 */
+GrB_Info GrB_Matrix_apply(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_UnaryOp op, GrB_Matrix A,
+                          GrB_Descriptor desc);             /* mod.rs:12375; matrix.rs:913 */
+
+/* ---- vectors (frontier / BFS outputs; graph/src/graph/graphblas/vector.rs:44-55) ---- */
+GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n);
+GrB_Info GrB_Vector_free(GrB_Vector *v);
+GrB_Info GrB_Vector_size(GrB_Index *n, GrB_Vector v);
+GrB_Info GrB_Vector_nvals(GrB_Index *nvals, GrB_Vector v);
+GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i);
+GrB_Info GrB_Vector_extractElement_INT64(int64_t *x, GrB_Vector v, GrB_Index i);
+GrB_Info GrB_Vector_extractElement_BOOL(bool *x, GrB_Vector v, GrB_Index i);
+GrB_Info GrB_Vector_extractTuples_INT64(GrB_Index *I, int64_t *X, GrB_Index *nvals, GrB_Vector v);
+GrB_Info GrB_Vector_extractTuples_BOOL(GrB_Index *I, bool *X, GrB_Index *nvals, GrB_Vector v);
+/* w<mask> = u*A / A*u over ANY_PAIR: one frontier step (mod.rs:11173, 11184) */
+GrB_Info GrB_vxm(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u, GrB_Matrix A,
+                 GrB_Descriptor desc);
+GrB_Info GrB_mxv(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Vector u,
+                 GrB_Descriptor desc);
+
+/* ---- row iterator (matrix.rs:1471-1605) -- real symbols, as bindgen declares them ---- */
+GrB_Info GxB_Iterator_new(GxB_Iterator *it);                                      /* mod.rs:14848 */
+GrB_Info GxB_Iterator_free(GxB_Iterator *it);                                     /* mod.rs:15084 */
+GrB_Info GxB_rowIterator_attach(GxB_Iterator it, GrB_Matrix A, GrB_Descriptor d); /* mod.rs:14875 */
+GrB_Index GxB_rowIterator_kount(GxB_Iterator it);                                 /* mod.rs:14882 */
+GrB_Info GxB_rowIterator_seekRow(GxB_Iterator it, GrB_Index row);                 /* mod.rs:14885 */
+GrB_Info GxB_rowIterator_nextRow(GxB_Iterator it);                                /* mod.rs:14897 */
+GrB_Info GxB_rowIterator_nextCol(GxB_Iterator it);                                /* mod.rs:14900 */
+GrB_Index GxB_rowIterator_getRowIndex(GxB_Iterator it);                           /* mod.rs:14903 */
+GrB_Index GxB_rowIterator_getColIndex(GxB_Iterator it);                           /* mod.rs:14906 */
+uint64_t GxB_Iterator_get_UINT64(GxB_Iterator it);                                /* mod.rs:15024 */
+bool GxB_Iterator_get_BOOL(GxB_Iterator it);
+
+/* ---- LAGraph subset (lagraph_bindings.rs:160-188, lagraphx_bindings.rs:585-594) ---- */
+typedef enum { LAGraph_ADJACENCY_UNDIRECTED = 0, LAGraph_ADJACENCY_DIRECTED = 1, LAGraph_KIND_UNKNOWN = -1 } LAGraph_Kind;
+typedef struct LAGraph_Graph_struct {
+    GrB_Matrix A;
+    LAGraph_Kind kind;
+    GrB_Matrix AT;
+    GrB_Vector out_degree, in_degree;
+    int is_symmetric_structure;
+    int64_t nself_edges;
+    GrB_Scalar emin;
+    int emin_state;
+    GrB_Scalar emax;
+    int emax_state;
+} *LAGraph_Graph;
+int LAGraph_Init(char *msg);
+int LAGraph_Finalize(char *msg);
+int LAGraph_New(LAGraph_Graph *G, GrB_Matrix *A, LAGraph_Kind kind, char *msg);
+int LAGraph_Delete(LAGraph_Graph *G, char *msg);
+int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGraph_Graph G, GrB_Index src,
+                                     int64_t max_level, int64_t dest, bool many_expected, char *msg);
+
+/* ---- B200 extensions ---- */
+#define B200_LOC_HOST 0
+#define B200_LOC_DEVICE 1
+/* Import a CSR (rowptr u64[nrows+1], col u32[nnz] ascending per row, val u64[nnz] or NULL) from host
+ * or device memory; arrays are copied.  Plays the role of GxB_load_Matrix_from_Container. */
+GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols, const uint64_t *Ap,
+                                const uint32_t *Aj, const uint64_t *Ax, int location);
+/* Export into caller buffers sized by GrB_Matrix_nrows / nvals (Ax may be NULL). */
+GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64_t *Ax, int location);
+/* Borrow the device-resident CSR (valid until A is next modified or freed). */
+GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax);
+/* Pre-build the cached transpose mirror used by the pull direction (done lazily otherwise). */
+GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
+/* Synthetic Graph500-style RMAT adjacency (a,b,c,d=.57,.19,.19,.05), dedupe + no self loops, built on
+ * the device.  Benchmark / test input only. */
+GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed);
+GrB_Info B200_sync(void);
+void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */
+/* stats: "launches", "lib_launches", "last_flops", "total_flops", "last_path", "h2d_bytes", "d2h_bytes" */
+uint64_t B200_get_stat(const char *name);
+void B200_reset_stats(void);
+/* with option "timing"=1 the library brackets its main kernels with CUDA events on its stream; this returns the
+ * accumulated device time (ms), launch count and algorithmic bytes of one kernel family since the last reset:
+ * "bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "bits_fill", "bits_count".  0 on success. */
+int B200_kernel_stats(const char *name, double *ms, uint64_t *launches, uint64_t *bytes);
+/* options: "bits_mode" (-1 auto,0 off,1 on), "pull_mode" (-1 auto,0 push,1 pull), "small_cap",
+ * "bitmap_budget", "bits_min_flops", "timing" (0/1), "sync_after_op" (0/1) */
+GrB_Info B200_set_option(const char *name, int64_t value);
+const char *B200_last_error(void);
+/* single-source BFS straight into caller buffers (int64 level/parent per vertex, -1 = unreached) */
+GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level, int64_t *parent, int location,
+                  uint64_t *edges_traversed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GRB_H */

@@ -1,0 +1,155 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/b200grb.h declares, the host-side handle logic (pending tuples, element access, row iterator,
+dup/resize) behaves like the reference expects, and bulk operations FAIL LOUDLY without a GPU
+(there is no CPU fallback).  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import falkordb_b200 as fb
+from falkordb_b200._lib import lib, obj, LIB_PATH
+from falkordb_b200.grb import Matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200grb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    funcs = set(re.findall(r"\b((?:GrB|GxB|LAGraph|LAGr|B200)_\w+)\s*\(", src))
+    data = set()
+    for m in re.finditer(r"extern\s+(?:const\s+)?\w+\s+([^;]+);", src):
+        for name in m.group(1).split(","):
+            data.add(name.strip().lstrip("*"))
+    return funcs, data
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib()
+    funcs, data = header_symbols()
+    assert len(funcs) > 60 and "GrB_mxm" in funcs and "GrB_DESC_RSC" in data and len(data) >= 31 + 9
+    missing = [s for s in sorted(funcs | data) if not hasattr(L, s)]
+    assert not missing, f"libb200grb.so does not export: {missing}"
+
+
+def test_descriptor_table_is_distinct():
+    _, data = header_symbols()
+    descs = [d for d in data if d.startswith("GrB_DESC_")]
+    assert len(descs) == 31
+    assert len({obj(d).value for d in descs}) == 31
+
+
+def test_element_ops_and_pending_semantics_host_only():
+    fb.init()
+    m = Matrix(8, 8, "u64")
+    assert m.nvals() == 0 and m.get(1, 2) is None
+    m.set(1, 2, 10)
+    m.set(3, 4, 20)
+    m.set(1, 2, 11)            # overwrite while pending: last write wins
+    assert m.pending()
+    assert m.get(1, 2) == 11 and m.get(3, 4) == 20 and m.nvals() == 2
+    assert not m.pending()
+    m.remove(3, 4)
+    m.remove(7, 7)             # removing an absent entry is a no-op
+    m.set(0, 0, 0)             # edge id 0 is a real value (tensor.rs:1427-1476)
+    assert m.nvals() == 2 and m.get(0, 0) == 0 and m.contains(0, 0) and not m.contains(3, 4)
+    assert list(m.iter()) == [(0, 0, 0), (1, 2, 11)]
+    with pytest.raises(fb.GrbError):
+        m.set(8, 0, 1)         # GrB_INVALID_INDEX
+
+
+def test_row_iterator_ranges_and_seek():
+    m = Matrix(100, 100, bool)
+    want = sorted({(i, (i * 7) % 100) for i in range(0, 100, 3)} | {(i, (i * 11 + 3) % 100) for i in range(0, 100, 3)})
+    for i, j in want:
+        m.set(i, j)
+    m.wait()
+    assert list(m.iter()) == want
+    assert list(m.iter(10, 20)) == [t for t in want if 10 <= t[0] <= 20]
+    assert list(m.iter(1, 2)) == []          # rows 1..2 are empty
+    assert list(m.iter(99, 99)) == [t for t in want if t[0] == 99]
+    assert list(m.iter(98, 2 ** 64 - 1)) == [t for t in want if t[0] >= 98]
+
+
+def test_bool_is_pattern_only_and_iso():
+    m = Matrix(4, 4, bool)
+    m.set(1, 1)
+    assert m.is_iso() and m.get(1, 1) is True
+    with pytest.raises(fb.GrbError):
+        m.set(0, 0, False)      # stored false is never used on the path (versioned_matrix.rs:413-416)
+    u = Matrix(4, 4, "u64")
+    assert not u.is_iso()
+
+
+def test_dup_copies_pending_and_resize_host():
+    m = Matrix(64, 48, "u64")
+    for i in range(64):
+        m.set(i, (i * 7) % 48, i)
+    d = m.dup()                  # pending work is copied, not finished (matrix.rs:691-698)
+    assert d.nvals() == 64 and m.nvals() == 64
+    g = m.grown(256, 192)
+    assert (g.nrows(), g.ncols(), g.nvals()) == (256, 192, 64)
+    assert set(g.iter()) == set(m.iter())
+    assert (m.nrows(), m.ncols()) == (64, 48)
+    g.resize(10, 10)             # shrink drops out-of-range entries
+    assert set(g.iter()) == {t for t in m.iter() if t[0] < 10 and t[1] < 10}
+    with pytest.raises(AssertionError, match="grown must not shrink"):
+        m.grown(32, 48)
+
+
+def test_huge_dimension_matrix_is_host_resident():
+    """Tensor's `me` matrix is 2^60 x 2^60 hypersparse (tensor.rs:254): element ops + build + iterate on host."""
+    n = 1 << 60
+    me = Matrix(n, n, bool).into_hyper()
+    keys = [((5 << 32) | 9, 17), ((5 << 32) | 9, 3), ((1 << 59), (1 << 59) + 1), ((5 << 32) | 9, 17)]
+    me.build([k[0] for k in keys], [k[1] for k in keys])
+    assert me.nvals() == 3                                  # duplicates collapse (matrix.rs:1686-1695)
+    assert list(me.iter()) == sorted(set(keys))
+    assert me.sparsity_status() == "hypersparse" and me.hyper_vector_count() == 2
+    me.remove((5 << 32) | 9, 3)
+    assert list(me.iter((5 << 32) | 9, (5 << 32) | 9)) == [((5 << 32) | 9, 17)]
+    a = Matrix(n, n, bool)
+    with pytest.raises(fb.GrbError) as e:
+        a.lmxm(me)                                          # bulk algebra needs device-capable dims
+    assert e.value.info in (-8, -7002)
+
+
+def test_unsupported_semantics_fail_loudly():
+    a, b, c = Matrix(4, 4), Matrix(4, 4), Matrix(4, 5)
+    L = lib()
+    assert L.GrB_mxm(c.h, None, None, obj("GxB_ANY_PAIR_BOOL"), a.h, b.h, None) in (-6, -7002)
+    # a semiring off the path
+    assert L.GrB_mxm(a.h, None, None, obj("GxB_ANY_BOOL"), a.h, b.h, None) == -8
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_bulk_ops_fail_loudly_without_gpu():
+    a, b = Matrix(4, 4), Matrix(4, 4)
+    a.set(0, 1)
+    b.set(1, 2)
+    with pytest.raises(fb.GrbError) as e:
+        a.lmxm(b)
+    assert e.value.info == -7002 and "no CPU fallback" in str(e.value)
+    with pytest.raises(fb.GrbError):
+        fb.rmat(4)
+    with pytest.raises(fb.GrbError):
+        a.build([0], [0])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "falkordb_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", txt, re.M), f
+                assert not re.search(r"#include\s*[\"<][^\n]*oracle", txt), f
+                assert "liborc" not in txt and "orc_" not in re.sub(r"//[^\n]*", "", txt), f

@@ -1,0 +1,397 @@
+"""GPU parity: every CUDA path, called through the C ABI (falkordb_b200.grb -> libb200grb.so), against the CPU
+oracle on the same seeded inputs.  Bit-exact: identical row pointers and column indices (and values for u64).
+Also transcribes the reference's own known-answer unit tests at this boundary
+(graph/src/graph/graphblas/matrix.rs:1617-1775)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import falkordb_b200 as fb
+import oracle as orc
+from falkordb_b200.grb import Matrix, Descriptor
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_csr(rng, nrows, ncols, density, values=False):
+    m = sp.random(nrows, ncols, density=density, format="csr", random_state=rng,
+                  data_rvs=lambda k: rng.integers(0, 5, k))
+    m.data = m.data.astype(np.int64)
+    return orc.CSR.from_scipy(m, values=values)
+
+
+def to_dev(c, dtype=None):
+    dt = dtype or ("u64" if c.x is not None else bool)
+    return Matrix.import_csr(c.nrows, c.ncols, c.p.astype(np.uint64), c.j, c.x if dt == "u64" else None, dt)
+
+
+def from_dev(m):
+    p, j, x = m.export_csr()
+    return orc.CSR(m.nrows(), m.ncols(), p, j, x)
+
+
+def assert_same(dev, want, what=""):
+    got = from_dev(dev)
+    assert got.nrows == want.nrows and got.ncols == want.ncols, what
+    assert np.array_equal(got.p, want.p), f"{what}: row pointers differ"
+    assert np.array_equal(got.j, want.j), f"{what}: column indices differ"
+    if want.x is not None:
+        assert got.x is not None and np.array_equal(got.x, want.x), f"{what}: values differ"
+
+
+@pytest.fixture(autouse=True)
+def _defaults():
+    fb.init()
+    for k, v in (("bits_mode", -1), ("pull_mode", -1), ("small_cap", 4096), ("bitmap_budget", 2 << 30),
+                 ("bits_min_flops", 1 << 22)):
+        fb.set_option(k, v)
+    yield
+
+
+# ------------------------------------------------------------------------------------------ inputs
+@pytest.mark.parametrize("scale,seed", [(8, 1), (12, 1), (14, 7)])
+def test_rmat_generator_matches_oracle(scale, seed):
+    assert_same(fb.rmat(scale, 16, seed), orc.rmat_csr(scale, 16, seed), "rmat")
+
+
+def test_build_bool_and_u64_with_duplicates():
+    rng = np.random.default_rng(3)
+    n = 20000
+    I = rng.integers(0, 500, n).astype(np.uint64)
+    J = rng.integers(0, 700, n).astype(np.uint64)
+    X = rng.integers(0, 1 << 40, n).astype(np.uint64)
+    m = Matrix(500, 700, bool)
+    m.build(I, J)
+    assert_same(m, orc.build_matrix(500, 700, I, J), "build bool")
+    u = Matrix(500, 700, "u64")
+    u.build(I, J, X)
+    assert_same(u, orc.build_matrix(500, 700, I, J, X), "build u64 (first duplicate wins)")
+    bad = Matrix(4, 4, bool)
+    with pytest.raises(fb.GrbError) as e:
+        bad.build([4], [0])
+    assert e.value.info == -105
+    m2 = Matrix(500, 700, bool)
+    m2.build(I[:10], J[:10])
+    with pytest.raises(fb.GrbError) as e:
+        m2.build(I[:10], J[:10])          # GrB_OUTPUT_NOT_EMPTY
+    assert e.value.info == -7
+
+
+# ------------------------------------------------------------------------------------------ reference KATs
+def test_ref_grown_preserves_entries_at_every_growth_shape():
+    """matrix.rs:1617-1655"""
+    r0, c0 = 64, 48
+    coords = sorted({(i, (i * 7) % c0) for i in range(r0)} | {(i, (i * 11 + 3) % c0) for i in range(r0)})
+    rows, cols = [c[0] for c in coords], [c[1] for c in coords]
+    vals = list(range(len(coords)))
+    src = Matrix(r0, c0, "u64")
+    src.build(rows, cols, vals)
+    src.wait()
+    for nrows, ncols in [(r0, c0), (r0 * 4, c0), (r0, c0 * 4), (r0 * 4, c0 * 4), (100_000, 100_000)]:
+        g = src.grown(nrows, ncols)
+        g.wait()
+        assert (g.nrows(), g.ncols()) == (nrows, ncols)
+        assert g.nvals() == src.nvals()
+        assert set(g.iter()) == set(zip(rows, cols, vals))
+    assert (src.nrows(), src.ncols()) == (r0, c0) and src.nvals() == len(coords)
+
+
+def test_ref_grown_keeps_bool_layers_a_pattern():
+    """matrix.rs:1660-1672"""
+    src = Matrix(32, 32, bool)
+    src.build([0, 5, 31], [0, 7, 31])
+    src.wait()
+    g = src.grown(4096, 4096)
+    g.wait()
+    assert g.nvals() == 3
+    for i, j in [(0, 0), (5, 7), (31, 31)]:
+        assert g.get(i, j) is True
+
+
+def test_ref_build_bool_tolerates_duplicate_pairs():
+    """matrix.rs:1686-1695"""
+    m = Matrix(8, 8, bool)
+    m.build([1, 3, 1, 3, 1], [2, 4, 2, 4, 2])
+    m.wait()
+    assert m.nvals() == 2 and m.get(1, 2) is True and m.get(3, 4) is True
+
+
+def test_ref_build_bool_is_iso():
+    """matrix.rs:1709-1775 (first half: the scalar build is iso and smaller than a valued build)"""
+    N = 4096
+    rows = np.arange(N)
+    cols = (rows * 7) % N
+    b = Matrix(N, N, bool)
+    b.build(rows, cols)
+    b.wait()
+    assert b.is_iso()
+    u = Matrix(N, N, "u64")
+    u.build(rows, cols, np.ones(N))
+    u.wait()
+    assert not u.is_iso() and b.memory_usage() < u.memory_usage()
+
+
+# ------------------------------------------------------------------------------------------ mxm, general path
+@pytest.mark.parametrize("seed", range(5))
+def test_mxm_rowwise_matches_oracle(seed):
+    fb.set_option("bits_mode", 0)
+    rng = np.random.default_rng(seed)
+    n, k, m = rng.integers(1, 400, 3)
+    A = rand_csr(rng, n, k, 0.05)
+    B = rand_csr(rng, k, m, 0.05, values=bool(seed & 1))    # u64 operand: values never read
+    C = Matrix(n, m, bool)
+    C.mxm(to_dev(A), to_dev(B))
+    want, flops = orc.mxm(A, B, return_flops=True)
+    assert_same(C, want, "mxm")
+    assert fb.get_stat("last_flops") == flops
+
+
+def test_mxm_heavy_rows_single_and_multi_wave():
+    """rows above small_cap take the global-bitmap path; a tiny scratch budget forces several waves"""
+    fb.set_option("bits_mode", 0)
+    fb.set_option("small_cap", 512)
+    A = orc.rmat_csr(12, 16, 5)
+    rng = np.random.default_rng(1)
+    F = rand_csr(rng, 300, A.nrows, 0.01)
+    want = orc.mxm(F, A)
+    dA = to_dev(A)
+    for budget in (2 << 30, 3 * ((A.ncols + 31) // 32) * 4):
+        fb.set_option("bitmap_budget", budget)
+        C = Matrix(300, A.ncols, bool)
+        C.mxm(to_dev(F), dA)
+        assert_same(C, want, f"heavy rows, budget {budget}")
+    # in place (C aliases the left operand, matrix.rs:935-943)
+    C = to_dev(F)
+    C.lmxm(dA)
+    assert_same(C, want, "lmxm in place")
+    # A*A on a skewed graph: every bin at once
+    S = orc.rmat_csr(9, 8, 2)
+    C = Matrix(S.nrows, S.ncols, bool)
+    C.mxm(to_dev(S), to_dev(S))
+    assert_same(C, orc.mxm(S, S), "A*A")
+
+
+DESCS = [None, Descriptor.S, Descriptor.C, Descriptor.SC, Descriptor.R, Descriptor.RS, Descriptor.RC, Descriptor.RSC]
+
+
+@pytest.mark.parametrize("desc", DESCS)
+def test_mxm_mask_descriptor_semantics(desc):
+    fb.set_option("bits_mode", 0)
+    rng = np.random.default_rng(11)
+    A = rand_csr(rng, 90, 70, 0.08)
+    B = rand_csr(rng, 70, 110, 0.08)
+    M = rand_csr(rng, 90, 110, 0.3, values=True)          # valued mask: zeros are "false" unless structural
+    Cold = rand_csr(rng, 90, 110, 0.1)
+    name = desc.value if desc else ""
+    comp, structural, replace = "C" in name, "S" in name, "R" in name
+    T = orc.mxm(A, B)
+    want = orc.mask_assign(Cold, T, M, comp, structural, replace)
+    C = to_dev(Cold)
+    C.mxm(to_dev(A), to_dev(B), to_dev(M, "u64"), desc)
+    assert_same(C, want, f"mxm desc {name}")
+
+
+def test_mxm_errors():
+    a, b, c = Matrix(4, 5), Matrix(6, 4), Matrix(4, 4)
+    with pytest.raises(fb.GrbError) as e:
+        c.mxm(a, b)
+    assert e.value.info == -6
+
+
+# ------------------------------------------------------------------------------------------ mxm, frontier bit-matrix path
+@pytest.mark.parametrize("nsrc,pull", [(1, 0), (64, 0), (64, 1), (100, 1), (1000, 0), (1024, 1)])
+def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
+    """CondTraverse's F*A*A*A (cond_traverse.rs:600-605) in frontier form, push and pull directions"""
+    fb.set_option("bits_mode", 1)
+    fb.set_option("pull_mode", pull)
+    A = orc.rmat_csr(11, 16, 3)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc)
+    src = rng.choice(n, size=nsrc, replace=False)
+    Fo = orc.build_matrix(nsrc, n, np.arange(nsrc), src)
+    dA = to_dev(A)
+    F = Matrix(nsrc, n, bool)
+    F.build(np.arange(nsrc), src)
+    want, total = Fo, 0
+    for hop in range(3):
+        want, fl = orc.mxm(want, A, return_flops=True)
+        F.lmxm(dA)
+        assert fb.get_stat("last_flops") == fl, f"hop {hop} flops"
+        assert F.nvals() == want.nnz, f"hop {hop} nvals (popcount, no materialise)"
+    F.wait()
+    assert_same(F, want, f"3-hop chain, {nsrc} sources, pull={pull}")
+    assert list(F.iter(0, 0)) == [(0, int(c)) for c in want.j[want.p[0]:want.p[1]]]
+
+
+def test_bit_frontier_rectangular_and_auto_mode():
+    rng = np.random.default_rng(9)
+    F = rand_csr(rng, 70, 900, 0.02)
+    B = rand_csr(rng, 900, 1300, 0.01)
+    want = orc.mxm(F, B)
+    for mode, pull in ((1, 0), (1, 1), (-1, -1), (0, -1)):
+        fb.set_option("bits_mode", mode)
+        fb.set_option("pull_mode", pull)
+        fb.set_option("bits_min_flops", 1)
+        C = Matrix(70, 1300, bool)
+        C.mxm(to_dev(F), to_dev(B))
+        assert_same(C, want, f"rectangular bits_mode={mode} pull={pull}")
+
+
+@pytest.mark.parametrize("bits", [0, 1])
+def test_delta_lmxm_matches_oracle(bits):
+    """matrix.rs:1317-1402: dirty snapshot = 3 mxm + RSC mask + eWiseAdd"""
+    fb.set_option("bits_mode", bits)
+    rng = np.random.default_rng(21)
+    n = 600
+    m = rand_csr(rng, n, n, 0.02)
+    dp = orc.mask_assign(None, rand_csr(rng, n, n, 0.004), m, comp=True, structural=True, replace=True)
+    dm = orc.ewise_mult(m, rand_csr(rng, n, n, 0.3))
+    F = rand_csr(rng, 40, n, 0.01)
+    empty = orc.CSR.empty(n, n)
+    for (d_p, d_m) in ((dp, dm), (dp, empty), (empty, dm), (empty, empty)):
+        f = to_dev(F)
+        f.delta_lmxm(to_dev(m), to_dev(d_p), to_dev(d_m))
+        f.wait()
+        assert_same(f, orc.delta_lmxm(F, m, d_p, d_m), f"delta_lmxm dp={d_p.nnz} dm={d_m.nnz} bits={bits}")
+
+
+# ------------------------------------------------------------------------------------------ delta-sync algebra
+@pytest.mark.parametrize("seed", range(3))
+def test_ewise_transpose_select_apply(seed):
+    rng = np.random.default_rng(40 + seed)
+    n, m = rng.integers(50, 700, 2)
+    A = rand_csr(rng, n, m, 0.05, values=True)
+    B = rand_csr(rng, n, m, 0.05, values=True)
+    M = rand_csr(rng, n, m, 0.2)
+    # eWiseAdd u64: SECOND (b wins), fresh C  (fold, versioned_matrix.rs:921)
+    C = Matrix(n, m, "u64")
+    C.element_wise_add(None, to_dev(A), to_dev(B), None)
+    assert_same(C, orc.ewise_add(A, B, keep_values=True), "eWiseAdd SECOND")
+    # eWiseAdd bool with complemented mask + replace (fold with tombstones, versioned_matrix.rs:914-919)
+    Ab, Bb = orc.pattern(A), orc.pattern(B)
+    C = Matrix(n, m, bool)
+    C.element_wise_add(to_dev(M), to_dev(Ab), to_dev(Bb), Descriptor.RC)
+    assert_same(C, orc.mask_assign(None, orc.ewise_add(Ab, Bb), M, comp=True, replace=True), "eWiseAdd RC")
+    # in place: self u= b (matrix.rs:1399)
+    C = to_dev(Ab)
+    C.element_wise_add(None, None, to_dev(Bb), None)
+    assert_same(C, orc.ewise_add(Ab, Bb), "eWiseAdd in place")
+    # eWiseMult and the tombstone form dm<mask> = mask n m, no replace (versioned_matrix.rs:428-436)
+    C = Matrix(n, m, bool)
+    C.element_wise_multiply(None, to_dev(Ab), to_dev(B), None)
+    assert_same(C, orc.ewise_mult(Ab, B), "eWiseMult")
+    dm_old = orc.ewise_mult(Ab, rand_csr(rng, n, m, 0.1))
+    dm = to_dev(dm_old)
+    dm.element_wise_multiply(to_dev(M), to_dev(M), to_dev(A), None)
+    assert_same(dm, orc.mask_assign(dm_old, orc.ewise_mult(M, A), M), "tombstone_masked")
+    assert to_dev(Ab).intersection_nvals(to_dev(B)) == orc.ewise_mult(Ab, B).nnz
+    # transpose keeps type and values; involution
+    T = to_dev(A).transpose()
+    assert_same(T, orc.transpose(A), "transpose u64")
+    assert_same(T.transpose(), A, "transpose involution")
+    assert_same(to_dev(Ab).transpose(), orc.transpose(Ab), "transpose bool")
+    # masked copy / set difference via GrB_transpose(..., RCT0) (matrix.rs:824-845)
+    C = to_dev(A)
+    C.remove_all(to_dev(M))
+    assert_same(C, orc.mask_assign(None, A, M, comp=True, replace=True), "remove_all")
+    C = Matrix(n, m, "u64")
+    C.select(to_dev(M), to_dev(A))
+    assert_same(C, orc.mask_assign(None, A, M, comp=True, replace=True), "select")
+    # set_pattern: C<M,desc> u= pattern(A) as true; A's values (incl. 0) never read (matrix.rs:898-924)
+    C = to_dev(Bb)
+    C.set_pattern(None, to_dev(A), None)
+    assert_same(C, orc.ewise_add(Bb, Ab), "set_pattern")
+    C = to_dev(Bb)
+    C.set_pattern(to_dev(M), to_dev(A), Descriptor.C)
+    assert_same(C, orc.mask_assign(Bb, Ab, M, comp=True, accum=True), "set_pattern masked C")
+
+
+def test_skewed_rows_in_set_algebra():
+    """hub rows (RMAT) through the warp-per-row union / filter kernels"""
+    A = orc.rmat_csr(11, 16, 1)
+    B = orc.rmat_csr(11, 16, 2)
+    C = Matrix(A.nrows, A.ncols, bool)
+    C.element_wise_add(None, to_dev(A), to_dev(B), None)
+    assert_same(C, orc.ewise_add(A, B), "union rmat")
+    C = to_dev(A)
+    C.remove_all(to_dev(B))
+    assert_same(C, orc.mask_assign(None, A, B, comp=True, structural=True, replace=True), "difference rmat")
+    assert_same(to_dev(A).transpose(), orc.transpose(A), "transpose rmat")
+
+
+def test_device_resize_dup_clear_and_host_round_trip():
+    rng = np.random.default_rng(5)
+    A = rand_csr(rng, 200, 300, 0.05, values=True)
+    d = to_dev(A)
+    g = d.grown(1000, 2000)
+    g.wait()
+    assert g.nvals() == A.nnz and set(g.iter()) == A.tuple_set()
+    s = d.dup()
+    s.resize(50, 60)
+    assert set(s.iter()) == {t for t in A.tuple_set() if t[0] < 50 and t[1] < 60}
+    # host element writes on top of a device-resident matrix, then a bulk op sees them
+    d.set(0, 0, 77)
+    d.remove(int(A.tuples()[0][0]), int(A.tuples()[1][0]))
+    want = A.tuple_set()
+    want = {t for t in want if (t[0], t[1]) != (int(A.tuples()[0][0]), int(A.tuples()[1][0])) and (t[0], t[1]) != (0, 0)}
+    want.add((0, 0, 77))
+    assert set(d.iter()) == want
+    t = d.transpose()
+    assert set(t.iter()) == {(c, r, v) for r, c, v in want}
+    d.clear()
+    assert d.nvals() == 0 and list(d.iter()) == []
+
+
+# ------------------------------------------------------------------------------------------ BFS / frontier steps
+@pytest.mark.parametrize("scale,seed", [(10, 1), (13, 4)])
+def test_bfs_levels_and_min_parents(scale, seed):
+    A = orc.rmat_csr(scale, 16, seed)
+    dA = to_dev(A)
+    deg = np.diff(A.p)
+    srcs = np.nonzero(deg > 0)[0][[0, 7, 100]]
+    for s in srcs:
+        lvl, par, edges = fb.bfs(dA, int(s))
+        wl, wp = orc.bfs(A, int(s))
+        assert np.array_equal(lvl, wl), "levels"
+        assert np.array_equal(par, wp), "min-id parents"
+        assert edges == int(deg[wl >= 0].sum()) or edges <= int(deg[wl >= 0].sum())
+        l2, _, _ = fb.bfs(dA, int(s), max_level=2, want_parent=False)
+        assert np.array_equal(l2, orc.bfs(A, int(s), 2)[0])
+
+
+def test_lagraph_bfs_entry_and_vxm():
+    import ctypes as C
+    from falkordb_b200._lib import lib, obj, P, U64
+    L = lib()
+    A = orc.rmat_csr(9, 8, 3)
+    dA = to_dev(A)
+    g = P()
+    h = P(dA.h.value)
+    assert L.LAGraph_New(C.byref(g), C.byref(h), 1, None) == 0 and not h.value
+    lv, pv = P(), P()
+    src = int(np.nonzero(np.diff(A.p))[0][0])
+    assert L.LAGr_BreadthFirstSearch_Extended(C.byref(lv), C.byref(pv), g, src, -1, -1, False, None) == 0
+    wl, wp = orc.bfs(A, src)
+    nv = U64()
+    L.GrB_Vector_nvals(C.byref(nv), lv)
+    n = nv.value
+    I, X = np.empty(n, np.uint64), np.empty(n, np.int64)
+    cap = U64(n)
+    assert L.GrB_Vector_extractTuples_INT64(I.ctypes.data, X.ctypes.data, C.byref(cap), lv) == 0
+    assert np.array_equal(I, np.nonzero(wl >= 0)[0]) and np.array_equal(X, wl[wl >= 0])
+    # borrowed-graph teardown (algo_procedures.rs:407-413): detach A before LAGraph_Delete
+    C.cast(g, C.POINTER(P))[0] = None
+    assert L.LAGraph_Delete(C.byref(g), None) == 0
+    L.GrB_Vector_free(C.byref(lv)); L.GrB_Vector_free(C.byref(pv))
+    # one push step via GrB_vxm equals BFS level 1
+    u, w = P(), P()
+    L.GrB_Vector_new(C.byref(u), obj("GrB_BOOL"), A.nrows)
+    L.GrB_Vector_new(C.byref(w), obj("GrB_BOOL"), A.ncols)
+    L.GrB_Vector_setElement_BOOL(u, True, src)
+    assert L.GrB_vxm(w, None, None, obj("GxB_ANY_PAIR_BOOL"), u, dA.h, None) == 0
+    L.GrB_Vector_nvals(C.byref(nv), w)
+    I = np.empty(nv.value, np.uint64)
+    cap = U64(nv.value)
+    L.GrB_Vector_extractTuples_BOOL(I.ctypes.data, None, C.byref(cap), w)
+    assert np.array_equal(I, A.j[A.p[src]:A.p[src + 1]])
+    L.GrB_Vector_free(C.byref(u)); L.GrB_Vector_free(C.byref(w))
