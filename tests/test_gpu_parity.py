@@ -331,9 +331,11 @@ def test_device_resize_dup_clear_and_host_round_trip():
     assert set(s.iter()) == {t for t in A.tuple_set() if t[0] < 50 and t[1] < 60}
     # host element writes on top of a device-resident matrix, then a bulk op sees them
     d.set(0, 0, 77)
-    d.remove(int(A.tuples()[0][0]), int(A.tuples()[1][0]))
+    rr, cc = int(A.tuples()[0][-1]), int(A.tuples()[1][-1])     # the last stored tuple, never (0,0)
+    assert (rr, cc) != (0, 0)
+    d.remove(rr, cc)
     want = A.tuple_set()
-    want = {t for t in want if (t[0], t[1]) != (int(A.tuples()[0][0]), int(A.tuples()[1][0])) and (t[0], t[1]) != (0, 0)}
+    want = {t for t in want if (t[0], t[1]) != (rr, cc) and (t[0], t[1]) != (0, 0)}
     want.add((0, 0, 77))
     assert set(d.iter()) == want
     t = d.transpose()
