@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-sources", type=int, default=0, help="sources per CPU sample (0 = auto: ~5 s of CPU work)")
     ap.add_argument("--bits-mode", type=int, default=-1)
     ap.add_argument("--pull-mode", type=int, default=-1)
+    ap.add_argument("--pull-kernel", type=int, default=-1, help="-1 library default, 0 = 8-lanes-per-row, 1 = merge-path")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -181,6 +183,11 @@ def run_b200(a):
     fb.init()
     fb.set_option("bits_mode", a.bits_mode)
     fb.set_option("pull_mode", a.pull_mode)
+    if a.pull_kernel >= 0:
+        fb.set_option("pull_kernel", a.pull_kernel)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        fb.set_option(k, int(v))
     n = 1 << a.scale
 
     # ---- setup (untimed): graph on device, transpose mirror, source batches ----

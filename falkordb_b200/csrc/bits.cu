@@ -58,52 +58,128 @@ void bits_from_csr(const DevCSR &F, DevBits &X) {
 }
 
 // ---------------------------------------------------------------------------- bits -> CSR
-// One CTA = 1024 consecutive vertices (32 warps).  For every frontier row (bit) the CTA counts /
-// ranks its set vertices with warp ballots; counts are laid out row-major-by-tile so ONE global
-// exclusive scan yields final CSR positions, ascending in vertex id within each row.
-template <bool FILL>
-__global__ void __launch_bounds__(1024)
-k_bits_tiles(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, u32 *__restrict__ tc,
-             const u64 *__restrict__ off, u32 *__restrict__ Cj) {
-    __shared__ unsigned short wc[32][64];
+// Materialise the sorted CSR the reference's row iterator walks (matrix.rs:1471-1605) from the vertex-major
+// bit-matrix.  A warp owns 32 consecutive vertices; a 5-stage shuffle butterfly transposes their 32x32 bit
+// block so lane b holds "which of my 32 vertices are in frontier row b" (and row 32+b for the high half).
+// Count pass: popcounts per (tile, row), laid out row-major-by-tile so ONE global exclusive scan yields final
+// CSR positions.  Fill pass: each lane expands its rows' masks into a shared-memory list (u16 tile-local ids),
+// then every row segment is copied out with coalesced stores -- ascending vertex id within each row.
+static const u32 TILE_V = 1024;          // vertices per CTA tile
+static const u32 TILE_THREADS = 512;     // 16 warps x 2 groups of 32 vertices
+
+__device__ __forceinline__ u32 transpose32(u32 x, u32 lane) {
+    // bit c of lane l  ->  bit l of lane c
+    u32 y;
+    y = __shfl_xor_sync(0xffffffffu, x, 16);
+    x = (lane & 16) ? ((x & 0xFFFF0000u) | ((y & 0xFFFF0000u) >> 16)) : ((x & 0x0000FFFFu) | ((y & 0x0000FFFFu) << 16));
+    y = __shfl_xor_sync(0xffffffffu, x, 8);
+    x = (lane & 8) ? ((x & 0xFF00FF00u) | ((y & 0xFF00FF00u) >> 8)) : ((x & 0x00FF00FFu) | ((y & 0x00FF00FFu) << 8));
+    y = __shfl_xor_sync(0xffffffffu, x, 4);
+    x = (lane & 4) ? ((x & 0xF0F0F0F0u) | ((y & 0xF0F0F0F0u) >> 4)) : ((x & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4));
+    y = __shfl_xor_sync(0xffffffffu, x, 2);
+    x = (lane & 2) ? ((x & 0xCCCCCCCCu) | ((y & 0xCCCCCCCCu) >> 2)) : ((x & 0x33333333u) | ((y & 0x33333333u) << 2));
+    y = __shfl_xor_sync(0xffffffffu, x, 1);
+    x = (lane & 1) ? ((x & 0xAAAAAAAAu) | ((y & 0xAAAAAAAAu) >> 1)) : ((x & 0x55555555u) | ((y & 0x55555555u) << 1));
+    return x;
+}
+
+// tc[(w*64 + row) * ntiles + tile] = number of vertices of the tile in frontier row 64w+row
+__global__ void __launch_bounds__(TILE_THREADS)
+k_bits_count(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, u32 *__restrict__ tc) {
+    __shared__ u32 wc[TILE_THREADS / 32][64];
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     u64 tile = blockIdx.x;
-    u64 v = tile * 1024 + tid;
+    u64 v0 = tile * TILE_V + (u64)warp * 64;
     for (u32 w = 0; w < W; w++) {
-        u64 word = (v < n) ? X[v * W + w] : 0ULL;
-        int any = __syncthreads_or(word != 0ULL);
-        if (!any) {
-            if (!FILL && tid < 64) tc[((u64)w * 64 + tid) * ntiles + tile] = 0;
-            continue;
-        }
-        u32 c0 = 0, c1 = 0;
-        u32 wany = __ballot_sync(0xffffffffu, word != 0ULL);
-        if (wany) {
-#pragma unroll 8
-            for (u32 b = 0; b < 64; b++) {
-                u32 m = __ballot_sync(0xffffffffu, (word >> b) & 1ULL);
-                if ((b & 31) == lane) { if (b < 32) c0 = __popc(m); else c1 = __popc(m); }
+        u32 clo = 0, chi = 0;
+#pragma unroll
+        for (u32 g = 0; g < 2; g++) {
+            u64 v = v0 + g * 32 + lane;
+            u64 word = (v < n) ? X[v * W + w] : 0ULL;
+            if (__ballot_sync(0xffffffffu, word != 0ULL)) {
+                clo += __popc(transpose32((u32)word, lane));
+                chi += __popc(transpose32((u32)(word >> 32), lane));
             }
         }
-        wc[warp][lane] = (unsigned short)c0;
-        wc[warp][lane + 32] = (unsigned short)c1;
+        wc[warp][lane] = clo;
+        wc[warp][lane + 32] = chi;
+        __syncthreads();
+        if (tid < 64) {
+            u32 s = 0;
+#pragma unroll
+            for (u32 q = 0; q < TILE_THREADS / 32; q++) s += wc[q][tid];
+            tc[((u64)w * 64 + tid) * ntiles + tile] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__restrict__ off, u32 *__restrict__ Cj) {
+    extern __shared__ unsigned short list[];             // up to 64 rows x 1024 vertices tile-local ids
+    __shared__ unsigned short wp[TILE_THREADS / 32][64];  // per-warp exclusive prefix, per row
+    __shared__ u32 sbase[65];                            // row segment starts inside `list`
+    __shared__ u64 goff[64];                             // row segment starts in the output
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u32 NW = TILE_THREADS / 32;
+    const u64 strm = policy_stream();
+    u64 tile = blockIdx.x;
+    u64 vbase = tile * TILE_V;
+    for (u32 w = 0; w < W; w++) {
+        u32 tlo[2], thi[2];
+        u32 clo = 0, chi = 0;
+#pragma unroll
+        for (u32 g = 0; g < 2; g++) {
+            u64 v = vbase + (u64)warp * 64 + g * 32 + lane;
+            u64 word = (v < n) ? X[v * W + w] : 0ULL;
+            tlo[g] = 0; thi[g] = 0;
+            if (__ballot_sync(0xffffffffu, word != 0ULL)) {
+                tlo[g] = transpose32((u32)word, lane);
+                thi[g] = transpose32((u32)(word >> 32), lane);
+            }
+            clo += __popc(tlo[g]);
+            chi += __popc(thi[g]);
+        }
+        wp[warp][lane] = (unsigned short)clo;
+        wp[warp][lane + 32] = (unsigned short)chi;
         __syncthreads();
         if (tid < 64) {
             u32 run = 0;
-            for (u32 q = 0; q < 32; q++) { u32 t = wc[q][tid]; wc[q][tid] = (unsigned short)run; run += t; }
-            if (!FILL) tc[((u64)w * 64 + tid) * ntiles + tile] = run;
+#pragma unroll
+            for (u32 q = 0; q < NW; q++) { u32 t = wp[q][tid]; wp[q][tid] = (unsigned short)run; run += t; }
+            sbase[tid + 1] = run; // totals for now
+            goff[tid] = off[((u64)w * 64 + tid) * ntiles + tile];
         }
         __syncthreads();
-        if (FILL && wany) {
-            u32 lt = (1u << lane) - 1u;
-            for (u32 b = 0; b < 64; b++) {
-                u32 bit = (u32)((word >> b) & 1ULL);
-                u32 m = __ballot_sync(0xffffffffu, bit);
-                if (bit) {
-                    u64 o = off[((u64)w * 64 + b) * ntiles + tile] + wc[warp][b] + __popc(m & lt);
-                    Cj[o] = (u32)v;
-                }
+        if (tid == 0) {
+            u32 run = 0;
+            sbase[0] = 0;
+            for (u32 r = 0; r < 64; r++) { u32 t = sbase[r + 1]; sbase[r + 1] = run + t; run += t; }
+        }
+        __syncthreads();
+        // expand: lane b owns rows b (low half) and 32+b (high half) of this warp's 64 vertices
+        {
+            u32 o = sbase[lane] + wp[warp][lane];
+#pragma unroll
+            for (u32 g = 0; g < 2; g++) {
+                u32 m = tlo[g];
+                u32 idb = warp * 64 + g * 32;
+                while (m) { u32 bit = __ffs(m) - 1; list[o++] = (unsigned short)(idb + bit); m &= m - 1; }
             }
+            o = sbase[lane + 32] + wp[warp][lane + 32];
+#pragma unroll
+            for (u32 g = 0; g < 2; g++) {
+                u32 m = thi[g];
+                u32 idb = warp * 64 + g * 32;
+                while (m) { u32 bit = __ffs(m) - 1; list[o++] = (unsigned short)(idb + bit); m &= m - 1; }
+            }
+        }
+        __syncthreads();
+        // coalesced copy-out: warp q handles rows q, q+NW, ...
+        for (u32 r = warp; r < 64; r += NW) {
+            u32 s = sbase[r], cnt = sbase[r + 1] - s;
+            u32 *dst = Cj + goff[r];
+            for (u32 i = lane; i < cnt; i += 32) st_u32_stream(dst + i, (u32)(vbase + list[s + i]), strm);
         }
         __syncthreads();
     }
@@ -121,13 +197,13 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     C.nrows = X.nrows; C.ncols = n;
     C.p.alloc(X.nrows + 1);
     if (n == 0) { C.p.zero(); C.nnz = 0; return; }
-    u64 ntiles = (n + 1023) / 1024;
+    u64 ntiles = (n + TILE_V - 1) / TILE_V;
     u64 ncnt = (u64)64 * W * ntiles;
     DevBuf<u32> tc(ncnt + 1);
     DevBuf<u64> off(ncnt + 1);
     {
         TimedScope ts(TK_BITS_COUNT, 8ULL * W * n);
-        LAUNCH((k_bits_tiles<false>), (u32)ntiles, 1024, 0, X.w.ptr, n, W, ntiles, tc.ptr, (const u64 *)nullptr, (u32 *)nullptr);
+        LAUNCH(k_bits_count, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr);
     }
     CUDA_TRY(cudaMemsetAsync(tc.ptr + ncnt, 0, sizeof(u32), stream()));
     exclusive_scan_u32_to_u64(tc.ptr, off.ptr, ncnt + 1);
@@ -136,8 +212,14 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     C.nnz = nnz;
     C.j.alloc(nnz);
     if (nnz) {
+        static bool attr_set = false;
+        const size_t smem = (size_t)64 * TILE_V * sizeof(unsigned short);
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_bits_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
         TimedScope ts(TK_BITS_FILL, 8ULL * W * n + 4 * nnz);
-        LAUNCH((k_bits_tiles<true>), (u32)ntiles, 1024, 0, X.w.ptr, n, W, ntiles, (u32 *)nullptr, off.ptr, C.j.ptr);
+        LAUNCH(k_bits_fill, (u32)ntiles, TILE_THREADS, smem, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
     }
 }
 
@@ -243,26 +325,44 @@ k_bits_push(const u32 *__restrict__ act, const u64 *__restrict__ cum, const u64 
 // ---------------------------------------------------------------------------- pull
 // 8 lanes per output vertex j: OR of X[k] over k in A'(j,:).  Rows longer than LONG_ROW are
 // zeroed here and finished by k_bits_pull_long (several CTAs per row, RED.OR into Y).
-template <int W>
+template <bool HINTS> __device__ __forceinline__ u32 ld_col(const u32 *p, u64 strm) { return HINTS ? ld_u32_stream(p, strm) : __ldg(p); }
+template <bool HINTS> __device__ __forceinline__ u64 ld_ptr(const u64 *p, u64 strm) { return HINTS ? ld_u64_stream(p, strm) : __ldg(p); }
+template <bool HINTS> __device__ __forceinline__ u64 ld_x(const u64 *p, u64 keep) { return HINTS ? ld_u64_hint(p, keep) : __ldg(p); }
+
+template <int W, bool HINTS, int U>
 __global__ void __launch_bounds__(256)
 k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
             u64 *__restrict__ Y) {
     const u32 lane8 = threadIdx.x & 7;
+    const u32 sub = (threadIdx.x & 31) >> 3;
+    const u64 keep = policy_keep(), strm = policy_stream();
     u64 group = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     u64 ngroups = ((u64)gridDim.x * blockDim.x) >> 3;
-    u64 warp_first = group - ((threadIdx.x & 31) >> 3); // group id of this warp's first 8-lane group
+    u64 warp_first = group - sub; // group id of this warp's first 8-lane group
+    // software pipeline: row pointers of the NEXT row are in flight while the current row gathers
+    u64 ns = 0, ne = 0;
+    if (warp_first + sub < n) { ns = ld_ptr<HINTS>(ATp + warp_first + sub, strm); ne = ld_ptr<HINTS>(ATp + warp_first + sub + 1, strm); }
     for (u64 base = warp_first; base < n; base += ngroups) {
-        u64 j = base + ((threadIdx.x & 31) >> 3);
-        u64 s = 0, e = 0;
-        if (j < n) { s = ATp[j]; e = ATp[j + 1]; }
+        u64 j = base + sub;
+        u64 s = ns, e = ne;
+        u64 jn = j + ngroups;
+        ns = 0; ne = 0;
+        if (jn < n) { ns = ld_ptr<HINTS>(ATp + jn, strm); ne = ld_ptr<HINTS>(ATp + jn + 1, strm); }
+        if (j >= n) { s = 0; e = 0; }
         if (e - s > LONG_ROW) e = s;
         u64 acc[W];
 #pragma unroll
         for (int w = 0; w < W; w++) acc[w] = 0;
-        for (u64 q = s + lane8; q < e; q += 8) {
-            u32 k = ATj[q];
+        for (u64 q = s + lane8; q < e; q += 8 * U) {
+            u32 k[U];
 #pragma unroll
-            for (int w = 0; w < W; w++) acc[w] |= X[(u64)k * W + w];
+            for (int u = 0; u < U; u++) k[u] = (q + 8 * u < e) ? ld_col<HINTS>(ATj + q + 8 * u, strm) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (k[u] != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int w = 0; w < W; w++) acc[w] |= ld_x<HINTS>(X + (u64)k[u] * W + w, keep);
+                }
         }
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -275,7 +375,7 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
         if (j < n) {
 #pragma unroll
             for (int w = 0; w < W; w++)
-                if ((w & 7) == (int)lane8) Y[j * W + w] = acc[w];
+                if ((w & 7) == (int)lane8) { if (HINTS) st_u64_stream(Y + j * W + w, acc[w], strm); else Y[j * W + w] = acc[w]; }
         }
     }
 }
@@ -297,10 +397,11 @@ k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, con
     u64 acc[W];
 #pragma unroll
     for (int w = 0; w < W; w++) acc[w] = 0;
+    const u64 keep = policy_keep(), strm = policy_stream();
     for (u64 q = c0 + threadIdx.x; q < c1; q += 256) {
-        u32 k = ATj[q];
+        u32 k = ld_u32_stream(ATj + q, strm);
 #pragma unroll
-        for (int w = 0; w < W; w++) acc[w] |= X[(u64)k * W + w];
+        for (int w = 0; w < W; w++) acc[w] |= ld_u64_hint(X + (u64)k * W + w, keep);
     }
 #pragma unroll
     for (int w = 0; w < W; w++) {
@@ -308,6 +409,119 @@ k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, con
         __syncthreads();
         if (threadIdx.x == 0 && r) atomicOr((unsigned long long *)&Y[(u64)j * W + w], r);
     }
+}
+
+// ---------------------------------------------------------------------------- pull, merge-path variant
+// Balanced over (rows + nnz) of A' exactly like merge-based CSR SpMV: every CTA takes TILE consecutive items of the
+// merged (row-end, nnz) sequence, so hub rows and runs of empty rows cost what they weigh.  Phase 1 gathers X[col]
+// for the tile's nnz with a flat coalesced mapping (IPT independent gather chains per thread: memory-level
+// parallelism), phase 2 is each thread's serial walk over its IPT merged items out of shared memory, phase 3 writes
+// finished rows with plain stores (tile-boundary rows with RED.OR; Y is pre-zeroed).
+template <int W> struct MpCfg { static const int TILE = (W <= 2) ? 2048 : (W == 4 ? 1024 : (W == 8 ? 512 : 256)); };
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_bits_pull_mp(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, u64 nnz, const u64 *__restrict__ X,
+               u64 *__restrict__ Y, const u64 *__restrict__ mp_r /* row coordinate of every 256th diagonal */) {
+    constexpr int T = 256, TILE = MpCfg<W>::TILE, IPT = TILE / T;
+    extern __shared__ u64 smem_mp[];
+    u64 *sx = smem_mp;                         // [TILE * W]   gathered words, nnz order
+    u64 *rowacc = sx + (size_t)TILE * W;       // [(TILE + 1) * W]
+    u32 *rend = (u32 *)(rowacc + (size_t)(TILE + 1) * W); // [TILE + 2] row ends relative to the tile's first nnz
+    const u32 tid = threadIdx.x;
+    const u64 keep = policy_keep(), strm = policy_stream();
+    const u64 total = n + nnz;
+    u64 d0 = (u64)blockIdx.x * TILE, d1 = d0 + TILE;
+    if (d1 > total) d1 = total;
+    // tile coordinates come from the per-matrix table built once by k_mp_coords (static for an immutable base)
+    const u64 r0 = mp_r[d0 / 256], r1 = (d1 == total) ? n : mp_r[d1 / 256];
+    const u64 z0 = d0 - r0, z1 = d1 - r1;
+    const u32 nr = (u32)(r1 - r0);   // row-ends consumed in this tile; row r1 may be entered but not finished
+    const u32 nz = (u32)(z1 - z0);
+    for (u32 i = tid; i <= nr; i += T) {
+        u64 r = r0 + i;
+        u64 e = (r < n) ? ld_u64_stream(ATp + r + 1, strm) : nnz;
+        u64 rel = e - z0;
+        rend[i] = rel > 0xffffffffULL ? 0xffffffffu : (u32)rel;  // rows ending past the tile clamp high
+#pragma unroll
+        for (int w = 0; w < W; w++) rowacc[(size_t)i * W + w] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        u32 e = tid + k * T;
+        if (e < nz) {
+            u32 col = ld_u32_stream(ATj + z0 + e, strm);
+#pragma unroll
+            for (int w = 0; w < W; w++) sx[(size_t)e * W + w] = ld_u64_hint(X + (u64)col * W + w, keep);
+        }
+    }
+    __syncthreads();
+    // per-thread merge-path start inside the tile
+    u32 dt = tid * IPT;
+    u32 items = (u32)(d1 - d0);
+    if (dt > items) dt = items;
+    u32 lo = dt > nz ? dt - nz : 0, hi = dt < nr ? dt : nr;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (rend[mid] <= dt - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    u32 r = lo, z = dt - lo;
+    u32 dend = dt + IPT;
+    if (dend > items) dend = items;
+    u64 acc[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) acc[w] = 0;
+    auto flush = [&](u32 row) {
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 a = acc[w];
+            if (a) {
+                u32 *p32 = (u32 *)&rowacc[(size_t)row * W + w];
+                if ((u32)a) atomicOr(p32, (u32)a);
+                if ((u32)(a >> 32)) atomicOr(p32 + 1, (u32)(a >> 32));
+            }
+            acc[w] = 0;
+        }
+    };
+    for (u32 d = dt; d < dend; d++) {
+        if (r < nr ? (z < rend[r]) : true) {          // consume one nnz of row r (r == nr: the unfinished last row)
+#pragma unroll
+            for (int w = 0; w < W; w++) acc[w] |= sx[(size_t)z * W + w];
+            z++;
+        } else {
+            flush(r);
+            r++;
+        }
+    }
+    flush(r);
+    __syncthreads();
+    for (u32 i = tid; i <= nr; i += T) {
+        u64 row = r0 + i;
+        if (row >= n) continue;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 v = rowacc[(size_t)i * W + w];
+            if (v) {
+                if (i == 0 || i == nr) atomicOr((unsigned long long *)&Y[row * W + w], v);
+                else st_u64_stream(Y + row * W + w, v, strm);
+            }
+        }
+    }
+}
+
+// merge-path coordinates of every 256th diagonal of (row-ends, nnz): r = #rows finished before the diagonal
+__global__ void k_mp_coords(const u64 *__restrict__ ATp, u64 n, u64 nnz, u64 ndiag, u64 *__restrict__ mp_r) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ndiag) return;
+    u64 d = t * 256;
+    u64 total = n + nnz;
+    if (d > total) d = total;
+    u64 lo = d > nnz ? d - nnz : 0, hi = d < n ? d : n;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (ATp[mid + 1] <= d - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    mp_r[t] = lo;
 }
 
 __global__ void k_flag_long(const u64 *__restrict__ p, u64 n, u32 *__restrict__ flag, u64 *__restrict__ maxdeg) {
@@ -347,6 +561,9 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
         lr.rows.alloc(nl);
         LAUNCH(k_scatter_flagged, grid_for(n, 256, 1 << 16), 256, 0, flag.ptr, pos.ptr, n, lr.rows.ptr);
     }
+    u64 ndiag = (n + AT.nnz) / 256 + 2;
+    lr.mp_r.alloc(ndiag);
+    LAUNCH(k_mp_coords, grid_for(ndiag, 256), 256, 0, AT.p.ptr, n, AT.nnz, ndiag, lr.mp_r.ptr);
 }
 
 template <int W>
@@ -373,12 +590,34 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, const 
         else pull = edges * 4 > A.nnz; // direction switch: frontier touches > 1/4 of the edges
     }
     if (edges == 0) { Y.w.zero(); if (path_out) *path_out = 0; return; }
-    if (pull) {
+    if (pull && cx.opt_pull_kernel == 1) {
+        constexpr int TILE = MpCfg<W>::TILE;
+        const size_t smem = ((size_t)TILE * W + (size_t)(TILE + 1) * W) * sizeof(u64) + (size_t)(TILE + 2) * sizeof(u32);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_bits_pull_mp<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        Y.w.zero();
+        u64 total = m + AT->nnz;
+        u64 ntiles = (total + TILE - 1) / TILE;
+        TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * n + 8ULL * W * m);
+        LAUNCH((k_bits_pull_mp<W>), (u32)ntiles, 256, smem, AT->p.ptr, AT->j.ptr, m, AT->nnz, X.w.ptr, Y.w.ptr, lr->mp_r.ptr);
+        if (path_out) *path_out = 4;
+    } else if (pull) {
         u32 grid = (u32)cx.num_sms * 16;
         {
             // compulsory traffic: stream A' col_idx + rowptr, read X once, write Y once (X gathers hit L2)
             TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * n + 8ULL * W * m);
-            LAUNCH((k_bits_pull<W>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+            if (cx.opt_hints) {
+                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, true, 4>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, true, 2>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                else LAUNCH((k_bits_pull<W, true, 1>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+            } else {
+                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, false, 4>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, false, 2>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                else LAUNCH((k_bits_pull<W, false, 1>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+            }
         }
         if (lr->n) {
             u32 gy = (u32)((lr->maxdeg + LONG_CHUNK - 1) / LONG_CHUNK);

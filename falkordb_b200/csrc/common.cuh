@@ -52,6 +52,9 @@ struct Context {
     i64 opt_bits_min_flops = 1 << 22;     // auto mode: use bit-frontier when flops >= this
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
+    i64 opt_pull_kernel = 0;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel
+    i64 opt_hints = 0;             // L2 createpolicy hints in the pull kernel
+    i64 opt_unroll = 4;            // gathers in flight per lane in the 8-lane pull kernel
 };
 Context &ctx();
 void ensure_init();
@@ -160,6 +163,29 @@ struct DevBits {
     bool valid() const { return w.ptr != nullptr; }
     void clear() { w.release(); W = 0; }
 };
+
+// ---- L2 residency hints (createpolicy descriptors; sm_80+) ---------------------------------------
+// keep  : data that is gathered at random and must stay L2-resident (the frontier bit-matrix X)
+// stream: data read or written exactly once (col_idx / rowptr streams, outputs)
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 ld_u64_hint(const u64 *p, u64 pol) {
+    u64 v; asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ u64 ld_u64_stream(const u64 *p, u64 pol) {
+    u64 v; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ u32 ld_u32_stream(const u32 *p, u64 pol) {
+    u32 v; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ void st_u64_stream(u64 *p, u64 v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_u32_stream(u32 *p, u32 v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+#endif
 
 // ---- primitive wrappers implemented in prims.cu (CUB scan / sort) ----------------------------
 void exclusive_scan_u64(const u64 *in, u64 *out, size_t n);           // out[i] = sum in[0..i)

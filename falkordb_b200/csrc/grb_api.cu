@@ -151,6 +151,7 @@ static void invalidate_aux(GrB_Matrix A) {
     A->devT_valid = false;
     A->devT.clear();
     A->lr.rows.release();
+    A->lr.mp_r.release();
     A->lr.built = false;
     A->lr.n = 0;
 }
@@ -1403,6 +1404,9 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "bitmap_budget") c.opt_bitmap_budget = value;
     else if (n == "bits_min_flops") c.opt_bits_min_flops = value;
     else if (n == "sync_after_op") c.opt_sync_after_op = value;
+    else if (n == "pull_kernel") c.opt_pull_kernel = value;
+    else if (n == "hints") c.opt_hints = value;
+    else if (n == "unroll") c.opt_unroll = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

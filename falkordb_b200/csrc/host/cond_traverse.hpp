@@ -1,0 +1,58 @@
+// cond_traverse.hpp -- C++ mirror of the batched F*A path of the reference's CondTraverse operator
+// (graph/src/runtime/ops/cond_traverse.rs:452-751), reduced to what sits on the GraphBLAS boundary:
+//   collect (row_i, src) + source-label pre-filter   :554-589
+//   F = Matrix<bool>(|batch|, n); F.build(rows, srcs) :600-601
+//   for hop: delta_lmxm_into(F)                        :602-605   (matrix.rs:1317-1402)
+//   F.wait(); for (row_i, dest) in F.iter()            :608, 644
+//   destination-label post-filter                      :646-652
+// Batch/column plumbing (gather, set_column, null padding) is runtime code outside the hot path.
+#pragma once
+#include "versioned_matrix.hpp"
+
+namespace fdb {
+
+// Graph::node_has_label_id (graph.rs:1057-1065): label matrices are n x n diagonal (graph.rs:1191)
+inline bool node_has_label(const VersionedMatrix &label, uint64_t id) { return label.get(id, id); }
+
+struct ExpandResult {
+    std::vector<uint64_t> row_idx; // index into the input batch (active_subset position)
+    std::vector<uint64_t> dest;    // destination node id
+};
+
+static const size_t BATCH_SIZE = 1024; // graph/src/runtime/batch.rs:81
+
+inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std::vector<const VersionedMatrix *> &hops,
+                                 const std::vector<const VersionedMatrix *> &src_labels,
+                                 const std::vector<const VersionedMatrix *> &dst_labels) {
+    ExpandResult out;
+    if (hops.empty() || src_ids.empty()) return out;
+    uint64_t ncols = hops[0]->ncols();
+    std::vector<uint64_t> row_idx_buf, col_idx_buf;
+    row_idx_buf.reserve(src_ids.size());
+    col_idx_buf.reserve(src_ids.size());
+    for (size_t i = 0; i < src_ids.size(); i++) {
+        bool ok = true;
+        for (const VersionedMatrix *l : src_labels) if (!node_has_label(*l, src_ids[i])) { ok = false; break; }
+        if (!ok) continue;                       // pre-filter src by label (= L_src * F)
+        row_idx_buf.push_back((uint64_t)i);
+        col_idx_buf.push_back(src_ids[i]);
+    }
+    if (row_idx_buf.empty()) return out;
+    Matrix<bool> f(src_ids.size(), ncols);
+    f.build(row_idx_buf, col_idx_buf);
+    for (const VersionedMatrix *h : hops) f.delta_lmxm(h->m(), h->dp(), h->dm());
+    f.wait();                                    // flush pending mxm work before attaching the row iterator
+    auto it = f.iter(0, UINT64_MAX);
+    std::tuple<uint64_t, uint64_t> t;
+    while (it.next(t)) {
+        uint64_t dest = std::get<1>(t);
+        bool ok = true;
+        for (const VersionedMatrix *l : dst_labels) if (!node_has_label(*l, dest)) { ok = false; break; }
+        if (!ok) continue;                       // post-filter final-hop dst label (= F * A * R_dst)
+        out.row_idx.push_back(std::get<0>(t));
+        out.dest.push_back(dest);
+    }
+    return out;
+}
+
+} // namespace fdb

@@ -1,0 +1,253 @@
+// host_capi.cpp -- flat C entry points over the C++ host mirror (matrix.hpp / versioned_matrix.hpp /
+// cond_traverse.hpp) so tests/ can drive it with ctypes, plus transcriptions of the reference's own unit tests
+// at this boundary (graph/src/graph/graphblas/versioned_matrix.rs:1278-1523).  Links against libb200grb.so only.
+#include "cond_traverse.hpp"
+#include <cstring>
+#include <set>
+#include <sstream>
+
+using namespace fdb;
+
+static thread_local std::string g_msg;
+#define REQUIRE(cond, text) do { if (!(cond)) { std::ostringstream os; os << "line " << __LINE__ << ": " << text; throw std::runtime_error(os.str()); } } while (0)
+
+// ---- versioned_matrix.rs:1265-1330 : fold-policy arithmetic (pure host) ----
+static uint64_t threshold(uint64_t k, uint64_t tx) { uint64_t target = k * tx; for (uint64_t d = 1;; d++) if (d * d >= target) return d; }
+static const uint64_t HUGE_BASE = UINT64_MAX / 4;
+
+static void t_read_path_balance_point_is_flat_in_base_size() {
+    REQUIRE(threshold(READ_FOLD_K, 1) == 287, "threshold(READ_FOLD_K,1)");
+    for (uint64_t base : {1000000ULL, 10000000ULL, 100000000ULL, (unsigned long long)HUGE_BASE}) {
+        REQUIRE(!should_fold_read(286, 1, base), "286 folds at base " << base);
+        REQUIRE(should_fold_read(287, 1, base), "287 does not fold at base " << base);
+    }
+}
+static void t_write_path_is_16x_looser_than_read_path() {
+    REQUIRE(threshold(WRITE_FOLD_K, 1) == 4528, "write threshold");
+    REQUIRE(threshold(WRITE_FOLD_K, 1) / threshold(READ_FOLD_K, 1) == 15, "ratio");
+    REQUIRE(!should_fold(4527, 1, HUGE_BASE), "4527");
+    REQUIRE(should_fold(4528, 1, HUGE_BASE), "4528");
+}
+static void t_balance_point_grows_as_sqrt_of_transaction_size() {
+    REQUIRE(threshold(READ_FOLD_K, 1) == 287 && threshold(READ_FOLD_K, 100) == 2864, "sqrt growth");
+    for (uint64_t tx : {1ULL, 10ULL, 100ULL, 1000ULL}) {
+        uint64_t d = threshold(READ_FOLD_K, tx);
+        REQUIRE(!should_fold_read(d - 1, tx, HUGE_BASE), "tx " << tx);
+        REQUIRE(should_fold_read(d, tx, HUGE_BASE), "tx " << tx);
+    }
+}
+static void t_delta_comparable_to_base_always_folds() {
+    REQUIRE(should_fold(512, UINT64_MAX, 1024), "write hatch");
+    REQUIRE(should_fold_read(512, UINT64_MAX, 1024), "read hatch");
+}
+static void t_tiny_deltas_and_read_only_transactions_never_fold() {
+    REQUIRE(!should_fold(MIN_FOLD_DELTA - 1, 1, 0) && !should_fold_read(MIN_FOLD_DELTA - 1, 1, 0), "tiny");
+    REQUIRE(!should_fold(UINT64_MAX, 0, 1024) && !should_fold_read(UINT64_MAX, 0, 1024), "tx_added == 0");
+}
+
+// ---- versioned_matrix.rs:1332-1472 : delta invariants under a deterministic LCG mutation sequence ----
+typedef std::set<std::pair<uint64_t, uint64_t>> Model;
+static const uint64_t DIM = 512;
+
+static void assert_invariants(const VersionedMatrix &v, const Model &model) {
+    v.wait_all();
+    {
+        auto it = v.dp().iter();
+        std::tuple<uint64_t, uint64_t> t;
+        while (it.next(t)) {
+            REQUIRE(!v.m().get(std::get<0>(t), std::get<1>(t)), "dp n m != 0 at (" << std::get<0>(t) << "," << std::get<1>(t) << ")");
+            REQUIRE(!v.dm().get(std::get<0>(t), std::get<1>(t)), "dp n dm != 0");
+        }
+    }
+    {
+        auto it = v.dm().iter();
+        std::tuple<uint64_t, uint64_t> t;
+        while (it.next(t)) REQUIRE(v.m().get(std::get<0>(t), std::get<1>(t)), "dm not subset of m at (" << std::get<0>(t) << "," << std::get<1>(t) << ")");
+    }
+    REQUIRE(v.nvals() == model.size(), "|m|+|dp|-|dm| = " << v.nvals() << " but the model holds " << model.size());
+    Model effective;
+    auto it = v.iter();
+    std::tuple<uint64_t, uint64_t> t;
+    std::pair<uint64_t, uint64_t> prev(0, 0);
+    bool first = true;
+    while (it.next(t)) {
+        std::pair<uint64_t, uint64_t> cur(std::get<0>(t), std::get<1>(t));
+        REQUIRE(first || prev < cur, "Iter is not strictly (row,col)-ascending");
+        prev = cur; first = false;
+        effective.insert(cur);
+    }
+    REQUIRE(effective == model, "effective state diverged from the model (" << effective.size() << " vs " << model.size() << ")");
+}
+
+static uint64_t next_rand(uint64_t &state) {
+    state = state * 6364136223846793005ULL + 1442695040888963407ULL;
+    return state >> 33;
+}
+
+static void t_delta_invariants_hold_across_mutation_sequences() {
+    VersionedMatrix v(DIM, DIM);
+    Model model;
+    uint64_t rng = 0x5eed1234ULL;
+    auto key = [](uint64_t r) { return std::make_pair((r % 24) * 7, (r / 24 % 24) * 11); };
+    for (int step = 0; step < 4000; step++) {
+        switch (next_rand(rng) % 16) {
+        case 0: {
+            std::vector<std::pair<uint64_t, uint64_t>> batch;
+            for (int q = 0; q < 16; q++) batch.push_back(key(next_rand(rng)));
+            v.set_all<false>(batch);
+            model.insert(batch.begin(), batch.end());
+            break;
+        }
+        case 1: {
+            Model batch;
+            for (int q = 0; q < 16; q++) batch.insert(key(next_rand(rng)));
+            std::vector<uint64_t> rows, cols;
+            for (auto &k : batch) { rows.push_back(k.first); cols.push_back(k.second); }
+            Matrix<bool> mask(DIM, DIM);
+            mask.build(rows, cols);
+            mask.wait();
+            v.remove_mask(mask);
+            for (auto &k : batch) model.erase(k);
+            break;
+        }
+        case 2: v = v.dup(); break;
+        case 3: v.wait(); break;
+        case 4: v.fold_oversized(); break;
+        case 5: case 6: case 7: case 8: {
+            auto k = key(next_rand(rng));
+            v.remove(k.first, k.second);
+            model.erase(k);
+            break;
+        }
+        default: {
+            auto k = key(next_rand(rng));
+            v.set(k.first, k.second);
+            model.insert(k);
+        }
+        }
+        if (step % 37 == 0) assert_invariants(v, model);
+    }
+    assert_invariants(v, model);
+    REQUIRE(v.m().nvals() > 0, "no fold ever happened: the `m` branches of set/remove were never taken");
+}
+
+// ---- versioned_matrix.rs:1481-1523 ----
+static void t_folded_entry_deleted_and_re_added_stays_out_of_dp() {
+    uint64_t filler = 4 * MIN_FOLD_DELTA;
+    VersionedMatrix v0(DIM, DIM);
+    std::vector<std::pair<uint64_t, uint64_t>> fill;
+    for (uint64_t i = 0; i < filler; i++) fill.push_back({i % DIM, (i / DIM + 1) % DIM});
+    v0.set_all<false>(fill);
+    std::pair<uint64_t, uint64_t> probe(7, 11);
+    v0.set(probe.first, probe.second);
+    VersionedMatrix v = v0.dup();
+    v.set(300, 301);
+    v.wait_all();
+    REQUIRE(v.m().get(probe.first, probe.second), "the fold did not move the probe into the committed base");
+    REQUIRE(!v.dp().get(probe.first, probe.second), "probe still in dp");
+    v.remove(probe.first, probe.second);
+    v.wait_all();
+    REQUIRE(v.dm().get(probe.first, probe.second), "no tombstone");
+    REQUIRE(v.m().get(probe.first, probe.second), "base entry vanished");
+    REQUIRE(!v.get(probe.first, probe.second), "deleted entry readable");
+    v.set(probe.first, probe.second);
+    v.wait_all();
+    REQUIRE(!v.dm().get(probe.first, probe.second), "tombstone survived the re-add");
+    REQUIRE(!v.dp().get(probe.first, probe.second), "re-add duplicated the committed entry into dp");
+    REQUIRE(v.get(probe.first, probe.second), "probe unreadable");
+    REQUIRE(v.nvals() == filler + 2, "nvals double-counted the re-add: " << v.nvals());
+}
+
+// ---- README.md:85-110 MotoGP demo: 3 riders -rides-> 3 teams; BASELINE config 1 (plumbing) ----
+static void t_motogp_two_hop() {
+    // node ids: riders 0 Rossi, 1 Marquez, 2 Pedrosa ; teams 3 Yamaha, 4 Honda, 5 Ducati (Ducati has no rider)
+    uint64_t n = 16384; // initial node capacity, src/graph_core.rs:471
+    VersionedMatrix rides(n, n), rider(n, n), team(n, n);
+    rides.set_all<true>({{0, 3}, {1, 4}, {2, 4}});
+    for (uint64_t i : {0, 1, 2}) rider.set(i, i);
+    for (uint64_t i : {3, 4, 5}) team.set(i, i);
+    // MATCH (r:Rider)-[:rides]->(t:Team) WHERE t.name = 'Yamaha' RETURN r.name  => "Valentino Rossi"
+    ExpandResult one = expand_batch({0, 1, 2}, {&rides}, {&rider}, {&team});
+    std::vector<uint64_t> who;
+    for (size_t k = 0; k < one.dest.size(); k++) if (one.dest[k] == 3) who.push_back(one.row_idx[k]);
+    REQUIRE(who.size() == 1 && who[0] == 0, "Yamaha's rider is not Valentino Rossi");
+    // MATCH (r:Rider)-[:rides]->(t:Team {name:'Ducati'}) RETURN count(r) ... README expects 1 for Yamaha riders
+    size_t yamaha = 0;
+    for (uint64_t d : one.dest) yamaha += d == 3;
+    REQUIRE(yamaha == 1, "count != 1");
+    // second hop through the maintained transpose: rider -> team -> team-mates
+    VersionedMatrix rides_t = rides.transpose();
+    ExpandResult two = expand_batch({0, 1, 2}, {&rides, &rides_t}, {&rider}, {&rider});
+    std::set<std::pair<uint64_t, uint64_t>> got;
+    for (size_t k = 0; k < two.dest.size(); k++) got.insert({two.row_idx[k], two.dest[k]});
+    std::set<std::pair<uint64_t, uint64_t>> want = {{0, 0}, {1, 1}, {1, 2}, {2, 1}, {2, 2}};
+    REQUIRE(got == want, "2-hop team-mates differ");
+    // a pending delete is honoured by the dirty-snapshot path (matrix.rs:1342-1400)
+    rides.remove(2, 4);
+    ExpandResult three = expand_batch({0, 1, 2}, {&rides}, {}, {});
+    REQUIRE(three.dest.size() == 2, "tombstoned edge still traversed");
+}
+
+struct TestEntry { const char *name; void (*fn)(); };
+static TestEntry TESTS[] = {
+    {"read_path_balance_point_is_flat_in_base_size", t_read_path_balance_point_is_flat_in_base_size},
+    {"write_path_is_16x_looser_than_read_path", t_write_path_is_16x_looser_than_read_path},
+    {"balance_point_grows_as_sqrt_of_transaction_size", t_balance_point_grows_as_sqrt_of_transaction_size},
+    {"delta_comparable_to_base_always_folds", t_delta_comparable_to_base_always_folds},
+    {"tiny_deltas_and_read_only_transactions_never_fold", t_tiny_deltas_and_read_only_transactions_never_fold},
+    {"delta_invariants_hold_across_mutation_sequences", t_delta_invariants_hold_across_mutation_sequences},
+    {"folded_entry_deleted_and_re_added_stays_out_of_dp", t_folded_entry_deleted_and_re_added_stays_out_of_dp},
+    {"motogp_two_hop", t_motogp_two_hop},
+};
+
+extern "C" {
+
+const char *fdbh_last_message(void) { return g_msg.c_str(); }
+
+// run one transcribed reference unit test by name; 0 = pass
+int fdbh_run_test(const char *name) {
+    for (auto &t : TESTS)
+        if (!strcmp(t.name, name)) {
+            try { GxB_init(GrB_NONBLOCKING, nullptr, nullptr, nullptr, nullptr); t.fn(); g_msg = "ok"; return 0; }
+            catch (const std::exception &e) { g_msg = e.what(); return 1; }
+        }
+    g_msg = "unknown test";
+    return 2;
+}
+
+void *fdbh_vm_from_csr(uint64_t nrows, uint64_t ncols, const uint64_t *Ap, const uint32_t *Aj) {
+    try {
+        GrB_Matrix raw = nullptr;
+        grb_ok(B200_Matrix_import_CSR(&raw, GrB_BOOL, nrows, ncols, Ap, Aj, nullptr, B200_LOC_HOST), "import_CSR");
+        return new VersionedMatrix(VersionedMatrix::from_matrix(Matrix<bool>::adopt(raw, false)));
+    } catch (const std::exception &e) { g_msg = e.what(); return nullptr; }
+}
+void *fdbh_vm_new(uint64_t nrows, uint64_t ncols) {
+    try { return new VersionedMatrix(nrows, ncols); } catch (const std::exception &e) { g_msg = e.what(); return nullptr; }
+}
+void fdbh_vm_free(void *vm) { delete (VersionedMatrix *)vm; }
+int fdbh_vm_set(void *vm, uint64_t i, uint64_t j) { try { ((VersionedMatrix *)vm)->set(i, j); return 0; } catch (const std::exception &e) { g_msg = e.what(); return 1; } }
+int fdbh_vm_remove(void *vm, uint64_t i, uint64_t j) { try { ((VersionedMatrix *)vm)->remove(i, j); return 0; } catch (const std::exception &e) { g_msg = e.what(); return 1; } }
+int64_t fdbh_vm_nvals(void *vm) { try { return (int64_t)((VersionedMatrix *)vm)->nvals(); } catch (const std::exception &e) { g_msg = e.what(); return -1; } }
+
+// CondTraverse batched path.  Outputs are malloc'ed; free with fdbh_free.
+int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint64_t nhops, void **src_labels, uint64_t nsl,
+                      void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout) {
+    try {
+        std::vector<uint64_t> src(src_ids, src_ids + nsrc);
+        std::vector<const VersionedMatrix *> h, sl, dl;
+        for (uint64_t k = 0; k < nhops; k++) h.push_back((const VersionedMatrix *)hops[k]);
+        for (uint64_t k = 0; k < nsl; k++) sl.push_back((const VersionedMatrix *)src_labels[k]);
+        for (uint64_t k = 0; k < ndl; k++) dl.push_back((const VersionedMatrix *)dst_labels[k]);
+        ExpandResult r = expand_batch(src, h, sl, dl);
+        *nout = r.dest.size();
+        *out_rows = (uint64_t *)malloc(sizeof(uint64_t) * (r.dest.size() + 1));
+        *out_dest = (uint64_t *)malloc(sizeof(uint64_t) * (r.dest.size() + 1));
+        memcpy(*out_rows, r.row_idx.data(), sizeof(uint64_t) * r.dest.size());
+        memcpy(*out_dest, r.dest.data(), sizeof(uint64_t) * r.dest.size());
+        return 0;
+    } catch (const std::exception &e) { g_msg = e.what(); return 1; }
+}
+void fdbh_free(void *p) { free(p); }
+
+} // extern "C"

@@ -1,0 +1,300 @@
+// versioned_matrix.hpp -- C++ mirror of the reference's delta matrix `VersionedMatrix<bool>`
+// (graph/src/graph/graphblas/versioned_matrix.rs:1-1253): base `m` + pending adds `dp` + tombstones `dm`,
+// effective state (m \ dm) U dp, copy-on-write layers (graph/src/graph/cow.rs:43-91), the sqrt fold policy
+// (:140-200) and the fold itself (flush :892-938) -- the eWiseAdd / masked-copy half of the hot path.
+// Written against the same C ABI calls the Rust file makes; every GraphBLAS bulk call lands in libb200grb.so.
+#pragma once
+#include "matrix.hpp"
+#include <algorithm>
+#include <optional>
+
+namespace fdb {
+
+// ---- fold policy, versioned_matrix.rs:140-200 ----
+static const uint64_t WRITE_FOLD_K = 20500000ULL;
+static const uint64_t READ_FOLD_K = 82000ULL;
+static const uint64_t MIN_FOLD_DELTA = 256ULL;
+
+inline uint64_t sat_mul(uint64_t a, uint64_t b) {
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return p > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)p;
+}
+inline bool fold_balance(uint64_t delta_nvals, uint64_t tx_added, uint64_t base_nvals, uint64_t k) {
+    return tx_added > 0 && delta_nvals >= MIN_FOLD_DELTA &&
+           (sat_mul(delta_nvals, 2) >= base_nvals || sat_mul(delta_nvals, delta_nvals) >= sat_mul(k, tx_added));
+}
+inline bool should_fold(uint64_t d, uint64_t tx, uint64_t base) { return fold_balance(d, tx, base, WRITE_FOLD_K); }
+inline bool should_fold_read(uint64_t d, uint64_t tx, uint64_t base) { return fold_balance(d, tx, base, READ_FOLD_K); }
+inline bool delta_dominates_base(uint64_t d, uint64_t base) { return d >= MIN_FOLD_DELTA && sat_mul(d, 2) >= base; }
+
+// ---- Cow, cow.rs:43-91 ----
+template <class M>
+class Cow {
+    M inner;
+    bool dup_ = false;
+  public:
+    Cow() {}
+    explicit Cow(M m) : inner(std::move(m)) {}
+    Cow new_version() const { Cow c; c.inner = inner; c.dup_ = true; return c; }
+    void replace(M m) { inner = std::move(m); dup_ = false; }
+    const M &get() const { return inner; }
+    M &get_mut() { if (dup_) { inner = inner.dup(); dup_ = false; } return inner; }
+};
+
+// ---- Delta<bool>, versioned_matrix.rs:214-449 ----
+class DeltaBool {
+    Cow<Matrix<bool>> layer;
+    mutable std::atomic<uint64_t> count{0};
+    uint64_t tx_nvals = 0;
+    mutable std::atomic<bool> fold{false};
+  public:
+    DeltaBool() {}
+    explicit DeltaBool(Matrix<bool> l) { uint64_t c = l.nvals(); l.into_hyper(); layer = Cow<Matrix<bool>>(l); count = c; }
+    DeltaBool(const DeltaBool &o) : layer(o.layer), count(o.count.load()), tx_nvals(o.tx_nvals), fold(o.fold.load()) {}
+    DeltaBool &operator=(const DeltaBool &o) { layer = o.layer; count = o.count.load(); tx_nvals = o.tx_nvals; fold = o.fold.load(); return *this; }
+
+    const Matrix<bool> &m() const { return layer.get(); }
+    DeltaBool transposed() const { DeltaBool d(*this); Matrix<bool> t = layer.get().transpose(); t.into_hyper(); d.layer = Cow<Matrix<bool>>(t); return d; }
+    DeltaBool new_version(bool f) const {
+        DeltaBool d;
+        uint64_t c = get_count();
+        d.layer = layer.new_version(); d.count = c; d.tx_nvals = c; d.fold = f;
+        return d;
+    }
+    uint64_t get_count() const { return count.load(std::memory_order_relaxed); }
+    void resync() const { layer.get().wait(); count.store(layer.get().nvals(), std::memory_order_relaxed); }
+    void latch(bool decision) const { if (decision) fold.store(true, std::memory_order_relaxed); }
+    bool fold_decision(bool (*policy)(uint64_t, uint64_t, uint64_t), uint64_t base) const {
+        uint64_t c = get_count();
+        return fold.load(std::memory_order_relaxed) || policy(c, c > tx_nvals ? c - tx_nvals : 0, base);
+    }
+    bool folding() const { return fold.load(std::memory_order_relaxed); }
+    bool take_fold() { return fold.exchange(false, std::memory_order_relaxed) && layer.get().nvals() > 0; }
+    void clear(uint64_t nrows, uint64_t ncols) {
+        Matrix<bool> e(nrows, ncols);
+        e.into_hyper();
+        layer.replace(e);
+        count = 0; tx_nvals = 0; fold = false;
+    }
+    void replace(Matrix<bool> l) { l.into_hyper(); layer.replace(l); }
+    void resize(uint64_t r, uint64_t c) { layer_mut().resize(r, c); }
+    Matrix<bool> &layer_mut() { return layer.get_mut(); }
+    void erase(uint64_t i, uint64_t j) { layer_mut().remove(i, j); uint64_t c = count.load(); count = c ? c - 1 : 0; }
+    void insert(uint64_t i, uint64_t j) { layer_mut().set(i, j, true); count++; }
+    // self<mask> = mask n base  (versioned_matrix.rs:428-436)
+    template <class TV> void tombstone_masked(const Matrix<bool> &mask, const Matrix<TV> &base) {
+        layer_mut().template element_wise_multiply<TV>(&mask, &mask, &base);
+        resync();
+    }
+    void remove_all(const Matrix<bool> &mask) { layer_mut().remove_all(mask); resync(); }
+};
+
+// ---- VersionedMatrix<bool>, versioned_matrix.rs:480-1080 ----
+class VersionedMatrix {
+    Cow<Matrix<bool>> m_;
+    DeltaBool dp_, dm_;
+    mutable std::atomic<bool> needs_flush{false};
+
+  public:
+    VersionedMatrix() {}
+    VersionedMatrix(uint64_t nrows, uint64_t ncols)
+        : m_(Matrix<bool>(nrows, ncols)), dp_(Matrix<bool>(nrows, ncols)), dm_(Matrix<bool>(nrows, ncols)) {}
+    VersionedMatrix(const VersionedMatrix &o) : m_(o.m_), dp_(o.dp_), dm_(o.dm_), needs_flush(o.needs_flush.load()) {}
+    VersionedMatrix &operator=(const VersionedMatrix &o) { m_ = o.m_; dp_ = o.dp_; dm_ = o.dm_; needs_flush = o.needs_flush.load(); return *this; }
+    static VersionedMatrix from_matrix(Matrix<bool> m) {       // :877-890
+        m.wait();
+        VersionedMatrix v;
+        uint64_t r = m.nrows(), c = m.ncols();
+        v.m_ = Cow<Matrix<bool>>(m);
+        v.dp_ = DeltaBool(Matrix<bool>(r, c));
+        v.dm_ = DeltaBool(Matrix<bool>(r, c));
+        return v;
+    }
+
+    const Matrix<bool> &m() const { return m_.get(); }
+    const Matrix<bool> &dp() const { return dp_.m(); }
+    const Matrix<bool> &dm() const { return dm_.m(); }
+    uint64_t nrows() const { return m().nrows(); }
+    uint64_t ncols() const { return m().ncols(); }
+
+    void wait() const {                                        // :545-569
+        if (dp().is_synced() && dm().is_synced()) return;
+        dp_.resync();
+        dm_.resync();
+        uint64_t base = m().nvals();
+        dp_.latch(dp_.fold_decision(should_fold_read, base));
+        dm_.latch(dm_.fold_decision(should_fold_read, base));
+    }
+    void wait_base() const { m().wait(); }
+    void wait_all() const { m().wait(); dp().wait(); dm().wait(); }
+    bool is_synced() const { return m().is_synced() && dp().is_synced() && dm().is_synced(); }
+
+    Matrix<bool> extract() const {                             // :609-620
+        wait();
+        Matrix<bool> out(nrows(), ncols());
+        out.set_pattern<bool>(nullptr, m());
+        if (dm().nvals() > 0) out.remove_all(dm());
+        if (dp().nvals() > 0) out.set_pattern<bool>(nullptr, dp());
+        return out;
+    }
+    uint64_t nvals() const { wait(); return m().nvals() + dp().nvals() - dm().nvals(); }   // :629-632
+
+    bool get(uint64_t i, uint64_t j) const {                    // :819-835
+        wait();
+        if (m().get(i, j)) return !dm().get(i, j);
+        return dp().get(i, j);
+    }
+    void set(uint64_t i, uint64_t j) {                          // :844-857
+        flush();
+        if (m().get(i, j)) dm_.erase(i, j);
+        else dp_.insert(i, j);
+    }
+    void remove(uint64_t i, uint64_t j) {                       // :780-791
+        flush();
+        if (m().get(i, j)) dm_.insert(i, j);
+        else dp_.erase(i, j);
+    }
+    void remove_mask(const Matrix<bool> &mask) {                // :799-816
+        flush();
+        m().wait();
+        dm_.tombstone_masked(mask, m());
+        dp_.remove_all(mask);
+    }
+    template <bool NEW>
+    void set_all(const std::vector<std::pair<uint64_t, uint64_t>> &entries) {  // :1006-1035
+        flush();
+        dm().wait();
+        if (dm().nvals() == 0) {
+            for (auto &e : entries) {
+                if (!NEW && m().get(e.first, e.second)) continue;
+                dp_.insert(e.first, e.second);
+            }
+        } else {
+            for (auto &e : entries) set(e.first, e.second);
+        }
+    }
+
+    void flush() {                                              // :892-938
+        if (!needs_flush.load(std::memory_order_relaxed)) return;
+        wait_all();
+        bool fold_dp = dp_.take_fold();
+        bool fold_dm = dm_.take_fold();
+        if (fold_dp || fold_dm) {
+            uint64_t nr = nrows(), nc = ncols();
+            Matrix<bool> new_m(nr, nc);
+            if (fold_dp && fold_dm) new_m.element_wise_add<bool>(&dm(), &m(), &dp(), Descriptor::RC); // new_m<!dm,replace> = m U dp
+            else if (fold_dp) new_m.element_wise_add<bool>(nullptr, &m(), &dp());
+            else new_m.select(dm(), m());                                                           // new_m<!dm,replace> = m
+            new_m.wait();
+            m_.replace(new_m);
+            if (fold_dp) dp_.clear(nr, nc);
+            if (fold_dm) dm_.clear(nr, nc);
+        }
+        needs_flush.store(false, std::memory_order_relaxed);
+    }
+    void fold_latched() {                                       // :948-954
+        wait();
+        if (dp_.folding() || dm_.folding()) { needs_flush = true; flush(); }
+    }
+    void fold_oversized() {                                     // :972-986
+        uint64_t base = m().nvals();
+        bool odp = delta_dominates_base(dp_.get_count(), base), odm = delta_dominates_base(dm_.get_count(), base);
+        if (odp || odm) {
+            dp_.latch(odp);
+            dm_.latch(odm);
+            needs_flush = true;
+            flush();
+        }
+    }
+    VersionedMatrix dup() const {                               // :1051-1061
+        uint64_t base = m().nvals();
+        bool fdp = dp_.fold_decision(should_fold, base), fdm = dm_.fold_decision(should_fold, base);
+        VersionedMatrix v;
+        v.m_ = m_.new_version();
+        v.dp_ = dp_.new_version(fdp);
+        v.dm_ = dm_.new_version(fdm);
+        v.needs_flush = fdp || fdm;
+        return v;
+    }
+    VersionedMatrix transpose() const {                         // :1070-1079
+        VersionedMatrix v;
+        v.m_ = Cow<Matrix<bool>>(m().transpose());
+        v.dp_ = dp_.transposed();
+        v.dm_ = dm_.transposed();
+        v.needs_flush = needs_flush.load();
+        return v;
+    }
+    void resize(uint64_t nr, uint64_t nc) {                     // :656-756 (grow = fold everything into a fresh base)
+        if (nr < nrows() || nc < ncols()) {
+            flush();
+            m_.get_mut().resize(nr, nc);
+            dp_.resize(nr, nc);
+            dm_.resize(nr, nc);
+            return;
+        }
+        wait_all();
+        if (dp().nvals() == 0 && dm().nvals() == 0) {
+            Matrix<bool> g = m().grown(nr, nc);
+            g.wait();
+            m_.replace(g);
+        } else {
+            // (m \ dm) U dp at the new dims.  The reference streams a 3-way iterator merge into build();
+            // here the same set expression runs as two bulk calls on the device.
+            Matrix<bool> merged = extract();
+            Matrix<bool> g = merged.grown(nr, nc);
+            g.wait();
+            m_.replace(g);
+        }
+        dp_.clear(nr, nc);
+        dm_.clear(nr, nc);
+        needs_flush = false;
+    }
+
+    // ---- Iter: sorted 3-way merge (m \ dm) U dp, versioned_matrix.rs:1116-1253 ----
+    class Iter {
+        typedef std::tuple<uint64_t, uint64_t> Item;
+        Matrix<bool>::Iter mit, dpit, dmit;
+        bool has_dp = false, has_dm = false;
+        std::optional<Item> m_next, dp_next, dm_next;
+      public:
+        Iter(const VersionedMatrix &v, uint64_t min_row, uint64_t max_row) {
+            mit = v.m().iter(min_row, max_row);
+            if (v.dm().nvals() != 0) { dmit = v.dm().iter(min_row, max_row); has_dm = true; Item t; if (dmit.next(t)) dm_next = t; }
+            if (v.dp().nvals() != 0) { dpit = v.dp().iter(min_row, max_row); has_dp = true; }
+        }
+        void seek(uint64_t min_row, uint64_t max_row) {
+            mit.seek(min_row, max_row);
+            m_next.reset();
+            if (has_dp) dpit.seek(min_row, max_row);
+            dp_next.reset();
+            if (has_dm) { dmit.seek(min_row, max_row); dm_next.reset(); Item t; if (dmit.next(t)) dm_next = t; }
+        }
+        bool next(Item &out) {
+            Item t;
+            if (!m_next && mit.next(t)) m_next = t;
+            while (m_next) {
+                while (dm_next && *dm_next < *m_next) { dm_next.reset(); if (has_dm && dmit.next(t)) dm_next = t; }
+                if (dm_next && *dm_next == *m_next) {
+                    dm_next.reset();
+                    if (has_dm && dmit.next(t)) dm_next = t;
+                    m_next.reset();
+                    if (mit.next(t)) m_next = t;
+                } else break;
+            }
+            if (!dp_next && has_dp && dpit.next(t)) dp_next = t;
+            if (m_next && dp_next) {
+                if (*dp_next <= *m_next) {
+                    if (*dp_next == *m_next) m_next.reset();
+                    out = *dp_next; dp_next.reset();
+                } else { out = *m_next; m_next.reset(); }
+                return true;
+            }
+            if (m_next) { out = *m_next; m_next.reset(); return true; }
+            if (dp_next) { out = *dp_next; dp_next.reset(); return true; }
+            return false;
+        }
+    };
+    Iter iter(uint64_t min_row = 0, uint64_t max_row = UINT64_MAX) const { wait(); return Iter(*this, min_row, max_row); }
+};
+
+} // namespace fdb

@@ -19,7 +19,7 @@ u32 bits_words_for(u64 nrows);
 void bits_from_csr(const DevCSR &F, DevBits &X);
 void bits_to_csr(const DevBits &X, DevCSR &C);
 u64 bits_nvals(const DevBits &X);
-struct LongRows { DevBuf<u32> rows; u64 n = 0; u64 maxdeg = 0; bool built = false; };
+struct LongRows { DevBuf<u32> rows; DevBuf<u64> mp_r; u64 n = 0; u64 maxdeg = 0; bool built = false; };
 void build_long_rows(const DevCSR &AT, LongRows &lr);
 // Y = X * A.  AT (= A') + its long-row list enable the pull direction; may be null (push only).
 void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, const LongRows *lr, DevBits &Y, u64 *flops_out,
