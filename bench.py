@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--bits-mode", type=int, default=-1)
     ap.add_argument("--pull-mode", type=int, default=-1)
     ap.add_argument("--pull-kernel", type=int, default=-1, help="-1 library default, 0 = 8-lanes-per-row, 1 = merge-path")
+    ap.add_argument("--workload", default="chain", choices=["chain", "bfs"],
+                    help="chain = the headline 3-hop mxm chain; bfs = 1-D row-partitioned BFS sweep (BASELINE config 5)")
+    ap.add_argument("--bfs-sources", type=int, default=16)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -163,6 +166,17 @@ def run_reference(a):
         "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": teps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def reduce_over_ranks(max_vals, sum_vals, device):
+    """Whole-job aggregation for N>1: times are the MAX over ranks, work counters the SUM (one all_reduce each)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(max_vals), device=device, dtype=torch.float64)
+    w = torch.tensor(list(sum_vals), device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    return t.tolist(), w.tolist()
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -293,12 +307,8 @@ def run_b200(a):
 
     # ---- reduce over ranks: time = max, work = sum ----
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([flops, e2e_flops, launches, nnz_out], device="cuda", dtype=torch.float64)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        ms, e2e_ms = t.tolist()
-        flops, e2e_flops, launches, nnz_out = [int(x) for x in w.tolist()]
+        (ms, e2e_ms), w = reduce_over_ranks([ms, e2e_ms], [flops, e2e_flops, launches, nnz_out, e2e_nnz], "cuda")
+        flops, e2e_flops, launches, nnz_out, e2e_nnz = [int(x) for x in w]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -368,9 +378,83 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def run_bfs(a):
+    """BASELINE config 5: BFS frontier sweep, adjacency 1-D row-block partitioned over the ranks, one NCCL all-gather of
+    the frontier bitmap per level (falkordb_b200/dist_bfs.py).  TEPS = edges incident to the reached vertices / time
+    (Graph500 convention), summed over sources; time = max over ranks (device events + barrier)."""
+    import torch
+    import torch.distributed as dist
+    import falkordb_b200 as fb
+    from falkordb_b200.dist_bfs import GpuBackend, bfs_gpu, partition
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fb.init()
+    n = 1 << a.scale
+    t0 = time.time()
+    be = GpuBackend(a.scale, a.edge_factor, a.seed, rank, world, need_parents=True)
+    setup_s = time.time() - t0
+    # sources: seeded, restricted to vertices with out-edges; owners publish their degrees through one all-gather
+    rng = np.random.default_rng(a.seed * 7919 + 3)
+    cand = rng.choice(n, size=a.bfs_sources * 8, replace=False)
+    p = np.empty(be.hi - be.lo + 1, np.uint64)
+    fb.check(fb.lib().B200_Matrix_export_CSR(be.A, p.ctypes.data, None, None, 0))
+    degl = np.diff(p.astype(np.int64))
+    flag = torch.zeros(len(cand), dtype=torch.int32, device="cuda")
+    mine = (cand >= be.lo) & (cand < be.hi)
+    vals = np.zeros(len(cand), np.int32)
+    vals[mine] = (degl[cand[mine] - be.lo] > 0).astype(np.int32)
+    flag.copy_(torch.from_numpy(vals))
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    srcs = [int(c) for c, f in zip(cand, flag.cpu().numpy()) if f][: a.bfs_sources + a.warmup]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s_ in srcs[: a.warmup]:
+        bfs_gpu(be, s_, want_parents=True)
+    barrier()
+    fb.reset_stats()
+    t0 = time.perf_counter()
+    edges = 0
+    reached = 0
+    depth = 0
+    for s_ in srcs[a.warmup:]:
+        lv, par, e, d = bfs_gpu(be, s_, want_parents=True)
+        edges += e
+        depth = max(depth, d)
+        reached += int((lv >= 0).sum().item())
+    barrier()
+    secs = time.perf_counter() - t0
+    launches = fb.get_stat("launches")
+    if world > 1:
+        (secs,), (edges, reached, launches) = reduce_over_ranks([secs], [edges, reached, launches], "cuda")
+    be.close()
+    if rank == 0:
+        k = len(srcs) - a.warmup
+        print(json.dumps({
+            "metric": "traversed edges/sec (BFS sweep, Graph500 TEPS)", "value": edges / secs, "unit": "edges/s", "n_gpus": world,
+            "steps": k, "warmup": a.warmup, "ms_per_step": 1e3 * secs / max(1, k), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
+            "config": {"workload": f"BFS level+parent sweep, RMAT scale-{a.scale} ef{a.edge_factor}, {k} sources", "n": n,
+                       "parallelism": f"1-D row-block partition x{world}, one NCCL all-gather of the n-bit frontier bitmap per level",
+                       "max_depth": depth, "setup_s": round(setup_s, 2)},
+            "edges_per_bfs": edges / max(1, k), "reached_per_bfs": reached / max(1, k), "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "bfs":
+        run_bfs(args)
     else:
         run_b200(args)

@@ -70,7 +70,11 @@ def lib():
         "B200_Matrix_export_CSR": [P, P, P, P, C.c_int],
         "B200_Matrix_device_view": [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)],
         "B200_Matrix_prepare": [P, C.c_int], "B200_Matrix_rmat": [C.POINTER(P), C.c_int, U64, U64], "B200_sync": [],
-        "B200_set_option": [C.c_char_p, I64], "B200_bfs": [P, U64, I64, P, P, C.c_int, C.POINTER(U64)],
+        "B200_set_option": [C.c_char_p, I64],
+        "B200_Matrix_rmat_block": [C.POINTER(P), C.c_int, U64, U64, U64, U64, C.c_int],
+        "B200_bfs_dist_expand": [P, U64, P, U64, P, P, U64, C.POINTER(U64)],
+        "B200_bfs_dist_merge": [P, C.c_int, U64, P, U64, U64, P, C.c_int32, P, P],
+        "B200_bfs_dist_parents": [P, U64, P, P], "B200_bfs": [P, U64, I64, P, P, C.c_int, C.POINTER(U64)],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -82,6 +86,8 @@ def lib():
         f.restype = U64
     L.GxB_Iterator_get_BOOL.argtypes = [P]
     L.GxB_Iterator_get_BOOL.restype = C.c_bool
+    L.B200_kernel_stats.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(U64), C.POINTER(U64)]
+    L.B200_kernel_stats.restype = C.c_int
     L.B200_stream.restype = P
     L.B200_get_stat.argtypes = [C.c_char_p]
     L.B200_get_stat.restype = U64

@@ -111,4 +111,137 @@ void bfs_run(const DevCSR &A, u64 src, i64 max_level, i64 *d_level, i64 *d_paren
     if (edges_traversed) *edges_traversed = edges;
 }
 
+
+// ================================================================================================================
+// 1-D row-block partitioned BFS (BASELINE config 5).  Rank g owns vertices [row_lo,row_hi) and holds
+// their out-edges (a row block of A, rows local-indexed, columns global).  Per level every rank expands the owned
+// part of the frontier into an n-bit "discovered" bitmap; the bitmaps are exchanged with ONE all-gather (NCCL, driven
+// by the host through torch.distributed) and merged locally; each rank keeps the full visited bitmap (n/8 bytes) and
+// the levels of its own vertices.  Parents (deterministic min id) come from a pull over the owned rows of A'.
+// ================================================================================================================
+__global__ void __launch_bounds__(256)
+k_bfs_dist_expand(const u32 *__restrict__ fr, const u64 *__restrict__ cum, const u64 *__restrict__ start, u64 nf, u64 total,
+                  const u32 *__restrict__ Aj, const u64 *__restrict__ visited, u32 *__restrict__ disc) {
+    __shared__ u64 s_e0, s_e1;
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    u64 lo = (u64)blockIdx.x * BFS_CHUNK, hi = lo + BFS_CHUNK;
+    if (hi > total) hi = total;
+    if (tid == 0) {
+        s_e0 = bfs_find_le(cum, 0, nf - 1, lo);
+        s_e1 = bfs_find_le(cum, 0, nf - 1, hi - 1);
+    }
+    __syncthreads();
+    u64 e0 = s_e0, e1 = s_e1;
+    for (u64 t0 = lo + (u64)warp * 32; t0 < hi; t0 += 8 * 32) {
+        u64 e = bfs_find_le(cum, e0, e1, t0);
+        u64 t = t0 + lane;
+        if (t < hi) {
+            while (e < e1 && cum[e + 1] <= t) e++;
+            u32 v = Aj[start[e] + (t - cum[e])];
+            if (!((visited[v >> 6] >> (v & 63)) & 1ULL)) atomicOr(&disc[v >> 5], 1u << (v & 31));
+        }
+    }
+}
+
+__global__ void k_frontier_deg_local(const u32 *__restrict__ fr, u64 nf, u64 row_lo, const u64 *__restrict__ Ap,
+                                     u64 *__restrict__ deg, u64 *__restrict__ start) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t <= nf; t += stride) {
+        if (t == nf) { deg[t] = 0; break; }
+        u64 u = fr[t] - row_lo;
+        u64 s = Ap[u];
+        deg[t] = Ap[u + 1] - s;
+        start[t] = s;
+    }
+}
+
+void bfs_dist_expand(const DevCSR &Aloc, u64 row_lo, const u32 *frontier, u64 nf, const u64 *visited, u64 *disc, u64 nwords,
+                     u64 *edges_out) {
+    CUDA_TRY(cudaMemsetAsync(disc, 0, nwords * sizeof(u64), stream()));
+    if (edges_out) *edges_out = 0;
+    if (nf == 0) return;
+    DevBuf<u64> cum(nf + 1), start(nf);
+    LAUNCH(k_frontier_deg_local, grid_for(nf + 1, 256, 148 * 16), 256, 0, frontier, nf, row_lo, Aloc.p.ptr, cum.ptr, start.ptr);
+    exclusive_scan_u64(cum.ptr, cum.ptr, nf + 1);
+    u64 total = read_scalar(cum.ptr + nf);
+    if (edges_out) *edges_out = total;
+    if (total == 0) return;
+    u32 grid = (u32)((total + BFS_CHUNK - 1) / BFS_CHUNK);
+    TimedScope ts(TK_BFS_EXPAND, 4 * total + 20 * nf);
+    LAUNCH(k_bfs_dist_expand, grid, 256, 0, frontier, cum.ptr, start.ptr, nf, total, Aloc.j.ptr, visited, (u32 *)disc);
+}
+
+// new = (OR over ranks of the gathered bitmaps) & ~visited ; visited |= new ; owned new vertices get their level and
+// join the next local frontier.  counters[0] = next frontier size, counters[1] = global number of new vertices.
+__global__ void __launch_bounds__(256)
+k_bfs_dist_merge(const u64 *__restrict__ gathered, int P, u64 nwords, u64 *__restrict__ visited, u64 row_lo, u64 row_hi,
+                 int *__restrict__ level_local, int lvl, u32 *__restrict__ next, u64 *__restrict__ counters) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 tot = 0;
+    for (; w < nwords; w += stride) {
+        u64 d = 0;
+        for (int g = 0; g < P; g++) d |= gathered[(u64)g * nwords + w];
+        u64 old = visited[w];
+        u64 nw = d & ~old;
+        if (!nw) continue;
+        visited[w] = old | nw;
+        tot += __popcll(nw);
+        u64 vb = w << 6;
+        if (vb + 64 <= row_lo || vb >= row_hi) continue;
+        while (nw) {
+            u64 bit = __ffsll((long long)nw) - 1;
+            nw &= nw - 1;
+            u64 v = vb + bit;
+            if (v >= row_lo && v < row_hi) {
+                level_local[v - row_lo] = lvl;
+                next[atomicAdd((unsigned long long *)&counters[0], 1ULL)] = (u32)v;
+            }
+        }
+    }
+    if (tot) atomicAdd((unsigned long long *)&counters[1], tot);
+}
+
+void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 row_lo, u64 row_hi, int *level_local, int lvl,
+                    u32 *next, u64 *host_counters) {
+    DevBuf<u64> cnt(2);
+    cnt.zero();
+    LAUNCH(k_bfs_dist_merge, grid_for(nwords, 256, 148 * 8), 256, 0, gathered, P, nwords, visited, row_lo, row_hi, level_local, lvl,
+           next, cnt.ptr);
+    d2h(host_counters, cnt.ptr, 2);
+    sync_stream();
+}
+
+// parent(v) = min { u : (u,v) in A, level(u) = level(v) - 1 }: rows of A' are ascending, so the first hit is the minimum
+__global__ void k_bfs_dist_parents(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 nloc, u64 row_lo,
+                                   const int *__restrict__ level_full, i64 *__restrict__ parent_local) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 r = warp; r < nloc; r += nwarps) {
+        int lv = level_full[row_lo + r];
+        i64 par = -1;
+        if (lv == 0) par = (i64)(row_lo + r);
+        else if (lv > 0) {
+            u64 s = ATp[r], e = ATp[r + 1];
+            for (u64 q0 = s; q0 < e && par < 0; q0 += 32) {
+                u64 q = q0 + lane;
+                bool hit = false;
+                u32 u = 0;
+                if (q < e) { u = ATj[q]; hit = level_full[u] == lv - 1; }
+                u32 m = __ballot_sync(0xffffffffu, hit);
+                if (m) par = (i64)__shfl_sync(0xffffffffu, u, __ffs(m) - 1);
+            }
+        }
+        if (lane == 0) parent_local[r] = par;
+    }
+}
+
+void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local) {
+    if (ATloc.nrows == 0) return;
+    LAUNCH(k_bfs_dist_parents, grid_for(ATloc.nrows * 32, 256, 148 * 32), 256, 0, ATloc.p.ptr, ATloc.j.ptr, ATloc.nrows, row_lo,
+           level_full, parent_local);
+}
+
 } // namespace b200

@@ -115,8 +115,9 @@ k_bits_count(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, u32 *__restric
 }
 
 __global__ void __launch_bounds__(TILE_THREADS)
-k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__restrict__ off, u32 *__restrict__ Cj) {
-    extern __shared__ unsigned short list[];             // up to 64 rows x 1024 vertices tile-local ids
+k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__restrict__ off, u32 *__restrict__ Cj,
+            u32 cap) {
+    extern __shared__ unsigned short list[];             // `cap` tile-local ids (sized from the average tile density)
     __shared__ unsigned short wp[TILE_THREADS / 32][64];  // per-warp exclusive prefix, per row
     __shared__ u32 sbase[65];                            // row segment starts inside `list`
     __shared__ u64 goff[64];                             // row segment starts in the output
@@ -157,6 +158,25 @@ k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__re
             for (u32 r = 0; r < 64; r++) { u32 t = sbase[r + 1]; sbase[r + 1] = run + t; run += t; }
         }
         __syncthreads();
+        const bool staged = sbase[64] <= cap;   // denser-than-provisioned tiles write straight to global memory
+        if (!staged) {
+            u64 o = goff[lane] + wp[warp][lane];
+#pragma unroll
+            for (u32 g = 0; g < 2; g++) {
+                u32 m = tlo[g];
+                u64 idb = vbase + warp * 64 + g * 32;
+                while (m) { u32 bit = __ffs(m) - 1; Cj[o++] = (u32)(idb + bit); m &= m - 1; }
+            }
+            o = goff[lane + 32] + wp[warp][lane + 32];
+#pragma unroll
+            for (u32 g = 0; g < 2; g++) {
+                u32 m = thi[g];
+                u64 idb = vbase + warp * 64 + g * 32;
+                while (m) { u32 bit = __ffs(m) - 1; Cj[o++] = (u32)(idb + bit); m &= m - 1; }
+            }
+            __syncthreads();
+            continue;
+        }
         // expand: lane b owns rows b (low half) and 32+b (high half) of this warp's 64 vertices
         {
             u32 o = sbase[lane] + wp[warp][lane];
@@ -213,13 +233,19 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     C.j.alloc(nnz);
     if (nnz) {
         static bool attr_set = false;
-        const size_t smem = (size_t)64 * TILE_V * sizeof(unsigned short);
         if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_bits_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_bits_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * TILE_V * sizeof(unsigned short))));
             attr_set = true;
         }
+        // staging capacity from the average (tile, word) population, 1.5x headroom, 8K-entry steps: sparse frontiers
+        // get small shared-memory footprints and therefore several resident CTAs per SM
+        u64 avg = nnz / (ntiles * W) + 1;
+        u32 cap = 8192;
+        while (cap < 65536 && (u64)cap < avg + avg / 2) cap += 8192;
+        if (ctx().opt_fill_cap > 0) cap = (u32)ctx().opt_fill_cap; // test hook: force the direct-write path
+        const size_t smem = (size_t)cap * sizeof(unsigned short);
         TimedScope ts(TK_BITS_FILL, 8ULL * W * n + 4 * nnz);
-        LAUNCH(k_bits_fill, (u32)ntiles, TILE_THREADS, smem, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
+        LAUNCH(k_bits_fill, (u32)ntiles, TILE_THREADS, smem, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr, cap);
     }
 }
 
@@ -325,6 +351,31 @@ k_bits_push(const u32 *__restrict__ act, const u64 *__restrict__ cum, const u64 
 // ---------------------------------------------------------------------------- pull
 // 8 lanes per output vertex j: OR of X[k] over k in A'(j,:).  Rows longer than LONG_ROW are
 // zeroed here and finished by k_bits_pull_long (several CTAs per row, RED.OR into Y).
+struct OrOp64 { __device__ u64 operator()(u64 a, u64 b) const { return a | b; } };
+
+// G[w] = OR over all vertices of word w: the terminal value of the OR monoid for this frontier.  A pull row whose
+// accumulator has reached G cannot change any more, so the rest of its neighbours need not be gathered (exact).
+template <int W>
+__global__ void __launch_bounds__(256) k_or_all(const u64 *__restrict__ X, u64 nv, u64 *__restrict__ G) {
+    typedef cub::BlockReduce<u64, 256> Red;
+    __shared__ typename Red::TempStorage ts;
+    u64 acc[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) acc[w] = 0;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < nv; t += stride) {
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] |= X[t * W + w];
+    }
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        u64 r = Red(ts).Reduce(acc[w], OrOp64());
+        __syncthreads();
+        if (threadIdx.x == 0 && r) atomicOr((unsigned long long *)&G[w], r);
+    }
+}
+
 template <bool HINTS> __device__ __forceinline__ u32 ld_col(const u32 *p, u64 strm) { return HINTS ? ld_u32_stream(p, strm) : __ldg(p); }
 template <bool HINTS> __device__ __forceinline__ u64 ld_ptr(const u64 *p, u64 strm) { return HINTS ? ld_u64_stream(p, strm) : __ldg(p); }
 template <bool HINTS> __device__ __forceinline__ u64 ld_x(const u64 *p, u64 keep) { return HINTS ? ld_u64_hint(p, keep) : __ldg(p); }
@@ -332,10 +383,14 @@ template <bool HINTS> __device__ __forceinline__ u64 ld_x(const u64 *p, u64 keep
 template <int W, bool HINTS, int U>
 __global__ void __launch_bounds__(256)
 k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
-            u64 *__restrict__ Y) {
+            u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
     const u32 lane8 = threadIdx.x & 7;
     const u32 sub = (threadIdx.x & 31) >> 3;
+    const u32 gmask = 0xFFu << (8 * sub);            // the 8 lanes that share a row
     const u64 keep = policy_keep(), strm = policy_stream();
+    u64 G[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) G[w] = Gp ? Gp[w] : ~0ULL;
     u64 group = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     u64 ngroups = ((u64)gridDim.x * blockDim.x) >> 3;
     u64 warp_first = group - sub; // group id of this warp's first 8-lane group
@@ -353,16 +408,30 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
         u64 acc[W];
 #pragma unroll
         for (int w = 0; w < W; w++) acc[w] = 0;
-        for (u64 q = s + lane8; q < e; q += 8 * U) {
+        // group-uniform trip count (all 8 lanes iterate together) so the lanes can vote inside the loop
+        for (u64 qb = s; qb < e; qb += 8 * U) {
             u32 k[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) k[u] = (q + 8 * u < e) ? ld_col<HINTS>(ATj + q + 8 * u, strm) : 0xFFFFFFFFu;
+            for (int u = 0; u < U; u++) { u64 q = qb + lane8 + 8 * u; k[u] = (q < e) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
 #pragma unroll
             for (int u = 0; u < U; u++)
                 if (k[u] != 0xFFFFFFFFu) {
 #pragma unroll
                     for (int w = 0; w < W; w++) acc[w] |= ld_x<HINTS>(X + (u64)k[u] * W + w, keep);
                 }
+            if (qb + 8 * U < e) {   // more to come: stop if the row already holds the terminal value
+                bool full = true;
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    u64 a = acc[w];
+                    a |= __shfl_xor_sync(gmask, a, 1);
+                    a |= __shfl_xor_sync(gmask, a, 2);
+                    a |= __shfl_xor_sync(gmask, a, 4);
+                    acc[w] = a;
+                    full = full && (a == G[w]);
+                }
+                if (full) break;
+            }
         }
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -380,12 +449,10 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
     }
 }
 
-struct OrOp64 { __device__ u64 operator()(u64 a, u64 b) const { return a | b; } };
-
 template <int W>
 __global__ void __launch_bounds__(256)
 k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, const u32 *__restrict__ ATj,
-                 const u64 *__restrict__ X, u64 *__restrict__ Y) {
+                 const u64 *__restrict__ X, u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
     typedef cub::BlockReduce<u64, 256> Red;
     __shared__ typename Red::TempStorage ts;
     u32 j = lrows[blockIdx.x];
@@ -397,11 +464,27 @@ k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, con
     u64 acc[W];
 #pragma unroll
     for (int w = 0; w < W; w++) acc[w] = 0;
-    const u64 keep = policy_keep(), strm = policy_stream();
-    for (u64 q = c0 + threadIdx.x; q < c1; q += 256) {
-        u32 k = ld_u32_stream(ATj + q, strm);
+    u64 G[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) acc[w] |= ld_u64_hint(X + (u64)k * W + w, keep);
+    for (int w = 0; w < W; w++) G[w] = Gp ? Gp[w] : ~0ULL;
+    // warp-uniform loop: every iteration the warp ORs its partials and leaves as soon as it holds the terminal value
+    for (u64 qb = c0 + (threadIdx.x & ~31u); qb < c1; qb += 256) {
+        u64 q = qb + (threadIdx.x & 31);
+        if (q < c1) {
+            u32 k = __ldg(ATj + q);
+#pragma unroll
+            for (int w = 0; w < W; w++) acc[w] |= __ldg(X + (u64)k * W + w);
+        }
+        bool full = true;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 a = acc[w];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) a |= __shfl_xor_sync(0xffffffffu, a, d);
+            acc[w] = a;
+            full = full && (a == G[w]);
+        }
+        if (full) break;
     }
 #pragma unroll
     for (int w = 0; w < W; w++) {
@@ -542,6 +625,200 @@ __global__ void k_scatter_flagged(const u32 *__restrict__ flag, const u64 *__res
         if (flag[r]) out[pos[r]] = (u32)r;
 }
 
+// ---- hot-set packing of the gather index space ------------------------------------------------------------------
+// The pull gathers X[k] with k distributed like the out-degree of k.  Relabel k -> slot, slots ordered by out-degree
+// descending and restricted to vertices that have out-edges at all (sinks are never gathered): the hot part of the
+// frontier words becomes contiguous (L1/L2 resident), and the gather footprint shrinks from 8*W*n to 8*W*n1 bytes.
+__global__ void k_degree_keys(const u64 *__restrict__ Ap, u64 n, u64 *__restrict__ keys, u64 *__restrict__ n1) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 cnt = 0;
+    for (; v < n; v += stride) {
+        u64 d = Ap[v + 1] - Ap[v];
+        if (d > 0xFFFFFFFEULL) d = 0xFFFFFFFEULL;
+        keys[v] = ((0xFFFFFFFFULL - d) << 32) | v;   // ascending sort => degree descending, then vertex id ascending
+        cnt += d != 0;
+    }
+    if (cnt) atomicAdd((unsigned long long *)n1, cnt);
+}
+__global__ void k_slots_from_keys(const u64 *__restrict__ keys, u64 n, u64 n1, u32 *__restrict__ vert, u32 *__restrict__ slot) {
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; s < n; s += stride) {
+        u32 v = (u32)(keys[s] & 0xFFFFFFFFULL);
+        if (s < n1) { vert[s] = v; slot[v] = (u32)s; } else slot[v] = 0xFFFFFFFFu;
+    }
+}
+__global__ void k_relabel_cols(const u32 *__restrict__ j, u64 nnz, const u32 *__restrict__ slot, u32 *__restrict__ jp) {
+    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; q < nnz; q += stride) jp[q] = slot[j[q]];
+}
+template <int W>
+__global__ void k_pack_frontier(const u32 *__restrict__ vert, u64 n1, const u64 *__restrict__ X, u64 *__restrict__ Xp) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < n1 * W; t += stride) {
+        u64 s = t / W, w = t % W;
+        Xp[t] = X[(u64)vert[s] * W + w];
+    }
+}
+
+void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
+    u64 n = A.nrows;
+    lr.vert.release(); lr.jp.release(); lr.slot.release(); lr.n1 = 0; lr.packed = false;
+    if (n == 0 || AT.nnz == 0 || n >= 0xFFFFFFFFULL) return;
+    DevBuf<u64> keys(n), cnt(1);
+    cnt.zero();
+    LAUNCH(k_degree_keys, grid_for(n, 256, 148 * 16), 256, 0, A.p.ptr, n, keys.ptr, cnt.ptr);
+    sort_keys_u64(keys.ptr, n, 64);
+    u64 n1 = read_scalar(cnt.ptr);
+    lr.n1 = n1;
+    lr.vert.alloc(n1 ? n1 : 1);
+    lr.slot.alloc(n);
+    LAUNCH(k_slots_from_keys, grid_for(n, 256, 148 * 16), 256, 0, keys.ptr, n, n1, lr.vert.ptr, lr.slot.ptr);
+    lr.packed = true;
+}
+
+// ---- CSR-stream form of A' ----------------------------------------------------------------------------------------
+__global__ void k_short_len(const u64 *__restrict__ p, u64 n, u64 LONG, u32 *__restrict__ len_s, u32 *__restrict__ lflag,
+                            u64 *__restrict__ maxlong) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 mx = 0;
+    for (; r <= n; r += stride) {
+        if (r == n) { len_s[r] = 0; lflag[r] = 0; break; }
+        u64 d = p[r + 1] - p[r];
+        bool lg = d > LONG;
+        len_s[r] = lg ? 0u : (u32)d;
+        lflag[r] = lg ? 1u : 0u;
+        if (lg && d > mx) mx = d;
+    }
+    if (mx) atomicMax((unsigned long long *)maxlong, mx);
+}
+__global__ void k_long_meta(const u64 *__restrict__ p, u64 n, const u32 *__restrict__ lflag, const u64 *__restrict__ lpos,
+                            u64 nlong, u32 *__restrict__ lrows, u64 *__restrict__ llen) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    if (r == 0) llen[nlong] = 0;
+    for (; r < n; r += stride)
+        if (lflag[r]) { lrows[lpos[r]] = (u32)r; llen[lpos[r]] = p[r + 1] - p[r]; }
+}
+__global__ void k_fill_stream(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 n, const u32 *__restrict__ slot,
+                              const u64 *__restrict__ rp_s, u32 *__restrict__ jp_s, const u32 *__restrict__ lflag,
+                              const u64 *__restrict__ lpos, const u64 *__restrict__ lrp, u32 *__restrict__ jp_l) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 r = warp; r < n; r += nwarps) {
+        u64 s = p[r], e = p[r + 1];
+        u32 *dst = lflag[r] ? (jp_l + lrp[lpos[r]]) : (jp_s + rp_s[r]);
+        for (u64 q = lane; q < e - s; q += 32) dst[q] = slot ? slot[j[s + q]] : j[s + q];
+    }
+}
+__global__ void k_window_starts(const u64 *__restrict__ rp_s, u64 n, u64 WIN, u64 nwin, u32 *__restrict__ wstart) {
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nwin) return;
+    if (k == nwin) { wstart[k] = (u32)n; return; }
+    u64 target = k * WIN, lo = 0, hi = n;      // first row r in [0,n) with rp_s[r] >= target, else n
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (rp_s[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    wstart[k] = (u32)lo;
+}
+
+static u64 stream_window(u32 W) { return 1024 / W; }   // window (and short-row limit) in nnz; W <= 4
+
+void build_stream(const DevCSR &AT, LongRows &lr, u32 W) {
+    u64 n = AT.nrows;
+    u64 WIN = stream_window(W);
+    lr.sW = W; lr.swin = WIN; lr.s_packed = lr.packed;
+    DevBuf<u32> len_s(n + 1), lflag(n + 1);
+    DevBuf<u64> lpos(n + 1), mx(1);
+    mx.zero();
+    LAUNCH(k_short_len, grid_for(n + 1, 256, 148 * 16), 256, 0, AT.p.ptr, n, WIN, len_s.ptr, lflag.ptr, mx.ptr);
+    lr.rp_s.alloc(n + 1);
+    exclusive_scan_u32_to_u64(len_s.ptr, lr.rp_s.ptr, n + 1);
+    exclusive_scan_u32_to_u64(lflag.ptr, lpos.ptr, n + 1);
+    lr.nnz_s = read_scalar(lr.rp_s.ptr + n);
+    lr.nlong = read_scalar(lpos.ptr + n);
+    lr.maxlong = read_scalar(mx.ptr);
+    lr.lrows.alloc(lr.nlong ? lr.nlong : 1);
+    lr.lrp.alloc(lr.nlong + 1);
+    LAUNCH(k_long_meta, grid_for(n ? n : 1, 256, 148 * 16), 256, 0, AT.p.ptr, n, lflag.ptr, lpos.ptr, lr.nlong, lr.lrows.ptr, lr.lrp.ptr);
+    exclusive_scan_u64(lr.lrp.ptr, lr.lrp.ptr, lr.nlong + 1);
+    lr.jp_s.alloc(lr.nnz_s ? lr.nnz_s : 1);
+    lr.jp_l.alloc(AT.nnz - lr.nnz_s ? AT.nnz - lr.nnz_s : 1);
+    if (n) LAUNCH(k_fill_stream, grid_for(n * 32, 256, 148 * 32), 256, 0, AT.p.ptr, AT.j.ptr, n, lr.packed ? lr.slot.ptr : (const u32 *)nullptr,
+                  lr.rp_s.ptr, lr.jp_s.ptr, lflag.ptr, lpos.ptr, lr.lrp.ptr, lr.jp_l.ptr);
+    lr.nwin = lr.nnz_s / WIN + 1;
+    lr.wstart.alloc(lr.nwin + 1);
+    LAUNCH(k_window_starts, grid_for(lr.nwin + 1, 256), 256, 0, lr.rp_s.ptr, n, WIN, lr.nwin, lr.wstart.ptr);
+}
+
+// flat coalesced gather of one window's nnz into shared memory, then one thread per row reduces its segment
+template <int W>
+__global__ void __launch_bounds__(128)
+k_bits_pull_stream(const u64 *__restrict__ rp_s, const u32 *__restrict__ jp_s, const u32 *__restrict__ wstart,
+                   const u64 *__restrict__ Xp, u64 *__restrict__ Y) {
+    extern __shared__ u64 sxs[];
+    const u32 tid = threadIdx.x;
+    u32 r0 = wstart[blockIdx.x], r1 = wstart[blockIdx.x + 1];
+    if (r0 == r1) return;
+    u64 base = rp_s[r0];
+    u32 nnzb = (u32)(rp_s[r1] - base);
+    const u32 *cols = jp_s + base;
+#pragma unroll 4
+    for (u32 e = tid; e < nnzb; e += 128) {
+        u32 col = cols[e];
+#pragma unroll
+        for (int w = 0; w < W; w++) sxs[(size_t)e * W + w] = Xp[(u64)col * W + w];
+    }
+    __syncthreads();
+    for (u32 r = r0 + tid; r < r1; r += 128) {
+        u32 s = (u32)(rp_s[r] - base), e = (u32)(rp_s[r + 1] - base);
+        u64 acc[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] = 0;
+        for (u32 q = s; q < e; q++) {
+#pragma unroll
+            for (int w = 0; w < W; w++) acc[w] |= sxs[(size_t)q * W + w];
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) Y[(u64)r * W + w] = acc[w];
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_bits_pull_stream_long(const u32 *__restrict__ lrows, const u64 *__restrict__ lrp, const u32 *__restrict__ jp_l,
+                        const u64 *__restrict__ Xp, u64 *__restrict__ Y) {
+    typedef cub::BlockReduce<u64, 256> Red;
+    __shared__ typename Red::TempStorage ts;
+    u64 s = lrp[blockIdx.x], e = lrp[blockIdx.x + 1];
+    u64 c0 = s + (u64)blockIdx.y * LONG_CHUNK;
+    if (c0 >= e) return;
+    u64 c1 = c0 + LONG_CHUNK;
+    if (c1 > e) c1 = e;
+    u64 acc[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) acc[w] = 0;
+#pragma unroll 4
+    for (u64 q = c0 + threadIdx.x; q < c1; q += 256) {
+        u32 k = jp_l[q];
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] |= Xp[(u64)k * W + w];
+    }
+    u32 row = lrows[blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        u64 r = Red(ts).Reduce(acc[w], OrOp64());
+        __syncthreads();
+        if (threadIdx.x == 0 && r) atomicOr((unsigned long long *)&Y[(u64)row * W + w], r);
+    }
+}
+
 void build_long_rows(const DevCSR &AT, LongRows &lr) {
     u64 n = AT.nrows;
     lr.rows.release();
@@ -561,13 +838,17 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
         lr.rows.alloc(nl);
         LAUNCH(k_scatter_flagged, grid_for(n, 256, 1 << 16), 256, 0, flag.ptr, pos.ptr, n, lr.rows.ptr);
     }
+    if (lr.packed) {
+        lr.jp.alloc(AT.nnz);
+        LAUNCH(k_relabel_cols, grid_for(AT.nnz, 256, 148 * 32), 256, 0, AT.j.ptr, AT.nnz, lr.slot.ptr, lr.jp.ptr);
+    }
     u64 ndiag = (n + AT.nnz) / 256 + 2;
     lr.mp_r.alloc(ndiag);
     LAUNCH(k_mp_coords, grid_for(ndiag, 256), 256, 0, AT.p.ptr, n, AT.nnz, ndiag, lr.mp_r.ptr);
 }
 
 template <int W>
-static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, const LongRows *lr, DevBits &Y,
+static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y,
                      u64 *flops_out, int *path_out) {
     Context &cx = ctx();
     u64 n = A.nrows, m = A.ncols;
@@ -584,12 +865,54 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, const 
     if (flops_out) *flops_out = hst[0];
     u64 edges = hst[1];
     bool pull = false;
-    if (AT && lr && lr->built) {
+    if (AT && lr) {
         if (cx.opt_pull_mode == 1) pull = true;
         else if (cx.opt_pull_mode == 0) pull = false;
         else pull = edges * 4 > A.nnz; // direction switch: frontier touches > 1/4 of the edges
     }
     if (edges == 0) { Y.w.zero(); if (path_out) *path_out = 0; return; }
+    const u32 *gj = AT ? AT->j.ptr : nullptr;   // gather index stream
+    const u64 *gx = X.w.ptr;                    // gather source
+    u64 gn = n;                                 // gather footprint in vertices
+    DevBuf<u64> Xp;
+    const bool stream_kernel = pull && W <= 4 && cx.opt_pull_kernel == 2;
+    if (pull) {   // auxiliary tables are built once per (immutable) matrix, lazily
+        if (!lr->packed && cx.opt_hot_pack) build_hot_pack(A, *AT, *lr);
+        if (stream_kernel) { if (lr->sW != (u32)W || lr->s_packed != lr->packed) build_stream(*AT, *lr, W); }
+        else if (!lr->built || (lr->packed && !lr->jp.ptr)) build_long_rows(*AT, *lr);
+    }
+    if (stream_kernel) {
+        if (lr->s_packed) {
+            Xp.alloc(lr->n1 * W);
+            if (lr->n1) LAUNCH((k_pack_frontier<W>), grid_for(lr->n1 * W, 256, 148 * 32), 256, 0, lr->vert.ptr, lr->n1, X.w.ptr, Xp.ptr);
+            gx = Xp.ptr; gn = lr->n1;
+        }
+        const size_t smem = (size_t)2 * lr->swin * W * sizeof(u64);
+        {
+            TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * gn + 8ULL * W * m);
+            LAUNCH((k_bits_pull_stream<W>), (u32)lr->nwin, 128, smem, lr->rp_s.ptr, lr->jp_s.ptr, lr->wstart.ptr, gx, Y.w.ptr);
+        }
+        if (lr->nlong) {
+            dim3 g((u32)lr->nlong, (u32)((lr->maxlong + LONG_CHUNK - 1) / LONG_CHUNK));
+            TimedScope ts(TK_BITS_PULL_LONG, 0);
+            LAUNCH((k_bits_pull_stream_long<W>), g, 256, 0, lr->lrows.ptr, lr->lrp.ptr, lr->jp_l.ptr, gx, Y.w.ptr);
+        }
+        if (path_out) *path_out = 5;
+        return;
+    }
+    if (pull && cx.opt_hot_pack && lr->packed && lr->jp.ptr) {
+        Xp.alloc(lr->n1 * W);
+        if (lr->n1) LAUNCH((k_pack_frontier<W>), grid_for(lr->n1 * W, 256, 148 * 32), 256, 0, lr->vert.ptr, lr->n1, X.w.ptr, Xp.ptr);
+        gj = lr->jp.ptr; gx = Xp.ptr; gn = lr->n1;
+    }
+    DevBuf<u64> Gd;
+    const u64 *Gp = nullptr;
+    if (pull && cx.opt_early_exit) {
+        Gd.alloc(W);
+        Gd.zero();
+        if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);
+        Gp = Gd.ptr;
+    }
     if (pull && cx.opt_pull_kernel == 1) {
         constexpr int TILE = MpCfg<W>::TILE;
         const size_t smem = ((size_t)TILE * W + (size_t)(TILE + 1) * W) * sizeof(u64) + (size_t)(TILE + 2) * sizeof(u32);
@@ -601,29 +924,29 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, const 
         Y.w.zero();
         u64 total = m + AT->nnz;
         u64 ntiles = (total + TILE - 1) / TILE;
-        TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * n + 8ULL * W * m);
-        LAUNCH((k_bits_pull_mp<W>), (u32)ntiles, 256, smem, AT->p.ptr, AT->j.ptr, m, AT->nnz, X.w.ptr, Y.w.ptr, lr->mp_r.ptr);
+        TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * gn + 8ULL * W * m);
+        LAUNCH((k_bits_pull_mp<W>), (u32)ntiles, 256, smem, AT->p.ptr, gj, m, AT->nnz, gx, Y.w.ptr, lr->mp_r.ptr);
         if (path_out) *path_out = 4;
     } else if (pull) {
         u32 grid = (u32)cx.num_sms * 16;
         {
             // compulsory traffic: stream A' col_idx + rowptr, read X once, write Y once (X gathers hit L2)
-            TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * n + 8ULL * W * m);
+            TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * gn + 8ULL * W * m);
             if (cx.opt_hints) {
-                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, true, 4>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
-                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, true, 2>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
-                else LAUNCH((k_bits_pull<W, true, 1>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, true, 4>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, true, 2>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                else LAUNCH((k_bits_pull<W, true, 1>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
             } else {
-                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, false, 4>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
-                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, false, 2>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
-                else LAUNCH((k_bits_pull<W, false, 1>), grid, 256, 0, AT->p.ptr, AT->j.ptr, m, X.w.ptr, Y.w.ptr);
+                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, false, 4>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, false, 2>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                else LAUNCH((k_bits_pull<W, false, 1>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
             }
         }
         if (lr->n) {
             u32 gy = (u32)((lr->maxdeg + LONG_CHUNK - 1) / LONG_CHUNK);
             dim3 g((u32)lr->n, gy);
             TimedScope ts(TK_BITS_PULL_LONG, 0);
-            LAUNCH((k_bits_pull_long<W>), g, 256, 0, lr->rows.ptr, AT->p.ptr, AT->j.ptr, X.w.ptr, Y.w.ptr);
+            LAUNCH((k_bits_pull_long<W>), g, 256, 0, lr->rows.ptr, AT->p.ptr, gj, gx, Y.w.ptr, Gp);
         }
         if (path_out) *path_out = 3;
     } else {
@@ -647,7 +970,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, const 
     }
 }
 
-void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, const LongRows *lr, DevBits &Y, u64 *flops_out,
+void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y, u64 *flops_out,
               int *path_out) {
     if (X.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
     switch (X.W) {

@@ -193,6 +193,41 @@ __global__ void k_rmat_keys(int scale, u64 nedges, u64 seed, u64 k1, u64 k2, u64
     }
 }
 
+// Row block [lo,hi) of the same RMAT matrix (by_col: row block of its transpose).  Every rank regenerates the global
+// counter-based edge stream and keeps what it owns, so the union of the blocks is exactly rmat_csr's matrix.
+__global__ void k_rmat_block_keys(int scale, u64 nedges, u64 seed, u64 k1, u64 k2, u64 lo, u64 hi, int by_col,
+                                  u64 *__restrict__ keys) {
+    const u32 TA = (u32)(0.57 * 4294967296.0), TB = (u32)((0.57 + 0.19) * 4294967296.0),
+              TC = (u32)((0.57 + 0.19 + 0.19) * 4294967296.0);
+    u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; e < nedges; e += stride) {
+        u64 r = 0, c = 0, h = 0;
+        for (int l = 0; l < scale; l++) {
+            if ((l & 1) == 0) h = splitmix64(seed * 0xD1342543DE82EF95ULL + e * 64 + (u64)(l >> 1));
+            u32 u = (l & 1) ? (u32)(h >> 32) : (u32)h;
+            u32 rb, cb;
+            if (u < TA) { rb = 0; cb = 0; } else if (u < TB) { rb = 0; cb = 1; }
+            else if (u < TC) { rb = 1; cb = 0; } else { rb = 1; cb = 1; }
+            r = (r << 1) | rb; c = (c << 1) | cb;
+        }
+        u64 i = scramble(r, scale, k1, k2), j = scramble(c, scale, k1, k2);
+        u64 own = by_col ? j : i, other = by_col ? i : j;
+        keys[e] = (i == j || own < lo || own >= hi) ? INVALID_KEY : (((own - lo) << 32) | other);
+    }
+}
+
+void rmat_block_csr(int scale, u64 edge_factor, u64 seed, u64 lo, u64 hi, int by_col, DevCSR &out) {
+    if (scale < 1 || scale > 31) throw GrbError(-3, "rmat scale must be in [1,31]");
+    u64 n = (u64)1 << scale, ne = n * edge_factor;
+    if (lo > hi || hi > n) throw GrbError(-3, "rmat block out of range");
+    u64 k1 = splitmix64(seed ^ 0xA5A5A5A5ULL) | 1ULL, k2 = splitmix64(seed ^ 0x5A5A5A5AULL) | 1ULL;
+    DevBuf<u64> keys(ne);
+    LAUNCH(k_rmat_block_keys, grid_for(ne, 256, 1 << 20), 256, 0, scale, ne, seed, k1, k2, lo, hi, by_col, keys.ptr);
+    sort_keys_u64(keys.ptr, ne, 64);
+    csr_from_sorted_keys(keys.ptr, ne, hi - lo, n, nullptr, nullptr, out);
+}
+
 void rmat_csr(int scale, u64 edge_factor, u64 seed, DevCSR &out) {
     if (scale < 1 || scale > 31) throw GrbError(-3, "rmat scale must be in [1,31]");
     u64 n = (u64)1 << scale, ne = n * edge_factor;

@@ -52,8 +52,11 @@ struct Context {
     i64 opt_bits_min_flops = 1 << 22;     // auto mode: use bit-frontier when flops >= this
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
-    i64 opt_pull_kernel = 0;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel
+    i64 opt_pull_kernel = 0;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4)
+    i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
     i64 opt_hints = 0;             // L2 createpolicy hints in the pull kernel
+    i64 opt_hot_pack = 1;          // gather through the degree-sorted, sink-free relabelling of the frontier
+    i64 opt_fill_cap = 0;          // 0 = auto; >0 forces the materialise staging capacity (test hook)
     i64 opt_unroll = 4;            // gathers in flight per lane in the 8-lane pull kernel
 };
 Context &ctx();
@@ -76,7 +79,16 @@ struct TimedScope {
 void timed_collect(double *ms, u64 *launches, u64 *bytes);
 void timed_reset();
 
-// ---- stream-ordered device buffers ----------------------------------------------------------
+// ---- caching device allocator (prims.cu) ----------------------------------------------------------
+// Size-class free lists over cudaMalloc.  Every buffer is only ever touched by work enqueued on the one library
+// stream, so a freed block can be handed out again immediately (stream order guarantees the previous user is done
+// before the next one starts): steady state has no driver allocation calls and no pool growth / fragmentation.
+void *pool_alloc(size_t bytes);
+void pool_free(void *p);
+void pool_trim();
+size_t pool_bytes_cached();
+
+// ---- device buffers -------------------------------------------------------------------------------
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
@@ -95,10 +107,10 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) { ptr = nullptr; return; }
-        CUDA_TRY(cudaMallocAsync((void **)&ptr, count * sizeof(T), stream()));
+        ptr = (T *)pool_alloc(count * sizeof(T));
     }
     void release() {
-        if (ptr) { cudaFreeAsync(ptr, stream()); ptr = nullptr; }
+        if (ptr) { pool_free(ptr); ptr = nullptr; }
         n = 0;
     }
     void zero() { if (n) CUDA_TRY(cudaMemsetAsync(ptr, 0, n * sizeof(T), stream())); }

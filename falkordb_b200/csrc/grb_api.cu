@@ -150,10 +150,7 @@ struct MultiLock {
 static void invalidate_aux(GrB_Matrix A) {
     A->devT_valid = false;
     A->devT.clear();
-    A->lr.rows.release();
-    A->lr.mp_r.release();
-    A->lr.built = false;
-    A->lr.n = 0;
+    A->lr.clear();
 }
 
 static void set_dev(GrB_Matrix A, DevCSR &&d) {
@@ -336,7 +333,7 @@ static void ensure_devT(GrB_Matrix A) {
         A->devT = std::move(t);
         A->devT_valid = true;
     }
-    if (!A->lr.built) build_long_rows(A->devT, A->lr);
+    // pull-direction auxiliaries (hot-set packing, CSR-stream form, long-row lists) are built lazily by bits_hop
 }
 
 static u64 matrix_nvals(GrB_Matrix A) {
@@ -856,7 +853,7 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
                 DevBits Y;
                 u64 fl = 0;
                 int path = 0;
-                bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : nullptr, Y, &fl, &path);
+                bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : (LongRows *)nullptr, Y, &fl, &path);
                 if (Mask) {
                     ensure_bits(Mask);
                     bits_andnot(Y, Mask->bits);
@@ -1355,6 +1352,61 @@ GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64
     });
 }
 
+GrB_Info B200_Matrix_rmat_block(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed, uint64_t lo, uint64_t hi, int by_col) {
+    CHECK_PTR(A);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        ensure_init();
+        GrB_Matrix m = new GB_Matrix_opaque();
+        m->type = T_BOOL; m->nrows = hi - lo; m->ncols = (u64)1 << scale;
+        DevCSR d;
+        rmat_block_csr(scale, edge_factor, seed, lo, hi, by_col, d);
+        sync_stream();
+        set_dev(m, std::move(d));
+        *A = m;
+        return GrB_SUCCESS;
+    });
+}
+
+// ---- 1-D row-partitioned BFS steps (all pointers are DEVICE pointers owned by the caller, e.g. torch tensors) ----
+GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t *frontier, uint64_t nf, const uint64_t *visited,
+                              uint64_t *disc, uint64_t nwords, uint64_t *edges_out) {
+    CHECK_MAT(Alocal);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{Alocal};
+        ensure_init();
+        ensure_dev(Alocal);
+        u64 edges = 0;
+        bfs_dist_expand(Alocal->dev, row_lo, frontier, nf, visited, disc, nwords, &edges);
+        sync_stream();   // the caller hands `disc` to NCCL on another stream next
+        if (edges_out) *edges_out = edges;
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwords, uint64_t *visited, uint64_t row_lo,
+                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2) {
+    CHECK_PTR(gathered); CHECK_PTR(counters2);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        ensure_init();
+        bfs_dist_merge(gathered, nranks, nwords, visited, row_lo, row_hi, level_local, lvl, next_frontier, counters2);
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local) {
+    CHECK_MAT(ATlocal);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{ATlocal};
+        ensure_init();
+        ensure_dev(ATlocal);
+        bfs_dist_parents(ATlocal->dev, row_lo, level_full, parent_local);
+        sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
 GrB_Info B200_sync(void) {
     return guarded([&]() {
         if (ctx().ready) sync_stream();
@@ -1406,6 +1458,9 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "sync_after_op") c.opt_sync_after_op = value;
     else if (n == "pull_kernel") c.opt_pull_kernel = value;
     else if (n == "hints") c.opt_hints = value;
+    else if (n == "hot_pack") c.opt_hot_pack = value;
+    else if (n == "early_exit") c.opt_early_exit = value;
+    else if (n == "fill_cap") c.opt_fill_cap = value;
     else if (n == "unroll") c.opt_unroll = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;

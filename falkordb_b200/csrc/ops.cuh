@@ -9,6 +9,7 @@ void build_from_device_coo(const u64 *dI, const u64 *dJ, const u64 *dX, u64 n, u
                            bool *index_error);
 void transpose_csr(const DevCSR &A, DevCSR &out, bool keep_values);
 void rmat_csr(int scale, u64 edge_factor, u64 seed, DevCSR &out);
+void rmat_block_csr(int scale, u64 edge_factor, u64 seed, u64 lo, u64 hi, int by_col, DevCSR &out);
 
 // spgemm.cu : C = pattern(A*B) over ANY_PAIR, row-wise push (Gustavson family)
 void spgemm_anypair(const DevCSR &A, const DevCSR &B, DevCSR &C, u64 *flops_out);
@@ -19,10 +20,31 @@ u32 bits_words_for(u64 nrows);
 void bits_from_csr(const DevCSR &F, DevBits &X);
 void bits_to_csr(const DevBits &X, DevCSR &C);
 u64 bits_nvals(const DevBits &X);
-struct LongRows { DevBuf<u32> rows; DevBuf<u64> mp_r; u64 n = 0; u64 maxdeg = 0; bool built = false; };
+struct LongRows {   // per-matrix auxiliary data of the pull direction, cached with the transpose mirror
+    bool built = false;
+    // legacy 8-lane / merge-path kernels
+    DevBuf<u32> rows; u64 n = 0; u64 maxdeg = 0;      // rows of A' longer than LONG_ROW
+    DevBuf<u64> mp_r;                                  // merge-path coordinates of every 256th diagonal
+    DevBuf<u32> jp;                                    // relabelled col_idx of A' (all rows)
+    // hot-set packing: vertices with out-edges, by out-degree descending
+    DevBuf<u32> vert, slot; u64 n1 = 0; bool packed = false;
+    // CSR-stream form for the pull kernel: short rows of A' (cols relabelled to slots), window -> first row,
+    // and the long rows kept apart; built per frontier word count W
+    u32 sW = 0; u64 swin = 0; bool s_packed = false;
+    DevBuf<u64> rp_s; DevBuf<u32> jp_s, wstart; u64 nwin = 0, nnz_s = 0;
+    DevBuf<u32> lrows, jp_l; DevBuf<u64> lrp; u64 nlong = 0, maxlong = 0;
+    void clear() {
+        built = false; rows.release(); n = 0; maxdeg = 0; mp_r.release(); jp.release();
+        vert.release(); slot.release(); n1 = 0; packed = false;
+        sW = 0; swin = 0; s_packed = false; rp_s.release(); jp_s.release(); wstart.release(); nwin = 0; nnz_s = 0;
+        lrows.release(); jp_l.release(); lrp.release(); nlong = 0; maxlong = 0;
+    }
+};
+void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr);
+void build_stream(const DevCSR &AT, LongRows &lr, u32 W);
 void build_long_rows(const DevCSR &AT, LongRows &lr);
 // Y = X * A.  AT (= A') + its long-row list enable the pull direction; may be null (push only).
-void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, const LongRows *lr, DevBits &Y, u64 *flops_out,
+void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y, u64 *flops_out,
               int *path_out);
 void bits_andnot(DevBits &Y, const DevBits &M); // Y &= ~M
 void bits_or(DevBits &Y, const DevBits &Z);     // Y |= Z
@@ -38,6 +60,11 @@ void csr_resize(const DevCSR &A, u64 nrows, u64 ncols, DevCSR &out); // grow/shr
 
 // bfs.cu
 void bfs_run(const DevCSR &A, u64 src, i64 max_level, i64 *d_level, i64 *d_parent, u64 *edges_traversed);
+void bfs_dist_expand(const DevCSR &Aloc, u64 row_lo, const u32 *frontier, u64 nf, const u64 *visited, u64 *disc, u64 nwords,
+                     u64 *edges_out);
+void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 row_lo, u64 row_hi, int *level_local, int lvl,
+                    u32 *next, u64 *host_counters);
+void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local);
 
 // hypersparse host form <-> dense device rowptr (ewise.cu)
 void rowptr_from_hyper(const u64 *d_hrow, const u64 *d_hptr, u64 nvec, u64 nrows, u64 *d_p);

@@ -5,7 +5,9 @@
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 
 namespace b200 {
 
@@ -31,12 +33,62 @@ void ensure_init() {
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     c.num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    // keep freed blocks cached in the stream-ordered pool: no cudaMalloc in steady state
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-    u64 thresh = ~0ULL;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     c.ready = true;
+}
+
+// ---- caching allocator ----------------------------------------------------------------------------------
+static std::mutex g_pool_mu;
+static std::map<size_t, std::vector<void *>> g_free;     // class size -> cached blocks
+static std::unordered_map<void *, size_t> g_size;        // live + cached block -> class size
+static size_t g_cached_bytes = 0;
+
+static size_t size_class(size_t b) {
+    if (b <= 512) return 512;
+    size_t p = 1;
+    while (p < b) p <<= 1;                 // next power of two
+    if (b <= ((size_t)1 << 20)) return p;
+    size_t step = p >> 4;                  // above 1 MiB: 1/16-of-a-power-of-two granularity (<= 6.7% slack)
+    return (b + step - 1) / step * step;
+}
+void pool_trim() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    cudaStreamSynchronize(stream());
+    for (auto &kv : g_free) for (void *p : kv.second) { cudaFree(p); g_size.erase(p); }
+    g_free.clear();
+    g_cached_bytes = 0;
+}
+size_t pool_bytes_cached() { return g_cached_bytes; }
+void *pool_alloc(size_t bytes) {
+    size_t cls = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_free.find(cls);
+        if (it != g_free.end() && !it->second.empty()) {
+            void *p = it->second.back();
+            it->second.pop_back();
+            g_cached_bytes -= cls;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(&p, cls);
+    }
+    if (e != cudaSuccess) throw CudaError(e, __FILE__, __LINE__);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_size[p] = cls;
+    return p;
+}
+void pool_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_size.find(p);
+    if (it == g_size.end()) { cudaFree(p); return; }
+    g_free[it->second].push_back(p);
+    g_cached_bytes += it->second;
 }
 
 // ---- per-kernel timing registry ------------------------------------------------------------------

@@ -224,6 +224,19 @@ GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
 /* Synthetic Graph500-style RMAT adjacency (a,b,c,d=.57,.19,.19,.05), dedupe + no self loops, built on
  * the device.  Benchmark / test input only. */
 GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed);
+/* Row block [lo,hi) of B200_Matrix_rmat's matrix ((hi-lo) x 2^scale, rows local-indexed); by_col != 0 gives the same
+ * block of the TRANSPOSE.  Every rank regenerates the counter-based edge stream and keeps what it owns. */
+GrB_Info B200_Matrix_rmat_block(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed, uint64_t lo, uint64_t hi,
+                                int by_col);
+/* 1-D row-partitioned BFS building blocks: one level = expand the owned part of the frontier into an
+ * n-bit `disc` bitmap; the caller all-gathers the bitmaps (NCCL); merge ORs them, updates `visited`, assigns levels to
+ * owned vertices and emits the next owned frontier.  counters2[0] = next owned frontier size, [1] = new vertices
+ * globally (0 => done).  Every pointer is a DEVICE pointer except counters2 / edges_out (host). */
+GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t *frontier, uint64_t nf, const uint64_t *visited,
+                              uint64_t *disc, uint64_t nwords, uint64_t *edges_out);
+GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwords, uint64_t *visited, uint64_t row_lo,
+                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2);
+GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local);
 GrB_Info B200_sync(void);
 void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */
 /* stats: "launches", "lib_launches", "last_flops", "total_flops", "last_path", "h2d_bytes", "d2h_bytes" */

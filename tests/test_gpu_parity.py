@@ -223,6 +223,33 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
     assert list(F.iter(0, 0)) == [(0, int(c)) for c in want.j[want.p[0]:want.p[1]]]
 
 
+@pytest.mark.parametrize("opts", [{"fill_cap": 64}, {"hot_pack": 0}, {"pull_kernel": 0, "hot_pack": 0}, {"pull_kernel": 0, "unroll": 1},
+                                  {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 1, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}])
+def test_bit_frontier_kernel_variants(opts):
+    """every selectable kernel variant (direct-write materialise, hot-set packing on/off, merge-path pull, L2 hints)"""
+    fb.set_option("bits_mode", 1)
+    fb.set_option("pull_mode", 1)
+    for k, v in opts.items():
+        fb.set_option(k, v)
+    try:
+        A = orc.rmat_csr(12, 16, 11)
+        rng = np.random.default_rng(5)
+        for nsrc in (64, 130, 200):
+            src = rng.choice(A.nrows, size=nsrc, replace=False)
+            F = Matrix(nsrc, A.nrows, bool)
+            F.build(np.arange(nsrc), src)
+            dA = to_dev(A)
+            want = orc.build_matrix(nsrc, A.nrows, np.arange(nsrc), src)
+            for _ in range(3):
+                F.lmxm(dA)
+                want = orc.mxm(want, A)
+            F.wait()
+            assert_same(F, want, f"variant {opts} nsrc={nsrc}")
+    finally:
+        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 0), ("hints", 0), ("early_exit", 1)):
+            fb.set_option(k, v)
+
+
 def test_bit_frontier_rectangular_and_auto_mode():
     rng = np.random.default_rng(9)
     F = rand_csr(rng, 70, 900, 0.02)
