@@ -379,8 +379,20 @@ __global__ void __launch_bounds__(256) k_or_all(const u64 *__restrict__ X, u64 n
 template <bool HINTS> __device__ __forceinline__ u32 ld_col(const u32 *p, u64 strm) { return HINTS ? ld_u32_stream(p, strm) : __ldg(p); }
 template <bool HINTS> __device__ __forceinline__ u64 ld_ptr(const u64 *p, u64 strm) { return HINTS ? ld_u64_stream(p, strm) : __ldg(p); }
 template <bool HINTS> __device__ __forceinline__ u64 ld_x(const u64 *p, u64 keep) { return HINTS ? ld_u64_hint(p, keep) : __ldg(p); }
+// acc |= the W frontier words of one vertex: ONE 16-byte load per word pair (a W=4 vertex is a single 32 B sector), so the
+// number of L1TEX wavefronts per gathered vertex does not grow with W
+template <int W, bool HINTS> __device__ __forceinline__ void or_words(u64 (&acc)[W], const u64 *__restrict__ p, u64 keep) {
+    if (W == 1) { acc[0] |= ld_x<HINTS>(p, keep); return; }
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p);
+#pragma unroll
+    for (int w2 = 0; w2 < W / 2; w2++) {
+        ulonglong2 v = __ldg(q + w2);
+        acc[2 * w2] |= v.x;
+        acc[2 * w2 + 1] |= v.y;
+    }
+}
 
-template <int W, bool HINTS, int U>
+template <int W, bool HINTS, int U, bool EARLY>
 __global__ void __launch_bounds__(256)
 k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
             u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
@@ -408,29 +420,41 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
         u64 acc[W];
 #pragma unroll
         for (int w = 0; w < W; w++) acc[w] = 0;
-        // group-uniform trip count (all 8 lanes iterate together) so the lanes can vote inside the loop
-        for (u64 qb = s; qb < e; qb += 8 * U) {
-            u32 k[U];
+        if (EARLY) {
+            // group-uniform trip count (all 8 lanes iterate together) so the lanes can vote inside the loop
+            for (u64 qb = s; qb < e; qb += 8 * U) {
+                u32 k[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) { u64 q = qb + lane8 + 8 * u; k[u] = (q < e) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+                for (int u = 0; u < U; u++) { u64 q = qb + lane8 + 8 * u; k[u] = (q < e) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
 #pragma unroll
-            for (int u = 0; u < U; u++)
-                if (k[u] != 0xFFFFFFFFu) {
+                for (int u = 0; u < U; u++)
+                    if (k[u] != 0xFFFFFFFFu) {
+                        or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
+                    }
+                if (qb + 8 * U < e) {   // more to come: stop if the row already holds the terminal value
+                    bool full = true;
 #pragma unroll
-                    for (int w = 0; w < W; w++) acc[w] |= ld_x<HINTS>(X + (u64)k[u] * W + w, keep);
+                    for (int w = 0; w < W; w++) {
+                        u64 a = acc[w];
+                        a |= __shfl_xor_sync(gmask, a, 1);
+                        a |= __shfl_xor_sync(gmask, a, 2);
+                        a |= __shfl_xor_sync(gmask, a, 4);
+                        acc[w] = a;
+                        full = full && (a == G[w]);
+                    }
+                    if (full) break;
                 }
-            if (qb + 8 * U < e) {   // more to come: stop if the row already holds the terminal value
-                bool full = true;
+            }
+        } else {
+            for (u64 q = s + lane8; q < e; q += 8 * U) {
+                u32 k[U];
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    u64 a = acc[w];
-                    a |= __shfl_xor_sync(gmask, a, 1);
-                    a |= __shfl_xor_sync(gmask, a, 2);
-                    a |= __shfl_xor_sync(gmask, a, 4);
-                    acc[w] = a;
-                    full = full && (a == G[w]);
-                }
-                if (full) break;
+                for (int u = 0; u < U; u++) k[u] = (q + 8 * u < e) ? ld_col<HINTS>(ATj + q + 8 * u, strm) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (k[u] != 0xFFFFFFFFu) {
+                        or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
+                    }
             }
         }
 #pragma unroll
@@ -472,8 +496,7 @@ k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, con
         u64 q = qb + (threadIdx.x & 31);
         if (q < c1) {
             u32 k = __ldg(ATj + q);
-#pragma unroll
-            for (int w = 0; w < W; w++) acc[w] |= __ldg(X + (u64)k * W + w);
+            or_words<W, false>(acc, X + (u64)k * W, 0);
         }
         bool full = true;
 #pragma unroll
@@ -907,7 +930,9 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     }
     DevBuf<u64> Gd;
     const u64 *Gp = nullptr;
-    if (pull && cx.opt_early_exit) {
+    // opt_early_exit: 0 never, 1 auto (dense frontiers only), 2 always
+    const bool dense_frontier = hst[0] >= (hst[1] * X.nrows) / 4;   // flops/edges = degree-weighted mean popcount of a gathered word
+    if (pull && (cx.opt_early_exit == 2 || (cx.opt_early_exit == 1 && dense_frontier))) {
         Gd.alloc(W);
         Gd.zero();
         if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);
@@ -932,15 +957,16 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         {
             // compulsory traffic: stream A' col_idx + rowptr, read X once, write Y once (X gathers hit L2)
             TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * gn + 8ULL * W * m);
+            // early termination only pays when the gathered words are dense (degree-weighted mean popcount >= 1/4 of the rows)
+            const bool early = Gp != nullptr;
+#define PULL_LAUNCH(H, UU) do { if (early) LAUNCH((k_bits_pull<W, H, UU, true>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp); \
+                               else LAUNCH((k_bits_pull<W, H, UU, false>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp); } while (0)
             if (cx.opt_hints) {
-                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, true, 4>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
-                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, true, 2>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
-                else LAUNCH((k_bits_pull<W, true, 1>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                if (cx.opt_unroll >= 4) PULL_LAUNCH(true, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(true, 2); else PULL_LAUNCH(true, 1);
             } else {
-                if (cx.opt_unroll >= 4) LAUNCH((k_bits_pull<W, false, 4>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
-                else if (cx.opt_unroll >= 2) LAUNCH((k_bits_pull<W, false, 2>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
-                else LAUNCH((k_bits_pull<W, false, 1>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp);
+                if (cx.opt_unroll >= 4) PULL_LAUNCH(false, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(false, 2); else PULL_LAUNCH(false, 1);
             }
+#undef PULL_LAUNCH
         }
         if (lr->n) {
             u32 gy = (u32)((lr->maxdeg + LONG_CHUNK - 1) / LONG_CHUNK);

@@ -264,6 +264,31 @@ void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out
 }
 
 
+// ---- batched point lookups (ExpandInto) -----------------------------------------------------------------
+// found[t] = 1 and val[t] = A(I[t],J[t]) if the entry is stored; one binary search per pair inside the row.
+__global__ void k_probe_pairs(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *__restrict__ Ax, u64 nrows,
+                              u64 ncols, const u64 *__restrict__ I, const u64 *__restrict__ J, u64 n,
+                              unsigned char *__restrict__ found, u64 *__restrict__ val) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        u64 i = I[t], j = J[t];
+        bool hit = false;
+        u64 v = 0;
+        if (i < nrows && j < ncols) {
+            u64 s = Ap[i], e = Ap[i + 1];
+            u64 q = lower_bound_u32(Aj, s, e, (u32)j);
+            if (q < e && Aj[q] == (u32)j) { hit = true; v = Ax ? Ax[q] : 1ULL; }
+        }
+        found[t] = hit ? 1 : 0;
+        if (val) val[t] = v;
+    }
+}
+void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val) {
+    if (n) LAUNCH(k_probe_pairs, grid_for(n, 256, 148 * 16), 256, 0, A.p.ptr, A.j.ptr, A.has_values() ? A.x.ptr : (const u64 *)nullptr,
+                  A.nrows, A.ncols, dI, dJ, n, d_found, d_val);
+}
+
 // ---- hypersparse host form <-> dense device rowptr ---------------------------------------------
 // p[r] = hptr[ first vector index with hrow >= r ]  (hrow ascending, nvec entries, hptr[nvec] = nnz)
 __global__ void k_rowptr_from_hyper(const u64 *__restrict__ hrow, const u64 *__restrict__ hptr, u64 nvec, u64 nrows,

@@ -380,6 +380,82 @@ static void write_back(GrB_Matrix C, DevCSR &&T, GrB_Matrix M, const Desc &d, bo
     set_dev(C, std::move(U));
 }
 
+// ------------------------------------------------------------------------------------------------ host-resident matrices
+// Matrices with a dimension >= 2^32 cannot be indexed by the device kernels (u32 column ids, dense rowptr).  The only
+// such matrix on the path is Tensor's multi-edge store `me` (2^60 x 2^60, hypersparse, a handful of entries per
+// multi-edge pair: tensor.rs:154-163, 254).  Its delta folds (VersionedMatrix::flush on `me`) still arrive as
+// eWiseAdd / eWiseMult / masked-copy calls, so those three set operations exist on the hypersparse host form.  This is
+// NOT a fallback: device-capable operands never take this branch (see is_huge), and mxm on such matrices is refused.
+struct HTup { u64 r, c, v; };
+static bool is_huge(GrB_Matrix A) { return A && (A->nrows >= ((u64)1 << 32) || A->ncols >= ((u64)1 << 32)); }
+static std::vector<HTup> host_tuples(GrB_Matrix A) {
+    ensure_host(A);
+    const HostStore &h = A->host;
+    std::vector<HTup> t;
+    t.reserve(h.nnz());
+    for (u64 k = 0; k < h.hrow.size(); k++)
+        for (u64 q = h.hptr[k]; q < h.hptr[k + 1]; q++) t.push_back(HTup{h.hrow[k], h.hcol[q], A->valued() ? h.hval[q] : 1});
+    return t;
+}
+static inline bool tup_lt(const HTup &a, const HTup &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; }
+static inline bool tup_eq(const HTup &a, const HTup &b) { return a.r == b.r && a.c == b.c; }
+static void host_store_from(GrB_Matrix C, const std::vector<HTup> &t) {
+    HostStore h;
+    h.hptr.clear();
+    for (const HTup &x : t) {
+        if (h.hrow.empty() || h.hrow.back() != x.r) { h.hrow.push_back(x.r); h.hptr.push_back(h.hcol.size()); }
+        h.hcol.push_back(x.c);
+        if (C->valued()) h.hval.push_back(x.v);
+    }
+    h.hptr.push_back(h.hcol.size());
+    set_empty(C);
+    C->host = std::move(h);
+}
+static std::vector<HTup> host_union(const std::vector<HTup> &A, const std::vector<HTup> &B) { // overlap: B's value
+    std::vector<HTup> o;
+    o.reserve(A.size() + B.size());
+    size_t i = 0, j = 0;
+    while (i < A.size() || j < B.size()) {
+        if (j >= B.size() || (i < A.size() && tup_lt(A[i], B[j]))) o.push_back(A[i++]);
+        else if (i >= A.size() || tup_lt(B[j], A[i])) o.push_back(B[j++]);
+        else { o.push_back(B[j]); i++; j++; }
+    }
+    return o;
+}
+static std::vector<HTup> host_intersect(const std::vector<HTup> &A, const std::vector<HTup> &B) {
+    std::vector<HTup> o;
+    size_t i = 0, j = 0;
+    while (i < A.size() && j < B.size()) {
+        if (tup_lt(A[i], B[j])) i++;
+        else if (tup_lt(B[j], A[i])) j++;
+        else { o.push_back(HTup{A[i].r, A[i].c, 1}); i++; j++; }
+    }
+    return o;
+}
+static std::vector<HTup> host_filter(const std::vector<HTup> &T, const std::vector<HTup> &M, bool comp, bool structural, bool mvalued) {
+    std::vector<HTup> o;
+    size_t j = 0;
+    for (const HTup &x : T) {
+        while (j < M.size() && tup_lt(M[j], x)) j++;
+        bool in = j < M.size() && tup_eq(M[j], x) && (structural || !mvalued || M[j].v != 0);
+        if (in != comp) o.push_back(x);
+    }
+    return o;
+}
+static void host_write_back(GrB_Matrix C, std::vector<HTup> T, GrB_Matrix M, const Desc &d, bool accum) {
+    std::vector<HTup> Z = accum ? host_union(host_tuples(C), T) : std::move(T);
+    if (!M) {
+        if (d.comp) { if (d.replace) set_empty(C); return; }
+        host_store_from(C, Z);
+        return;
+    }
+    std::vector<HTup> Mt = host_tuples(M);
+    std::vector<HTup> Zm = host_filter(Z, Mt, d.comp, d.structure, M->valued());
+    if (d.replace) { host_store_from(C, Zm); return; }
+    std::vector<HTup> Ck = host_filter(host_tuples(C), Mt, !d.comp, d.structure, M->valued());
+    host_store_from(C, host_union(Ck, Zm));
+}
+
 static void check_mask_dims(GrB_Matrix C, GrB_Matrix M) {
     if (M && (M->nrows != C->nrows || M->ncols != C->ncols)) throw GrbError(GrB_DIMENSION_MISMATCH, "mask dimensions differ from C");
 }
@@ -902,7 +978,7 @@ GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryO
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         MultiLock lk{C, Mask, A, B};
-        ensure_init();
+        if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
         u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
         u64 br = d.t1 ? B->ncols : B->nrows, bc = d.t1 ? B->nrows : B->ncols;
@@ -911,6 +987,11 @@ GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryO
         check_mask_dims(C, Mask);
         if (!C->valued() && (A->valued() || B->valued()))
             throw GrbError(GrB_NOT_IMPLEMENTED, "eWiseAdd: valued -> BOOL typecast is not on the path (use apply(ONE): matrix.rs:898-905)");
+        if (is_huge(C)) {   // Tensor.me delta fold
+            if (d.t0 || d.t1) throw GrbError(GrB_NOT_IMPLEMENTED, "eWiseAdd: transposed operands on a host-resident matrix");
+            host_write_back(C, host_union(host_tuples(A), host_tuples(B)), Mask, d, false);
+            return GrB_SUCCESS;
+        }
         // frontier form: C = A u B with no mask is a word-wise OR (delta_lmxm's accum step, matrix.rs:1398-1400)
         if (!Mask && !d.comp && !d.t0 && !d.t1 && !C->valued() && (A->bits_valid || B->bits_valid) &&
             A->pending.empty() && B->pending.empty() && bits_words_for(A->nrows) != 0 &&
@@ -941,13 +1022,18 @@ GrB_Info GrB_Matrix_eWiseMult_Semiring(GrB_Matrix C, GrB_Matrix Mask, GrB_Binary
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         MultiLock lk{C, Mask, A, B};
-        ensure_init();
+        if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
         u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
         u64 br = d.t1 ? B->ncols : B->nrows, bc = d.t1 ? B->nrows : B->ncols;
         if (ar != br || ac != bc) throw GrbError(GrB_DIMENSION_MISMATCH, "eWiseMult: operand dimensions differ");
         check_same_dims(C, ar, ac, "eWiseMult");
         check_mask_dims(C, Mask);
+        if (is_huge(C)) {
+            if (d.t0 || d.t1) throw GrbError(GrB_NOT_IMPLEMENTED, "eWiseMult: transposed operands on a host-resident matrix");
+            host_write_back(C, host_intersect(host_tuples(A), host_tuples(B)), Mask, d, false);
+            return GrB_SUCCESS;
+        }
         const DevCSR *Ad = operand(A, d.t0), *Bd = operand(B, d.t1);
         DevCSR T;
         ewise_intersect(*Ad, *Bd, T);
@@ -963,7 +1049,7 @@ GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Ma
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         MultiLock lk{C, Mask, A};
-        ensure_init();
+        if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
         // T = (A^T0)' : with T0 set the double transpose is the identity (masked copy, matrix.rs:824-845)
         bool eff_transpose = !d.t0;
@@ -972,6 +1058,16 @@ GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Ma
         check_mask_dims(C, Mask);
         if (!C->valued() && A->valued())
             throw GrbError(GrB_NOT_IMPLEMENTED, "transpose: valued -> BOOL typecast is not on the path");
+        if (is_huge(C) || is_huge(A)) {
+            std::vector<HTup> T = host_tuples(A);
+            if (eff_transpose) {
+                for (HTup &x : T) std::swap(x.r, x.c);
+                std::sort(T.begin(), T.end(), tup_lt);
+            }
+            if (!C->valued()) for (HTup &x : T) x.v = 1;
+            host_write_back(C, std::move(T), Mask, d, false);
+            return GrB_SUCCESS;
+        }
         ensure_dev(A);
         DevCSR T;
         if (eff_transpose) transpose_csr(A->dev, T, C->valued());
@@ -989,11 +1085,18 @@ GrB_Info GrB_Matrix_apply(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         MultiLock lk{C, Mask, A};
-        ensure_init();
+        if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
         u64 ar = d.t0 ? A->ncols : A->nrows, ac = d.t0 ? A->nrows : A->ncols;
         check_same_dims(C, ar, ac, "apply");
         check_mask_dims(C, Mask);
+        if (is_huge(C)) {
+            if (d.t0) throw GrbError(GrB_NOT_IMPLEMENTED, "apply: transposed operand on a host-resident matrix");
+            std::vector<HTup> T = host_tuples(A);
+            for (HTup &x : T) x.v = 1;
+            host_write_back(C, std::move(T), Mask, d, accum != nullptr);
+            return GrB_SUCCESS;
+        }
         const DevCSR *Ad = operand(A, d.t0);
         DevCSR T;
         csr_copy(*Ad, T, false); // ONE: pattern of A, every value true -- A's values are never read
@@ -1348,6 +1451,30 @@ GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64
         sync_stream();
         set_dev(m, std::move(d));
         *A = m;
+        return GrB_SUCCESS;
+    });
+}
+
+// ExpandInto's per-row point lookups (expand_into.rs:195-249, Tensor::get -> GrB_Matrix_extractElement) as one batched call
+GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_Index *J, GrB_Index n, uint8_t *found,
+                                   uint64_t *values) {
+    CHECK_MAT(A); CHECK_PTR(found);
+    if (n) { CHECK_PTR(I); CHECK_PTR(J); }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        if (n == 0) return GrB_SUCCESS;
+        DevBuf<u64> dI(n), dJ(n), dV;
+        DevBuf<unsigned char> dF(n);
+        h2d(dI.ptr, (const u64 *)I, n);
+        h2d(dJ.ptr, (const u64 *)J, n);
+        if (values) dV.alloc(n);
+        probe_pairs(A->dev, dI.ptr, dJ.ptr, n, dF.ptr, values ? dV.ptr : nullptr);
+        d2h(found, dF.ptr, n);
+        if (values) d2h(values, dV.ptr, n);
+        sync_stream();
         return GrB_SUCCESS;
     });
 }

@@ -7,7 +7,7 @@
 //   destination-label post-filter                      :646-652
 // Batch/column plumbing (gather, set_column, null padding) is runtime code outside the hot path.
 #pragma once
-#include "versioned_matrix.hpp"
+#include "tensor.hpp"
 
 namespace fdb {
 
@@ -21,12 +21,25 @@ struct ExpandResult {
 
 static const size_t BATCH_SIZE = 1024; // graph/src/runtime/batch.rs:81
 
-inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std::vector<const VersionedMatrix *> &hops,
+// TraversalMatrix (cond_traverse.rs:64-90): the adjacency VersionedMatrix<bool>, or one relationship type's Tensor
+struct TraversalMatrix {
+    const VersionedMatrix *vm = nullptr;
+    const Tensor *t = nullptr;
+    TraversalMatrix(const VersionedMatrix *v) : vm(v) {}
+    TraversalMatrix(const Tensor *x) : t(x) {}
+    uint64_t ncols() const { return vm ? vm->ncols() : t->fwd_m().ncols(); }
+    void delta_lmxm_into(Matrix<bool> &f) const {                // cond_traverse.rs:77-85
+        if (vm) f.delta_lmxm(vm->m(), vm->dp(), vm->dm());
+        else f.delta_lmxm(t->fwd_m(), t->fwd_dp(), t->fwd_dm());
+    }
+};
+
+inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std::vector<TraversalMatrix> &hops,
                                  const std::vector<const VersionedMatrix *> &src_labels,
                                  const std::vector<const VersionedMatrix *> &dst_labels) {
     ExpandResult out;
     if (hops.empty() || src_ids.empty()) return out;
-    uint64_t ncols = hops[0]->ncols();
+    uint64_t ncols = hops[0].ncols();
     std::vector<uint64_t> row_idx_buf, col_idx_buf;
     row_idx_buf.reserve(src_ids.size());
     col_idx_buf.reserve(src_ids.size());
@@ -40,7 +53,7 @@ inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std
     if (row_idx_buf.empty()) return out;
     Matrix<bool> f(src_ids.size(), ncols);
     f.build(row_idx_buf, col_idx_buf);
-    for (const VersionedMatrix *h : hops) f.delta_lmxm(h->m(), h->dp(), h->dm());
+    for (const TraversalMatrix &h : hops) h.delta_lmxm_into(f);
     f.wait();                                    // flush pending mxm work before attaching the row iterator
     auto it = f.iter(0, UINT64_MAX);
     std::tuple<uint64_t, uint64_t> t;

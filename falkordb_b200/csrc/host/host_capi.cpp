@@ -167,7 +167,7 @@ static void t_motogp_two_hop() {
     for (uint64_t i : {0, 1, 2}) rider.set(i, i);
     for (uint64_t i : {3, 4, 5}) team.set(i, i);
     // MATCH (r:Rider)-[:rides]->(t:Team) WHERE t.name = 'Yamaha' RETURN r.name  => "Valentino Rossi"
-    ExpandResult one = expand_batch({0, 1, 2}, {&rides}, {&rider}, {&team});
+    ExpandResult one = expand_batch({0, 1, 2}, {TraversalMatrix(&rides)}, {&rider}, {&team});
     std::vector<uint64_t> who;
     for (size_t k = 0; k < one.dest.size(); k++) if (one.dest[k] == 3) who.push_back(one.row_idx[k]);
     REQUIRE(who.size() == 1 && who[0] == 0, "Yamaha's rider is not Valentino Rossi");
@@ -177,15 +177,158 @@ static void t_motogp_two_hop() {
     REQUIRE(yamaha == 1, "count != 1");
     // second hop through the maintained transpose: rider -> team -> team-mates
     VersionedMatrix rides_t = rides.transpose();
-    ExpandResult two = expand_batch({0, 1, 2}, {&rides, &rides_t}, {&rider}, {&rider});
+    ExpandResult two = expand_batch({0, 1, 2}, {TraversalMatrix(&rides), TraversalMatrix(&rides_t)}, {&rider}, {&rider});
     std::set<std::pair<uint64_t, uint64_t>> got;
     for (size_t k = 0; k < two.dest.size(); k++) got.insert({two.row_idx[k], two.dest[k]});
     std::set<std::pair<uint64_t, uint64_t>> want = {{0, 0}, {1, 1}, {1, 2}, {2, 1}, {2, 2}};
     REQUIRE(got == want, "2-hop team-mates differ");
     // a pending delete is honoured by the dirty-snapshot path (matrix.rs:1342-1400)
     rides.remove(2, 4);
-    ExpandResult three = expand_batch({0, 1, 2}, {&rides}, {}, {});
+    ExpandResult three = expand_batch({0, 1, 2}, {TraversalMatrix(&rides)}, {}, {});
     REQUIRE(three.dest.size() == 2, "tombstoned edge still traversed");
+}
+
+// ---- tensor.rs:1340-1669 : the per-relationship-type edge store ----
+static uint64_t count_sentinels(const Tensor &t, uint64_t pairs) {
+    uint64_t s = 0, v;
+    for (uint64_t i = 0; i < pairs; i++) if (t.eff_get(i, i + 1, &v) && v == MULTI_EDGE) s++;
+    return s;
+}
+static void t_multi_pairs_after_within_batch_duplicates() {      // tensor.rs:1340-1380
+    for (auto cfg : {std::make_pair(64ULL, 2ULL), std::make_pair(1000ULL, 2ULL), std::make_pair(1000ULL, 4ULL)}) {
+        uint64_t pairs = cfg.first, dup = cfg.second, n = pairs + 1, next_id = 0;
+        Tensor t(n, n);
+        std::vector<uint64_t> srcs, dsts, ids;
+        for (uint64_t i = 0; i < pairs; i++) for (uint64_t d = 0; d < dup; d++) { srcs.push_back(i); dsts.push_back(i + 1); ids.push_back(next_id++); }
+        t.set_all_from_slices(srcs, dsts, ids);
+        t.wait_fwd();
+        uint64_t sentinels = count_sentinels(t, pairs), derived = t.multi_pairs(), edges = 0;
+        for (uint64_t i = 0; i < pairs; i++) edges += t.get(i, i + 1).size();
+        REQUIRE(derived == sentinels, "multi_pairs disagrees (within-batch dups): " << derived << " vs " << sentinels);
+        REQUIRE(edges == pairs * dup, "lost edges: " << edges);
+        REQUIRE(t.edge_count() == edges, "edge_count " << t.edge_count() << " disagrees with a full scan " << edges);
+    }
+}
+static void t_multi_pairs_matches_the_sentinel_count() {         // tensor.rs:1382-1425
+    for (auto cfg : {std::make_pair(64ULL, 2ULL), std::make_pair(1000ULL, 3ULL), std::make_pair(2000ULL, 2ULL)}) {
+        uint64_t pairs = cfg.first, dup = cfg.second, n = pairs + 1;
+        Tensor t(n, n);
+        std::vector<uint64_t> srcs, dsts;
+        for (uint64_t i = 0; i < pairs; i++) { srcs.push_back(i); dsts.push_back(i + 1); }
+        for (uint64_t round = 0; round < dup; round++) {
+            std::vector<uint64_t> ids;
+            for (uint64_t i = 0; i < pairs; i++) ids.push_back(round * pairs + i);
+            t.set_all_from_slices(srcs, dsts, ids);
+        }
+        t.wait_fwd();
+        uint64_t sentinels = count_sentinels(t, pairs), derived = t.multi_pairs(), edges = 0;
+        for (uint64_t i = 0; i < pairs; i++) edges += t.get(i, i + 1).size();
+        REQUIRE(derived == sentinels && sentinels == pairs, "multi_pairs " << derived << " sentinels " << sentinels);
+        REQUIRE(t.edge_count() == edges && edges == pairs * dup, "edge_count " << t.edge_count() << " vs " << edges);
+    }
+}
+static void t_bulk_remove_and_extract_edge_id_zero() {           // tensor.rs:1427-1476
+    const uint64_t N = 10000;
+    Tensor t0(N + 1, N + 1);
+    std::vector<uint64_t> srcs, dsts, ids;
+    for (uint64_t i = 0; i < N; i++) { srcs.push_back(i); dsts.push_back(i + 1); ids.push_back(i); }
+    t0.set_all_from_slices(srcs, dsts, ids);
+    Tensor t = t0.dup();
+    t.flush();
+    t.fwd_m().wait();
+    REQUIRE(t.fwd_m().contains(0, 1), "edge id 0 not folded into base");
+    uint64_t v = 77;
+    REQUIRE(t.fwd_m().get(0, 1, &v) && v == 0, "edge id 0 changed value in the fold");
+    t.remove_all({std::make_tuple(0ULL, 0ULL, 1ULL), std::make_tuple(5ULL, 5ULL, 6ULL)});
+    REQUIRE(t.get(0, 1).empty(), "edge id 0 still readable");
+    REQUIRE(t.get(5, 6).empty(), "edge id 5 still readable");
+    Matrix<bool> ex = t.extract();
+    ex.wait();
+    REQUIRE(ex.contains(1, 2), "unrelated live pair (1,2) disappeared");
+    REQUIRE(!ex.contains(5, 6), "control pair (5,6) not deleted");
+    REQUIRE(!ex.contains(0, 1), "deleted pair (0,1) still present in extract: edge id 0 was typecast to false in dm");
+}
+static void t_deleting_everything_folds_the_tombstones_away() {  // tensor.rs:1503-1530
+    const uint64_t N = 10000;
+    Tensor t0(N + 1, N + 1);
+    std::vector<uint64_t> srcs, dsts, ids;
+    for (uint64_t i = 0; i < N; i++) { srcs.push_back(i); dsts.push_back(i + 1); ids.push_back(i); }
+    t0.set_all_from_slices(srcs, dsts, ids);
+    Tensor t1 = t0.dup();
+    t1.flush();
+    t1.wait_fwd();
+    REQUIRE(t1.fwd_m().nvals() == N, "adds did not fold into the base");
+    Tensor t = t1.dup();
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> rels;
+    for (uint64_t i = 0; i < N; i++) rels.push_back(std::make_tuple(i, i, i + 1));
+    t.remove_all(rels);
+    t.fold_oversized();
+    t.wait_fwd();
+    REQUIRE(t.fwd_m().nvals() == 0, "base kept its deleted entries");
+    REQUIRE(t.fwd_dm().nvals() == 0, "tombstones kept alongside the base");
+    REQUIRE(t.get(0, 1).empty(), "deleted edge still readable");
+}
+static Tensor committed_pairs(uint64_t n) {                      // tensor.rs:1534-1546
+    Tensor t(n + 1, n + 1);
+    std::vector<uint64_t> srcs, dsts, ids;
+    for (uint64_t i = 0; i < n; i++) for (int k = 0; k < 2; k++) { srcs.push_back(i); dsts.push_back(i + 1); ids.push_back(2 * i + k); }
+    t.set_all_from_slices(srcs, dsts, ids);
+    t.fold_oversized();
+    t.wait();
+    REQUIRE(t.fwd_m().nvals() == n, "sentinels not folded into the base");
+    return t.dup();
+}
+static void t_batch_demote_leaves_every_survivor_inline() {      // tensor.rs:1548-1571
+    const uint64_t N = 512;
+    Tensor t = committed_pairs(N);
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> rels;
+    for (uint64_t i = 0; i < N; i++) rels.push_back(std::make_tuple(2 * i + 1, i, i + 1));
+    auto emptied = t.remove_all(rels);
+    REQUIRE(emptied.empty(), "demoted pairs reported as emptied");
+    REQUIRE(t.edge_count() == N, "edge count after demoting every pair: " << t.edge_count());
+    REQUIRE(t.multi_pairs() == 0, "a demoted pair still counts as multi");
+    REQUIRE(t.edge_versioned().nvals() == 0, "`me` still holds ids of demoted pairs");
+    for (uint64_t i = 0; i < N; i++) { auto g = t.get(i, i + 1); REQUIRE(g.size() == 1 && g[0] == 2 * i, "pair " << i << " lost its surviving edge"); }
+}
+static void t_batch_can_demote_and_then_empty_the_same_pair() {  // tensor.rs:1573-1615
+    const uint64_t N = 512;
+    Tensor t = committed_pairs(N);
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> rels;
+    for (uint64_t i = 0; i < N; i++) {
+        rels.push_back(std::make_tuple(2 * i + 1, i, i + 1));
+        rels.push_back(std::make_tuple(2 * i + 1, i, i + 1));
+        rels.push_back(std::make_tuple(7 * N + i, i, i + 1));
+        rels.push_back(std::make_tuple(2 * i, i, i + 1));
+        rels.push_back(std::make_tuple(2 * i, i, i + 1));
+    }
+    auto emptied = t.remove_all(rels);
+    std::sort(emptied.begin(), emptied.end());
+    REQUIRE(emptied.size() == N, "every pair should be reported emptied exactly once: " << emptied.size());
+    for (uint64_t i = 0; i < N; i++) REQUIRE(emptied[i] == std::make_pair(i, i + 1), "emptied list wrong at " << i);
+    REQUIRE(t.edge_count() == 0, "edges left after removing all of them: " << t.edge_count());
+    REQUIRE(t.multi_pairs() == 0 && t.edge_versioned().nvals() == 0, "`me` still holds ids");
+    t.matrix_t().wait();
+    REQUIRE(t.matrix_t().extract().nvals() == 0, "backward adjacency kept the pairs");
+    for (uint64_t i = 0; i < N; i++) REQUIRE(t.get(i, i + 1).empty(), "pair " << i << " still readable");
+}
+// CondTraverse over a relationship tensor (TraversalMatrix::U64, cond_traverse.rs:83): the u64 edge ids -- including
+// id 0 and the MULTI_EDGE sentinel -- are never read by ANY_PAIR; only the pattern matters.
+static void t_traverse_over_tensor_operand() {
+    uint64_t n = 64;
+    Tensor t(n, n);
+    t.set_all_from_slices({0, 0, 1, 2, 2, 3}, {1, 2, 3, 3, 3, 4}, {0, 1, 2, 3, 4, 5});   // (2,3) is a multi-edge pair, edge id 0 on (0,1)
+    ExpandResult r1 = expand_batch({0, 2}, {TraversalMatrix(&t)}, {}, {});
+    std::set<std::pair<uint64_t, uint64_t>> got, want = {{0, 1}, {0, 2}, {1, 3}};
+    for (size_t k = 0; k < r1.dest.size(); k++) got.insert({r1.row_idx[k], r1.dest[k]});
+    REQUIRE(got == want, "1 hop over pending tensor deltas");
+    Tensor t2 = t.dup();
+    t2.flush();                                                   // fold: ids now live in the committed u64 base
+    t2.remove_all({std::make_tuple(0ULL, 0ULL, 1ULL)});           // tombstone the edge whose id is 0
+    ExpandResult r2 = expand_batch({0}, {TraversalMatrix(&t2), TraversalMatrix(&t2), TraversalMatrix(&t2)}, {}, {});
+    got.clear();
+    for (size_t k = 0; k < r2.dest.size(); k++) got.insert({r2.row_idx[k], r2.dest[k]});
+    want = {{0, 4}};                                              // 0 -> 2 -> 3 -> 4 ; (0,1) is gone
+    REQUIRE(got == want, "3 fused hops over a dirty tensor snapshot");
 }
 
 struct TestEntry { const char *name; void (*fn)(); };
@@ -198,6 +341,13 @@ static TestEntry TESTS[] = {
     {"delta_invariants_hold_across_mutation_sequences", t_delta_invariants_hold_across_mutation_sequences},
     {"folded_entry_deleted_and_re_added_stays_out_of_dp", t_folded_entry_deleted_and_re_added_stays_out_of_dp},
     {"motogp_two_hop", t_motogp_two_hop},
+    {"multi_pairs_after_within_batch_duplicates", t_multi_pairs_after_within_batch_duplicates},
+    {"multi_pairs_matches_the_sentinel_count", t_multi_pairs_matches_the_sentinel_count},
+    {"bulk_remove_and_extract_edge_id_zero", t_bulk_remove_and_extract_edge_id_zero},
+    {"deleting_everything_folds_the_tombstones_away", t_deleting_everything_folds_the_tombstones_away},
+    {"batch_demote_leaves_every_survivor_inline", t_batch_demote_leaves_every_survivor_inline},
+    {"batch_can_demote_and_then_empty_the_same_pair", t_batch_can_demote_and_then_empty_the_same_pair},
+    {"traverse_over_tensor_operand", t_traverse_over_tensor_operand},
 };
 
 extern "C" {
@@ -235,8 +385,9 @@ int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint6
                       void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout) {
     try {
         std::vector<uint64_t> src(src_ids, src_ids + nsrc);
-        std::vector<const VersionedMatrix *> h, sl, dl;
-        for (uint64_t k = 0; k < nhops; k++) h.push_back((const VersionedMatrix *)hops[k]);
+        std::vector<TraversalMatrix> h;
+        std::vector<const VersionedMatrix *> sl, dl;
+        for (uint64_t k = 0; k < nhops; k++) h.push_back(TraversalMatrix((const VersionedMatrix *)hops[k]));
         for (uint64_t k = 0; k < nsl; k++) sl.push_back((const VersionedMatrix *)src_labels[k]);
         for (uint64_t k = 0; k < ndl; k++) dl.push_back((const VersionedMatrix *)dst_labels[k]);
         ExpandResult r = expand_batch(src, h, sl, dl);

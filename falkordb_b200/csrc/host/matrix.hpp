@@ -77,6 +77,18 @@ class Matrix {
         GrB_Matrix_set_INT32(h->m, 0, GxB_HYPER_HASH);
         return *this;
     }
+    // matrix.rs:596-625: number of stored vectors of a hypersparse matrix, -1 otherwise
+    int64_t hyper_vector_count() const {
+        int32_t st = 0;
+        GrB_Matrix_get_INT32(h->m, &st, GxB_SPARSITY_STATUS);
+        if (st != GxB_HYPERSPARSE) return -1;
+        GxB_Iterator it = nullptr;
+        grb_ok(GxB_Iterator_new(&it), "Iterator_new");
+        grb_ok(GxB_rowIterator_attach(it, h->m, nullptr), "attach");
+        int64_t k = (int64_t)GxB_rowIterator_kount(it);
+        GxB_Iterator_free(&it);
+        return k;
+    }
     uint64_t nrows() const { GrB_Index n = 0; grb_ok(GrB_Matrix_nrows(&n, h->m), "nrows"); return n; }
     uint64_t ncols() const { GrB_Index n = 0; grb_ok(GrB_Matrix_ncols(&n, h->m), "ncols"); return n; }
     uint64_t nvals() const { GrB_Index n = 0; grb_ok(GrB_Matrix_nvals(&n, h->m), "nvals"); return n; }

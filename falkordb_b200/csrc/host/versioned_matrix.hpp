@@ -41,22 +41,23 @@ class Cow {
     M &get_mut() { if (dup_) { inner = inner.dup(); dup_ = false; } return inner; }
 };
 
-// ---- Delta<bool>, versioned_matrix.rs:214-449 ----
-class DeltaBool {
-    Cow<Matrix<bool>> layer;
+// ---- Delta<T>, versioned_matrix.rs:214-469 ----
+template <class T>
+class Delta {
+    Cow<Matrix<T>> layer;
     mutable std::atomic<uint64_t> count{0};
     uint64_t tx_nvals = 0;
     mutable std::atomic<bool> fold{false};
   public:
-    DeltaBool() {}
-    explicit DeltaBool(Matrix<bool> l) { uint64_t c = l.nvals(); l.into_hyper(); layer = Cow<Matrix<bool>>(l); count = c; }
-    DeltaBool(const DeltaBool &o) : layer(o.layer), count(o.count.load()), tx_nvals(o.tx_nvals), fold(o.fold.load()) {}
-    DeltaBool &operator=(const DeltaBool &o) { layer = o.layer; count = o.count.load(); tx_nvals = o.tx_nvals; fold = o.fold.load(); return *this; }
+    Delta() {}
+    explicit Delta(Matrix<T> l) { uint64_t c = l.nvals(); l.into_hyper(); layer = Cow<Matrix<T>>(l); count = c; }
+    Delta(const Delta &o) : layer(o.layer), count(o.count.load()), tx_nvals(o.tx_nvals), fold(o.fold.load()) {}
+    Delta &operator=(const Delta &o) { layer = o.layer; count = o.count.load(); tx_nvals = o.tx_nvals; fold = o.fold.load(); return *this; }
 
-    const Matrix<bool> &m() const { return layer.get(); }
-    DeltaBool transposed() const { DeltaBool d(*this); Matrix<bool> t = layer.get().transpose(); t.into_hyper(); d.layer = Cow<Matrix<bool>>(t); return d; }
-    DeltaBool new_version(bool f) const {
-        DeltaBool d;
+    const Matrix<T> &m() const { return layer.get(); }
+    Delta transposed() const { Delta d(*this); Matrix<T> t = layer.get().transpose(); t.into_hyper(); d.layer = Cow<Matrix<T>>(t); return d; }
+    Delta new_version(bool f) const {
+        Delta d;
         uint64_t c = get_count();
         d.layer = layer.new_version(); d.count = c; d.tx_nvals = c; d.fold = f;
         return d;
@@ -71,22 +72,80 @@ class DeltaBool {
     bool folding() const { return fold.load(std::memory_order_relaxed); }
     bool take_fold() { return fold.exchange(false, std::memory_order_relaxed) && layer.get().nvals() > 0; }
     void clear(uint64_t nrows, uint64_t ncols) {
-        Matrix<bool> e(nrows, ncols);
+        Matrix<T> e(nrows, ncols);
         e.into_hyper();
         layer.replace(e);
         count = 0; tx_nvals = 0; fold = false;
     }
-    void replace(Matrix<bool> l) { l.into_hyper(); layer.replace(l); }
+    void replace(Matrix<T> l) { l.into_hyper(); layer.replace(l); }
     void resize(uint64_t r, uint64_t c) { layer_mut().resize(r, c); }
-    Matrix<bool> &layer_mut() { return layer.get_mut(); }
+    Matrix<T> &layer_mut() { return layer.get_mut(); }
     void erase(uint64_t i, uint64_t j) { layer_mut().remove(i, j); uint64_t c = count.load(); count = c ? c - 1 : 0; }
-    void insert(uint64_t i, uint64_t j) { layer_mut().set(i, j, true); count++; }
+    void insert(uint64_t i, uint64_t j, T v = (T)1) { layer_mut().set(i, j, v); count++; }   // :416-423 / :460-468
     // self<mask> = mask n base  (versioned_matrix.rs:428-436)
     template <class TV> void tombstone_masked(const Matrix<bool> &mask, const Matrix<TV> &base) {
+        static_assert(std::is_same<T, bool>::value, "tombstones are a bool layer");
         layer_mut().template element_wise_multiply<TV>(&mask, &mask, &base);
         resync();
     }
     void remove_all(const Matrix<bool> &mask) { layer_mut().remove_all(mask); resync(); }
+};
+typedef Delta<bool> DeltaBool;
+
+// ---- effective-content iterator over three layers, versioned_matrix.rs:1116-1253 (`Iter::from_layers`) ----
+template <class T>
+class LayerIter {
+  public:
+    typedef typename Matrix<T>::Item Item;
+  private:
+    typedef std::tuple<uint64_t, uint64_t> Pos;
+    typename Matrix<T>::Iter mit, dpit;
+    Matrix<bool>::Iter dmit;
+    bool has_dp = false, has_dm = false;
+    std::optional<Item> m_next, dp_next;
+    std::optional<Pos> dm_next;
+    static Pos pos(const std::tuple<uint64_t, uint64_t> &t) { return t; }
+    static Pos pos(const std::tuple<uint64_t, uint64_t, uint64_t> &t) { return Pos(std::get<0>(t), std::get<1>(t)); }
+  public:
+    LayerIter(const Matrix<T> &m, const Matrix<T> &dp, const Matrix<bool> &dm, uint64_t min_row, uint64_t max_row) {
+        mit = m.iter(min_row, max_row);
+        if (dm.nvals() != 0) { dmit = dm.iter(min_row, max_row); has_dm = true; Pos t; if (dmit.next(t)) dm_next = t; }
+        if (dp.nvals() != 0) { dpit = dp.iter(min_row, max_row); has_dp = true; }
+    }
+    void seek(uint64_t min_row, uint64_t max_row) {
+        mit.seek(min_row, max_row);
+        m_next.reset();
+        if (has_dp) dpit.seek(min_row, max_row);
+        dp_next.reset();
+        if (has_dm) { dmit.seek(min_row, max_row); dm_next.reset(); Pos t; if (dmit.next(t)) dm_next = t; }
+    }
+    bool next(Item &out) {
+        Item t;
+        Pos d;
+        if (!m_next && mit.next(t)) m_next = t;
+        while (m_next) {
+            Pos mp = pos(*m_next);
+            while (dm_next && *dm_next < mp) { dm_next.reset(); if (has_dm && dmit.next(d)) dm_next = d; }
+            if (dm_next && *dm_next == mp) {
+                dm_next.reset();
+                if (has_dm && dmit.next(d)) dm_next = d;
+                m_next.reset();
+                if (mit.next(t)) m_next = t;
+            } else break;
+        }
+        if (!dp_next && has_dp && dpit.next(t)) dp_next = t;
+        if (m_next && dp_next) {
+            Pos mp = pos(*m_next), dpp = pos(*dp_next);
+            if (dpp <= mp) {
+                if (dpp == mp) m_next.reset();   // shadowed: dp yields the live value
+                out = *dp_next; dp_next.reset();
+            } else { out = *m_next; m_next.reset(); }
+            return true;
+        }
+        if (m_next) { out = *m_next; m_next.reset(); return true; }
+        if (dp_next) { out = *dp_next; dp_next.reset(); return true; }
+        return false;
+    }
 };
 
 // ---- VersionedMatrix<bool>, versioned_matrix.rs:480-1080 ----
@@ -196,6 +255,7 @@ class VersionedMatrix {
         wait();
         if (dp_.folding() || dm_.folding()) { needs_flush = true; flush(); }
     }
+    bool is_empty_fast() const { return m().nvals() == 0 && dp_.get_count() == 0; }
     void fold_oversized() {                                     // :972-986
         uint64_t base = m().nvals();
         bool odp = delta_dominates_base(dp_.get_count(), base), odm = delta_dominates_base(dm_.get_count(), base);
@@ -250,51 +310,8 @@ class VersionedMatrix {
         needs_flush = false;
     }
 
-    // ---- Iter: sorted 3-way merge (m \ dm) U dp, versioned_matrix.rs:1116-1253 ----
-    class Iter {
-        typedef std::tuple<uint64_t, uint64_t> Item;
-        Matrix<bool>::Iter mit, dpit, dmit;
-        bool has_dp = false, has_dm = false;
-        std::optional<Item> m_next, dp_next, dm_next;
-      public:
-        Iter(const VersionedMatrix &v, uint64_t min_row, uint64_t max_row) {
-            mit = v.m().iter(min_row, max_row);
-            if (v.dm().nvals() != 0) { dmit = v.dm().iter(min_row, max_row); has_dm = true; Item t; if (dmit.next(t)) dm_next = t; }
-            if (v.dp().nvals() != 0) { dpit = v.dp().iter(min_row, max_row); has_dp = true; }
-        }
-        void seek(uint64_t min_row, uint64_t max_row) {
-            mit.seek(min_row, max_row);
-            m_next.reset();
-            if (has_dp) dpit.seek(min_row, max_row);
-            dp_next.reset();
-            if (has_dm) { dmit.seek(min_row, max_row); dm_next.reset(); Item t; if (dmit.next(t)) dm_next = t; }
-        }
-        bool next(Item &out) {
-            Item t;
-            if (!m_next && mit.next(t)) m_next = t;
-            while (m_next) {
-                while (dm_next && *dm_next < *m_next) { dm_next.reset(); if (has_dm && dmit.next(t)) dm_next = t; }
-                if (dm_next && *dm_next == *m_next) {
-                    dm_next.reset();
-                    if (has_dm && dmit.next(t)) dm_next = t;
-                    m_next.reset();
-                    if (mit.next(t)) m_next = t;
-                } else break;
-            }
-            if (!dp_next && has_dp && dpit.next(t)) dp_next = t;
-            if (m_next && dp_next) {
-                if (*dp_next <= *m_next) {
-                    if (*dp_next == *m_next) m_next.reset();
-                    out = *dp_next; dp_next.reset();
-                } else { out = *m_next; m_next.reset(); }
-                return true;
-            }
-            if (m_next) { out = *m_next; m_next.reset(); return true; }
-            if (dp_next) { out = *dp_next; dp_next.reset(); return true; }
-            return false;
-        }
-    };
-    Iter iter(uint64_t min_row = 0, uint64_t max_row = UINT64_MAX) const { wait(); return Iter(*this, min_row, max_row); }
+    typedef LayerIter<bool> Iter;   // sorted 3-way merge (m \ dm) U dp
+    Iter iter(uint64_t min_row = 0, uint64_t max_row = UINT64_MAX) const { wait(); return Iter(m(), dp(), dm(), min_row, max_row); }
 };
 
 } // namespace fdb

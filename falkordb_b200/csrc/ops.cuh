@@ -66,6 +66,8 @@ void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 ro
                     u32 *next, u64 *host_counters);
 void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local);
 
+void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
+
 // hypersparse host form <-> dense device rowptr (ewise.cu)
 void rowptr_from_hyper(const u64 *d_hrow, const u64 *d_hptr, u64 nvec, u64 nrows, u64 *d_p);
 u64 hyper_from_rowptr(const u64 *d_p, u64 nrows, u64 nnz, DevBuf<u64> &d_hrow, DevBuf<u64> &d_hptr);

@@ -312,6 +312,15 @@ class Matrix:
         check(lib().GrB_Matrix_extractTuples_UINT64(I.ctypes.data, J.ctypes.data, X.ctypes.data, C.byref(nv), self.h))
         return I, J, X
 
+    def extract_pairs(self, rows, cols):
+        """Batched `get`: (found bool[n], values u64[n]) for the pairs (rows[t], cols[t]) -- ExpandInto's probe."""
+        rows, cols = _u64arr(rows), _u64arr(cols)
+        found = np.zeros(len(rows), np.uint8)
+        vals = np.zeros(len(rows), np.uint64)
+        check(lib().B200_Matrix_extract_pairs(self.h, rows.ctypes.data, cols.ctypes.data, len(rows), found.ctypes.data,
+                                              vals.ctypes.data))
+        return found.astype(bool), vals
+
     def prepare(self, want_transpose=True):
         check(lib().B200_Matrix_prepare(self.h, int(want_transpose)))
         return self

@@ -237,6 +237,11 @@ GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t
 GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwords, uint64_t *visited, uint64_t row_lo,
                              uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2);
 GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local);
+/* Batched point lookup: found[t] = 1 (and values[t] = A(I[t],J[t]) when `values` is non-NULL) iff the entry is stored.
+ * ExpandInto's per-row Tensor::get (graph/src/runtime/ops/expand_into.rs:195-249 -> GrB_Matrix_extractElement_UINT64)
+ * for a whole 1024-row batch in one device call; host arrays in, host arrays out. */
+GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_Index *J, GrB_Index n, uint8_t *found,
+                                   uint64_t *values);
 GrB_Info B200_sync(void);
 void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */
 /* stats: "launches", "lib_launches", "last_flops", "total_flops", "last_path", "h2d_bytes", "d2h_bytes" */

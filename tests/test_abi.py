@@ -153,3 +153,33 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle", txt, re.M), f
                 assert not re.search(r"#include\s*[\"<][^\n]*oracle", txt), f
                 assert "liborc" not in txt and "orc_" not in re.sub(r"//[^\n]*", "", txt), f
+
+
+def test_host_resident_set_ops_for_multi_edge_store():
+    """Tensor.me (2^60 x 2^60) folds its deltas with eWiseAdd(RC) / masked copy / eWiseMult like any VersionedMatrix
+    (versioned_matrix.rs:909-926, 799-816); those run on the hypersparse host form, no device involved."""
+    n = 1 << 60
+    K = (7 << 32) | 9
+    m, dp, dm = Matrix(n, n, bool), Matrix(n, n, bool), Matrix(n, n, bool)
+    m.build([K, K, K + 1, 5], [1, 2, 3, 4])
+    dp.build([K, 99], [7, 1])
+    dm.build([K], [2])
+    new_m = Matrix(n, n, bool)
+    new_m.element_wise_add(dm, m, dp, fb.Descriptor.RC)            # new_m<!dm,replace> = m u dp
+    assert list(new_m.iter()) == [(5, 4), (99, 1), (K, 1), (K, 7), (K + 1, 3)]
+    sel = Matrix(n, n, bool)
+    sel.select(dm, m)                                             # sel<!dm,replace> = m
+    assert list(sel.iter()) == [(5, 4), (K, 1), (K + 1, 3)]
+    mask = Matrix(n, n, bool)
+    mask.build([K, K, 42], [1, 2, 0])
+    tomb = Matrix(n, n, bool)
+    tomb.element_wise_multiply(mask, mask, m, None)               # tombstone_masked: dm<mask> = mask n m
+    assert list(tomb.iter()) == [(K, 1), (K, 2)]
+    assert m.intersection_nvals(mask) == 2
+    ex = Matrix(n, n, bool)
+    ex.set_pattern(None, m, None)
+    ex.remove_all(dm)
+    ex.set_pattern(None, dp, None)                                # extract(): (m \ dm) u dp
+    assert ex.nvals() == 5 and ex.contains(K, 7) and not ex.contains(K, 2)
+    t = m.transpose()
+    assert list(t.iter()) == sorted((c, r) for r, c in m.iter())

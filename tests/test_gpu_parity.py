@@ -224,7 +224,7 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
 
 
 @pytest.mark.parametrize("opts", [{"fill_cap": 64}, {"hot_pack": 0}, {"pull_kernel": 0, "hot_pack": 0}, {"pull_kernel": 0, "unroll": 1},
-                                  {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 1, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}])
+                                  {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 1, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}, {"early_exit": 2}])
 def test_bit_frontier_kernel_variants(opts):
     """every selectable kernel variant (direct-write materialise, hot-set packing on/off, merge-path pull, L2 hints)"""
     fb.set_option("bits_mode", 1)
@@ -424,3 +424,23 @@ def test_lagraph_bfs_entry_and_vxm():
     L.GrB_Vector_extractTuples_BOOL(I.ctypes.data, None, C.byref(cap), w)
     assert np.array_equal(I, A.j[A.p[src]:A.p[src + 1]])
     L.GrB_Vector_free(C.byref(u)); L.GrB_Vector_free(C.byref(w))
+
+
+def test_extract_pairs_batched_probe():
+    """ExpandInto (expand_into.rs:195-249): both endpoints bound -> one lookup per row, here one call per batch"""
+    rng = np.random.default_rng(8)
+    A = rand_csr(rng, 500, 600, 0.03, values=True)
+    d = to_dev(A)
+    r, c, x = A.tuples()
+    pick = rng.choice(A.nnz, 300, replace=False)
+    I = np.concatenate([r[pick], rng.integers(0, 500, 300).astype(np.uint64), [499, 10 ** 9]])
+    J = np.concatenate([c[pick], rng.integers(0, 600, 300).astype(np.uint64), [10 ** 9, 3]])
+    found, vals = d.extract_pairs(I, J)
+    have = {(int(a), int(b)): int(v) for a, b, v in zip(r, c, x)}
+    for t in range(len(I)):
+        key = (int(I[t]), int(J[t]))
+        assert found[t] == (key in have)
+        if found[t]:
+            assert vals[t] == have[key] == d.get(*key)
+    fb_, vb = to_dev(orc.pattern(A)).extract_pairs(I[:10], J[:10])
+    assert fb_.all() and (vb == 1).all()
