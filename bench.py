@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=24)
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--sources", type=int, default=64, help="frontier rows per batch (per GPU)")
+    ap.add_argument("--sources", type=int, default=256,
+                    help="frontier rows per batch per GPU (the reference's operator batch is <= 1024 rows, batch.rs:81)")
     ap.add_argument("--hops", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sources", type=int, default=0, help="sources per CPU sample (0 = auto: ~5 s of CPU work)")

@@ -172,11 +172,54 @@ void bfs_dist_expand(const DevCSR &Aloc, u64 row_lo, const u32 *frontier, u64 nf
     LAUNCH(k_bfs_dist_expand, grid, 256, 0, frontier, cum.ptr, start.ptr, nf, total, Aloc.j.ptr, visited, (u32 *)disc);
 }
 
+// Bottom-up step (direction-optimising BFS): every owned, still-unvisited vertex scans its in-neighbours (a row of the
+// owned block of A') for a member of the current frontier bitmap and stops at the first hit.  8 lanes per vertex.
+__global__ void __launch_bounds__(256)
+k_bfs_dist_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 nloc, u64 row_lo,
+                const u64 *__restrict__ frontier, const u64 *__restrict__ visited, u32 *__restrict__ disc,
+                u64 *__restrict__ scanned) {
+    const u32 lane8 = threadIdx.x & 7, sub = (threadIdx.x & 31) >> 3;
+    const u32 gmask = 0xFFu << (8 * sub);
+    u64 group = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    u64 ngroups = ((u64)gridDim.x * blockDim.x) >> 3;
+    u64 cnt = 0;
+    for (u64 r = group; r < nloc; r += ngroups) {
+        u64 v = row_lo + r;
+        if ((visited[v >> 6] >> (v & 63)) & 1ULL) continue;       // uniform within the 8-lane group
+        u64 s = ATp[r], e = ATp[r + 1];
+        bool found = false;
+        for (u64 qb = s; qb < e && !found; qb += 8) {
+            u64 q = qb + lane8;
+            bool hit = false;
+            if (q < e) { u32 u = ATj[q]; hit = (frontier[u >> 6] >> (u & 63)) & 1ULL; cnt++; }
+            found = __ballot_sync(gmask, hit) & gmask;
+        }
+        if (found && lane8 == 0) atomicOr(&disc[v >> 5], 1u << (v & 31));
+    }
+    if (scanned && cnt) atomicAdd((unsigned long long *)scanned, cnt);
+}
+
+void bfs_dist_pull(const DevCSR &ATloc, u64 row_lo, const u64 *frontier, const u64 *visited, u64 *disc, u64 nwords,
+                   u64 *scanned_out) {
+    CUDA_TRY(cudaMemsetAsync(disc, 0, nwords * sizeof(u64), stream()));
+    if (scanned_out) *scanned_out = 0;
+    if (ATloc.nrows == 0) return;
+    DevBuf<u64> sc(1);
+    sc.zero();
+    {
+        TimedScope ts(TK_BFS_EXPAND, 0);
+        LAUNCH(k_bfs_dist_pull, grid_for(ATloc.nrows * 8, 256, 148 * 16), 256, 0, ATloc.p.ptr, ATloc.j.ptr, ATloc.nrows, row_lo,
+               frontier, visited, (u32 *)disc, sc.ptr);
+    }
+    if (scanned_out) *scanned_out = read_scalar(sc.ptr);
+}
+
 // new = (OR over ranks of the gathered bitmaps) & ~visited ; visited |= new ; owned new vertices get their level and
 // join the next local frontier.  counters[0] = next frontier size, counters[1] = global number of new vertices.
 __global__ void __launch_bounds__(256)
 k_bfs_dist_merge(const u64 *__restrict__ gathered, int P, u64 nwords, u64 *__restrict__ visited, u64 row_lo, u64 row_hi,
-                 int *__restrict__ level_local, int lvl, u32 *__restrict__ next, u64 *__restrict__ counters) {
+                 int *__restrict__ level_local, int lvl, u32 *__restrict__ next, u64 *__restrict__ counters,
+                 u64 *__restrict__ frontier_bits) {
     u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 stride = (u64)gridDim.x * blockDim.x;
     u64 tot = 0;
@@ -185,6 +228,7 @@ k_bfs_dist_merge(const u64 *__restrict__ gathered, int P, u64 nwords, u64 *__res
         for (int g = 0; g < P; g++) d |= gathered[(u64)g * nwords + w];
         u64 old = visited[w];
         u64 nw = d & ~old;
+        if (frontier_bits) frontier_bits[w] = nw;   // the next level's frontier as a global bitmap (for the pull step)
         if (!nw) continue;
         visited[w] = old | nw;
         tot += __popcll(nw);
@@ -204,11 +248,11 @@ k_bfs_dist_merge(const u64 *__restrict__ gathered, int P, u64 nwords, u64 *__res
 }
 
 void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 row_lo, u64 row_hi, int *level_local, int lvl,
-                    u32 *next, u64 *host_counters) {
+                    u32 *next, u64 *host_counters, u64 *frontier_bits) {
     DevBuf<u64> cnt(2);
     cnt.zero();
     LAUNCH(k_bfs_dist_merge, grid_for(nwords, 256, 148 * 8), 256, 0, gathered, P, nwords, visited, row_lo, row_hi, level_local, lvl,
-           next, cnt.ptr);
+           next, cnt.ptr, frontier_bits);
     d2h(host_counters, cnt.ptr, 2);
     sync_stream();
 }

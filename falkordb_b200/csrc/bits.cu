@@ -930,9 +930,11 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     }
     DevBuf<u64> Gd;
     const u64 *Gp = nullptr;
-    // opt_early_exit: 0 never, 1 auto (dense frontiers only), 2 always
+    // opt_early_exit: 0 never, 1 auto, 2 always.  Measured on B200 (RMAT-24, hop 3): the in-loop vote pays for itself at
+    // W = 2 and 4 (hub rows saturate: pull 2.92 -> 2.56 ms and 4.07 -> 3.66 ms), costs more than it saves at W = 1
+    // (2.08 -> 3.14 ms, few rows ever hold all 64 bits) and at W >= 8; very dense frontiers always benefit.
     const bool dense_frontier = hst[0] >= (hst[1] * X.nrows) / 4;   // flops/edges = degree-weighted mean popcount of a gathered word
-    if (pull && (cx.opt_early_exit == 2 || (cx.opt_early_exit == 1 && dense_frontier))) {
+    if (pull && (cx.opt_early_exit == 2 || (cx.opt_early_exit == 1 && (dense_frontier || W == 2 || W == 4)))) {
         Gd.alloc(W);
         Gd.zero();
         if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);

@@ -31,7 +31,7 @@ __device__ __forceinline__ u64 lower_bound_u32(const u32 *__restrict__ j, u64 lo
 // ---- predicates -------------------------------------------------------------------------------
 struct MaskPred {
     const u64 *Mp; const u32 *Mj; const u64 *Mx; bool comp, structural;
-    __device__ bool operator()(u64 i, u32 c) const {
+    __device__ bool operator()(u64 i, u32 c, u64) const {
         u64 s = Mp[i], e = Mp[i + 1];
         u64 q = lower_bound_u32(Mj, s, e, c);
         bool in = (q < e && Mj[q] == c);
@@ -41,7 +41,16 @@ struct MaskPred {
 };
 struct RangePred {
     u32 ncols;
-    __device__ bool operator()(u64, u32 c) const { return c < ncols; }
+    __device__ bool operator()(u64, u32 c, u64) const { return c < ncols; }
+};
+// keep entry q of the filtered matrix iff its flag bit is set (and, for a valued mask, its own value is non-zero)
+struct FlagPred {
+    const u32 *flag; const u64 *Mx; bool structural;
+    __device__ bool operator()(u64, u32, u64 q) const {
+        bool in = (flag[q >> 5] >> (q & 31)) & 1u;
+        if (in && !structural && Mx) in = (Mx[q] != 0);
+        return in;
+    }
 };
 
 template <class Pred>
@@ -55,7 +64,7 @@ __global__ void k_rowfilter_count(const u64 *__restrict__ Tp, const u32 *__restr
         u32 c = 0;
         for (u64 q0 = s; q0 < e; q0 += 32) {
             u64 q = q0 + lane;
-            bool keep = (q < e) && pred(i, Tj[q]);
+            bool keep = (q < e) && pred(i, Tj[q], q);
             c += __popc(__ballot_sync(0xffffffffu, keep));
         }
         if (lane == 0) cnt[i] = c;
@@ -77,7 +86,7 @@ __global__ void k_rowfilter_fill(const u64 *__restrict__ Tp, const u32 *__restri
         for (u64 q0 = s; q0 < e; q0 += 32) {
             u64 q = q0 + lane;
             u32 col = (q < e) ? Tj[q] : 0u;
-            bool keep = (q < e) && pred(i, col);
+            bool keep = (q < e) && pred(i, col, q);
             u32 m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 u64 d = o + __popc(m & lt);
@@ -155,6 +164,63 @@ void csr_resize(const DevCSR &A, u64 nrows, u64 ncols, DevCSR &out) {
     }
     RangePred p{(u32)(ncols > 0xffffffffULL ? 0xffffffffULL : ncols)};
     rowfilter(A, p, nrows, ncols, true, out);
+}
+
+// ---- fused masked SpGEMM: Z = pattern(A*B) restricted to the structure of M ---------------------------------------
+// C<M> = A*B (ExpandInto-style "which of these candidate pairs are connected through k", BASELINE config 4; also the
+// non-complemented mask forms of GrB_mxm).  The output is a subset of M, so nothing outside M is ever materialised: one
+// warp per (i,k) entry of A intersects the sorted lists B(k,:) and M(i,:) (the shorter drives, binary search in the
+// longer) and sets a flag bit per mask entry; the flagged entries of M are then compacted in order.
+// Algorithmic bytes: 4*nnz(A) + 4*flops' + 4*nnz(M) + nnz(M)/8, flops' = sum over (i,k) of min(|B(k,:)|, |M(i,:)|).
+__global__ void k_row_ids(const u64 *__restrict__ p, u64 nrows, u32 *__restrict__ rid) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 r = warp; r < nrows; r += nwarps)
+        for (u64 q = p[r] + lane; q < p[r + 1]; q += 32) rid[q] = (u32)r;
+}
+__global__ void __launch_bounds__(256)
+k_masked_pairs(const u32 *__restrict__ Arid, const u32 *__restrict__ Aj, u64 nnzA, const u64 *__restrict__ Bp,
+               const u32 *__restrict__ Bj, const u64 *__restrict__ Mp, const u32 *__restrict__ Mj, u32 *__restrict__ flag) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 e = warp; e < nnzA; e += nwarps) {
+        u32 i = Arid[e], k = Aj[e];
+        u64 bs = Bp[k], be = Bp[k + 1], ms = Mp[i], me = Mp[i + 1];
+        if (bs == be || ms == me) continue;
+        if (be - bs <= me - ms) {                         // B(k,:) drives, probe M(i,:)
+            for (u64 q = bs + lane; q < be; q += 32) {
+                u32 j = Bj[q];
+                u64 pos = lower_bound_u32(Mj, ms, me, j);
+                if (pos < me && Mj[pos] == j) atomicOr(&flag[pos >> 5], 1u << (pos & 31));
+            }
+        } else {                                          // M(i,:) drives, probe B(k,:); skip already-flagged entries
+            for (u64 pz = ms + lane; pz < me; pz += 32) {
+                if ((flag[pz >> 5] >> (pz & 31)) & 1u) continue;
+                u32 j = Mj[pz];
+                u64 pos = lower_bound_u32(Bj, bs, be, j);
+                if (pos < be && Bj[pos] == j) atomicOr(&flag[pz >> 5], 1u << (pz & 31));
+            }
+        }
+    }
+}
+
+void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out) {
+    if (A.ncols != B.nrows || M.nrows != A.nrows || M.ncols != B.ncols) throw GrbError(-6, "masked mxm: dimension mismatch");
+    out.clear();
+    out.nrows = M.nrows; out.ncols = M.ncols;
+    if (A.nnz == 0 || B.nnz == 0 || M.nnz == 0) { out.p.alloc(M.nrows + 1); out.p.zero(); out.nnz = 0; return; }
+    DevBuf<u32> rid(A.nnz), flag((M.nnz + 31) / 32 + 1);
+    flag.zero();
+    LAUNCH(k_row_ids, grid_for(A.nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.nrows, rid.ptr);
+    {
+        TimedScope ts(TK_FILTER, 0);
+        LAUNCH(k_masked_pairs, grid_for(A.nnz * 32, 256, 148 * 64), 256, 0, rid.ptr, A.j.ptr, A.nnz, B.p.ptr, B.j.ptr, M.p.ptr,
+               M.j.ptr, flag.ptr);
+    }
+    FlagPred pr{flag.ptr, M.has_values() ? M.x.ptr : nullptr, structural};
+    rowfilter(M, pr, M.nrows, M.ncols, false, out);
 }
 
 // ---- union ------------------------------------------------------------------------------------

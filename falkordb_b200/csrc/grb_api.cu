@@ -946,6 +946,24 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
         const DevCSR *Ad = &A->dev, *Bd = &B->dev;
         if (d.t0) { ensure_devT(A); Ad = &A->devT; }
         if (d.t1) { ensure_devT(B); Bd = &B->devT; }
+        if (Mask && !d.comp && !accum) {
+            // C<M> = A*B: fused -- the product is only ever evaluated at M's positions (matrix-level ExpandInto)
+            ensure_dev(Mask);
+            u64 fl = spgemm_flops(*Ad, *Bd);
+            DevCSR Zm;
+            spgemm_masked(*Ad, *Bd, Mask->dev, d.structure, Zm);
+            cx.last_flops = fl; cx.total_flops += fl; cx.last_path = 6;
+            if (d.replace) set_dev(C, std::move(Zm));
+            else {
+                ensure_dev(C);
+                DevCSR Ck, U;
+                filter_by_mask(C->dev, Mask->dev, true, d.structure, Ck);
+                ewise_union(Ck, Zm, C->valued(), U);
+                set_dev(C, std::move(U));
+            }
+            if (cx.opt_sync_after_op) sync_stream();
+            return GrB_SUCCESS;
+        }
         DevCSR T;
         u64 fl = 0;
         spgemm_anypair(*Ad, *Bd, T, &fl);
@@ -1512,12 +1530,28 @@ GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t
     });
 }
 GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwords, uint64_t *visited, uint64_t row_lo,
-                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2) {
+                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2,
+                             uint64_t *frontier_bits) {
     CHECK_PTR(gathered); CHECK_PTR(counters2);
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         ensure_init();
-        bfs_dist_merge(gathered, nranks, nwords, visited, row_lo, row_hi, level_local, lvl, next_frontier, counters2);
+        bfs_dist_merge(gathered, nranks, nwords, visited, row_lo, row_hi, level_local, lvl, next_frontier, counters2, frontier_bits);
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info B200_bfs_dist_pull(GrB_Matrix ATlocal, uint64_t row_lo, const uint64_t *frontier_bits, const uint64_t *visited,
+                            uint64_t *disc, uint64_t nwords, uint64_t *scanned_out) {
+    CHECK_MAT(ATlocal);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{ATlocal};
+        ensure_init();
+        ensure_dev(ATlocal);
+        u64 sc = 0;
+        bfs_dist_pull(ATlocal->dev, row_lo, frontier_bits, visited, disc, nwords, &sc);
+        sync_stream();
+        if (scanned_out) *scanned_out = sc;
         return GrB_SUCCESS;
     });
 }

@@ -57,13 +57,17 @@ void ewise_intersect(const DevCSR &A, const DevCSR &B, DevCSR &out);            
 // keep t in T iff (t in M [and M's value != 0 unless structural]) XOR comp
 void filter_by_mask(const DevCSR &T, const DevCSR &M, bool comp, bool structural, DevCSR &out);
 void csr_resize(const DevCSR &A, u64 nrows, u64 ncols, DevCSR &out); // grow/shrink dims (drops out-of-range)
+// Z = pattern(A*B) restricted to M's structure (valued mask: entries of M with value 0 excluded unless structural)
+void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out);
 
 // bfs.cu
 void bfs_run(const DevCSR &A, u64 src, i64 max_level, i64 *d_level, i64 *d_parent, u64 *edges_traversed);
 void bfs_dist_expand(const DevCSR &Aloc, u64 row_lo, const u32 *frontier, u64 nf, const u64 *visited, u64 *disc, u64 nwords,
                      u64 *edges_out);
+void bfs_dist_pull(const DevCSR &ATloc, u64 row_lo, const u64 *frontier, const u64 *visited, u64 *disc, u64 nwords,
+                   u64 *scanned_out);
 void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 row_lo, u64 row_hi, int *level_local, int lvl,
-                    u32 *next, u64 *host_counters);
+                    u32 *next, u64 *host_counters, u64 *frontier_bits);
 void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local);
 
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);

@@ -26,20 +26,26 @@ def partition(n, rank, world):
     return lo, hi
 
 
-def run_levels(backend, n, rank, world, src, all_gather, max_level=-1):
-    """Level loop.  Returns (levels of owned vertices as int32, edges expanded by this rank, number of levels)."""
+def run_levels(backend, n, rank, world, src, all_gather, max_level=-1, pull_threshold=1 / 64):
+    """Level loop.  Returns (levels of owned vertices as int32, out-edges of the owned reached vertices, depth).
+    Direction-optimising: when the previous level discovered more than `pull_threshold * n` vertices the next level runs
+    bottom-up (owned unvisited vertices look for a frontier in-neighbour) if the backend offers it."""
     lo, hi = partition(n, rank, world)
     backend.reset(src)
     nf = 1 if lo <= src < hi else 0
-    lvl, edges = 0, 0
+    lvl, total_new = 0, 1
+    can_pull = hasattr(backend, "expand_pull") and backend.can_pull()
     while max_level < 0 or lvl < max_level:
-        edges += backend.expand(nf)
+        if can_pull and total_new > pull_threshold * n:
+            backend.expand_pull()
+        else:
+            backend.expand(nf)
         gathered = all_gather(backend.disc())
         nf, total_new = backend.merge(gathered, lvl + 1)
         if total_new == 0:
             break
         lvl += 1
-    return backend.levels(), edges, lvl
+    return backend.levels(), backend.reached_edges(), lvl
 
 
 class GpuBackend:
@@ -65,7 +71,11 @@ class GpuBackend:
         nloc = max(1, self.hi - self.lo)
         self.visited = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
         self._disc = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
+        self.frontier_bits = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
         self.level = torch.full((nloc,), -1, dtype=torch.int32, device=dev)
+        p = np.empty(self.hi - self.lo + 1, np.uint64)
+        check(self.L.B200_Matrix_export_CSR(self.A, p.ctypes.data, None, None, 0))
+        self.deg = torch.from_numpy(np.diff(p.astype(np.int64))).to(dev)
         self.fa = torch.zeros(nloc, dtype=torch.int32, device=dev)
         self.fb = torch.zeros(nloc, dtype=torch.int32, device=dev)
         self.cnt = np.zeros(2, np.uint64)
@@ -87,13 +97,28 @@ class GpuBackend:
                                                self._disc.data_ptr(), self.nwords, C.byref(e)))
         return e.value
 
+    def can_pull(self):
+        return self.AT is not None
+
+    def expand_pull(self):
+        sc = C.c_uint64(0)
+        self.check(self.L.B200_bfs_dist_pull(self.AT, self.lo, self.frontier_bits.data_ptr(), self.visited.data_ptr(),
+                                             self._disc.data_ptr(), self.nwords, C.byref(sc)))
+        return sc.value
+
+    def reached_edges(self):
+        """Graph500 edge count: out-edges of the owned vertices that were reached."""
+        lv = self.level[: self.hi - self.lo]
+        return int(self.deg[lv >= 0].sum().item()) if self.hi > self.lo else 0
+
     def disc(self):
         return self._disc
 
     def merge(self, gathered, lvl):
         self.torch.cuda.synchronize()                     # NCCL ran on torch's stream; the library has its own
         self.check(self.L.B200_bfs_dist_merge(gathered.data_ptr(), self.world, self.nwords, self.visited.data_ptr(), self.lo,
-                                              self.hi, self.level.data_ptr(), lvl, self.fb.data_ptr(), self.cnt.ctypes.data))
+                                              self.hi, self.level.data_ptr(), lvl, self.fb.data_ptr(), self.cnt.ctypes.data,
+                                              self.frontier_bits.data_ptr()))
         self.fa, self.fb = self.fb, self.fa
         return int(self.cnt[0]), int(self.cnt[1])
 

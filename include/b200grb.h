@@ -235,7 +235,11 @@ GrB_Info B200_Matrix_rmat_block(GrB_Matrix *A, int scale, uint64_t edge_factor, 
 GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t *frontier, uint64_t nf, const uint64_t *visited,
                               uint64_t *disc, uint64_t nwords, uint64_t *edges_out);
 GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwords, uint64_t *visited, uint64_t row_lo,
-                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2);
+                             uint64_t row_hi, int32_t *level_local, int32_t lvl, uint32_t *next_frontier, uint64_t *counters2,
+                             uint64_t *frontier_bits /* optional: receives the new frontier as an n-bit bitmap */);
+/* bottom-up step: owned unvisited vertices scan their in-neighbours (row block of A') for a frontier member */
+GrB_Info B200_bfs_dist_pull(GrB_Matrix ATlocal, uint64_t row_lo, const uint64_t *frontier_bits, const uint64_t *visited,
+                            uint64_t *disc, uint64_t nwords, uint64_t *scanned_out);
 GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local);
 /* Batched point lookup: found[t] = 1 (and values[t] = A(I[t],J[t]) when `values` is non-NULL) iff the entry is stored.
  * ExpandInto's per-row Tensor::get (graph/src/runtime/ops/expand_into.rs:195-249 -> GrB_Matrix_extractElement_UINT64)

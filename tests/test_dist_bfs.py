@@ -62,6 +62,9 @@ class NumpyBackend:
     def levels(self):
         return self.level
 
+    def reached_edges(self):
+        return int(np.diff(self.p)[self.level >= 0].sum())
+
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

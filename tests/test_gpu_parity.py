@@ -444,3 +444,26 @@ def test_extract_pairs_batched_probe():
             assert vals[t] == have[key] == d.get(*key)
     fb_, vb = to_dev(orc.pattern(A)).extract_pairs(I[:10], J[:10])
     assert fb_.all() and (vb == 1).all()
+
+
+def test_masked_mxm_fused_triangle_pattern():
+    """BASELINE config 4: C<L,struct> = L*L on a symmetrised lower-triangular RMAT (edges that close a wedge); the fused
+    kernel only ever evaluates the product at the mask's positions"""
+    fb.set_option("bits_mode", 0)
+    A = orc.rmat_csr(11, 8, 6)
+    S = orc.ewise_add(A, orc.transpose(A))
+    r, c, _ = S.tuples()
+    keep = r > c
+    L = orc.build_matrix(S.nrows, S.ncols, r[keep], c[keep])
+    want = orc.mxm(L, L, L, 1)
+    dL = to_dev(L)
+    C = Matrix(L.nrows, L.ncols, bool)
+    C.mxm(dL, dL, dL, Descriptor.S)
+    assert_same(C, want, "C<L> = L*L")
+    assert fb.get_stat("last_path") == 6 and want.nnz > 0
+    # no-replace form keeps C's old entries outside the mask
+    rng = np.random.default_rng(1)
+    Cold = rand_csr(rng, L.nrows, L.ncols, 0.001)
+    C2 = to_dev(Cold)
+    C2.mxm(dL, dL, dL, Descriptor.S)
+    assert_same(C2, orc.mask_assign(Cold, orc.mxm(L, L), L, False, True, False), "C<L> = L*L, no replace")
