@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--bits-mode", type=int, default=-1)
     ap.add_argument("--pull-mode", type=int, default=-1)
     ap.add_argument("--pull-kernel", type=int, default=-1, help="-1 library default, 0 = 8-lanes-per-row, 1 = merge-path")
-    ap.add_argument("--workload", default="chain", choices=["chain", "bfs"],
-                    help="chain = the headline 3-hop mxm chain; bfs = 1-D row-partitioned BFS sweep (BASELINE config 5)")
+    ap.add_argument("--workload", default="chain", choices=["chain", "bfs", "triangles"],
+                    help="chain = the headline 3-hop mxm chain; bfs = 1-D row-partitioned BFS sweep (BASELINE config 5); "
+                         "triangles = masked SpGEMM C<L> = L*L on the symmetrised lower triangle (BASELINE config 4)")
     ap.add_argument("--bfs-sources", type=int, default=16)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -324,8 +325,15 @@ def run_b200(a):
         per_launch_bytes = ks["bytes"] / ks["launches"]
         per_launch_ms = ks["ms"] / ks["launches"]
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        try:   # dram__bytes_read+write per launch from the committed ncu --set full capture of this configuration
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+            if tj["config"]["scale"] == a.scale and tj["config"]["sources"] == a.sources and tj["config"]["edge_factor"] == a.edge_factor:
+                traffic = tj["dram_bytes_per_launch"].get(dom)
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": None, "launch_ms": per_launch_ms, "launches": ks["launches"],
+                "peak_source": peak_src, "traffic": traffic, "launch_ms": per_launch_ms, "launches": ks["launches"],
                 "share_of_step": ks["ms"] / ms,
                 "algorithmic_bytes_per_launch": per_launch_bytes}
     # SURVEY 8d's row-wise formula (4 B per flop dominant) for the whole step, for reference: a frontier kernel that
@@ -451,11 +459,87 @@ def run_bfs(a):
         dist.destroy_process_group()
 
 
+def run_triangles(a):
+    """BASELINE config 4: masked ExpandInto SpGEMM, C<L,struct,replace> = L*L over ANY_PAIR with L = tril(A u A') of the
+    RMAT graph: which edges close at least one wedge.  Row blocks of the OUTPUT are independent (mask and left operand
+    are row-local), so ranks take row blocks of L as the left operand / mask with L replicated as the right operand and
+    no exchange.  TEPS = flops / time with flops = sum_{(i,k) in L_block} deg_L(k)."""
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import falkordb_b200 as fb
+    from falkordb_b200._lib import lib, check, P
+    from falkordb_b200.grb import Matrix, Descriptor
+    from falkordb_b200.dist_bfs import partition
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fb.init()
+    fb.set_option("bits_mode", 0)
+    n = 1 << a.scale
+    L_ = lib()
+    h = P()
+    check(L_.B200_Matrix_rmat_block(C.byref(h), a.scale, a.edge_factor, a.seed, 0, n, 2))
+    Lfull = Matrix(0, 0, bool, _handle=h)
+    lo, hi = partition(n, rank, world)
+    if world > 1:
+        hb = P()
+        check(L_.B200_Matrix_rmat_block(C.byref(hb), a.scale, a.edge_factor, a.seed, lo, hi, 2))
+        Lblk = Matrix(0, 0, bool, _handle=hb)
+    else:
+        Lblk = Lfull
+    stream = torch.cuda.ExternalStream(L_.B200_stream())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        Cm = Matrix(hi - lo, n, bool)
+        Cm.mxm(Lblk, Lfull, Lblk, Descriptor.RS)
+        fl = fb.get_stat("last_flops")
+        return fl, Cm.nvals()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    fb.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    flops = nnz = 0
+    for _ in range(a.steps):
+        fl, nv = step()
+        flops += fl
+        nnz += nv
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = fb.get_stat("launches")
+    if world > 1:
+        (ms,), (flops, nnz, launches) = reduce_over_ranks([ms], [flops, nnz, launches], "cuda")
+    if rank == 0:
+        print(json.dumps({
+            "metric": "traversed edges/sec (masked mxm TEPS, C<L> = L*L)", "value": flops / (ms * 1e-3), "unit": "edges/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
+            "config": {"workload": f"masked SpGEMM C<L,struct> = L*L, L = tril(A u A'), RMAT scale-{a.scale} ef{a.edge_factor}",
+                       "n": n, "nnz_L": Lfull.nvals(), "parallelism": f"row blocks of L x{world}, L replicated, no exchange"},
+            "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz / a.steps, "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "bfs":
         run_bfs(args)
+    elif args.workload == "triangles":
+        run_triangles(args)
     else:
         run_b200(args)

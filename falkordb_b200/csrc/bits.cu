@@ -386,7 +386,7 @@ template <int W, bool HINTS> __device__ __forceinline__ void or_words(u64 (&acc)
     const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p);
 #pragma unroll
     for (int w2 = 0; w2 < W / 2; w2++) {
-        ulonglong2 v = __ldg(q + w2);
+        ulonglong2 v = HINTS ? ld_v2_hint(q + w2, keep) : __ldg(q + w2);
         acc[2 * w2] |= v.x;
         acc[2 * w2 + 1] |= v.y;
     }
@@ -395,11 +395,11 @@ template <int W, bool HINTS> __device__ __forceinline__ void or_words(u64 (&acc)
 template <int W, bool HINTS, int U, bool EARLY>
 __global__ void __launch_bounds__(256)
 k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
-            u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
+            u64 *__restrict__ Y, const u64 *__restrict__ Gp, u32 hot_bytes, u32 tot_bytes) {
     const u32 lane8 = threadIdx.x & 7;
     const u32 sub = (threadIdx.x & 31) >> 3;
     const u32 gmask = 0xFFu << (8 * sub);            // the 8 lanes that share a row
-    const u64 keep = policy_keep(), strm = policy_stream();
+    const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0, strm = policy_stream();
     u64 G[W];
 #pragma unroll
     for (int w = 0; w < W; w++) G[w] = Gp ? Gp[w] : ~0ULL;
@@ -961,8 +961,11 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
             TimedScope ts(TK_BITS_PULL, 4 * AT->nnz + 8 * (m + 1) + 8ULL * W * gn + 8ULL * W * m);
             // early termination only pays when the gathered words are dense (degree-weighted mean popcount >= 1/4 of the rows)
             const bool early = Gp != nullptr;
-#define PULL_LAUNCH(H, UU) do { if (early) LAUNCH((k_bits_pull<W, H, UU, true>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp); \
-                               else LAUNCH((k_bits_pull<W, H, UU, false>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp); } while (0)
+            u64 totb = gn * W * 8;
+            const u32 tot_bytes = totb > 0xFFFFFFF0ULL ? 0xFFFFFFF0u : (u32)totb;
+            const u32 hot_bytes = (u64)cx.opt_hot_bytes < tot_bytes ? (u32)cx.opt_hot_bytes : tot_bytes;
+#define PULL_LAUNCH(H, UU) do { if (early) LAUNCH((k_bits_pull<W, H, UU, true>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp, hot_bytes, tot_bytes); \
+                               else LAUNCH((k_bits_pull<W, H, UU, false>), grid, 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, Gp, hot_bytes, tot_bytes); } while (0)
             if (cx.opt_hints) {
                 if (cx.opt_unroll >= 4) PULL_LAUNCH(true, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(true, 2); else PULL_LAUNCH(true, 1);
             } else {

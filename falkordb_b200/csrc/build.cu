@@ -212,7 +212,8 @@ __global__ void k_rmat_block_keys(int scale, u64 nedges, u64 seed, u64 k1, u64 k
             r = (r << 1) | rb; c = (c << 1) | cb;
         }
         u64 i = scramble(r, scale, k1, k2), j = scramble(c, scale, k1, k2);
-        u64 own = by_col ? j : i, other = by_col ? i : j;
+        if (by_col == 2) { u64 a = i > j ? i : j, c2 = i > j ? j : i; i = a; j = c2; }   // symmetrised lower triangle: (max, min)
+        u64 own = by_col == 1 ? j : i, other = by_col == 1 ? i : j;
         keys[e] = (i == j || own < lo || own >= hi) ? INVALID_KEY : (((own - lo) << 32) | other);
     }
 }

@@ -54,7 +54,8 @@ struct Context {
     i64 opt_timing = 0;
     i64 opt_pull_kernel = 0;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4)
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
-    i64 opt_hints = 0;             // L2 createpolicy hints in the pull kernel
+    i64 opt_hints = 0;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
+    i64 opt_hot_bytes = 64 << 20;  // size of that hot prefix
     i64 opt_hot_pack = 1;          // gather through the degree-sorted, sink-free relabelling of the frontier
     i64 opt_fill_cap = 0;          // 0 = auto; >0 forces the materialise staging capacity (test hook)
     i64 opt_unroll = 4;            // gathers in flight per lane in the 8-lane pull kernel
@@ -182,6 +183,18 @@ struct DevBits {
 #ifdef __CUDACC__
 __device__ __forceinline__ u64 policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ u64 policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+// [base, base+primary) evict_last (kept resident), the rest of [base, base+total) evict_first: the hot prefix of the
+// degree-sorted packed frontier stays in L2 while its cold tail streams through
+__device__ __forceinline__ u64 policy_range(const void *base, u32 primary_bytes, u32 total_bytes) {
+    u64 p;
+    asm volatile("createpolicy.range.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;" : "=l"(p) : "l"(base), "r"(primary_bytes), "r"(total_bytes));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_v2_hint(const ulonglong2 *p, u64 pol) {
+    ulonglong2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ u64 ld_u64_hint(const u64 *p, u64 pol) {
     u64 v; asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
 }

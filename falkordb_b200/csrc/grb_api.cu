@@ -1620,6 +1620,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "pull_kernel") c.opt_pull_kernel = value;
     else if (n == "hints") c.opt_hints = value;
     else if (n == "hot_pack") c.opt_hot_pack = value;
+    else if (n == "hot_bytes") c.opt_hot_bytes = value;
     else if (n == "early_exit") c.opt_early_exit = value;
     else if (n == "fill_cap") c.opt_fill_cap = value;
     else if (n == "unroll") c.opt_unroll = value;

@@ -224,8 +224,8 @@ GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
 /* Synthetic Graph500-style RMAT adjacency (a,b,c,d=.57,.19,.19,.05), dedupe + no self loops, built on
  * the device.  Benchmark / test input only. */
 GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed);
-/* Row block [lo,hi) of B200_Matrix_rmat's matrix ((hi-lo) x 2^scale, rows local-indexed); by_col != 0 gives the same
- * block of the TRANSPOSE.  Every rank regenerates the counter-based edge stream and keeps what it owns. */
+/* Row block [lo,hi) of B200_Matrix_rmat's matrix ((hi-lo) x 2^scale, rows local-indexed); by_col == 1 gives the same
+ * block of the TRANSPOSE, by_col == 2 of the symmetrised strictly-lower-triangular matrix L = tril(A u A') (config 4).  Every rank regenerates the counter-based edge stream and keeps what it owns. */
 GrB_Info B200_Matrix_rmat_block(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed, uint64_t lo, uint64_t hi,
                                 int by_col);
 /* 1-D row-partitioned BFS building blocks: one level = expand the owned part of the frontier into an

@@ -123,7 +123,10 @@ def test_rmat_blocks_tile_the_full_matrix():
     fb.init()
     A = orc.rmat_csr(11, 16, 5)
     T = orc.transpose(A)
-    for by_col, ref in ((0, A), (1, T)):
+    S = orc.ewise_add(A, T)
+    r, c, _ = S.tuples()
+    Lo = orc.build_matrix(S.nrows, S.ncols, r[r > c], c[r > c])     # tril(A u A'), the masked-SpGEMM operand (config 4)
+    for by_col, ref in ((0, A), (1, T), (2, Lo)):
         for lo, hi in ((0, 704), (704, 2048), (0, 2048)):
             h = P()
             check(lib().B200_Matrix_rmat_block(C.byref(h), 11, 16, 5, lo, hi, by_col))
