@@ -145,8 +145,10 @@ def run_reference(a):
         probe = pick_sources(deg, 1, max(8, cores), a.seed + 17, 0)[0]
         t0 = time.perf_counter()
         cpu_chain(orc, A, probe, a.hops)
-        per_src = (time.perf_counter() - t0) / len(probe)
-        S = int(min(256, max(cores, round(5.0 / max(per_src, 1e-6)))))
+        per_src = (time.perf_counter() - t0) / len(probe)       # wall seconds per source with every thread busy
+        # one source per thread keeps the OpenMP team busy; then bound the whole run (warm-up + K steps) to ~150 s
+        S = int(min(256, max(8, min(max(cores, round(5.0 / max(per_src, 1e-6))),
+                                   round(150.0 / ((a.steps + a.warmup) * max(per_src, 1e-6)))))))
     a.cpu_sources = S
     batches = pick_sources(deg, a.steps + a.warmup, a.cpu_sources, a.seed, 0)
     for b in batches[:a.warmup]:

@@ -198,8 +198,22 @@ k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__re
         // coalesced copy-out: warp q handles rows q, q+NW, ...
         for (u32 r = warp; r < 64; r += NW) {
             u32 s = sbase[r], cnt = sbase[r + 1] - s;
-            u32 *dst = Cj + goff[r];
-            for (u32 i = lane; i < cnt; i += 32) st_u32_stream(dst + i, (u32)(vbase + list[s + i]), strm);
+            u64 g0 = goff[r];
+            u32 *dst = Cj + g0;
+            u32 head = (u32)((4 - (g0 & 3)) & 3);            // scalar stores up to the first 16-byte boundary
+            if (head > cnt) head = cnt;
+            if (lane < head) dst[lane] = (u32)(vbase + list[s + lane]);
+            u32 nvec = (cnt - head) >> 2;                    // then one 16-byte store per 4 entries
+            uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+            const unsigned short *ls = list + s + head;
+            for (u32 i = lane; i < nvec; i += 32) {
+                uint4 v;
+                v.x = (u32)(vbase + ls[4 * i]); v.y = (u32)(vbase + ls[4 * i + 1]);
+                v.z = (u32)(vbase + ls[4 * i + 2]); v.w = (u32)(vbase + ls[4 * i + 3]);
+                __stcs(dv + i, v);
+            }
+            u32 done = head + 4 * nvec;
+            if (lane < cnt - done) dst[done + lane] = (u32)(vbase + list[s + done + lane]);
         }
         __syncthreads();
     }
@@ -432,15 +446,22 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
                         or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
                     }
                 if (qb + 8 * U < e) {   // more to come: stop if the row already holds the terminal value
+                    // cheap test every iteration (each lane's own partial saturated), exact cross-lane OR every 4th
                     bool full = true;
+                    if ((((qb - s) / (8 * U)) & 3) == 3) {
 #pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        u64 a = acc[w];
-                        a |= __shfl_xor_sync(gmask, a, 1);
-                        a |= __shfl_xor_sync(gmask, a, 2);
-                        a |= __shfl_xor_sync(gmask, a, 4);
-                        acc[w] = a;
-                        full = full && (a == G[w]);
+                        for (int w = 0; w < W; w++) {
+                            u64 a = acc[w];
+                            a |= __shfl_xor_sync(gmask, a, 1);
+                            a |= __shfl_xor_sync(gmask, a, 2);
+                            a |= __shfl_xor_sync(gmask, a, 4);
+                            acc[w] = a;
+                            full = full && (a == G[w]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; w++) full = full && (acc[w] == G[w]);
+                        full = __all_sync(gmask, full);
                     }
                     if (full) break;
                 }
@@ -475,13 +496,21 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
 
 template <int W>
 __global__ void __launch_bounds__(256)
-k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ ATp, const u32 *__restrict__ ATj,
-                 const u64 *__restrict__ X, u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
+k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ choff, u32 nlong, const u64 *__restrict__ ATp,
+                 const u32 *__restrict__ ATj, const u64 *__restrict__ X, u64 *__restrict__ Y, const u64 *__restrict__ Gp) {
     typedef cub::BlockReduce<u64, 256> Red;
     __shared__ typename Red::TempStorage ts;
-    u32 j = lrows[blockIdx.x];
+    __shared__ u32 s_li;
+    if (threadIdx.x == 0) {   // chunk -> (long row, chunk within the row): binary search in the per-row chunk prefix
+        u64 c = blockIdx.x, lo = 0, hi = nlong - 1;
+        while (lo < hi) { u64 mid = (lo + hi + 1) >> 1; if (choff[mid] <= c) lo = mid; else hi = mid - 1; }
+        s_li = (u32)lo;
+    }
+    __syncthreads();
+    const u32 li = s_li;
+    u32 j = lrows[li];
     u64 s = ATp[j], e = ATp[j + 1];
-    u64 c0 = s + (u64)blockIdx.y * LONG_CHUNK;
+    u64 c0 = s + ((u64)blockIdx.x - choff[li]) * LONG_CHUNK;
     if (c0 >= e) return;
     u64 c1 = c0 + LONG_CHUNK;
     if (c1 > e) c1 = e;
@@ -640,6 +669,13 @@ __global__ void k_flag_long(const u64 *__restrict__ p, u64 n, u32 *__restrict__ 
         if (d > mx) mx = d;
     }
     if (mx > LONG_ROW) atomicMax((unsigned long long *)maxdeg, mx);
+}
+__global__ void k_long_chunks(const u32 *__restrict__ lrows, u64 nl, const u64 *__restrict__ p, u64 *__restrict__ nch) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nl) return;
+    if (t == nl) { nch[t] = 0; return; }
+    u32 r = lrows[t];
+    nch[t] = (p[r + 1] - p[r] + LONG_CHUNK - 1) / LONG_CHUNK;
 }
 __global__ void k_scatter_flagged(const u32 *__restrict__ flag, const u64 *__restrict__ pos, u64 n, u32 *__restrict__ out) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -860,6 +896,10 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
     if (nl) {
         lr.rows.alloc(nl);
         LAUNCH(k_scatter_flagged, grid_for(n, 256, 1 << 16), 256, 0, flag.ptr, pos.ptr, n, lr.rows.ptr);
+        lr.choff.alloc(nl + 1);
+        LAUNCH(k_long_chunks, grid_for(nl + 1, 256), 256, 0, lr.rows.ptr, nl, AT.p.ptr, lr.choff.ptr);
+        exclusive_scan_u64(lr.choff.ptr, lr.choff.ptr, nl + 1);
+        lr.nchunks = read_scalar(lr.choff.ptr + nl);
     }
     if (lr.packed) {
         lr.jp.alloc(AT.nnz);
@@ -974,10 +1014,8 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
 #undef PULL_LAUNCH
         }
         if (lr->n) {
-            u32 gy = (u32)((lr->maxdeg + LONG_CHUNK - 1) / LONG_CHUNK);
-            dim3 g((u32)lr->n, gy);
             TimedScope ts(TK_BITS_PULL_LONG, 0);
-            LAUNCH((k_bits_pull_long<W>), g, 256, 0, lr->rows.ptr, AT->p.ptr, gj, gx, Y.w.ptr, Gp);
+            LAUNCH((k_bits_pull_long<W>), (u32)lr->nchunks, 256, 0, lr->rows.ptr, lr->choff.ptr, (u32)lr->n, AT->p.ptr, gj, gx, Y.w.ptr, Gp);
         }
         if (path_out) *path_out = 3;
     } else {

@@ -54,7 +54,7 @@ struct Context {
     i64 opt_timing = 0;
     i64 opt_pull_kernel = 0;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4)
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
-    i64 opt_hints = 0;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
+    i64 opt_hints = 1;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
     i64 opt_hot_bytes = 64 << 20;  // size of that hot prefix
     i64 opt_hot_pack = 1;          // gather through the degree-sorted, sink-free relabelling of the frontier
     i64 opt_fill_cap = 0;          // 0 = auto; >0 forces the materialise staging capacity (test hook)

@@ -110,7 +110,6 @@ struct GB_Iterator_opaque {
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string tl_error;
 static std::mutex g_gpu_mu; // serialises GPU submission across caller threads
-static bool g_initialised = false;
 
 template <class F>
 static GrB_Info guarded(F &&f) {
@@ -469,11 +468,10 @@ GrB_Info GxB_init(int mode, void *(*)(size_t), void *(*)(size_t, size_t), void *
     (void)mode;
     // Host containers use the C++ allocator; the user allocator hooks only matter for Redis memory
     // accounting in the reference (matrix.rs:104-107) and are accepted for signature compatibility.
-    g_initialised = true;
     return GrB_SUCCESS; // the CUDA context is created lazily by the first bulk operation
 }
 GrB_Info GrB_init(int mode) { return GxB_init(mode, nullptr, nullptr, nullptr, nullptr); }
-GrB_Info GrB_finalize(void) { g_initialised = false; return GrB_SUCCESS; }
+GrB_Info GrB_finalize(void) { return GrB_SUCCESS; }
 GrB_Info GrB_Global_set_INT32(GrB_Global, int32_t, int field) {
     if (field == GxB_JIT_C_CONTROL || field == GxB_BURBLE) return GrB_SUCCESS;
     return GrB_INVALID_VALUE;
