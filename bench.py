@@ -51,6 +51,8 @@ def parse():
                          "triangles = masked SpGEMM C<L> = L*L on the symmetrised lower triangle (BASELINE config 4)")
     ap.add_argument("--bfs-sources", type=int, default=16)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
+    ap.add_argument("--e2e-format", default="auto", choices=["auto", "csr", "bitmap"],
+                    help="result hand-off of the e2e arm: auto = Matrix.export_auto (bitmap when denser than 1/32, else CSR)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -70,6 +72,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -82,7 +91,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -95,7 +104,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the sampler is started before the warm-up (its NVML start-up stalls launches for a few ms if it lands inside the
+        # timed region); samples stamped inside the timed window are used when there are any, else the ones under warm-up
+        lines = self.lines
+        if self.t0 is not None and self.t1 is not None:
+            inside = [x for x in lines if self.t0 <= x[0] <= self.t1 + 0.1]
+            lines = inside or lines
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -242,13 +257,15 @@ def run_b200(a):
         F.build(rows, b)
         F.wait()
         F0.append(F)
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)                   # let nvidia-smi finish its start-up before anything is timed
     for i in range(a.warmup):
         chain(F0[i].dup())
     fb.set_option("timing", 1)
     fb.reset_stats()
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
+    clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     flops = 0
@@ -260,6 +277,7 @@ def run_b200(a):
         del F
     e1.record(stream)
     barrier()
+    clocks.mark_end()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
     launches = fb.get_stat("launches")
@@ -277,42 +295,92 @@ def run_b200(a):
     src_pin = [torch.from_numpy(b.astype(np.int64)).pin_memory().numpy().view(np.uint64) for b in batches]
     rows_pin = torch.from_numpy(rows.astype(np.int64)).pin_memory().numpy().view(np.uint64)
 
-    def e2e_step(i):
+    wpr = (n + 63) // 64
+    bm_pin = None
+    if a.e2e_format != "csr":
+        bm_pin = torch.empty(a.sources * wpr, dtype=torch.int64).pin_memory().numpy().view(np.uint64).reshape(a.sources, wpr)
+
+    def hops_only(F):
+        fl = 0
+        for _ in range(a.hops):
+            F.lmxm(A)
+            fl += fb.get_stat("last_flops")
+        return fl
+
+    def e2e_step(i, fmt):
+        """host sources in -> host result out through the public API; returns (flops, nvals, d2h bytes, format)"""
         F = Matrix(a.sources, n, bool)
         F.build(rows_pin, src_pin[i])          # H2D of the step's inputs inside GxB_Matrix_build_Scalar
-        fl = chain(F)
-        nv = F.nvals()
         nonlocal out_j
+        if fmt != "csr":
+            fl = hops_only(F)                  # the result stays a device bit-matrix; no CSR is built for a bitmap hand-off
+            nv = F.nvals()
+            if fmt == "bitmap" or nv * 32 > a.sources * n:
+                F.export_bitmap(bm_pin)        # D2H of the result (row-major packed bitmap)
+                return fl, nv, bm_pin.nbytes, "bitmap"
+            F.wait()
+        else:
+            fl = chain(F)
+            nv = F.nvals()
         if nv > len(out_j):
             out_j = torch.empty(int(nv * 1.2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
         fb.check(L.B200_Matrix_export_CSR(F.h, out_p.ctypes.data, out_j.ctypes.data, None, 0))  # D2H of the result
-        return fl, nv
+        return fl, nv, 8 * (a.sources + 1) + 4 * nv, "csr"
 
-    for i in range(a.warmup):
-        e2e_step(i)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    f0.record(stream)
-    e2e_flops, e2e_nnz = 0, 0
-    for i in range(a.warmup, nb):
-        fl, nv = e2e_step(i)
-        e2e_flops += fl
-        e2e_nnz += nv
-    f1.record(stream)
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)  # device clock on the library stream; spans the host-side gaps between calls too
-    e2e_wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    def e2e_run(fmt, first, last):
+        for i in range(a.warmup):
+            e2e_step(i, fmt)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        f0.record(stream)
+        tot_fl, tot_nv, tot_d2h, kinds = 0, 0, 0, set()
+        for i in range(first, last):
+            fl, nv, by, kind = e2e_step(i, fmt)
+            tot_fl += fl
+            tot_nv += nv
+            tot_d2h += by
+            kinds.add(kind)
+        f1.record(stream)
+        barrier()
+        # device clock on the library stream; spans the host-side gaps between calls too
+        return f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_wall), tot_fl, tot_nv, tot_d2h, "+".join(sorted(kinds))
+
+    e2e_ms, e2e_wall_ms, e2e_flops, e2e_nnz, e2e_d2h, e2e_kind = e2e_run(a.e2e_format, a.warmup, nb)
+    # secondary: the same arm with a CSR hand-off (3 steps), so both interchange formats are on record
+    csr_steps = min(a.steps, 3)
+    csr_ms, _, csr_flops, _, csr_d2h, _ = e2e_run("csr", a.warmup, a.warmup + csr_steps) if a.e2e_format != "csr" else (e2e_ms, 0, e2e_flops, 0, e2e_d2h, "csr")
+    if a.e2e_format == "csr":
+        csr_steps = a.steps
+    # full-size parity property between the two hand-offs: the bitmap of the last step against the CSR of the same sources
+    if e2e_kind == "bitmap":
+        Fc = Matrix(a.sources, n, bool)
+        Fc.build(rows_pin, src_pin[nb - 1])
+        chain(Fc)
+        nvc = Fc.nvals()
+        if nvc > len(out_j):
+            out_j = torch.empty(int(nvc * 1.2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        fb.check(L.B200_Matrix_export_CSR(Fc.h, out_p.ctypes.data, out_j.ctypes.data, None, 0))
+        lp = out_p.astype(np.int64)
+        pc = np.bitwise_count(bm_pin).sum(axis=1) if hasattr(np, "bitwise_count") else None
+        if pc is not None:
+            assert np.array_equal(pc.astype(np.int64), np.diff(lp)), "bitmap row populations differ from the CSR row lengths"
+        for r in (0, a.sources - 1):
+            cols = out_j[lp[r]:lp[r + 1]].astype(np.int64)
+            assert np.all((bm_pin[r, cols >> 6] >> (cols & 63).astype(np.uint64)) & np.uint64(1)), "bitmap misses CSR entries"
+        del Fc
+    else:
+        lp = out_p.astype(np.int64)
     # sortedness + checksum property of the last result (size-independent parity property, cheap)
-    lastp = out_p.astype(np.int64)
+    lastp = lp
     assert lastp[0] == 0 and np.all(np.diff(lastp) >= 0)
     r0 = out_j[lastp[0]:lastp[1]]
     assert np.all(np.diff(r0.astype(np.int64)) > 0), "row 0 of the result is not strictly ascending"
 
     # ---- reduce over ranks: time = max, work = sum ----
     if world > 1:
-        (ms, e2e_ms), w = reduce_over_ranks([ms, e2e_ms], [flops, e2e_flops, launches, nnz_out, e2e_nnz], "cuda")
-        flops, e2e_flops, launches, nnz_out, e2e_nnz = [int(x) for x in w]
+        (ms, e2e_ms, csr_ms), w = reduce_over_ranks([ms, e2e_ms, csr_ms], [flops, e2e_flops, launches, nnz_out, e2e_nnz, csr_flops], "cuda")
+        flops, e2e_flops, launches, nnz_out, e2e_nnz, csr_flops = [int(x) for x in w]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,7 +438,7 @@ def run_b200(a):
             cpu = {"value": None, "error": repr(ex)}
 
     h2d = 16 * a.sources
-    d2h = int(4 * e2e_nnz / a.steps + 8 * (a.sources + 1))
+    d2h = int(e2e_d2h / a.steps)              # per rank: counted from the buffers export_bitmap / export_CSR copy out
     line = {
         "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": flops / (ms * 1e-3), "unit": "edges/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -381,7 +449,11 @@ def run_b200(a):
                    "bits_mode": a.bits_mode, "pull_mode": a.pull_mode, "setup_s": round(setup_s, 2)},
         "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz_out / a.steps,
         "e2e": {"value": e2e_flops / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": e2e_wall_ms / a.steps},
+                "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": e2e_wall_ms / a.steps, "result_format": e2e_kind,
+                "api": "GrB_Matrix_new + GxB_Matrix_build_Scalar (host sources) -> 3 x GrB_mxm -> "
+                       + ("B200_Matrix_export_bitmap" if e2e_kind == "bitmap" else "B200_Matrix_export_CSR") + " (host result)",
+                "csr_handoff": {"value": csr_flops / (csr_ms * 1e-3), "unit": "edges/s", "steps": csr_steps,
+                                "ms_per_step": csr_ms / csr_steps, "d2h_bytes_per_step": int(csr_d2h / csr_steps)}},
         "gpu_launches": int(launches), "kernels": kstats, "roofline": roof, "roofline_survey_formula": survey,
         "cpu_baseline": cpu, "clocks": clk}
     print(json.dumps(line))

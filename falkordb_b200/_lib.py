@@ -68,6 +68,7 @@ def lib():
         "LAGr_BreadthFirstSearch_Extended": [C.POINTER(P), C.POINTER(P), P, U64, I64, I64, C.c_bool, C.c_char_p],
         "B200_Matrix_import_CSR": [C.POINTER(P), P, U64, U64, P, P, P, C.c_int],
         "B200_Matrix_export_CSR": [P, P, P, P, C.c_int],
+        "B200_Matrix_export_bitmap": [P, P, U64, C.POINTER(U64), C.c_int],
         "B200_Matrix_device_view": [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)],
         "B200_Matrix_prepare": [P, C.c_int], "B200_Matrix_rmat": [C.POINTER(P), C.c_int, U64, U64], "B200_sync": [],
         "B200_set_option": [C.c_char_p, I64],

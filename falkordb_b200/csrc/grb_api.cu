@@ -1427,6 +1427,37 @@ GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64
     });
 }
 
+GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, uint64_t *nvals_out, int location) {
+    CHECK_MAT(A);
+    if (!bits_out) { tl_error = "export_bitmap: null output"; return GrB_NULL_POINTER; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        finish_pending(A);
+        const u64 wpr = (A->ncols + 63) / 64;
+        if (words_per_row != wpr) throw GrbError(GrB_DIMENSION_MISMATCH, "export_bitmap: words_per_row must be ceil(ncols / 64)");
+        if (A->nrows && wpr > (1ULL << 36) / A->nrows) throw GrbError(GrB_OUT_OF_MEMORY, "export_bitmap: bitmap larger than 512 GiB");
+        const u64 total = A->nrows * wpr;
+        const bool from_bits = A->bits_valid && A->bits.nrows == A->nrows;
+        if (!from_bits) ensure_dev(A);
+        DevBuf<u64> stage;
+        u64 *dst = (u64 *)bits_out;
+        if (location != B200_LOC_DEVICE) { stage.alloc(total); dst = stage.ptr; }
+        if (from_bits) {
+            bits_to_rowmajor(A->bits, dst, wpr);
+            if (nvals_out) *nvals_out = bits_nvals(A->bits);
+        } else {
+            if (total) CUDA_TRY(cudaMemsetAsync(dst, 0, total * sizeof(u64), stream()));
+            csr_to_rowmajor(A->dev, dst, wpr);
+            if (nvals_out) *nvals_out = A->dev.nnz;
+        }
+        if (location != B200_LOC_DEVICE && total) d2h((u64 *)bits_out, dst, total);
+        sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax) {
     CHECK_MAT(A);
     return guarded([&]() {
@@ -1622,6 +1653,8 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "early_exit") c.opt_early_exit = value;
     else if (n == "fill_cap") c.opt_fill_cap = value;
     else if (n == "unroll") c.opt_unroll = value;
+    else if (n == "pull_grid") c.opt_pull_grid = value;
+    else if (n == "fill_kernel") c.opt_fill_kernel = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

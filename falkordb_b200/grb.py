@@ -88,6 +88,28 @@ class Matrix:
                                            None if x is None else x.ctypes.data, 0))
         return p.astype(np.int64), j, x
 
+    def export_bitmap(self, out=None):
+        """Row-major packed bitmap (B200_Matrix_export_bitmap): uint64[nrows, ceil(ncols/64)], bit (j & 63) of word j >> 6 of
+        row i set iff (i, j) is an entry.  Returns (bitmap, nvals).  `out` may be a caller (pinned) buffer of that shape."""
+        nr, nc = self.nrows(), self.ncols()
+        wpr = (nc + 63) // 64
+        if out is None:
+            out = np.empty((nr, wpr), np.uint64)
+        assert out.dtype == np.uint64 and out.size >= nr * wpr and out.flags.c_contiguous
+        nv = U64()
+        check(lib().B200_Matrix_export_bitmap(self.h, out.ctypes.data, wpr, C.byref(nv), 0))
+        return out, nv.value
+
+    def export_auto(self, out_bitmap=None):
+        """The result hand-off a traversal operator makes: bitmap when the result is denser than one entry per 32 slots
+        (1 bit per slot beats a 4-byte column index per entry), CSR otherwise -- the rule SuiteSparse applies when it
+        switches a matrix to GxB_BITMAP.  Returns ("bitmap", bitmap, nvals) or ("csr", (p, j, x), nvals)."""
+        nv = self.nvals()
+        if nv * 32 > self.nrows() * self.ncols():
+            bm, nv2 = self.export_bitmap(out_bitmap)
+            return "bitmap", bm, nv2
+        return "csr", self.export_csr(), nv
+
     def into_hyper(self):
         """matrix.rs:558-575"""
         check(lib().GrB_Matrix_set_INT32(self.h, GxB_HYPERSPARSE, GxB_SPARSITY_CONTROL))

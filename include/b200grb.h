@@ -217,6 +217,12 @@ GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, G
                                 const uint32_t *Aj, const uint64_t *Ax, int location);
 /* Export into caller buffers sized by GrB_Matrix_nrows / nvals (Ax may be NULL). */
 GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64_t *Ax, int location);
+/* Export as a row-major packed bitmap: word `bits_out[i * words_per_row + (j >> 6)]` has bit (j & 63) set iff A(i,j) is an
+ * entry; words_per_row must be ceil(ncols / 64) and every word of the nrows x words_per_row array is written.  The
+ * interchange format for dense results (SuiteSparse keeps such matrices in GxB_BITMAP form and exports them with
+ * GxB_Matrix_export_BitmapR; this is the 1-bit-per-slot equivalent): a frontier chain result that is still in device
+ * bit-matrix form is exported without ever building its CSR.  Cheaper than CSR when nvals * 32 > nrows * ncols. */
+GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, uint64_t *nvals_out, int location);
 /* Borrow the device-resident CSR (valid until A is next modified or freed). */
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax);
 /* Pre-build the cached transpose mirror used by the pull direction (done lazily otherwise). */

@@ -224,7 +224,9 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
 
 
 @pytest.mark.parametrize("opts", [{"fill_cap": 64}, {"hot_pack": 0}, {"pull_kernel": 0, "hot_pack": 0}, {"pull_kernel": 0, "unroll": 1},
-                                  {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 0, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}, {"early_exit": 2}])
+                                  {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 0, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}, {"early_exit": 2},
+                                  {"pull_kernel": 3}, {"pull_kernel": 3, "early_exit": 2, "unroll": 2}, {"pull_kernel": 3, "early_exit": 0, "hints": 0},
+                                  {"pull_kernel": 3, "pull_grid": 1}, {"pull_kernel": 0, "pull_grid": 16}, {"fill_kernel": 0}])
 def test_bit_frontier_kernel_variants(opts):
     """every selectable kernel variant (direct-write materialise, hot-set packing on/off, merge-path pull, L2 hints)"""
     fb.set_option("bits_mode", 1)
@@ -246,7 +248,7 @@ def test_bit_frontier_kernel_variants(opts):
             F.wait()
             assert_same(F, want, f"variant {opts} nsrc={nsrc}")
     finally:
-        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 0), ("hints", 1), ("early_exit", 1)):
+        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 3), ("hints", 1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 1)):
             fb.set_option(k, v)
 
 
@@ -467,3 +469,49 @@ def test_masked_mxm_fused_triangle_pattern():
     C2 = to_dev(Cold)
     C2.mxm(dL, dL, dL, Descriptor.S)
     assert_same(C2, orc.mask_assign(Cold, orc.mxm(L, L), L, False, True, False), "C<L> = L*L, no replace")
+
+
+def bitmap_of(csr):
+    """numpy restatement of the packed row-major bitmap format"""
+    wpr = (csr.ncols + 63) // 64
+    bm = np.zeros((csr.nrows, wpr), np.uint64)
+    rows = np.repeat(np.arange(csr.nrows), np.diff(csr.p))
+    np.bitwise_or.at(bm, (rows, csr.j.astype(np.int64) >> 6), np.uint64(1) << (csr.j.astype(np.uint64) & np.uint64(63)))
+    return bm
+
+
+@pytest.mark.parametrize("nsrc,ncols_log", [(64, 12), (100, 12), (257, 11), (1, 10)])
+def test_export_bitmap_of_frontier_chain(nsrc, ncols_log):
+    """the bit-matrix result of a chain leaves as a row-major bitmap without building its CSR; CSR-form matrices too"""
+    fb.set_option("bits_mode", 1)
+    A = orc.rmat_csr(ncols_log, 8, 21)
+    rng = np.random.default_rng(nsrc)
+    src = rng.choice(A.nrows, size=nsrc, replace=False)
+    F = Matrix(nsrc, A.nrows, bool)
+    F.build(np.arange(nsrc), src)
+    dA = to_dev(A)
+    want = orc.build_matrix(nsrc, A.nrows, np.arange(nsrc), src)
+    for _ in range(2):
+        F.lmxm(dA)
+        want = orc.mxm(want, A)
+    kind, bm, nv = F.export_auto()          # 2-hop results on these graphs are far denser than 1/32
+    assert kind == "bitmap" and nv == want.nnz
+    assert np.array_equal(bm, bitmap_of(want))
+    F.wait()                                 # materialise the CSR; same answer from the CSR-form path
+    assert_same(F, want, "after bitmap export")
+    G = to_dev(want)
+    bm2, nv2 = G.export_bitmap()
+    assert nv2 == want.nnz and np.array_equal(bm2, bitmap_of(want))
+
+
+def test_export_bitmap_rectangular_and_empty():
+    rng = np.random.default_rng(77)
+    for (m, n, d) in ((5, 130, 0.2), (70, 64, 0.5), (3, 1000, 0.0), (1025, 70, 0.05)):
+        M = rand_csr(rng, m, n, d)
+        bm, nv = to_dev(M).export_bitmap()
+        assert nv == M.nnz and np.array_equal(bm, bitmap_of(M))
+    with pytest.raises(Exception):
+        lib = fb.lib()
+        h = to_dev(rand_csr(rng, 4, 100, 0.1))
+        out = np.zeros(4 * 5, np.uint64)
+        fb.check(lib.B200_Matrix_export_bitmap(h.h, out.ctypes.data, 5, None, 0))   # wrong words_per_row
