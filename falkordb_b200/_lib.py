@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200grb.so")
+LIB_PATH = os.environ.get("B200GRB_LIB") or os.path.join(_HERE, "libb200grb.so")   # override: A/B builds of the same ABI
 
 INFO = {0: "GrB_SUCCESS", 1: "GrB_NO_VALUE", 7089: "GxB_EXHAUSTED", -1: "GrB_UNINITIALIZED_OBJECT",
         -2: "GrB_NULL_POINTER", -3: "GrB_INVALID_VALUE", -4: "GrB_INVALID_INDEX", -5: "GrB_DOMAIN_MISMATCH",

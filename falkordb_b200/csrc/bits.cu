@@ -627,8 +627,16 @@ k_bits_pull(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, con
 // rowptr -> col_idx batch -> X gathers; here all three stages of consecutive batches overlap: row pointers are loaded two
 // rows ahead, and the col_idx batch that follows the current one (the next 8*U entries of the same row, or the first
 // batch of the group's next row when this is the last) is in flight while the current batch gathers.
+#ifndef PIPE_MINB
+#define PIPE_MINB 0    // resident CTAs per SM the compiler must leave room for (0 = its own choice); fewer = more landing registers
+#endif
+#if PIPE_MINB > 0
+#define PIPE_BOUNDS __launch_bounds__(256, PIPE_MINB)
+#else
+#define PIPE_BOUNDS __launch_bounds__(256)
+#endif
 template <int W, bool HINTS, int U, bool EARLY>
-__global__ void __launch_bounds__(256, (W <= 4 ? 6 : W == 8 ? 4 : 3))
+__global__ void PIPE_BOUNDS
 k_bits_pull_pipe(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
                  u64 *__restrict__ Y, const u64 *__restrict__ Gp, u32 hot_bytes, u32 tot_bytes) {
     const u32 lane8 = threadIdx.x & 7;

@@ -62,19 +62,26 @@ void *pool_alloc(size_t bytes) {
     size_t cls = size_class(bytes);
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        auto it = g_free.find(cls);
-        if (it != g_free.end() && !it->second.empty()) {
+        // exact class first; large requests also take the smallest cached block of up to twice the size, so a result
+        // buffer whose size drifts from step to step (nnz of a frontier batch) reuses one block instead of growing a new
+        // multi-GB cudaMalloc per size class (each costs milliseconds inside a timed step)
+        const size_t limit = cls >= ((size_t)1 << 20) ? cls * 2 : cls;
+        for (auto it = g_free.lower_bound(cls); it != g_free.end() && it->first <= limit; ++it) {
+            if (it->second.empty()) continue;
             void *p = it->second.back();
             it->second.pop_back();
-            g_cached_bytes -= cls;
+            g_cached_bytes -= it->first;
             return p;
         }
     }
     void *p = nullptr;
+    const size_t want = cls;
+    if (cls >= ((size_t)256 << 20)) cls = size_class(cls + cls / 4);   // headroom: the next, slightly larger, request fits too
     cudaError_t e = cudaMalloc(&p, cls);
-    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once, without the headroom
         cudaGetLastError();
         pool_trim();
+        cls = want;
         e = cudaMalloc(&p, cls);
     }
     if (e != cudaSuccess) throw CudaError(e, __FILE__, __LINE__);
