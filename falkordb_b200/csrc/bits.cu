@@ -181,6 +181,94 @@ k_bits_fill_rows(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 
     }
 }
 
+// Materialise with the transposed masks kept (fill_kernel = 2, default).  k_bits_count_keep counts like k_bits_count and also
+// writes the 64 x 32 row masks of every (word column, tile) to global memory, coalesced (8 KB per tile); k_bits_fill_masks is
+// then phase B of k_bits_fill_rows alone: a warp reads one row's 32 mask words with one 128-byte load -- no second transpose,
+// no shared tile, no block barrier.  The masks cost one extra write + read of the bit-matrix (2 x 8*W*n bytes), cheap for
+// kernels that are instruction-bound, not DRAM-bound.
+__global__ void __launch_bounds__(TILE_THREADS)
+k_bits_count_keep(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, u32 *__restrict__ tc, u32 *__restrict__ Tg) {
+    __shared__ __align__(16) u32 T[64 * FILL2_TSTRIDE];
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 tile = blockIdx.x;
+    const u64 vbase = tile * TILE_V;
+    for (u32 w = 0; w < W; w++) {
+#pragma unroll
+        for (u32 g = 0; g < 2; g++) {
+            u64 v = vbase + (u64)warp * 64 + g * 32 + lane;
+            u64 word = (v < n) ? X[v * W + w] : 0ULL;
+            u32 tl = 0, th = 0;
+            if (__ballot_sync(0xffffffffu, word != 0ULL)) {
+                tl = transpose32((u32)word, lane);
+                th = transpose32((u32)(word >> 32), lane);
+            }
+            T[lane * FILL2_TSTRIDE + 2 * warp + g] = tl;
+            T[(lane + 32) * FILL2_TSTRIDE + 2 * warp + g] = th;
+        }
+        __syncthreads();
+        {   // thread (r, c4): 4 consecutive mask words of row r -> one 16-byte store; 8 threads cover the row
+            const u32 r = tid >> 3, c4 = (tid & 7) * 4;
+            uint4 q;
+            q.x = T[r * FILL2_TSTRIDE + c4]; q.y = T[r * FILL2_TSTRIDE + c4 + 1];
+            q.z = T[r * FILL2_TSTRIDE + c4 + 2]; q.w = T[r * FILL2_TSTRIDE + c4 + 3];
+            u32 c = __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            c += __shfl_xor_sync(0xffffffffu, c, 4);
+            if ((tid & 7) == 0) tc[((u64)w * 64 + r) * ntiles + tile] = c;
+            *reinterpret_cast<uint4 *>(Tg + (((u64)w * ntiles + tile) * 64 + r) * 32 + c4) = q;
+        }
+        __syncthreads();
+    }
+}
+
+static const u32 FILLM_WARPS = 8;                          // warps per CTA of k_bits_fill_masks (one list each)
+__global__ void __launch_bounds__(FILLM_WARPS * 32)
+k_bits_fill_masks(const u32 *__restrict__ Tg, u32 W, u64 ntiles, const u64 *__restrict__ off, u32 *__restrict__ Cj) {
+    __shared__ __align__(16) unsigned short lists[FILLM_WARPS][FILL2_LIST];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned short *L = lists[warp];
+    const u64 strm = policy_stream();
+    const u64 ntasks = (u64)W * ntiles * 64;               // task = (word column, tile, row), masks stored in that order
+    const u64 nwarps = (u64)gridDim.x * FILLM_WARPS;
+    u64 task = (u64)blockIdx.x * FILLM_WARPS + warp;
+    u32 mnext = task < ntasks ? __ldg(Tg + task * 32 + lane) : 0;
+    for (; task < ntasks; task += nwarps) {
+        u32 m = mnext;
+        if (task + nwarps < ntasks) mnext = __ldg(Tg + (task + nwarps) * 32 + lane);   // next task's masks in flight
+        u32 c = __popc(m), incl = c;
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const u32 cnt = __shfl_sync(0xffffffffu, incl, 31);
+        if (cnt == 0) continue;
+        const u32 r = (u32)(task & 63);
+        const u64 wt = task >> 6, w = wt / ntiles, tile = wt - w * ntiles;
+        const u32 vb = (u32)(tile * TILE_V);
+        const u64 g0 = off[(w * 64 + r) * ntiles + tile];
+        const u32 a = (u32)(g0 & 3);
+        u32 o = a + incl - c;
+        const u32 idb = lane * 32;
+        while (m) { u32 bit = __ffs(m) - 1; L[o++] = (unsigned short)(idb + bit); m &= m - 1; }
+        __syncwarp();
+        u32 *dst = Cj + (g0 - a);                           // 16-byte aligned; dst[i] <-> L[i] for i in [a, a + cnt)
+        const u32 total = a + cnt;
+        const u32 head_end = a ? (total < 4 ? total : 4) : 0;
+        if (lane >= a && lane < head_end) st_u32_stream(dst + lane, vb + L[lane], strm);
+        const u32 nfull = total >> 2;
+        const uint2 *L2 = reinterpret_cast<const uint2 *>(L);
+        uint4 *dv = reinterpret_cast<uint4 *>(dst);
+        for (u32 i = (a ? 1 : 0) + lane; i < nfull; i += 32) {
+            uint2 p = L2[i];
+            uint4 q;
+            q.x = vb + (p.x & 0xFFFFu); q.y = vb + (p.x >> 16); q.z = vb + (p.y & 0xFFFFu); q.w = vb + (p.y >> 16);
+            __stcs(dv + i, q);
+        }
+        const u32 tail = nfull * 4 > head_end ? nfull * 4 : head_end;
+        if (tail + lane < total) st_u32_stream(dst + tail + lane, vb + L[tail + lane], strm);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(TILE_THREADS)
 k_bits_fill(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 *__restrict__ off, u32 *__restrict__ Cj,
             u32 cap) {
@@ -288,9 +376,13 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     u64 ncnt = (u64)64 * W * ntiles;
     DevBuf<u32> tc(ncnt + 1);
     DevBuf<u64> off(ncnt + 1);
+    const bool keep_masks = ctx().opt_fill_kernel == 2 && ctx().opt_fill_cap <= 0;
+    DevBuf<u32> masks;
+    if (keep_masks) masks.alloc((u64)W * ntiles * 64 * 32);
     {
-        TimedScope ts(TK_BITS_COUNT, 8ULL * W * n);
-        LAUNCH(k_bits_count, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr);
+        TimedScope ts(TK_BITS_COUNT, 8ULL * W * n + (keep_masks ? 8ULL * W * ntiles * TILE_V : 0));
+        if (keep_masks) LAUNCH(k_bits_count_keep, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr, masks.ptr);
+        else LAUNCH(k_bits_count, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr);
     }
     CUDA_TRY(cudaMemsetAsync(tc.ptr + ncnt, 0, sizeof(u32), stream()));
     exclusive_scan_u32_to_u64(tc.ptr, off.ptr, ncnt + 1);
@@ -306,7 +398,9 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
             attr_set = true;
         }
         TimedScope ts(TK_BITS_FILL, 8ULL * W * n + 4 * nnz);
-        if (ctx().opt_fill_kernel == 1 && ctx().opt_fill_cap <= 0) {
+        if (keep_masks) {
+            LAUNCH(k_bits_fill_masks, (u32)ctx().num_sms * 8, FILLM_WARPS * 32, 0, masks.ptr, W, ntiles, off.ptr, C.j.ptr);
+        } else if (ctx().opt_fill_kernel == 1 && ctx().opt_fill_cap <= 0) {
             LAUNCH(k_bits_fill_rows, (u32)ntiles, TILE_THREADS, FILL2_SMEM, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
         } else {
             // staging capacity from the average (tile, word) population, 1.5x headroom, 8K-entry steps: sparse frontiers
@@ -518,7 +612,10 @@ template <int W, bool HINTS> __device__ __forceinline__ void or_words(u64 (&acc)
     if (W >= 4) {
 #pragma unroll
         for (int w4 = 0; w4 < W / 4; w4++) {
-            u64x4 v = HINTS ? ld_v4_hint(p + 4 * w4, keep) : ld_v4(p + 4 * w4);
+            // plain 256-bit loads: a cache-hint operand is not encoded for LDG.256, and the .L2::evict_last / evict_first
+            // qualifiers (hot prefix / cold tail) measured slower (1.72 vs 1.62 ms) -- with enough gathers in flight the
+            // skewed access stream keeps its hot set in L2 by itself (scripts/ubench/gather_skew.cu)
+            u64x4 v = ld_v4(p + 4 * w4);
             acc[4 * w4] |= v.a;
             acc[4 * w4 + 1] |= v.b;
             acc[4 * w4 + 2] |= v.c;
@@ -718,6 +815,208 @@ k_bits_pull_pipe(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n
 #pragma unroll
             for (int w = 0; w < W; w++)
                 if ((w & 7) == (int)lane8) { if (HINTS) st_u64_stream(Y + j * W + w, acc[w], strm); else Y[j * W + w] = acc[w]; }
+        }
+        s0 = s1; e0 = e1; s1 = s2; e1 = e2;
+    }
+}
+
+// ---------------------------------------------------------------------------- degree-binned pull (pull_kernel = 4)
+// The in-degree distribution of a power-law graph is what starves the 8-lane kernels: 86 % of the rows of A' hold <= 8
+// entries (56 % none) and ride in the same warp as rows hundreds of entries long, so most 8-lane groups idle while one
+// gathers -- and the rate of this kernel is set by the number of gathers in flight (scripts/ubench/gather_skew.cu: 240 G
+// gathers/s with every lane busy, against ~70 G/s here).  Rows are therefore binned once per matrix:
+//   small (<= SMALL_ROW) : one lane per row in natural order (k_bits_pull_small; also zero-fills empty and long rows)
+//   mid   (<= LONG_ROW)  : a list sorted by length, descending; the four 8-lane groups of a warp take ADJACENT list entries,
+//                          i.e. rows of (nearly) the same length, so they finish their batches together (k_bits_pull_mid)
+//   long                 : k_bits_pull_long, as before
+static const u32 SMALL_ROW = 8;
+
+__global__ void k_flag_mid(const u64 *__restrict__ p, u64 n, u32 *__restrict__ flag) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; r < n; r += stride) {
+        u64 d = p[r + 1] - p[r];
+        flag[r] = (d > SMALL_ROW && d <= LONG_ROW) ? 1u : 0u;
+    }
+}
+// key = (LONG_ROW - len) << 32 | row : ascending sort = length descending, row ascending inside one length
+__global__ void k_mid_keys(const u32 *__restrict__ flag, const u64 *__restrict__ pos, u64 n, const u64 *__restrict__ p,
+                           u64 *__restrict__ keys) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; r < n; r += stride)
+        if (flag[r]) keys[pos[r]] = ((LONG_ROW - (p[r + 1] - p[r])) << 32) | r;
+}
+__global__ void k_mid_unpack(const u64 *__restrict__ keys, u64 nm, const u64 *__restrict__ p, u32 *__restrict__ m_row,
+                             u32 *__restrict__ m_len, u64 *__restrict__ m_start) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    u32 r = (u32)keys[i];
+    m_row[i] = r;
+    m_start[i] = p[r];
+    m_len[i] = (u32)(p[r + 1] - p[r]);
+}
+static void build_mid_list(const DevCSR &AT, LongRows &lr) {
+    u64 n = AT.nrows;
+    lr.nm = 0;
+    lr.m_row.release(); lr.m_len.release(); lr.m_start.release();
+    if (!n) return;
+    DevBuf<u32> flag(n + 1);
+    DevBuf<u64> pos(n + 1);
+    LAUNCH(k_flag_mid, grid_for(n, 256, 1 << 16), 256, 0, AT.p.ptr, n, flag.ptr);
+    CUDA_TRY(cudaMemsetAsync(flag.ptr + n, 0, sizeof(u32), stream()));
+    exclusive_scan_u32_to_u64(flag.ptr, pos.ptr, n + 1);
+    u64 nm = read_scalar(pos.ptr + n);
+    lr.nm = nm;
+    if (!nm) return;
+    DevBuf<u64> keys(nm);
+    LAUNCH(k_mid_keys, grid_for(n, 256, 1 << 16), 256, 0, flag.ptr, pos.ptr, n, AT.p.ptr, keys.ptr);
+    sort_keys_u64(keys.ptr, nm, 46);            // LONG_ROW = 2^12: 32 row bits + 13 length bits, rounded up
+    lr.m_row.alloc(nm); lr.m_len.alloc(nm); lr.m_start.alloc(nm);
+    LAUNCH(k_mid_unpack, grid_for(nm, 256), 256, 0, keys.ptr, nm, AT.p.ptr, lr.m_row.ptr, lr.m_len.ptr, lr.m_start.ptr);
+}
+
+template <int W> __device__ __forceinline__ void store_row(u64 *dst, const u64 (&acc)[W]) {
+    if constexpr (W == 1) { dst[0] = acc[0]; }
+    else if constexpr (W == 2) { *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(acc[0], acc[1]); }
+    else {
+#pragma unroll
+        for (int w4 = 0; w4 < W / 4; w4++)
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * w4), "l"(acc[4 * w4]), "l"(acc[4 * w4 + 1]),
+                         "l"(acc[4 * w4 + 2]), "l"(acc[4 * w4 + 3]) : "memory");
+    }
+}
+
+// one lane per row, natural order: rows of <= SMALL_ROW entries are finished here, long rows are zero-filled (k_bits_pull_long
+// ORs into them), mid rows are left to k_bits_pull_mid
+template <int W, bool HINTS>
+__global__ void __launch_bounds__(256)
+k_bits_pull_small(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
+                  u64 *__restrict__ Y, u32 hot_bytes, u32 tot_bytes) {
+    const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0;
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    // three-stage pipeline per lane: row pointers two rows ahead, first col_idx batch one row ahead, gathers now
+    u64 s = 0, e = 0, s1 = 0, e1 = 0;
+    if (j < n) { s = __ldg(ATp + j); e = __ldg(ATp + j + 1); }
+    if (j + stride < n) { s1 = __ldg(ATp + j + stride); e1 = __ldg(ATp + j + stride + 1); }
+    u32 k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) k[u] = (e - s <= SMALL_ROW && s + u < e) ? __ldg(ATj + s + u) : 0xFFFFFFFFu;
+    for (; j < n; j += stride) {
+        u64 s2 = 0, e2 = 0;
+        if (j + 2 * stride < n) { s2 = __ldg(ATp + j + 2 * stride); e2 = __ldg(ATp + j + 2 * stride + 1); }
+        u32 kn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) kn[u] = (e1 - s1 <= SMALL_ROW && s1 + u < e1) ? __ldg(ATj + s1 + u) : 0xFFFFFFFFu;
+        u64 acc[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] = 0;
+        if (e - s <= SMALL_ROW) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != 0xFFFFFFFFu) or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
+            if (e - s > 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) k[u] = (s + 4 + u < e) ? __ldg(ATj + s + 4 + u) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k[u] != 0xFFFFFFFFu) or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
+            }
+        }
+        if (e - s <= SMALL_ROW || e - s > LONG_ROW) store_row<W>(Y + j * W, acc);
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = kn[u];
+        s = s1; e = e1; s1 = s2; e1 = e2;
+    }
+}
+
+// 8 lanes per mid row, rows taken from the length-sorted list; same three-stage software pipeline as k_bits_pull_pipe
+// (list entry two steps ahead, col_idx batch one step ahead, gathers now).  Step t of group g handles list entry
+// t * ngroups + g on even steps and t * ngroups + (ngroups - 1 - g) on odd ones, which evens out the totals per group.
+template <int W, bool HINTS, int U, bool EARLY>
+__global__ void PIPE_BOUNDS
+k_bits_pull_mid(const u32 *__restrict__ m_row, const u64 *__restrict__ m_start, const u32 *__restrict__ m_len, u64 nm,
+                const u32 *__restrict__ ATj, const u64 *__restrict__ X, u64 *__restrict__ Y, const u64 *__restrict__ Gp,
+                u32 hot_bytes, u32 tot_bytes) {
+    const u32 lane8 = threadIdx.x & 7;
+    const u32 sub = (threadIdx.x & 31) >> 3;
+    const u32 gmask = 0xFFu << (8 * sub);
+    const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0, strm = policy_stream();
+    u64 G[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) G[w] = (EARLY && Gp) ? Gp[w] : ~0ULL;
+    const u64 ngroups = ((u64)gridDim.x * blockDim.x) >> 3;
+    const u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const u64 steps = (nm + ngroups - 1) / ngroups;
+    auto entry = [&](u64 t) -> u64 { return t * ngroups + ((t & 1) ? ngroups - 1 - g : g); };
+    auto fetch = [&](u64 t, u64 &s, u64 &e) {
+        s = 0; e = 0;
+        if (t < steps) { u64 i = entry(t); if (i < nm) { s = m_start[i]; e = s + m_len[i]; } }
+    };
+    u64 s0, e0, s1, e1;
+    fetch(0, s0, e0);
+    fetch(1, s1, e1);
+    u32 k[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { u64 q = s0 + lane8 + 8 * u; k[u] = (q < e0) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+    for (u64 t = 0; t < steps; t++) {
+        u64 s2, e2;
+        fetch(t + 2, s2, e2);
+        u64 acc[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] = 0;
+        u64 qb = s0;
+        u32 it = 0;
+        while (true) {
+            const bool more = qb + 8 * U < e0;
+            const u64 nb = more ? qb + 8 * U : s1, ne = more ? e0 : e1;
+            u32 kn[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { u64 q = nb + lane8 + 8 * u; kn[u] = (q < ne) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (k[u] != 0xFFFFFFFFu) or_words<W, HINTS>(acc, X + (u64)k[u] * W, keep);
+#pragma unroll
+            for (int u = 0; u < U; u++) k[u] = kn[u];
+            if (!more) break;
+            if (EARLY) {
+                bool full = true;
+                if ((it & 3) == 3) {
+#pragma unroll
+                    for (int w = 0; w < W; w++) {
+                        u64 a = acc[w];
+                        a |= __shfl_xor_sync(gmask, a, 1);
+                        a |= __shfl_xor_sync(gmask, a, 2);
+                        a |= __shfl_xor_sync(gmask, a, 4);
+                        acc[w] = a;
+                        full = full && (a == G[w]);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W; w++) full = full && (acc[w] == G[w]);
+                    full = __all_sync(gmask, full);
+                }
+                if (full) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) { u64 q = s1 + lane8 + 8 * u; k[u] = (q < e1) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+                    break;
+                }
+            }
+            qb += 8 * U;
+            it++;
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 a = acc[w];
+            a |= __shfl_xor_sync(gmask, a, 1);
+            a |= __shfl_xor_sync(gmask, a, 2);
+            a |= __shfl_xor_sync(gmask, a, 4);
+            acc[w] = a;
+        }
+        if (e0 > s0 && lane8 == 0) {
+            const u64 i = entry(t);
+            store_row<W>(Y + (u64)m_row[i] * W, acc);
         }
         s0 = s1; e0 = e1; s1 = s2; e1 = e2;
     }
@@ -1138,6 +1437,7 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
         exclusive_scan_u64(lr.choff.ptr, lr.choff.ptr, nl + 1);
         lr.nchunks = read_scalar(lr.choff.ptr + nl);
     }
+    build_mid_list(AT, lr);
     if (lr.packed) {
         lr.jp.alloc(AT.nnz);
         LAUNCH(k_relabel_cols, grid_for(AT.nnz, 256, 148 * 32), 256, 0, AT.j.ptr, AT.nnz, lr.slot.ptr, lr.jp.ptr);
@@ -1242,6 +1542,26 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
             const u32 hot_bytes = (u64)cx.opt_hot_bytes < tot_bytes ? (u32)cx.opt_hot_bytes : tot_bytes;
             // grid = every CTA resident at once (occupancy x SMs) unless pull_grid overrides it: rows are dealt round-robin to
             // 8-lane groups, so one full wave keeps all SMs busy to the end (measured: 3.41 ms at 16 CTAs/SM, 3.12 ms resident)
+            if (cx.opt_pull_kernel == 4) {
+                auto occ = [&](auto kern) {
+                    int per_sm = 0;
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+                    if (per_sm < 1) per_sm = 1;
+                    if (cx.opt_pull_grid > 0) per_sm = (int)cx.opt_pull_grid;
+                    return (u32)cx.num_sms * (u32)per_sm;
+                };
+                auto small = [&](auto kern) { LAUNCH(kern, grid_for(m, 256, (u64)cx.num_sms * 32), 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, hot_bytes, tot_bytes); };
+                auto mid = [&](auto kern) {
+                    if (lr->nm) LAUNCH(kern, occ(kern), 256, 0, lr->m_row.ptr, lr->m_start.ptr, lr->m_len.ptr, lr->nm, gj, gx, Y.w.ptr, Gp, hot_bytes, tot_bytes);
+                };
+#define MID_LAUNCH(H) do { \
+        if (cx.opt_unroll >= 8) { if (early) mid(k_bits_pull_mid<W, H, 8, true>); else mid(k_bits_pull_mid<W, H, 8, false>); } \
+        else if (cx.opt_unroll >= 4) { if (early) mid(k_bits_pull_mid<W, H, 4, true>); else mid(k_bits_pull_mid<W, H, 4, false>); } \
+        else { if (early) mid(k_bits_pull_mid<W, H, 2, true>); else mid(k_bits_pull_mid<W, H, 2, false>); } } while (0)
+                if (cx.opt_hints) { small(k_bits_pull_small<W, true>); MID_LAUNCH(true); }
+                else { small(k_bits_pull_small<W, false>); MID_LAUNCH(false); }
+#undef MID_LAUNCH
+            } else {
             auto go = [&](auto kern) {
                 int per_sm = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
@@ -1259,6 +1579,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
                 if (cx.opt_unroll >= 4) PULL_LAUNCH(false, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(false, 2); else PULL_LAUNCH(false, 1);
             }
 #undef PULL_LAUNCH
+            }
         }
         if (lr->n) {
             TimedScope ts(TK_BITS_PULL_LONG, 0);

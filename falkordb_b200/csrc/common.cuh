@@ -52,13 +52,13 @@ struct Context {
     i64 opt_bits_min_flops = 1 << 22;     // auto mode: use bit-frontier when flops >= this
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
-    i64 opt_pull_kernel = 3;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4), 3 = pipelined 8-lane
+    i64 opt_pull_kernel = 4;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4), 3 = pipelined 8-lane, 4 = degree-binned (small / mid / long)
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
     i64 opt_hints = 1;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
     i64 opt_hot_bytes = 64 << 20;  // size of that hot prefix
     i64 opt_hot_pack = 1;          // gather through the degree-sorted, sink-free relabelling of the frontier
     i64 opt_fill_cap = 0;          // 0 = auto; >0 forces the materialise staging capacity (test hook)
-    i64 opt_fill_kernel = 1;       // materialise: 0 = block-staged lists, 1 = row-per-warp lists with 16-byte stores
+    i64 opt_fill_kernel = 1;       // materialise: 0 = block-staged lists, 1 = row-per-warp lists (default), 2 = row-per-warp from kept masks (slower: 1.92 vs 1.47 ms)
     i64 opt_pull_grid = 0;         // CTAs per SM of the grid-stride pull kernels (0 = occupancy: one resident wave)
     i64 opt_unroll = 4;            // gathers in flight per lane in the 8-lane pull kernel
 };
@@ -202,12 +202,6 @@ struct u64x4 { u64 a, b, c, d; };
 __device__ __forceinline__ u64x4 ld_v4(const u64 *p) {
     u64x4 v;
     asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ u64x4 ld_v4_hint(const u64 *p, u64 pol) {
-    u64x4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ u64 ld_u64_hint(const u64 *p, u64 pol) {

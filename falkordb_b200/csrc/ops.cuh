@@ -28,6 +28,7 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u32> rows; u64 n = 0; u64 maxdeg = 0;      // rows of A' longer than LONG_ROW
     DevBuf<u64> choff; u64 nchunks = 0;               // chunk table of those rows (prefix of ceil(len / LONG_CHUNK))
     DevBuf<u64> mp_r;                                  // merge-path coordinates of every 256th diagonal
+    DevBuf<u32> m_row, m_len; DevBuf<u64> m_start; u64 nm = 0;   // mid rows (SMALL_ROW < len <= LONG_ROW), longest first
     DevBuf<u32> jp;                                    // relabelled col_idx of A' (all rows)
     // hot-set packing: vertices with out-edges, by out-degree descending
     DevBuf<u32> vert, slot; u64 n1 = 0; bool packed = false;
@@ -37,7 +38,7 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u64> rp_s; DevBuf<u32> jp_s, wstart; u64 nwin = 0, nnz_s = 0;
     DevBuf<u32> lrows, jp_l; DevBuf<u64> lrp; u64 nlong = 0, maxlong = 0;
     void clear() {
-        built = false; rows.release(); n = 0; maxdeg = 0; choff.release(); nchunks = 0; mp_r.release(); jp.release();
+        built = false; rows.release(); n = 0; maxdeg = 0; choff.release(); nchunks = 0; mp_r.release(); jp.release(); m_row.release(); m_len.release(); m_start.release(); nm = 0;
         vert.release(); slot.release(); n1 = 0; packed = false;
         sW = 0; swin = 0; s_packed = false; rp_s.release(); jp_s.release(); wstart.release(); nwin = 0; nnz_s = 0;
         lrows.release(); jp_l.release(); lrp.release(); nlong = 0; maxlong = 0;
