@@ -102,9 +102,26 @@ struct GB_Vector_opaque {
 
 struct GB_Iterator_opaque {
     GrB_Matrix A = nullptr;
-    u64 k = 0; // vector (non-empty row) position
-    u64 q = 0; // entry position
+    u64 k = 0; // vector (non-empty row) position; the row itself in bitmap mode
+    u64 q = 0; // entry position; the column itself in bitmap mode
     bool exhausted = true;
+    // bitmap mode: a dense frontier-chain result is walked from a row-major packed bitmap snapshot (1 bit per slot over
+    // PCIe instead of a 64-bit column index per entry); same ascending (row, col) order as the sparse walk
+    bool bitmap = false;
+    u64 wpr = 0, nrows = 0, ncols = 0;
+    std::vector<u64> bm;
+    // first set bit of `row` at column >= from, or ncols
+    u64 first_set(u64 row, u64 from) const {
+        if (from >= ncols) return ncols;
+        const u64 *w = bm.data() + row * wpr;
+        u64 i = from >> 6;
+        u64 cur = w[i] & (~0ULL << (from & 63));
+        while (true) {
+            if (cur) { u64 c = (i << 6) + (u64)__builtin_ctzll(cur); return c < ncols ? c : ncols; }
+            if (++i >= wpr) return ncols;
+            cur = w[i];
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -1130,13 +1147,29 @@ GrB_Info GxB_rowIterator_attach(GxB_Iterator it, GrB_Matrix A, GrB_Descriptor) {
     return guarded([&]() {
         std::lock_guard<std::mutex> g(g_gpu_mu);
         MultiLock lk{A};
-        if (!A->host_valid || !A->pending.empty()) ensure_host(A);
         it->A = A; it->k = 0; it->q = 0; it->exhausted = true;
+        it->bitmap = false; it->bm.clear(); it->bm.shrink_to_fit();
+        if (A->pending.empty() && !A->host_valid && A->bits_valid && A->bits.nrows == A->nrows && !A->valued() && !is_huge(A)) {
+            ensure_init();
+            const u64 nv = A->dev_valid ? A->dev.nnz : bits_nvals(A->bits);
+            if (A->nrows && A->ncols && nv > (A->nrows * A->ncols) / 32) {   // denser than one entry per 32 slots
+                const u64 wpr = (A->ncols + 63) / 64;
+                it->bm.resize(A->nrows * wpr);
+                DevBuf<u64> stage(A->nrows * wpr);
+                bits_to_rowmajor(A->bits, stage.ptr, wpr);
+                d2h(it->bm.data(), stage.ptr, A->nrows * wpr);
+                sync_stream();
+                it->bitmap = true; it->wpr = wpr; it->nrows = A->nrows; it->ncols = A->ncols;
+                return GrB_SUCCESS;
+            }
+        }
+        if (!A->host_valid || !A->pending.empty()) ensure_host(A);
         return GrB_SUCCESS;
     });
 }
 GrB_Index GxB_rowIterator_kount(GxB_Iterator it) {
     if (!it || !it->A) return 0;
+    if (it->bitmap) return it->nrows;
     GrB_Matrix A = it->A;
     int32_t st = GxB_SPARSE;
     GrB_Matrix_get_INT32(A, &st, GxB_SPARSITY_STATUS);
@@ -1146,6 +1179,14 @@ GrB_Index GxB_rowIterator_kount(GxB_Iterator it) {
 // reference loops over GrB_NO_VALUE rows anyway, matrix.rs:1523-1531)
 GrB_Info GxB_rowIterator_seekRow(GxB_Iterator it, GrB_Index row) {
     CHECK_PTR(it); CHECK_PTR(it->A);
+    if (it->bitmap) {
+        for (u64 r = row; r < it->nrows; r++) {
+            u64 c = it->first_set(r, 0);
+            if (c < it->ncols) { it->k = r; it->q = c; it->exhausted = false; return GrB_SUCCESS; }
+        }
+        it->exhausted = true;
+        return GxB_EXHAUSTED;
+    }
     const HostStore &h = it->A->host;
     u64 k = (u64)(std::lower_bound(h.hrow.begin(), h.hrow.end(), row) - h.hrow.begin());
     it->k = k;
@@ -1156,6 +1197,10 @@ GrB_Info GxB_rowIterator_seekRow(GxB_Iterator it, GrB_Index row) {
 }
 GrB_Info GxB_rowIterator_nextRow(GxB_Iterator it) {
     CHECK_PTR(it); CHECK_PTR(it->A);
+    if (it->bitmap) {
+        if (it->exhausted) return GxB_EXHAUSTED;
+        return GxB_rowIterator_seekRow(it, it->k + 1);
+    }
     const HostStore &h = it->A->host;
     if (it->exhausted) return GxB_EXHAUSTED;
     it->k++;
@@ -1165,6 +1210,12 @@ GrB_Info GxB_rowIterator_nextRow(GxB_Iterator it) {
 }
 GrB_Info GxB_rowIterator_nextCol(GxB_Iterator it) {
     CHECK_PTR(it); CHECK_PTR(it->A);
+    if (it->bitmap) {
+        if (it->exhausted) return GxB_EXHAUSTED;
+        u64 c = it->first_set(it->k, it->q + 1);
+        if (c < it->ncols) { it->q = c; return GrB_SUCCESS; }
+        return GrB_NO_VALUE;
+    }
     const HostStore &h = it->A->host;
     if (it->exhausted) return GxB_EXHAUSTED;
     if (it->q + 1 < h.hptr[it->k + 1]) { it->q++; return GrB_SUCCESS; }
@@ -1172,16 +1223,19 @@ GrB_Info GxB_rowIterator_nextCol(GxB_Iterator it) {
 }
 GrB_Index GxB_rowIterator_getRowIndex(GxB_Iterator it) {
     if (!it || !it->A) return 0;
+    if (it->bitmap) return it->exhausted ? it->nrows : it->k;
     const HostStore &h = it->A->host;
     if (it->exhausted || it->k >= h.hrow.size()) return it->A->nrows; // SuiteSparse returns nrows when exhausted
     return h.hrow[it->k];
 }
 GrB_Index GxB_rowIterator_getColIndex(GxB_Iterator it) {
     if (!it || !it->A || it->exhausted) return 0;
+    if (it->bitmap) return it->q;
     return it->A->host.hcol[it->q];
 }
 uint64_t GxB_Iterator_get_UINT64(GxB_Iterator it) {
     if (!it || !it->A || it->exhausted) return 0;
+    if (it->bitmap) return 1;
     return it->A->valued() ? it->A->host.hval[it->q] : 1;
 }
 bool GxB_Iterator_get_BOOL(GxB_Iterator it) { return GxB_Iterator_get_UINT64(it) != 0; }

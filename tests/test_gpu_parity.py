@@ -517,3 +517,32 @@ def test_export_bitmap_rectangular_and_empty():
         h = to_dev(rand_csr(rng, 4, 100, 0.1))
         out = np.zeros(4 * 5, np.uint64)
         fb.check(lib.B200_Matrix_export_bitmap(h.h, out.ctypes.data, 5, None, 0))   # wrong words_per_row
+
+
+@pytest.mark.parametrize("materialise_first", [False, True])
+def test_row_iterator_walks_dense_chain_result_from_bitmap(materialise_first):
+    """GxB_rowIterator over a dense frontier-chain result (bitmap snapshot inside the iterator): same ascending
+    (row, col) stream as the sparse walk, incl. seek into the middle, empty rows and the exhausted state"""
+    fb.set_option("bits_mode", 1)
+    A = orc.rmat_csr(10, 8, 5)
+    rng = np.random.default_rng(12)
+    nsrc = 70
+    src = rng.choice(A.nrows, size=nsrc, replace=False)
+    rows = np.arange(nsrc)
+    keep = rows != 3                                   # row 3 stays empty
+    F = Matrix(nsrc, A.nrows, bool)
+    F.build(rows[keep], src[keep])
+    want = orc.build_matrix(nsrc, A.nrows, rows[keep], src[keep])
+    dA = to_dev(A)
+    for _ in range(2):
+        F.lmxm(dA)
+        want = orc.mxm(want, A)
+    assert want.nnz * 32 > nsrc * A.nrows              # dense enough for the bitmap walk
+    if materialise_first:
+        F.wait()
+    wr = np.repeat(np.arange(nsrc), np.diff(want.p))
+    expect = list(zip(wr.tolist(), want.j.tolist()))
+    assert list(F.iter()) == expect
+    assert list(F.iter(3, 5)) == [t for t in expect if 3 <= t[0] <= 5]
+    assert list(F.iter(nsrc - 1)) == [t for t in expect if t[0] >= nsrc - 1]
+    assert_same(F, want, "after iterating")
