@@ -396,10 +396,12 @@ def run_b200(a):
         per_launch_ms = ks["ms"] / ks["launches"]
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         traffic = None
-        try:   # dram__bytes_read+write per launch from the committed ncu --set full capture of this configuration
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-            if tj["config"]["scale"] == a.scale and tj["config"]["sources"] == a.sources and tj["config"]["edge_factor"] == a.edge_factor:
-                traffic = tj["dram_bytes_per_launch"].get(dom)
+        try:   # dram__bytes_read+write per launch from the committed ncu --set full captures of this configuration
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            fam = {"bits_pull": ("k_bits_pull_mid", "k_bits_pull_small"), "bits_fill": ("k_bits_fill_rows",)}
+            if (tj["config"]["scale"] == a.scale and tj["config"]["sources"] == a.sources and tj["config"]["edge_factor"] == a.edge_factor
+                    and dom in fam and not a.opt):
+                traffic = int(sum(tj["dram_bytes_by_kernel"][k] for k in fam[dom]))
         except Exception:
             traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
