@@ -29,17 +29,18 @@ struct GB_Global_opaque { int x; };
 struct GB_Descriptor_opaque { bool t0, t1, comp, structure, replace; };
 struct GB_Scalar_opaque { int type; bool has; uint64_t val; };
 
-enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3 };
+enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3, T_UINT32 = 4 };
 enum { OP_ANY_BOOL = 1, OP_SECOND_UINT64 = 2, OP_ANY_UINT64 = 3 };
 
-static GB_Type_opaque t_bool = {T_BOOL, 1, "bool"}, t_u64 = {T_UINT64, 8, "uint64_t"}, t_i64 = {T_INT64, 8, "int64_t"};
+static GB_Type_opaque t_bool = {T_BOOL, 1, "bool"}, t_u64 = {T_UINT64, 8, "uint64_t"}, t_i64 = {T_INT64, 8, "int64_t"},
+                      t_u32 = {T_UINT32, 4, "uint32_t"};
 static GB_Semiring_opaque s_any_pair = {1};
 static GB_BinaryOp_opaque b_any_bool = {OP_ANY_BOOL}, b_second_u64 = {OP_SECOND_UINT64}, b_any_u64 = {OP_ANY_UINT64};
 static GB_UnaryOp_opaque u_one_bool = {1};
 static GB_Global_opaque g_global = {0};
 
 extern "C" {
-GrB_Type GrB_BOOL = &t_bool, GrB_UINT64 = &t_u64, GrB_INT64 = &t_i64;
+GrB_Type GrB_BOOL = &t_bool, GrB_UINT64 = &t_u64, GrB_INT64 = &t_i64, GrB_UINT32 = &t_u32;
 GrB_Semiring GxB_ANY_PAIR_BOOL = &s_any_pair;
 GrB_BinaryOp GxB_ANY_BOOL = &b_any_bool, GrB_SECOND_UINT64 = &b_second_u64, GxB_ANY_UINT64 = &b_any_u64;
 GrB_UnaryOp GxB_ONE_BOOL = &u_one_bool;
@@ -69,6 +70,9 @@ struct HostStore {
 struct PendingOp { u64 i, j, v; u64 seq; bool del; };
 
 static const u32 MAGIC = 0xB200A7u;
+// allocator of buffers that are handed to the caller (set by GxB_init; see the serialization section)
+static void *(*g_user_malloc)(size_t) = malloc;
+static void (*g_user_free)(void *) = free;
 
 struct GB_Matrix_opaque {
     u32 magic = MAGIC;
@@ -98,6 +102,10 @@ struct GB_Vector_opaque {
     u64 n = 0;
     std::vector<u64> idx; // ascending
     std::vector<i64> val; // same length (bool: 1)
+    // full (dense) form of the GxB_Container payload vectors: n entries of `type` in fx (user allocator), idx / val unused
+    bool full = false;
+    void *fx = nullptr;
+    u64 fbytes = 0;
 };
 
 struct GB_Iterator_opaque {
@@ -481,10 +489,12 @@ extern "C" {
 
 const char *B200_last_error(void) { return tl_error.c_str(); }
 
-GrB_Info GxB_init(int mode, void *(*)(size_t), void *(*)(size_t, size_t), void *(*)(void *, size_t), void (*)(void *)) {
+GrB_Info GxB_init(int mode, void *(*um)(size_t), void *(*)(size_t, size_t), void *(*)(void *, size_t), void (*uf)(void *)) {
     (void)mode;
-    // Host containers use the C++ allocator; the user allocator hooks only matter for Redis memory
-    // accounting in the reference (matrix.rs:104-107) and are accepted for signature compatibility.
+    // Internal host containers use the C++ allocator (the hooks only matter for Redis memory accounting in the reference,
+    // matrix.rs:104-107); buffers that are HANDED to the caller (GxB_Vector_unload arrays, GxB_Vector_serialize blobs) come
+    // from the caller's allocator, because the caller frees them with it (vector.rs:171-172).
+    if (um && uf) { g_user_malloc = um; g_user_free = uf; }
     return GrB_SUCCESS; // the CUDA context is created lazily by the first bulk operation
 }
 GrB_Info GrB_init(int mode) { return GxB_init(mode, nullptr, nullptr, nullptr, nullptr); }
@@ -1248,9 +1258,9 @@ GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n) {
     *v = x;
     return GrB_SUCCESS;
 }
-GrB_Info GrB_Vector_free(GrB_Vector *v) { if (v && *v) { delete *v; *v = nullptr; } return GrB_SUCCESS; }
+GrB_Info GrB_Vector_free(GrB_Vector *v) { if (v && *v) { if ((*v)->fx) g_user_free((*v)->fx); delete *v; *v = nullptr; } return GrB_SUCCESS; }
 GrB_Info GrB_Vector_size(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->n; return GrB_SUCCESS; }
-GrB_Info GrB_Vector_nvals(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->idx.size(); return GrB_SUCCESS; }
+GrB_Info GrB_Vector_nvals(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->full ? v->n : v->idx.size(); return GrB_SUCCESS; }
 GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i) {
     CHECK_PTR(v);
     if (i >= v->n) return GrB_INVALID_INDEX;
@@ -1712,6 +1722,298 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;
+}
+
+} // extern "C"
+
+// ====================================================================================================================
+// Serialization boundary: GxB_Container, GxB_Vector_load / unload, GxB_Vector_serialize / deserialize.
+// The reference's RDB encoder (matrix.rs:428-546, vector.rs:150-420) unloads a matrix into a container, writes the
+// 608-byte struct plus the five payload vectors (x, h, p, i, b) as raw arrays, and loads it back; decode feeds
+// attacker-controlled bytes through the same calls, so every length / offset below is validated before use.
+// Host-side plumbing only: nothing here touches the device except fetching a device-resident matrix once.
+// Layout written by unload: row-major; GxB_SPARSE (p has nrows+1 entries) when nrows < 2^32, else GxB_HYPERSPARSE
+// (h = ids of the non-empty rows, p has nvec+1 entries); p, h: UINT64; i: UINT32 when ncols <= 2^32, else UINT64;
+// x: one BOOL `true` (iso) for pattern matrices, UINT64[nvals] otherwise; b: empty.
+// Buffers handed to the caller (unloaded arrays, blobs) come from the allocator given to GxB_init (matrix.rs:125-131),
+// because the caller releases them with its own allocator (vector.rs:171-172).
+// ====================================================================================================================
+static size_t type_size(int code) { return code == T_BOOL ? 1 : code == T_UINT32 ? 4 : 8; }
+static GrB_Type type_of(int code) { return code == T_BOOL ? GrB_BOOL : code == T_UINT32 ? GrB_UINT32 : code == T_INT64 ? GrB_INT64 : GrB_UINT64; }
+
+// replace the content of a container vector with a full (dense) array copied from `src`
+static void vec_set_full(GrB_Vector v, int type, const void *src, u64 n) {
+    if (v->fx) { g_user_free(v->fx); v->fx = nullptr; }
+    v->idx.clear(); v->val.clear();
+    v->type = type; v->n = n; v->full = true; v->fbytes = n * type_size(type);
+    if (v->fbytes) {
+        v->fx = g_user_malloc(v->fbytes);
+        if (!v->fx) throw std::bad_alloc();
+        memcpy(v->fx, src, v->fbytes);
+    }
+}
+static void vec_set_empty(GrB_Vector v) {
+    if (v->fx) { g_user_free(v->fx); v->fx = nullptr; }
+    v->idx.clear(); v->val.clear();
+    v->n = 0; v->full = true; v->fbytes = 0;
+}
+// read entry k of a full integer vector (UINT32 / UINT64 / INT64)
+static bool vec_full_int(GrB_Vector v) { return v && v->full && (v->type == T_UINT32 || v->type == T_UINT64 || v->type == T_INT64); }
+static u64 vec_at(GrB_Vector v, u64 k) { return v->type == T_UINT32 ? (u64)((const u32 *)v->fx)[k] : ((const u64 *)v->fx)[k]; }
+
+extern "C" {
+
+GrB_Info GxB_Container_new(GxB_Container *Container) {
+    CHECK_PTR(Container);
+    return guarded([&]() {
+        GxB_Container c = (GxB_Container)calloc(1, sizeof(struct GxB_Container_struct));
+        if (!c) throw std::bad_alloc();
+        GrB_Vector *vs[5] = {&c->p, &c->h, &c->b, &c->i, &c->x};
+        for (GrB_Vector *pv : vs) { *pv = new GB_Vector_opaque(); (*pv)->full = true; (*pv)->n = 0; }
+        c->format = GxB_SPARSE; c->orientation = GrB_ROWMAJOR; c->nrows_nonempty = -1; c->ncols_nonempty = -1;
+        *Container = c;
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GxB_Container_free(GxB_Container *Container) {
+    if (!Container || !*Container) return GrB_SUCCESS;
+    GxB_Container c = *Container;
+    GrB_Vector *vs[5] = {&c->p, &c->h, &c->b, &c->i, &c->x};
+    for (GrB_Vector *pv : vs) GrB_Vector_free(pv);
+    if (c->Y) GrB_Matrix_free(&c->Y);
+    free(c);
+    *Container = nullptr;
+    return GrB_SUCCESS;
+}
+
+GrB_Info GxB_unload_Matrix_into_Container(GrB_Matrix A, GxB_Container c, GrB_Descriptor) {
+    CHECK_MAT(A); CHECK_PTR(c);
+    if (!c->p || !c->h || !c->b || !c->i || !c->x) { tl_error = "unload: container vectors missing"; return GrB_NULL_POINTER; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_host(A);
+        const HostStore &h = A->host;
+        const u64 nvec = h.hrow.size(), nnz = h.nnz();
+        const bool hyper = A->nrows >= ((u64)1 << 32);
+        if (hyper) {
+            vec_set_full(c->p, T_UINT64, h.hptr.data(), nvec + 1);
+            vec_set_full(c->h, T_UINT64, h.hrow.data(), nvec);
+        } else {
+            std::vector<u64> p(A->nrows + 1, 0);
+            for (u64 k = 0; k < nvec; k++) p[h.hrow[k] + 1] = h.hptr[k + 1] - h.hptr[k];
+            for (u64 r = 0; r < A->nrows; r++) p[r + 1] += p[r];
+            vec_set_full(c->p, T_UINT64, p.data(), A->nrows + 1);
+            vec_set_empty(c->h);
+        }
+        if (A->ncols <= ((u64)1 << 32)) {
+            std::vector<u32> i32(nnz);
+            for (u64 q = 0; q < nnz; q++) i32[q] = (u32)h.hcol[q];
+            vec_set_full(c->i, T_UINT32, i32.data(), nnz);
+        } else vec_set_full(c->i, T_UINT64, h.hcol.data(), nnz);
+        if (A->valued()) vec_set_full(c->x, A->type, h.hval.data(), nnz);
+        else { const unsigned char one = 1; vec_set_full(c->x, T_BOOL, &one, 1); }
+        vec_set_empty(c->b);
+        c->nrows = A->nrows; c->ncols = A->ncols; c->nvals = nnz;
+        c->nrows_nonempty = (int64_t)nvec; c->ncols_nonempty = -1;
+        c->format = hyper ? GxB_HYPERSPARSE : GxB_SPARSE; c->orientation = GrB_ROWMAJOR;
+        c->iso = !A->valued(); c->jumbled = false;
+        // the matrix keeps its handle but gives up its content and dimensions
+        A->nrows = 0; A->ncols = 0;
+        set_empty(A);
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container c, GrB_Descriptor) {
+    CHECK_MAT(A); CHECK_PTR(c);
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        auto bad = [](const char *m) { throw GrbError(GrB_INVALID_OBJECT, m); };
+        if (c->nrows > ((u64)1 << 60) || c->ncols > ((u64)1 << 60)) bad("load: dimensions out of range");
+        if (c->orientation != GrB_ROWMAJOR) bad("load: only row-major containers are supported");
+        if (c->format != GxB_SPARSE && c->format != GxB_HYPERSPARSE) bad("load: only sparse / hypersparse containers are supported");
+        if (!vec_full_int(c->p) || !vec_full_int(c->i) || !c->x || !c->x->full) bad("load: p / i / x must be full vectors");
+        const bool hyper = c->format == GxB_HYPERSPARSE;
+        if (hyper && !vec_full_int(c->h)) bad("load: hypersparse container without h");
+        const u64 nvec = hyper ? c->h->n : c->nrows;
+        if (c->p->n != nvec + 1) bad("load: p has the wrong length");
+        if (c->p->n && vec_at(c->p, 0) != 0) bad("load: p[0] != 0");
+        const u64 nnz = c->p->n ? vec_at(c->p, nvec) : 0;
+        if (nnz != c->nvals || c->i->n < nnz) bad("load: nvals / i disagree with p");
+        const int xtype = c->x->type;
+        if (xtype != T_BOOL && xtype != T_UINT64 && xtype != T_INT64) bad("load: unsupported value type");
+        const bool iso = c->iso;
+        if (c->x->n < (iso ? (nnz ? 1 : 0) : nnz)) bad("load: x too short");
+        if (xtype == T_BOOL && !iso)
+            for (u64 q = 0; q < nnz; q++) if (!((const unsigned char *)c->x->fx)[q]) bad("load: explicit false entries are not representable");
+        HostStore h;
+        h.clear();
+        h.hcol.resize(nnz);
+        if (xtype != T_BOOL) h.hval.resize(nnz);
+        u64 prev_row = 0;
+        for (u64 k = 0; k < nvec; k++) {
+            const u64 s = vec_at(c->p, k), e = vec_at(c->p, k + 1);
+            if (e < s || e > nnz) bad("load: p is not monotone");
+            const u64 row = hyper ? vec_at(c->h, k) : k;
+            if (row >= c->nrows || (hyper && k && row <= prev_row)) bad("load: row ids out of range or not ascending");
+            prev_row = row;
+            if (e == s) continue;
+            for (u64 q = s; q < e; q++) {
+                const u64 col = vec_at(c->i, q);
+                if (col >= c->ncols) bad("load: column index out of range");
+                h.hcol[q] = col;
+                if (xtype != T_BOOL) h.hval[q] = iso ? ((const u64 *)c->x->fx)[0] : ((const u64 *)c->x->fx)[q];
+            }
+            if (c->jumbled) {   // sort the row by column, values along
+                std::vector<std::pair<u64, u64>> t(e - s);
+                for (u64 q = s; q < e; q++) t[q - s] = {h.hcol[q], xtype != T_BOOL ? h.hval[q] : 1};
+                std::sort(t.begin(), t.end());
+                for (u64 q = s; q < e; q++) { h.hcol[q] = t[q - s].first; if (xtype != T_BOOL) h.hval[q] = t[q - s].second; }
+            }
+            for (u64 q = s + 1; q < e; q++) if (h.hcol[q] <= h.hcol[q - 1]) bad("load: duplicate or unsorted column indices");
+            h.hrow.push_back(row);
+            h.hptr.push_back(e);
+        }
+        // rows may leave gaps in p (s > previous e): compact so that hptr is contiguous
+        {
+            u64 w = 0;
+            std::vector<u64> ncol, nval;
+            ncol.reserve(nnz); if (xtype != T_BOOL) nval.reserve(nnz);
+            std::vector<u64> nptr(1, 0);
+            u64 kk = 0;
+            for (u64 k = 0; k < nvec; k++) {
+                const u64 s = vec_at(c->p, k), e = vec_at(c->p, k + 1);
+                if (e == s) continue;
+                for (u64 q = s; q < e; q++) { ncol.push_back(h.hcol[q]); if (xtype != T_BOOL) nval.push_back(h.hval[q]); }
+                w += e - s; nptr.push_back(w); kk++;
+            }
+            h.hcol.swap(ncol); h.hval.swap(nval); h.hptr.swap(nptr);
+            (void)kk;
+        }
+        A->type = xtype;
+        A->nrows = c->nrows; A->ncols = c->ncols;
+        set_empty(A);
+        A->host = std::move(h);
+        A->host_valid = true;
+        // the container gives up its content
+        vec_set_empty(c->p); vec_set_empty(c->h); vec_set_empty(c->i); vec_set_empty(c->x); vec_set_empty(c->b);
+        c->nvals = 0;
+        return GrB_SUCCESS;
+    });
+}
+
+// V must be a full vector (the container payload vectors are); the array leaves with the caller, V becomes empty
+GrB_Info GxB_Vector_unload(GrB_Vector V, void **X, GrB_Type *type, uint64_t *n, uint64_t *X_memsize, int *handling, GrB_Descriptor) {
+    CHECK_PTR(V); CHECK_PTR(X); CHECK_PTR(type); CHECK_PTR(n); CHECK_PTR(X_memsize); CHECK_PTR(handling);
+    return guarded([&]() {
+        if (!V->full) {
+            if (V->idx.size() != V->n) throw GrbError(GrB_INVALID_OBJECT, "Vector_unload: the vector is not full (every entry present)");
+            // densify a sparse-API vector that happens to be full
+            std::vector<unsigned char> bytes(V->n * type_size(V->type));
+            for (u64 k = 0; k < V->n; k++) {
+                if (V->type == T_BOOL) bytes[k] = V->val[k] != 0;
+                else ((u64 *)bytes.data())[k] = (u64)V->val[k];
+            }
+            vec_set_full(V, V->type, bytes.data(), V->n);
+        }
+        *X = V->fx; *type = type_of(V->type); *n = V->n; *X_memsize = V->fbytes; *handling = 0 /* GrB_DEFAULT: owned, now by the caller */;
+        V->fx = nullptr; V->fbytes = 0; V->n = 0;
+        return GrB_SUCCESS;
+    });
+}
+// V adopts *X (n entries of `type`, X_memsize bytes) and *X is set to NULL
+GrB_Info GxB_Vector_load(GrB_Vector V, void **X, GrB_Type type, uint64_t n, uint64_t X_memsize, int handling, GrB_Descriptor) {
+    CHECK_PTR(V); CHECK_PTR(X); CHECK_PTR(type);
+    return guarded([&]() {
+        const int code = type->code;
+        if (code != T_BOOL && code != T_UINT32 && code != T_UINT64 && code != T_INT64) throw GrbError(GrB_DOMAIN_MISMATCH, "Vector_load: unsupported type");
+        if (handling != 0) throw GrbError(GrB_NOT_IMPLEMENTED, "Vector_load: read-only (GxB_IS_READONLY) arrays are not supported");
+        if (n > ((u64)1 << 60) || n * type_size(code) > X_memsize) throw GrbError(GrB_INVALID_VALUE, "Vector_load: X_memsize smaller than n entries");
+        if (n && !*X) throw GrbError(GrB_NULL_POINTER, "Vector_load: null array");
+        if (V->fx) g_user_free(V->fx);
+        V->idx.clear(); V->val.clear();
+        V->type = code; V->n = n; V->full = true; V->fx = *X; V->fbytes = X_memsize;
+        *X = nullptr;
+        return GrB_SUCCESS;
+    });
+}
+
+// ---- blob: "B2GV" | version | type | flags | n | nvals | idx[nvals] | (val[nvals] unless every value is 1) ; all little-endian u64 after the
+// 16-byte head.  Opaque to the caller, like SuiteSparse's (whose blobs it does not try to read: a dump written by one
+// library must be restored by the same one).
+struct BlobHead { u32 magic, version; int32_t type; u32 flags; u64 n, nvals; };
+static const u32 BLOB_MAGIC = 0x56473242u; // "B2GV"
+
+GrB_Info GxB_Vector_serialize(void **blob_handle, GrB_Index *blob_size, GrB_Vector u, GrB_Descriptor) {
+    CHECK_PTR(blob_handle); CHECK_PTR(blob_size); CHECK_PTR(u);
+    return guarded([&]() {
+        std::vector<u64> idx, val;
+        if (u->full) {
+            idx.resize(u->n); val.resize(u->n);
+            for (u64 k = 0; k < u->n; k++) { idx[k] = k; val[k] = u->type == T_BOOL ? ((const unsigned char *)u->fx)[k] : vec_at(u, k); }
+        } else {
+            idx = u->idx;
+            val.assign(u->val.begin(), u->val.end());
+        }
+        bool all_one = true;
+        for (u64 x : val) if (x != 1) { all_one = false; break; }
+        BlobHead hd{BLOB_MAGIC, 1, u->type, all_one ? 1u : 0u, u->n, (u64)idx.size()};
+        const size_t bytes = sizeof(hd) + 8 * idx.size() * (all_one ? 1 : 2);
+        unsigned char *b = (unsigned char *)g_user_malloc(bytes);
+        if (!b) throw std::bad_alloc();
+        memcpy(b, &hd, sizeof(hd));
+        memcpy(b + sizeof(hd), idx.data(), 8 * idx.size());
+        if (!all_one) memcpy(b + sizeof(hd) + 8 * idx.size(), val.data(), 8 * val.size());
+        *blob_handle = b; *blob_size = bytes;
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GxB_Vector_deserialize(GrB_Vector *w, GrB_Type type, const void *blob, GrB_Index blob_size, GrB_Descriptor) {
+    CHECK_PTR(w); CHECK_PTR(blob);
+    return guarded([&]() {
+        auto bad = [](const char *m) { throw GrbError(GrB_INVALID_OBJECT, m); };
+        BlobHead hd;
+        if (blob_size < sizeof(hd)) bad("deserialize: blob shorter than its header");
+        memcpy(&hd, blob, sizeof(hd));
+        if (hd.magic != BLOB_MAGIC || hd.version != 1) bad("deserialize: not a blob written by this library");
+        if (hd.type != T_BOOL && hd.type != T_UINT64 && hd.type != T_INT64 && hd.type != T_UINT32) bad("deserialize: unknown type");
+        if (type && type->code != hd.type) throw GrbError(GrB_DOMAIN_MISMATCH, "deserialize: type differs from the blob's");
+        const bool all_one = hd.flags & 1;
+        if (hd.n > ((u64)1 << 60) || hd.nvals > hd.n || hd.nvals > (blob_size - sizeof(hd)) / (all_one ? 8 : 16)) bad("deserialize: lengths disagree with the blob size");
+        if (blob_size != sizeof(hd) + 8 * hd.nvals * (all_one ? 1 : 2)) bad("deserialize: trailing or missing bytes");
+        GrB_Vector v = new GB_Vector_opaque();
+        v->type = hd.type; v->n = hd.n;
+        v->idx.resize(hd.nvals); v->val.resize(hd.nvals);
+        const unsigned char *p = (const unsigned char *)blob + sizeof(hd);
+        memcpy(v->idx.data(), p, 8 * hd.nvals);
+        if (all_one) std::fill(v->val.begin(), v->val.end(), 1);
+        else memcpy(v->val.data(), p + 8 * hd.nvals, 8 * hd.nvals);
+        for (u64 k = 0; k < hd.nvals; k++)
+            if (v->idx[k] >= hd.n || (k && v->idx[k] <= v->idx[k - 1])) { delete v; bad("deserialize: indices out of range or not ascending"); }
+        *w = v;
+        return GrB_SUCCESS;
+    });
+}
+
+GrB_Info GrB_Type_get_String(GrB_Type type, char *value, int field) {
+    CHECK_PTR(type); CHECK_PTR(value);
+    if (field != GrB_NAME && field != GxB_JIT_C_NAME) return GrB_INVALID_VALUE;
+    const char *nm = field == GxB_JIT_C_NAME ? type->name
+                   : type->code == T_BOOL ? "GrB_BOOL" : type->code == T_UINT32 ? "GrB_UINT32" : type->code == T_UINT64 ? "GrB_UINT64" : "GrB_INT64";
+    strncpy(value, nm, GxB_MAX_NAME_LEN - 1);
+    value[GxB_MAX_NAME_LEN - 1] = 0;
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_Type_from_name(GrB_Type *type, const char *type_name) {
+    CHECK_PTR(type); CHECK_PTR(type_name);
+    struct { const char *a, *b; GrB_Type t; } tab[] = {{"bool", "GrB_BOOL", GrB_BOOL}, {"uint32_t", "GrB_UINT32", GrB_UINT32},
+                                                      {"uint64_t", "GrB_UINT64", GrB_UINT64}, {"int64_t", "GrB_INT64", GrB_INT64}};
+    for (auto &e : tab) if (!strcmp(type_name, e.a) || !strcmp(type_name, e.b)) { *type = e.t; return GrB_SUCCESS; }
+    *type = nullptr;
+    tl_error = "Type_from_name: unknown type name";
+    return GrB_INVALID_VALUE;
 }
 
 } // extern "C"

@@ -187,6 +187,47 @@ GrB_Index GxB_rowIterator_getColIndex(GxB_Iterator it);                         
 uint64_t GxB_Iterator_get_UINT64(GxB_Iterator it);                                /* mod.rs:15024 */
 bool GxB_Iterator_get_BOOL(GxB_Iterator it);
 
+/* ---- serialization (matrix.rs:428-546 Encode/Decode via GxB_Container; vector.rs:150-420) ---- */
+#define GrB_NAME 10                 /* mod.rs:2879 */
+#define GxB_JIT_C_NAME 7041         /* mod.rs:2897 */
+#define GxB_MAX_NAME_LEN 128        /* mod.rs:158 */
+extern GrB_Type GrB_UINT32;         /* mod.rs:541 (type of the `i` payload vector when ncols <= 2^32) */
+/* 608 bytes, field offsets as asserted in mod.rs:14165-14237; the reference copies the struct bytes into its RDB stream
+ * (pointer fields are nulled and re-created on decode, matrix.rs:455-470). */
+struct GxB_Container_struct {
+    uint64_t nrows, ncols;
+    int64_t nrows_nonempty, ncols_nonempty;
+    uint64_t nvals;
+    uint64_t u64_future[11];
+    int32_t format, orientation, header_arena;
+    uint32_t u32_future[13];
+    GrB_Vector p, h, b, i, x;
+    GrB_Vector vector_future[11];
+    GrB_Matrix Y;
+    GrB_Matrix matrix_future[15];
+    bool iso, jumbled;
+    bool bool_future[30];
+    void *void_future[16];
+};
+typedef struct GxB_Container_struct *GxB_Container;                                            /* mod.rs:14238 */
+GrB_Info GxB_Container_new(GxB_Container *Container);                                          /* mod.rs:14240 */
+GrB_Info GxB_Container_free(GxB_Container *Container);                                         /* mod.rs:15081 */
+/* A's content moves into the container's p/h/b/i/x vectors (row-major sparse or hypersparse, see grb_api.cu); A is left empty */
+GrB_Info GxB_unload_Matrix_into_Container(GrB_Matrix A, GxB_Container Container, GrB_Descriptor desc);  /* mod.rs:14264 */
+/* A takes type, dimensions and content from the container (validated: the payload may come from GRAPH.RESTORE) */
+GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container Container, GrB_Descriptor desc);    /* mod.rs:14250 */
+/* full (dense) payload vectors <-> raw arrays; arrays handed out are allocated with GxB_init's malloc */
+GrB_Info GxB_Vector_load(GrB_Vector V, void **X, GrB_Type type, uint64_t n, uint64_t X_memsize, int handling,
+                         GrB_Descriptor desc);                                                  /* mod.rs:14278 */
+GrB_Info GxB_Vector_unload(GrB_Vector V, void **X, GrB_Type *type, uint64_t *n, uint64_t *X_memsize, int *handling,
+                           GrB_Descriptor desc);                                                /* mod.rs:14289 */
+/* opaque blob of a (sparse) vector: Tensor's multi-edge id lists (vector.rs:150-195); round-trips through this library only */
+GrB_Info GxB_Vector_serialize(void **blob_handle, GrB_Index *blob_size, GrB_Vector u, GrB_Descriptor desc);   /* mod.rs:14717 */
+GrB_Info GxB_Vector_deserialize(GrB_Vector *w, GrB_Type type, const void *blob, GrB_Index blob_size,
+                                GrB_Descriptor desc);                                           /* mod.rs:14768 */
+GrB_Info GrB_Type_get_String(GrB_Type type, char *value, int field);                            /* mod.rs:10503 */
+GrB_Info GxB_Type_from_name(GrB_Type *type, const char *type_name);                             /* mod.rs:8075 */
+
 /* ---- LAGraph subset (lagraph_bindings.rs:160-188, lagraphx_bindings.rs:585-594) ---- */
 typedef enum { LAGraph_ADJACENCY_UNDIRECTED = 0, LAGraph_ADJACENCY_DIRECTED = 1, LAGraph_KIND_UNKNOWN = -1 } LAGraph_Kind;
 typedef struct LAGraph_Graph_struct {

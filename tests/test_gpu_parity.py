@@ -546,3 +546,45 @@ def test_row_iterator_walks_dense_chain_result_from_bitmap(materialise_first):
     assert list(F.iter(3, 5)) == [t for t in expect if 3 <= t[0] <= 5]
     assert list(F.iter(nsrc - 1)) == [t for t in expect if t[0] >= nsrc - 1]
     assert_same(F, want, "after iterating")
+
+
+@pytest.mark.parametrize("opts", [{"pull_kernel": 4}, {"pull_kernel": 4, "early_exit": 2}, {"pull_kernel": 4, "early_exit": 0, "hot_pack": 0},
+                                  {"pull_kernel": 3}, {"pull_kernel": 0, "early_exit": 2}, {"pull_kernel": 1}])
+def test_pull_bins_small_mid_long_rows(opts):
+    """a graph whose transpose has empty, small (<= 8), mid and long (> 4096 entries) rows, so every bin of the
+    degree-binned pull (and the long-row chunk table) is exercised; W = 1, 8 and 16 word columns"""
+    rng = np.random.default_rng(2024)
+    n = 20000
+    src, dst = [], []
+    for hub, deg in ((5, 9000), (17, 6000), (19999, 4097), (300, 4096)):       # long rows and the boundary case
+        s_ = rng.choice(n, size=deg, replace=False)
+        src.append(s_); dst.append(np.full(deg, hub))
+    for j in range(1000, 1400):                                               # mid rows, 9..500 entries
+        deg = 9 + (j * 37) % 492
+        src.append(rng.choice(n, size=deg, replace=False)); dst.append(np.full(deg, j))
+    m = 30000                                                                 # sprinkle: rows of 0..8 entries
+    src.append(rng.integers(0, n, m)); dst.append(rng.integers(2000, n, m))
+    src = np.concatenate(src); dst = np.concatenate(dst)
+    A = orc.build_matrix(n, n, src, dst)
+    indeg = np.bincount(A.j, minlength=n)
+    assert indeg.max() > 4096 and (indeg == 0).any() and ((indeg > 0) & (indeg <= 8)).any() and ((indeg > 8) & (indeg <= 4096)).any()
+    fb.set_option("bits_mode", 1)
+    fb.set_option("pull_mode", 1)
+    for k, v in opts.items():
+        fb.set_option(k, v)
+    try:
+        dA = to_dev(A)
+        for nsrc in (40, 300, 1000):
+            s0 = rng.choice(n, size=nsrc, replace=False)
+            F = Matrix(nsrc, n, bool)
+            F.build(np.arange(nsrc), s0)
+            want = orc.build_matrix(nsrc, n, np.arange(nsrc), s0)
+            for _ in range(3):
+                F.lmxm(dA)
+                want = orc.mxm(want, A)
+            assert fb.get_stat("last_path") in (3, 4), "the pull direction was not taken"
+            F.wait()
+            assert_same(F, want, f"binned pull {opts} nsrc={nsrc}")
+    finally:
+        for k, v in (("hot_pack", 1), ("pull_kernel", 4), ("early_exit", 1), ("pull_mode", -1), ("bits_mode", -1)):
+            fb.set_option(k, v)
