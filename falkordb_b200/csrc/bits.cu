@@ -415,6 +415,54 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     }
 }
 
+// ---------------------------------------------------------------------------- diagonal operand = column filter
+// Label matrices are n x n diagonal (graph.rs:1191): F * L keeps column j of F iff L(j,j) is present -- an elementwise pass
+// over the bit-matrix instead of a hop (label-filter fusion).
+__global__ void __launch_bounds__(256) k_is_diagonal(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 n, u32 *__restrict__ bad) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    bool b = false;
+    for (; r < n; r += stride) {
+        u64 s = p[r], e = p[r + 1];
+        if (e - s > 1 || (e - s == 1 && j[s] != (u32)r)) b = true;
+    }
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
+}
+bool csr_is_diagonal(const DevCSR &A) {
+    if (A.nrows != A.ncols || A.nnz > A.nrows) return false;
+    if (A.nrows == 0) return true;
+    DevBuf<u32> bad(1);
+    bad.zero();
+    LAUNCH(k_is_diagonal, grid_for(A.nrows, 256, 148 * 16), 256, 0, A.p.ptr, A.j.ptr, A.nrows, bad.ptr);
+    return read_scalar(bad.ptr) == 0;
+}
+__global__ void __launch_bounds__(256)
+k_bits_diag(const u64 *__restrict__ X, const u64 *__restrict__ Ap, u64 n, u32 W, u64 *__restrict__ Y, u64 *__restrict__ flops) {
+    typedef cub::BlockReduce<u64, 256> Red;
+    __shared__ typename Red::TempStorage ts;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x, total = n * W;
+    u64 c = 0;
+    for (; t < total; t += stride) {
+        const u64 v = t / W;
+        const u64 x = (Ap[v + 1] > Ap[v]) ? X[t] : 0ULL;
+        Y[t] = x;
+        c += __popcll(x);
+    }
+    u64 tot = Red(ts).Sum(c);
+    if (threadIdx.x == 0 && tot) atomicAdd((unsigned long long *)flops, tot);
+}
+void bits_diag(const DevBits &X, const DevCSR &A, DevBits &Y, u64 *flops_out) {
+    if (X.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
+    Y.clear();
+    Y.nrows = X.nrows; Y.ncols = A.ncols; Y.W = X.W;
+    Y.w.alloc(A.ncols * X.W);
+    DevBuf<u64> fl(1);
+    fl.zero();
+    if (A.nrows) LAUNCH(k_bits_diag, grid_for(A.nrows * X.W, 256, 148 * 16), 256, 0, X.w.ptr, A.p.ptr, A.nrows, X.W, Y.w.ptr, fl.ptr);
+    if (flops_out) *flops_out = read_scalar(fl.ptr);
+}
+
 // ---------------------------------------------------------------------------- row-major bitmap (GxB_BITMAP-like export)
 // out[row * wpr + (v >> 6)] bit (v & 63) <=> X(row, v).  Same 64 x 1024 transposed tile as the materialise kernels, written
 // out as 128-byte row segments; rows >= nrows (padding of the last word column) are dropped.

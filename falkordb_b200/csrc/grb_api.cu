@@ -85,6 +85,7 @@ struct GB_Matrix_opaque {
     bool dev_valid = false;
     DevCSR dev;
     bool bits_valid = false;
+    int diag_state = -1;   // -1 unknown, 0 no, 1 the device CSR is a diagonal matrix (label matrix): mxm by it is a column filter
     DevBits bits;
     bool devT_valid = false;
     DevCSR devT;
@@ -172,6 +173,7 @@ struct MultiLock {
 
 // ------------------------------------------------------------------------------------------------ form management
 static void invalidate_aux(GrB_Matrix A) {
+    A->diag_state = -1;
     A->devT_valid = false;
     A->devT.clear();
     A->lr.clear();
@@ -950,11 +952,15 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
             if (use_bits) {
                 ensure_bits(A);
                 ensure_dev(B);
-                if (cx.opt_pull_mode != 0) ensure_devT(B);
+                if (B->diag_state < 0) B->diag_state = csr_is_diagonal(B->dev) ? 1 : 0;   // cached until B changes
                 DevBits Y;
                 u64 fl = 0;
                 int path = 0;
-                bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : (LongRows *)nullptr, Y, &fl, &path);
+                if (B->diag_state == 1 && cx.opt_diag_filter) { bits_diag(A->bits, B->dev, Y, &fl); path = 5; }
+                else {
+                    if (cx.opt_pull_mode != 0) ensure_devT(B);
+                    bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : (LongRows *)nullptr, Y, &fl, &path);
+                }
                 if (Mask) {
                     ensure_bits(Mask);
                     bits_andnot(Y, Mask->bits);
@@ -1719,6 +1725,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "unroll") c.opt_unroll = value;
     else if (n == "pull_grid") c.opt_pull_grid = value;
     else if (n == "fill_kernel") c.opt_fill_kernel = value;
+    else if (n == "diag_filter") c.opt_diag_filter = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

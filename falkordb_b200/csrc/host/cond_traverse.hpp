@@ -34,9 +34,12 @@ struct TraversalMatrix {
     }
 };
 
+// fuse_dst_labels: label matrices are diagonal (graph.rs:1191), so the destination filter F*A*L_dst
+// (graph.rs:2600-2626) is one more delta_lmxm against the label's VersionedMatrix -- a column filter in frontier form on
+// the device -- instead of a node_has_label probe (1-3 extractElement calls) per output pair on the host.
 inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std::vector<TraversalMatrix> &hops,
                                  const std::vector<const VersionedMatrix *> &src_labels,
-                                 const std::vector<const VersionedMatrix *> &dst_labels) {
+                                 const std::vector<const VersionedMatrix *> &dst_labels, bool fuse_dst_labels = false) {
     ExpandResult out;
     if (hops.empty() || src_ids.empty()) return out;
     uint64_t ncols = hops[0].ncols();
@@ -54,13 +57,16 @@ inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std
     Matrix<bool> f(src_ids.size(), ncols);
     f.build(row_idx_buf, col_idx_buf);
     for (const TraversalMatrix &h : hops) h.delta_lmxm_into(f);
+    if (fuse_dst_labels)
+        for (const VersionedMatrix *l : dst_labels) TraversalMatrix(l).delta_lmxm_into(f);
     f.wait();                                    // flush pending mxm work before attaching the row iterator
     auto it = f.iter(0, UINT64_MAX);
     std::tuple<uint64_t, uint64_t> t;
     while (it.next(t)) {
         uint64_t dest = std::get<1>(t);
         bool ok = true;
-        for (const VersionedMatrix *l : dst_labels) if (!node_has_label(*l, dest)) { ok = false; break; }
+        if (!fuse_dst_labels)
+            for (const VersionedMatrix *l : dst_labels) if (!node_has_label(*l, dest)) { ok = false; break; }
         if (!ok) continue;                       // post-filter final-hop dst label (= F * A * R_dst)
         out.row_idx.push_back(std::get<0>(t));
         out.dest.push_back(dest);

@@ -381,8 +381,8 @@ int fdbh_vm_remove(void *vm, uint64_t i, uint64_t j) { try { ((VersionedMatrix *
 int64_t fdbh_vm_nvals(void *vm) { try { return (int64_t)((VersionedMatrix *)vm)->nvals(); } catch (const std::exception &e) { g_msg = e.what(); return -1; } }
 
 // CondTraverse batched path.  Outputs are malloc'ed; free with fdbh_free.
-int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint64_t nhops, void **src_labels, uint64_t nsl,
-                      void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout) {
+static int expand_batch_c(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint64_t nhops, void **src_labels, uint64_t nsl,
+                          void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout, bool fuse) {
     try {
         std::vector<uint64_t> src(src_ids, src_ids + nsrc);
         std::vector<TraversalMatrix> h;
@@ -390,7 +390,7 @@ int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint6
         for (uint64_t k = 0; k < nhops; k++) h.push_back(TraversalMatrix((const VersionedMatrix *)hops[k]));
         for (uint64_t k = 0; k < nsl; k++) sl.push_back((const VersionedMatrix *)src_labels[k]);
         for (uint64_t k = 0; k < ndl; k++) dl.push_back((const VersionedMatrix *)dst_labels[k]);
-        ExpandResult r = expand_batch(src, h, sl, dl);
+        ExpandResult r = expand_batch(src, h, sl, dl, fuse);
         *nout = r.dest.size();
         *out_rows = (uint64_t *)malloc(sizeof(uint64_t) * (r.dest.size() + 1));
         *out_dest = (uint64_t *)malloc(sizeof(uint64_t) * (r.dest.size() + 1));
@@ -398,6 +398,15 @@ int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint6
         memcpy(*out_dest, r.dest.data(), sizeof(uint64_t) * r.dest.size());
         return 0;
     } catch (const std::exception &e) { g_msg = e.what(); return 1; }
+}
+int fdbh_expand_batch(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint64_t nhops, void **src_labels, uint64_t nsl,
+                      void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout) {
+    return expand_batch_c(src_ids, nsrc, hops, nhops, src_labels, nsl, dst_labels, ndl, out_rows, out_dest, nout, false);
+}
+// destination-label filters applied on the device as extra diagonal hops
+int fdbh_expand_batch_fused(const uint64_t *src_ids, uint64_t nsrc, void **hops, uint64_t nhops, void **src_labels, uint64_t nsl,
+                            void **dst_labels, uint64_t ndl, uint64_t **out_rows, uint64_t **out_dest, uint64_t *nout) {
+    return expand_batch_c(src_ids, nsrc, hops, nhops, src_labels, nsl, dst_labels, ndl, out_rows, out_dest, nout, true);
 }
 void fdbh_free(void *p) { free(p); }
 

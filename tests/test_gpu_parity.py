@@ -588,3 +588,40 @@ def test_pull_bins_small_mid_long_rows(opts):
     finally:
         for k, v in (("hot_pack", 1), ("pull_kernel", 4), ("early_exit", 1), ("pull_mode", -1), ("bits_mode", -1)):
             fb.set_option(k, v)
+
+
+@pytest.mark.parametrize("diag_filter", [1, 0])
+def test_frontier_times_diagonal_label_matrix(diag_filter):
+    """F*A*L with a diagonal label matrix L (graph.rs:1191): the column-filter fast path and the ordinary hop agree with
+    the oracle; a non-diagonal matrix with nnz <= n must not be mistaken for one; the cached verdict follows updates"""
+    fb.set_option("bits_mode", 1)
+    fb.set_option("diag_filter", diag_filter)
+    try:
+        A = orc.rmat_csr(11, 8, 31)
+        n = A.nrows
+        rng = np.random.default_rng(8)
+        lab = np.sort(rng.choice(n, n // 4, replace=False))
+        Ld = orc.build_matrix(n, n, lab, lab)
+        perm = orc.build_matrix(n, n, np.arange(n), np.roll(np.arange(n), 1))        # nnz == n but off-diagonal
+        for nsrc in (50, 300):
+            src = rng.choice(n, size=nsrc, replace=False)
+            F = Matrix(nsrc, n, bool)
+            F.build(np.arange(nsrc), src)
+            want = orc.build_matrix(nsrc, n, np.arange(nsrc), src)
+            dA, dL, dP = to_dev(A), to_dev(Ld), to_dev(perm)
+            F.lmxm(dA); want = orc.mxm(want, A)
+            F.lmxm(dA); want = orc.mxm(want, A)
+            F.lmxm(dL); want = orc.mxm(want, Ld)
+            assert fb.get_stat("last_path") == (5 if diag_filter else fb.get_stat("last_path"))
+            assert fb.get_stat("last_flops") == want.nnz                 # every kept entry is one multiply
+            F.lmxm(dP); want = orc.mxm(want, perm)
+            assert fb.get_stat("last_path") != 5
+            dL.set(int(lab[0]), int((lab[0] + 1) % n))                   # no longer diagonal
+            F.lmxm(dL)
+            L2 = orc.build_matrix(n, n, np.append(lab, lab[0]), np.append(lab, (lab[0] + 1) % n))
+            want = orc.mxm(want, L2)
+            assert fb.get_stat("last_path") != 5
+            F.wait()
+            assert_same(F, want, f"diag_filter={diag_filter} nsrc={nsrc}")
+    finally:
+        fb.set_option("diag_filter", 1)

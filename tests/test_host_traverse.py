@@ -28,6 +28,7 @@ def host():
     L.fdbh_vm_nvals.restype = C.c_int64
     L.fdbh_expand_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.fdbh_expand_batch_fused.argtypes = L.fdbh_expand_batch.argtypes
     L.fdbh_free.argtypes = [C.c_void_p]
     return L
 
@@ -45,11 +46,11 @@ def vm_from(L, c):
     return h
 
 
-def expand(L, src, hops, sl=(), dl=()):
+def expand(L, src, hops, sl=(), dl=(), fused=False):
     src = np.ascontiguousarray(src, dtype=np.uint64)
     arr = lambda hs: (C.c_void_p * max(1, len(hs)))(*hs)
     rows, dest, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    rc = L.fdbh_expand_batch(src.ctypes.data, len(src), arr(hops), len(hops), arr(sl), len(sl), arr(dl), len(dl),
+    rc = (L.fdbh_expand_batch_fused if fused else L.fdbh_expand_batch)(src.ctypes.data, len(src), arr(hops), len(hops), arr(sl), len(sl), arr(dl), len(dl),
                              C.byref(rows), C.byref(dest), C.byref(n))
     assert rc == 0, L.fdbh_last_message().decode()
     r = np.ctypeslib.as_array(C.cast(rows, C.POINTER(C.c_uint64)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
@@ -104,4 +105,38 @@ def test_expand_batch_three_hops_with_labels_and_dirty_snapshot():
     wr, wc, _ = W3.tuples()
     assert np.array_equal(r, wr) and np.array_equal(d, wc)
     for h in (vA, vB, vs, vd):
+        L.fdbh_vm_free(h)
+
+
+def test_destination_label_filter_fused_as_a_diagonal_hop():
+    """F*A*L_dst with the label filter on the device (one more delta_lmxm against the diagonal label
+    VersionedMatrix, clean and dirty) gives exactly the pairs the per-output node_has_label probes keep"""
+    L = host()
+    A = orc.rmat_csr(11, 8, 13)
+    n = A.nrows
+    rng = np.random.default_rng(4)
+    src = rng.choice(np.nonzero(np.diff(A.p))[0], 300, replace=False)
+    vA = vm_from(L, A)
+    lab = np.sort(rng.choice(n, n // 3, replace=False))
+    vd = vm_from(L, orc.build_matrix(n, n, lab, lab))
+    F = orc.build_matrix(len(src), n, np.arange(len(src)), src)
+    W = orc.mxm(orc.mxm(F, A), A)
+    wr, wc, _ = W.tuples()
+    for fused in (False, True):
+        r, d = expand(L, src, [vA, vA], [], [vd], fused=fused)
+        sel = np.isin(wc, lab)
+        assert np.array_equal(r, wr[sel]) and np.array_equal(d, wc[sel]), f"fused={fused}"
+    # dirty label matrix: some labels dropped, some added since the base was written
+    drop = rng.choice(lab, 100, replace=False)
+    add = np.setdiff1d(rng.choice(n, 200, replace=False), lab)
+    for v in drop:
+        assert L.fdbh_vm_remove(vd, int(v), int(v)) == 0
+    for v in add:
+        assert L.fdbh_vm_set(vd, int(v), int(v)) == 0
+    lab2 = np.union1d(np.setdiff1d(lab, drop), add)
+    for fused in (False, True):
+        r, d = expand(L, src, [vA, vA], [], [vd], fused=fused)
+        sel = np.isin(wc, lab2)
+        assert np.array_equal(r, wr[sel]) and np.array_equal(d, wc[sel]), f"dirty labels, fused={fused}"
+    for h in (vA, vd):
         L.fdbh_vm_free(h)
