@@ -242,11 +242,17 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def chain(F):
+    pull_flops = [0, 0]               # [flops, hops] that took the pull direction (last_path 3), device-resident arm only
+
+    def chain(F, tally=False):
         fl = 0
         for _ in range(a.hops):
             F.lmxm(A)
-            fl += fb.get_stat("last_flops")
+            f1 = fb.get_stat("last_flops")
+            fl += f1
+            if tally and fb.get_stat("last_path") == 3:
+                pull_flops[0] += f1
+                pull_flops[1] += 1
         F.wait()                      # materialise sorted CSR on the device
         return fl
 
@@ -272,7 +278,7 @@ def run_b200(a):
     nnz_out = 0
     for i in range(a.warmup, nb):
         F = F0[i].dup()
-        flops += chain(F)
+        flops += chain(F, tally=True)
         nnz_out += F.nvals()
         del F
     e1.record(stream)
@@ -407,7 +413,20 @@ def run_b200(a):
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": peak_src, "traffic": traffic, "launch_ms": per_launch_ms, "launches": ks["launches"],
                 "share_of_step": ks["ms"] / ms,
-                "algorithmic_bytes_per_launch": per_launch_bytes}
+                "algorithmic_bytes_per_launch": per_launch_bytes,
+                "basis": "bytes this kernel family must move per launch (DESIGN.md 4.1), not SURVEY 8(d)'s row-wise figure"}
+        if dom == "bits_pull" and pull_flops[1]:
+            # SURVEY 8(d) bytes_mxm for the same launches: 4 B per flop (A's col_idx segment re-read for every frontier row) is
+            # the dominant term.  The bit-matrix kernel serves 64*W frontier rows per pass over A, so it never moves these bytes.
+            sb = 4.0 * pull_flops[0] / pull_flops[1]
+            roof["survey_8d"] = {"bytes_per_launch": sb, "achieved": sb / (per_launch_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                 "frac": sb / (per_launch_ms * 1e-3) / 1e9 / peak}
+            # what actually bounds it: random 32-byte gathers through L1TEX/L2 (one per edge of A'), against the rate the
+            # gather micro-benchmark sustains on this access pattern with every lane busy (profiles/r1c_ubench_gather.txt)
+            tl = ks["ms"] + kstats.get("bits_pull_long", {"ms": 0.0})["ms"]
+            gps = nnzA * ks["launches"] / (tl * 1e-3) / 1e9
+            roof["gather_bound"] = {"gathers_per_launch": nnzA, "achieved_ggathers_per_s": gps, "ceiling_ggathers_per_s": 240.0,
+                                    "frac": gps / 240.0, "time_ms_incl_long_rows": tl / ks["launches"]}
     # SURVEY 8d's row-wise formula (4 B per flop dominant) for the whole step, for reference: a frontier kernel that
     # serves 64*W rows per pass over A reads far fewer bytes than this, so this fraction may exceed 1.
     survey_bytes = 4 * flops + 4 * nnz_out
