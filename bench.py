@@ -150,6 +150,9 @@ def run_reference(a):
     if rank != 0:
         return
     import oracle as orc
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 per rank; this arm runs on rank 0 alone and is entitled to every host core
+        orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     t0 = time.time()
     A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
     gen_s = time.time() - t0
@@ -434,7 +437,7 @@ def run_b200(a):
               "frac_of_peak": survey_bytes / (ms * 1e-3) / 1e9 / peak}
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:      # the CPU baseline is an N=1 measurement (torchrun also pins OMP to 1 thread)
         try:
             import oracle as orc
             from oracle import CSR
