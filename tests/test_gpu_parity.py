@@ -625,3 +625,63 @@ def test_frontier_times_diagonal_label_matrix(diag_filter):
             assert_same(F, want, f"diag_filter={diag_filter} nsrc={nsrc}")
     finally:
         fb.set_option("diag_filter", 1)
+
+
+@pytest.mark.parametrize("frontier_log", [None, 9])
+def test_config2_single_mxm_on_rmat(frontier_log):
+    """BASELINE config 2 at test scale: one GrB_mxm over ANY_PAIR on an RMAT graph, F = A (full) and F = the rows of A
+    for a random frontier of 2^k vertices (the frontier path takes it when it has <= 1024 rows)"""
+    A = orc.rmat_csr(13, 16, 22)
+    n = A.nrows
+    dA = to_dev(A)
+    if frontier_log is None:
+        F, dF = A, to_dev(A)
+    else:
+        rng = np.random.default_rng(2)
+        front = np.sort(rng.choice(n, size=1 << frontier_log, replace=False))
+        rows = np.repeat(np.arange(len(front)), np.diff(A.p)[front])
+        cols = np.concatenate([A.j[A.p[v]:A.p[v + 1]] for v in front])
+        F = orc.build_matrix(len(front), n, rows, cols)
+        dF = to_dev(F)
+    want = orc.mxm(F, A)
+    C_ = Matrix(F.nrows, n, bool)
+    C_.mxm(dF, dA)
+    C_.wait()
+    assert fb.get_stat("last_flops") == int(np.diff(A.p)[F.j].sum())        # flops = sum of deg_A(k) over F's entries (SURVEY 8d)
+    assert_same(C_, want, f"config 2, frontier_log={frontier_log}")
+
+
+def ldbc_shaped(persons, posts, tags, seed):
+    """SF-shaped synthetic social graph, all matrices n x n with label ranges (graph.rs:1191, 1211): persons [0, P),
+    posts [P, P+Q), tags [P+Q, n).  KNOWS power-law among persons, one creator per post (person -> post), 1-3 tags per post
+    with a Zipf-like tag popularity.  Counts used are printed by the test on failure through the assertion message."""
+    rng = np.random.default_rng(seed)
+    n = persons + posts + tags
+    deg = np.minimum(persons - 1, (rng.pareto(1.6, persons) * 6 + 1).astype(np.int64))
+    ks = np.repeat(np.arange(persons), deg)
+    kd = rng.integers(0, persons, len(ks))
+    keep = ks != kd
+    knows = orc.build_matrix(n, n, np.concatenate([ks[keep], kd[keep]]), np.concatenate([kd[keep], ks[keep]]))   # symmetric
+    creator = np.minimum(persons - 1, (rng.pareto(1.2, posts) * persons / 20).astype(np.int64))
+    created = orc.build_matrix(n, n, creator, persons + np.arange(posts))
+    ntag = rng.integers(1, 4, posts)
+    ps = np.repeat(persons + np.arange(posts), ntag)
+    tg = persons + posts + np.minimum(tags - 1, (rng.pareto(1.1, len(ps)) * tags / 50).astype(np.int64))
+    hastag = orc.build_matrix(n, n, ps, tg)
+    return n, knows, created, hastag
+
+
+@pytest.mark.parametrize("persons,posts,tags", [(700, 9000, 300), (3000, 30000, 800)])
+def test_config3_three_hop_chain_over_three_relationship_matrices(persons, posts, tags):
+    """BASELINE config 3 at test scale: F = all Persons; F <- F*KNOWS*CREATED*HASTAG (friends' posts' tags).  <= 1024
+    persons ride the frontier bit-matrix path, more take the row-wise SpGEMM; both must match the oracle"""
+    n, knows, created, hastag = ldbc_shaped(persons, posts, tags, 5)
+    F = Matrix(persons, n, bool)
+    F.build(np.arange(persons), np.arange(persons))
+    want = orc.build_matrix(persons, n, np.arange(persons), np.arange(persons))
+    for M_ in (knows, created, hastag):
+        F.lmxm(to_dev(M_))
+        want = orc.mxm(want, M_)
+    F.wait()
+    assert want.nnz > 0 and want.j.min() >= persons + posts, "the chain must land in the tag range"
+    assert_same(F, want, f"config 3: persons={persons} posts={posts} tags={tags} nnz={knows.nnz},{created.nnz},{hastag.nnz}")
