@@ -228,6 +228,31 @@ __global__ void k_gather_small(const u32 *__restrict__ list, u32 nlist, const u6
     }
 }
 
+// ---- rows of A with at most one entry: C(i,:) is a copy of one row of B (the first hop of a traversal batch, where
+// F(i, src_i) = 1, cond_traverse.rs:600-601).  No sort, no dedupe, no binning: row pointers come straight from the prefix of
+// the entry degrees and one warp copies each row.
+__global__ void k_single_entry_rows(const u64 *__restrict__ Ap, u64 nrows, u32 *__restrict__ multi) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool b = r < nrows && Ap[r + 1] - Ap[r] > 1;
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(multi, 1u);
+}
+__global__ void k_copy_rowptr(const u64 *__restrict__ Ap, u64 nrows, const u64 *__restrict__ cum, u64 *__restrict__ Cp) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= nrows) Cp[r] = cum[Ap[r]];          // cum[e] = flops of the entries before e = entries of C before row(e)
+}
+__global__ void k_copy_rows(const u64 *__restrict__ Ap, u64 nrows, const u64 *__restrict__ cum, const u64 *__restrict__ bstart,
+                            const u32 *__restrict__ Bj, u32 *__restrict__ Cj) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 r = warp; r < nrows; r += nwarps) {
+        u64 e = Ap[r];
+        if (Ap[r + 1] == e) continue;
+        u64 dst = cum[e], n = cum[e + 1] - dst, src = bstart[e];
+        for (u64 q = lane; q < n; q += 32) Cj[dst + q] = Bj[src + q];
+    }
+}
+
 u64 spgemm_flops(const DevCSR &A, const DevCSR &B) {
     if (A.nnz == 0 || B.nnz == 0) return 0;
     DevBuf<u64> w(A.nnz + 1);
@@ -249,9 +274,29 @@ void spgemm_anypair(const DevCSR &A, const DevCSR &B, DevCSR &C, u64 *flops_out)
     DevBuf<u64> cum(A.nnz + 1), bstart(A.nnz);
     LAUNCH(k_entry_deg, grid_for(A.nnz + 1, 256, 1 << 16), 256, 0, A.j.ptr, A.nnz, B.p.ptr, cum.ptr, bstart.ptr);
     exclusive_scan_u64(cum.ptr, cum.ptr, A.nnz + 1);
-    u64 flops = read_scalar(cum.ptr + A.nnz);
+    DevBuf<u32> multi;
+    const bool maybe_single = A.nnz <= nrows;
+    if (maybe_single) {
+        multi.alloc(1);
+        multi.zero();
+        LAUNCH(k_single_entry_rows, grid_for(nrows, 256), 256, 0, A.p.ptr, nrows, multi.ptr);
+    }
+    u64 flops = 0;
+    u32 hm = 1;
+    d2h(&flops, cum.ptr + A.nnz, 1);
+    if (maybe_single) d2h(&hm, multi.ptr, 1);
+    sync_stream();                                 // the only host round trip of the single-entry path
     if (flops_out) *flops_out = flops;
     if (flops == 0) { C.p.zero(); C.nnz = 0; return; }
+    if (maybe_single) {
+        if (!hm) {
+            C.nnz = flops;
+            C.j.alloc(flops);
+            LAUNCH(k_copy_rowptr, grid_for(nrows + 1, 256), 256, 0, A.p.ptr, nrows, cum.ptr, C.p.ptr);
+            LAUNCH(k_copy_rows, grid_for(nrows * 32, 256, 148 * 16), 256, 0, A.p.ptr, nrows, cum.ptr, bstart.ptr, B.j.ptr, C.j.ptr);
+            return;
+        }
+    }
 
     // 2. classify rows
     u64 cap = (u64)cx.opt_small_cap;

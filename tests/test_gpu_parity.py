@@ -685,3 +685,27 @@ def test_config3_three_hop_chain_over_three_relationship_matrices(persons, posts
     F.wait()
     assert want.nnz > 0 and want.j.min() >= persons + posts, "the chain must land in the tag range"
     assert_same(F, want, f"config 3: persons={persons} posts={posts} tags={tags} nnz={knows.nnz},{created.nnz},{hastag.nnz}")
+
+
+def test_first_hop_copy_path_for_single_entry_rows():
+    """F(i, src_i) = 1 (cond_traverse.rs:600-601): the row-wise path copies rows of A instead of sorting; empty rows,
+    repeated sources, sinks and a valued operand included; one extra entry anywhere must fall back to the general path"""
+    fb.set_option("bits_mode", 0)
+    A = orc.rmat_csr(12, 16, 77)
+    n = A.nrows
+    rng = np.random.default_rng(6)
+    nsrc = 500
+    src = rng.integers(0, n, nsrc)                      # repeats allowed, sinks included
+    rows = np.arange(nsrc)
+    keep = rng.random(nsrc) < 0.8                       # some rows of F stay empty
+    F = orc.build_matrix(nsrc, n, rows[keep], src[keep])
+    Av = orc.CSR(n, n, A.p.copy(), A.j.copy(), np.arange(A.nnz, dtype=np.uint64) + 5)      # u64 operand: values never read
+    for B in (A, Av):
+        C_ = Matrix(nsrc, n, bool)
+        C_.mxm(to_dev(F), to_dev(B))
+        assert_same(C_, orc.mxm(F, A), "single-entry rows")
+        assert fb.get_stat("last_flops") == int(np.diff(A.p)[F.j].sum())
+    F2 = orc.build_matrix(nsrc, n, np.append(rows[keep], 7), np.append(src[keep], (src[7] + 1) % n))
+    C_ = Matrix(nsrc, n, bool)
+    C_.mxm(to_dev(F2), to_dev(A))
+    assert_same(C_, orc.mxm(F2, A), "one row with two entries")
