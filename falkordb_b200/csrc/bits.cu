@@ -622,6 +622,83 @@ k_bits_push(const u32 *__restrict__ act, const u64 *__restrict__ cum, const u64 
     }
 }
 
+// ---------------------------------------------------------------------------- push straight from a CSR frontier
+// Early hops of a traversal batch have a tiny frontier (F in CSR form, a few thousand entries).  Going through the
+// bit-matrix there means O(n*W) passes that dwarf the real work (zeroing X, scanning it for flops / active vertices,
+// compacting n flags); this path expands F's entries directly: entry (i, k) ORs bit i into Y[j] for every j in A(k,:).
+__global__ void k_csr_entry_info(const u64 *__restrict__ Fp, const u32 *__restrict__ Fj, u64 nrows, const u64 *__restrict__ Ap,
+                                 u32 *__restrict__ erow, u64 *__restrict__ edeg) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    for (u64 q = Fp[warp] + lane; q < Fp[warp + 1]; q += 32) {
+        u32 k = Fj[q];
+        erow[q] = (u32)warp;
+        edeg[q] = Ap[k + 1] - Ap[k];
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(256)
+k_csr_push(const u32 *__restrict__ erow, const u32 *__restrict__ Fj, const u64 *__restrict__ cum, u64 nent, u64 total,
+           const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, u64 *__restrict__ Y) {
+    __shared__ u64 s_e0, s_e1;
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    u64 lo = (u64)blockIdx.x * PUSH_CHUNK, hi = lo + PUSH_CHUNK;
+    if (hi > total) hi = total;
+    if (tid == 0) {
+        s_e0 = find_le64(cum, 0, nent - 1, lo);
+        s_e1 = find_le64(cum, 0, nent - 1, hi - 1);
+    }
+    __syncthreads();
+    u64 e0 = s_e0, e1 = s_e1;
+    for (u64 t0 = lo + (u64)warp * 32; t0 < hi; t0 += 8 * 32) {
+        u64 e = find_le64(cum, e0, e1, t0);
+        u64 t = t0 + lane;
+        if (t < hi) {
+            while (e < e1 && cum[e + 1] <= t) e++;
+            const u32 i = erow[e];
+            const u32 col = Aj[Ap[Fj[e]] + (t - cum[e])];
+            atomicOr((unsigned long long *)&Y[(u64)col * W + (i >> 6)], 1ULL << (i & 63));
+        }
+    }
+}
+template <int W>
+static void csr_push_impl(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 flops, const u32 *erow, const u64 *cum) {
+    u64 nchunks = (flops + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    TimedScope ts(TK_BITS_PUSH, 4 * flops + 16 * F.nnz + 8 * flops);
+    LAUNCH((k_csr_push<W>), (u32)nchunks, 256, 0, erow, F.j.ptr, cum, F.nnz, flops, A.p.ptr, A.j.ptr, Y.w.ptr);
+}
+// Y = F * A from the CSR form of F.  Returns false (nothing done) when the expansion is large enough that the
+// direction-optimising bit-matrix hop should take it: flops * 4 > nnz(A), the same switch bits_hop applies to edges.
+bool bits_push_from_csr(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 *flops_out) {
+    if (F.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
+    const u32 W = bits_words_for(F.nrows);
+    u64 flops = 0;
+    DevBuf<u32> erow(F.nnz);
+    DevBuf<u64> cum(F.nnz + 1);
+    if (F.nnz) {
+        LAUNCH(k_csr_entry_info, grid_for(F.nrows * 32, 256), 256, 0, F.p.ptr, F.j.ptr, F.nrows, A.p.ptr, erow.ptr, cum.ptr);
+        CUDA_TRY(cudaMemsetAsync(cum.ptr + F.nnz, 0, sizeof(u64), stream()));
+        exclusive_scan_u64(cum.ptr, cum.ptr, F.nnz + 1);
+        flops = read_scalar(cum.ptr + F.nnz);
+    }
+    if (flops * 4 > A.nnz) return false;
+    Y.clear();
+    Y.nrows = F.nrows; Y.ncols = A.ncols; Y.W = W;
+    Y.w.alloc(A.ncols * W);
+    Y.w.zero();
+    if (flops_out) *flops_out = flops;
+    if (flops == 0) return true;
+    switch (W) {
+    case 1: csr_push_impl<1>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    case 2: csr_push_impl<2>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    case 4: csr_push_impl<4>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    case 8: csr_push_impl<8>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    default: csr_push_impl<16>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------- pull
 // 8 lanes per output vertex j: OR of X[k] over k in A'(j,:).  Rows longer than LONG_ROW are
 // zeroed here and finished by k_bits_pull_long (several CTAs per row, RED.OR into Y).

@@ -950,13 +950,18 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
                 }
             }
             if (use_bits) {
-                ensure_bits(A);
                 ensure_dev(B);
                 if (B->diag_state < 0) B->diag_state = csr_is_diagonal(B->dev) ? 1 : 0;   // cached until B changes
                 DevBits Y;
                 u64 fl = 0;
                 int path = 0;
-                if (B->diag_state == 1 && cx.opt_diag_filter) { bits_diag(A->bits, B->dev, Y, &fl); path = 5; }
+                // a frontier that is still a (small) CSR expands straight from its entries; large expansions decline
+                const bool from_csr = cx.opt_csr_push && A->dev_valid && !A->bits_valid && cx.opt_pull_mode != 1 &&
+                                      !(B->diag_state == 1 && cx.opt_diag_filter) && bits_push_from_csr(A->dev, B->dev, Y, &fl);
+                if (from_csr) path = 7;
+                else ensure_bits(A);
+                if (from_csr) {}
+                else if (B->diag_state == 1 && cx.opt_diag_filter) { bits_diag(A->bits, B->dev, Y, &fl); path = 5; }
                 else {
                     if (cx.opt_pull_mode != 0) ensure_devT(B);
                     bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : (LongRows *)nullptr, Y, &fl, &path);
@@ -1726,6 +1731,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "pull_grid") c.opt_pull_grid = value;
     else if (n == "fill_kernel") c.opt_fill_kernel = value;
     else if (n == "diag_filter") c.opt_diag_filter = value;
+    else if (n == "csr_push") c.opt_csr_push = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

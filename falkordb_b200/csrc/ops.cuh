@@ -20,6 +20,8 @@ u32 bits_words_for(u64 nrows);
 void bits_from_csr(const DevCSR &F, DevBits &X);
 void bits_to_csr(const DevBits &X, DevCSR &C);
 u64 bits_nvals(const DevBits &X);
+// Y = F * A expanded straight from F's CSR (tiny frontiers); false = too much work for this path, nothing was done
+bool bits_push_from_csr(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 *flops_out);
 bool csr_is_diagonal(const DevCSR &A);                          // square, every entry (i,i)
 void bits_diag(const DevBits &X, const DevCSR &A, DevBits &Y, u64 *flops_out);   // Y = X * A for diagonal A
 void bits_to_rowmajor(const DevBits &X, u64 *out, u64 wpr);   // out[row * wpr + (col >> 6)], every word written

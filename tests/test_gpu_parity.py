@@ -709,3 +709,41 @@ def test_first_hop_copy_path_for_single_entry_rows():
     C_ = Matrix(nsrc, n, bool)
     C_.mxm(to_dev(F2), to_dev(A))
     assert_same(C_, orc.mxm(F2, A), "one row with two entries")
+
+
+@pytest.mark.parametrize("nsrc", [3, 64, 200, 1000])
+def test_push_straight_from_a_csr_frontier(nsrc):
+    """a tiny CSR frontier expands from its entries (path 7) without a bit-matrix of its own; duplicates of a source,
+    sinks, a structural-complement mask (delta_lmxm's RSC form) and the decline rule for large expansions"""
+    A = orc.rmat_csr(12, 8, 3)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc)
+    src = rng.integers(0, n, nsrc)
+    F0 = orc.build_matrix(nsrc, n, np.arange(nsrc), src)
+    dA = to_dev(A)
+    for csr_push in (1, 0):
+        fb.set_option("bits_mode", 1)
+        fb.set_option("csr_push", csr_push)
+        try:
+            F = to_dev(F0)
+            F.lmxm(dA)
+            assert fb.get_stat("last_path") == (7 if csr_push else fb.get_stat("last_path"))
+            want = orc.mxm(F0, A)
+            assert fb.get_stat("last_flops") == int(np.diff(A.p)[F0.j].sum())
+            assert F.nvals() == want.nnz
+            F.wait()
+            assert_same(F, want, f"csr push={csr_push} nsrc={nsrc}")
+            # masked form C<!struct(M), replace> = F0 * A (matrix.rs:1386, GrB_DESC_RSC)
+            M = rand_csr(rng, nsrc, n, 0.3)
+            C_ = to_dev(F0)
+            C_.mxm(C_, dA, to_dev(M), Descriptor.RSC)
+            assert_same(C_, orc.mxm(F0, A, M, mask_mode=2), "masked csr push")
+        finally:
+            fb.set_option("csr_push", 1)
+    # a dense CSR frontier must decline (flops * 4 > nnz(A)) and take the bit-matrix hop instead
+    Fd = rand_csr(rng, 64, n, 0.2)
+    G = to_dev(Fd)
+    G.lmxm(dA)
+    assert fb.get_stat("last_path") != 7
+    G.wait()
+    assert_same(G, orc.mxm(Fd, A), "declined csr push")
