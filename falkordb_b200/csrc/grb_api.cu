@@ -85,6 +85,7 @@ struct GB_Matrix_opaque {
     bool dev_valid = false;
     DevCSR dev;
     bool bits_valid = false;
+    u64 bits_nv = ~0ULL;   // nvals of `bits` once counted (~0 = not yet)
     int diag_state = -1;   // -1 unknown, 0 no, 1 the device CSR is a diagonal matrix (label matrix): mxm by it is a column filter
     DevBits bits;
     bool devT_valid = false;
@@ -199,6 +200,7 @@ static void set_dev(GrB_Matrix A, DevCSR &&d) {
 
 static void set_bits(GrB_Matrix A, DevBits &&b) {
     A->bits = std::move(b);
+    A->bits_nv = ~0ULL;
     A->bits_valid = true;
     A->dev_valid = false;
     A->dev.clear();
@@ -348,6 +350,7 @@ static void ensure_bits(GrB_Matrix A) {
     DevBits b;
     bits_from_csr(A->dev, b);
     A->bits = std::move(b);
+    A->bits_nv = A->dev.nnz;
     A->bits_valid = true;
 }
 
@@ -366,7 +369,8 @@ static u64 matrix_nvals(GrB_Matrix A) {
     finish_pending(A);
     if (A->host_valid) return A->host.nnz();
     if (A->dev_valid) return A->dev.nnz;
-    return bits_nvals(A->bits);
+    if (A->bits_nv == ~0ULL) A->bits_nv = bits_nvals(A->bits);   // popcount pass, remembered until the bit-matrix changes
+    return A->bits_nv;
 }
 
 // ------------------------------------------------------------------------------------------------ write-back
@@ -548,7 +552,7 @@ GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A) {
         m->host_valid = A->host_valid;
         if (A->host_valid) m->host = A->host;
         if (A->dev_valid) { csr_copy(A->dev, m->dev, true); m->dev_valid = true; }
-        if (A->bits_valid && !A->dev_valid) { bits_copy(A->bits, m->bits); m->bits_valid = true; }
+        if (A->bits_valid && !A->dev_valid) { bits_copy(A->bits, m->bits); m->bits_valid = true; m->bits_nv = A->bits_nv; }
         *C = m;
         return GrB_SUCCESS;
     });
@@ -1521,7 +1525,7 @@ GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t wo
         if (location != B200_LOC_DEVICE) { stage.alloc(total); dst = stage.ptr; }
         if (from_bits) {
             bits_to_rowmajor(A->bits, dst, wpr);
-            if (nvals_out) *nvals_out = bits_nvals(A->bits);
+            if (nvals_out) { if (A->bits_nv == ~0ULL) A->bits_nv = bits_nvals(A->bits); *nvals_out = A->bits_nv; }
         } else {
             if (total) CUDA_TRY(cudaMemsetAsync(dst, 0, total * sizeof(u64), stream()));
             csr_to_rowmajor(A->dev, dst, wpr);
