@@ -944,12 +944,14 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
         // ---- frontier bit-matrix path (short-fat A, CondTraverse's F*A) ----
         if (!accum && !d.t0 && !d.t1 && cx.opt_bits_mode != 0 && bits_legal(C, Mask, A, B, d)) {
             bool use_bits = (cx.opt_bits_mode == 1);
+            u64 known_flops = ~0ULL;
             finish_pending(A);
             if (!use_bits) {
                 if (A->bits_valid && !A->dev_valid && !A->host_valid) use_bits = true; // stay in frontier form mid-chain
                 else {
                     ensure_dev(A); ensure_dev(B);
                     u64 fl = spgemm_flops(A->dev, B->dev);
+                    known_flops = fl;
                     use_bits = fl >= (u64)cx.opt_bits_min_flops;
                 }
             }
@@ -960,7 +962,9 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
                 u64 fl = 0;
                 int path = 0;
                 // a frontier that is still a (small) CSR expands straight from its entries; large expansions decline
+                // (only worth probing for a small CSR: its preparation is O(nnz(F)); an expansion already known to be large skips it)
                 const bool from_csr = cx.opt_csr_push && A->dev_valid && !A->bits_valid && cx.opt_pull_mode != 1 &&
+                                      A->dev.nnz <= ((u64)1 << 20) && (known_flops == ~0ULL || known_flops * 4 <= B->dev.nnz) &&
                                       !(B->diag_state == 1 && cx.opt_diag_filter) && bits_push_from_csr(A->dev, B->dev, Y, &fl);
                 if (from_csr) path = 7;
                 else ensure_bits(A);
