@@ -406,7 +406,7 @@ def run_b200(a):
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         traffic = None
         try:   # dram__bytes_read+write per launch from the committed ncu --set full captures of this configuration
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))
             fam = {"bits_pull": ("k_bits_pull_mid", "k_bits_pull_small"), "bits_fill": ("k_bits_fill_rows",)}
             if (tj["config"]["scale"] == a.scale and tj["config"]["sources"] == a.sources and tj["config"]["edge_factor"] == a.edge_factor
                     and dom in fam and not a.opt):
