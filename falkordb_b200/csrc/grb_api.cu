@@ -14,6 +14,7 @@
 #include "ops.cuh"
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1537,6 +1538,68 @@ GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t wo
         }
         if (location != B200_LOC_DEVICE && total) d2h((u64 *)bits_out, dst, total);
         sync_stream();
+        return GrB_SUCCESS;
+    });
+}
+
+// ---- asynchronous bitmap hand-off: the D2H copy runs on a second stream, so the next batch's hops overlap it ----
+struct B200_Ticket_opaque {
+    DevBuf<u64> stage;          // row-major bitmap on the device, alive until the copy has finished
+    cudaEvent_t done = nullptr; // recorded on the copy stream after the D2H
+};
+static cudaStream_t g_copy_stream = nullptr;
+
+GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, B200_Ticket *ticket) {
+    CHECK_MAT(A);
+    if (!bits_out || !ticket) { tl_error = "export_bitmap_async: null argument"; return GrB_NULL_POINTER; }
+    return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);
+        MultiLock lk{A};
+        ensure_init();
+        finish_pending(A);
+        const u64 wpr = (A->ncols + 63) / 64;
+        if (words_per_row != wpr) throw GrbError(GrB_DIMENSION_MISMATCH, "export_bitmap_async: words_per_row must be ceil(ncols / 64)");
+        if (A->nrows && wpr > (1ULL << 36) / A->nrows) throw GrbError(GrB_OUT_OF_MEMORY, "export_bitmap_async: bitmap larger than 512 GiB");
+        const u64 total = A->nrows * wpr;
+        const bool from_bits = A->bits_valid && A->bits.nrows == A->nrows;
+        if (!from_bits) ensure_dev(A);
+        if (!g_copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        std::unique_ptr<B200_Ticket_opaque> t(new B200_Ticket_opaque());
+        t->stage.alloc(total);
+        if (from_bits) bits_to_rowmajor(A->bits, t->stage.ptr, wpr);
+        else {
+            if (total) CUDA_TRY(cudaMemsetAsync(t->stage.ptr, 0, total * sizeof(u64), stream()));
+            csr_to_rowmajor(A->dev, t->stage.ptr, wpr);
+        }
+        cudaEvent_t ready;
+        CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ready, stream()));
+        CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, ready, 0));
+        CUDA_TRY(cudaEventDestroy(ready));                  // released once the wait it feeds has been satisfied
+        if (total) {
+            CUDA_TRY(cudaMemcpyAsync(bits_out, t->stage.ptr, total * sizeof(u64), cudaMemcpyDeviceToHost, g_copy_stream));
+            ctx().d2h_bytes += total * sizeof(u64);
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(t->done, g_copy_stream));
+        *ticket = t.release();
+        return GrB_SUCCESS;
+    });
+}
+// blocks until the copy behind `ticket` has landed in the caller's buffer, then releases the ticket
+GrB_Info B200_Ticket_wait(B200_Ticket *ticket) {
+    if (!ticket || !*ticket) return GrB_SUCCESS;
+    return guarded([&]() {
+        B200_Ticket t = *ticket;
+        *ticket = nullptr;
+        cudaError_t e = cudaEventSynchronize(t->done);
+        cudaEventDestroy(t->done);
+        {
+            std::lock_guard<std::mutex> g(g_gpu_mu);     // the staging block goes back to the (single-stream) pool
+            t->stage.release();
+        }
+        delete t;
+        if (e != cudaSuccess) throw CudaError(e, __FILE__, __LINE__);
         return GrB_SUCCESS;
     });
 }

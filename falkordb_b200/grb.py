@@ -100,6 +100,16 @@ class Matrix:
         check(lib().B200_Matrix_export_bitmap(self.h, out.ctypes.data, wpr, C.byref(nv), 0))
         return out, nv.value
 
+    def export_bitmap_async(self, out):
+        """Non-blocking export_bitmap into `out` (pinned uint64[nrows, ceil(ncols/64)]): returns a ticket for `wait_ticket`;
+        the copy runs on the library's second stream, so further mxm calls overlap it.  The matrix may be dropped at once."""
+        nr, nc = self.nrows(), self.ncols()
+        wpr = (nc + 63) // 64
+        assert out.dtype == np.uint64 and out.size >= nr * wpr and out.flags.c_contiguous
+        t = P()
+        check(lib().B200_Matrix_export_bitmap_async(self.h, out.ctypes.data, wpr, C.byref(t)))
+        return t
+
     def export_auto(self, out_bitmap=None):
         """The result hand-off a traversal operator makes: bitmap when the result is denser than one entry per 32 slots
         (1 bit per slot beats a 4-byte column index per entry), CSR otherwise -- the rule SuiteSparse applies when it
@@ -378,3 +388,31 @@ def set_option(name, value):
 
 def sync():
     check(lib().B200_sync())
+
+
+def wait_ticket(ticket):
+    """B200_Ticket_wait: the buffer given to export_bitmap_async is complete when this returns."""
+    check(lib().B200_Ticket_wait(C.byref(ticket)))
+
+
+def traverse_to_host(sources, A, hops, out_bitmap, sub_batches=4):
+    """The batched traversal an operator runs (cond_traverse.rs:600-608), host to host: F(i, sources[i]) = 1, `hops` x
+    F <- F*A, result rows into `out_bitmap` (pinned uint64[len(sources), ceil(n/64)], packed row-major bitmap).
+    The batch is processed in `sub_batches` row slices (multiples of 64 rows): while slice k's bitmap crosses PCIe on the
+    copy stream, slice k+1's hops run -- the result transfer, not the GPU, is what bounds this call.
+    Returns the flops (edges traversed).  For dense results; sparse ones are cheaper through Matrix.export_auto."""
+    sources = _u64arr(sources)
+    nsrc, n = len(sources), A.ncols()
+    per = max(64, -(-nsrc // max(1, sub_batches)) + 63 & ~63)
+    tickets, flops = [], 0
+    for r0 in range(0, nsrc, per):
+        r1 = min(nsrc, r0 + per)
+        F = Matrix(r1 - r0, n, bool)
+        F.build(np.arange(r1 - r0, dtype=np.uint64), sources[r0:r1])
+        for _ in range(hops):
+            F.lmxm(A)
+            flops += get_stat("last_flops")
+        tickets.append(F.export_bitmap_async(out_bitmap[r0:r1]))
+    for t in tickets:
+        wait_ticket(t)
+    return flops

@@ -264,6 +264,12 @@ GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64
  * GxB_Matrix_export_BitmapR; this is the 1-bit-per-slot equivalent): a frontier chain result that is still in device
  * bit-matrix form is exported without ever building its CSR.  Cheaper than CSR when nvals * 32 > nrows * ncols. */
 GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, uint64_t *nvals_out, int location);
+/* Same hand-off without blocking: the device-to-host copy runs on a second stream, so the caller can submit the next
+ * batch's GrB_mxm calls while it is in flight (bits_out should be pinned).  A may be modified or freed right away; bits_out
+ * is complete once B200_Ticket_wait returns.  Every ticket must be waited on exactly once. */
+typedef struct B200_Ticket_opaque *B200_Ticket;
+GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, B200_Ticket *ticket);
+GrB_Info B200_Ticket_wait(B200_Ticket *ticket);
 /* Borrow the device-resident CSR (valid until A is next modified or freed). */
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax);
 /* Pre-build the cached transpose mirror used by the pull direction (done lazily otherwise). */

@@ -747,3 +747,32 @@ def test_push_straight_from_a_csr_frontier(nsrc):
     assert fb.get_stat("last_path") != 7
     G.wait()
     assert_same(G, orc.mxm(Fd, A), "declined csr push")
+
+
+@pytest.mark.parametrize("nsrc,subs", [(256, 4), (200, 3), (64, 4), (70, 1), (1000, 5)])
+def test_traverse_to_host_sliced_async_hand_off(nsrc, subs):
+    """falkordb_b200.traverse_to_host: row slices of the batch, each slice's bitmap copied on the second stream while the
+    next slice computes; the assembled bitmap and the flops equal the one-shot chain's"""
+    import torch
+    A = orc.rmat_csr(12, 8, 41)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc * 7 + subs)
+    src = rng.choice(n, size=nsrc, replace=False)
+    dA = to_dev(A)
+    wpr = (n + 63) // 64
+    out = torch.zeros(nsrc * wpr, dtype=torch.int64).pin_memory().numpy().view(np.uint64).reshape(nsrc, wpr)
+    out[:] = np.uint64(0xDEADBEEF)                          # every word must be overwritten
+    fl = fb.traverse_to_host(src, dA, 3, out, subs)
+    want = orc.build_matrix(nsrc, n, np.arange(nsrc), src)
+    wfl = 0
+    for _ in range(3):
+        wfl += int(np.diff(A.p)[want.j].sum())
+        want = orc.mxm(want, A)
+    assert fl == wfl
+    assert np.array_equal(out, bitmap_of(want))
+    # tickets: waiting twice is a no-op, an un-issued ticket too
+    F = to_dev(want)
+    t = F.export_bitmap_async(out)
+    fb.wait_ticket(t)
+    fb.wait_ticket(t)
+    assert np.array_equal(out, bitmap_of(want))
