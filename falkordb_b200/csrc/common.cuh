@@ -123,12 +123,18 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
-inline void sync_stream() { CUDA_TRY(cudaStreamSynchronize(stream())); }
+// Small device-to-host reads (scalars the host steers by: flops, nnz, bin counts) do not use the copy engine: a one-warp
+// kernel stores them into mapped pinned memory and sync_stream() hands them to their destinations.  A DMA read-back would
+// queue behind whatever the D2H engine is busy with -- e.g. the 100+ MB result bitmap of the previous batch slice travelling
+// on the copy stream -- and stall the compute stream for milliseconds (prims.cu).
+bool small_read(void *dst, const void *src, size_t bytes);   // false: not taken (too large / no slot), use a memcpy
+void flush_small_reads();                                    // after the stream has been synchronised
+inline void sync_stream() { CUDA_TRY(cudaStreamSynchronize(stream())); flush_small_reads(); }
 
 template <typename T>
 inline T read_scalar(const T *dptr) {
     T v;
-    CUDA_TRY(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, stream()));
+    if (!small_read(&v, dptr, sizeof(T))) CUDA_TRY(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, stream()));
     sync_stream();
     return v;
 }
@@ -138,7 +144,10 @@ inline void h2d(T *dst, const T *src, size_t n) {
 }
 template <typename T>
 inline void d2h(T *dst, const T *src, size_t n) {
-    if (n) { CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream())); ctx().d2h_bytes += n * sizeof(T); }
+    if (n) {
+        if (!small_read(dst, src, n * sizeof(T))) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+        ctx().d2h_bytes += n * sizeof(T);
+    }
 }
 template <typename T>
 inline void d2d(T *dst, const T *src, size_t n) {

@@ -1745,6 +1745,7 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
 
 GrB_Info B200_sync(void) {
     return guarded([&]() {
+        std::lock_guard<std::mutex> g(g_gpu_mu);   // sync_stream also delivers pending small reads: not under a submitter's feet
         if (ctx().ready) sync_stream();
         return GrB_SUCCESS;
     });

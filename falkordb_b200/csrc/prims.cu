@@ -36,6 +36,38 @@ void ensure_init() {
     c.ready = true;
 }
 
+// ---- small reads through mapped pinned memory (see common.cuh) -------------------------------------------------------
+static const size_t SMALL_READ_MAX = 64, SMALL_SLOTS_BYTES = 8192;
+static unsigned char *g_slots_host = nullptr, *g_slots_dev = nullptr;
+static size_t g_slots_used = 0;
+struct SmallPending { void *dst; size_t off, bytes; };
+static std::vector<SmallPending> g_small_pending;
+static std::mutex g_small_mu;
+__global__ void k_small_read(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src, u32 bytes) {
+    for (u32 i = threadIdx.x; i < bytes; i += 32) dst[i] = src[i];
+}
+bool small_read(void *dst, const void *src, size_t bytes) {
+    if (bytes == 0 || bytes > SMALL_READ_MAX || !ctx().ready) return false;
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    if (!g_slots_host) {
+        if (cudaHostAlloc((void **)&g_slots_host, SMALL_SLOTS_BYTES, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaHostGetDevicePointer((void **)&g_slots_dev, g_slots_host, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(g_slots_host); g_slots_host = nullptr; return false; }
+    }
+    size_t off = (g_slots_used + 15) & ~(size_t)15;
+    if (off + bytes > SMALL_SLOTS_BYTES) return false;
+    g_slots_used = off + bytes;
+    k_small_read<<<1, 32, 0, stream()>>>(g_slots_dev + off, (const unsigned char *)src, (u32)bytes);
+    if (cudaGetLastError() != cudaSuccess) { g_slots_used = off; return false; }
+    g_small_pending.push_back({dst, off, bytes});
+    return true;
+}
+void flush_small_reads() {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    for (const SmallPending &p : g_small_pending) memcpy(p.dst, g_slots_host + p.off, p.bytes);
+    g_small_pending.clear();
+    g_slots_used = 0;
+}
+
 // ---- caching allocator ----------------------------------------------------------------------------------
 static std::mutex g_pool_mu;
 static std::map<size_t, std::vector<void *>> g_free;     // class size -> cached blocks
