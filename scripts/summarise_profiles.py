@@ -51,7 +51,8 @@ def table(seg, title, out):
 
 def main():
     tag, lpath, bpath, reps = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4:]
-    out = [f"# {tag}: ncu evidence for `python bench.py` (B200, RMAT-24 ef16, 256 sources/batch = W=4, 3-hop chain)",
+    b0 = json.load(open(bpath))
+    out = [f"# {tag}: ncu evidence for `python bench.py` (B200, RMAT-24 ef16, {b0['config']['sources_per_gpu_per_step']} sources/batch, 3-hop chain)",
            "# launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv python bench.py --steps 2 --warmup 1"
            " --no-cpu-baseline --e2e-format csr", ""]
     recs = launches(lpath)
@@ -84,7 +85,7 @@ def main():
             "  cpu_baseline: " + json.dumps(b.get("cpu_baseline"))]
     out += ["", "# measured DRAM bytes per launch (ncu, read + write): " + json.dumps({k: round(x / 1e9, 3) for k, x in traffic.items()}) + " GB"]
     open(f"profiles/{tag}_launches_and_kernels.txt", "w").write("\n".join(out) + "\n")
-    json.dump({"config": {"scale": 24, "edge_factor": 16, "sources": 256}, "dram_bytes_by_kernel": traffic},
+    json.dump({"config": {"scale": 24, "edge_factor": 16, "sources": b["config"]["sources_per_gpu_per_step"]}, "dram_bytes_by_kernel": traffic},
               open(f"profiles/{tag}_traffic.json", "w"), indent=1)
     print("\n".join(out))
 
