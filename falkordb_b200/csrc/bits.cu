@@ -1361,12 +1361,13 @@ __global__ void k_degree_keys(const u64 *__restrict__ Ap, u64 n, u64 *__restrict
     }
     if (cnt) atomicAdd((unsigned long long *)n1, cnt);
 }
-__global__ void k_slots_from_keys(const u64 *__restrict__ keys, u64 n, u64 n1, u32 *__restrict__ vert, u32 *__restrict__ slot) {
+__global__ void k_slots_from_keys(const u64 *__restrict__ keys, u64 n, u64 n1, u32 *__restrict__ vert, u32 *__restrict__ slot,
+                                  u32 *__restrict__ hdeg) {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 stride = (u64)gridDim.x * blockDim.x;
     for (; s < n; s += stride) {
         u32 v = (u32)(keys[s] & 0xFFFFFFFFULL);
-        if (s < n1) { vert[s] = v; slot[v] = (u32)s; } else slot[v] = 0xFFFFFFFFu;
+        if (s < n1) { vert[s] = v; slot[v] = (u32)s; hdeg[s] = 0xFFFFFFFFu - (u32)(keys[s] >> 32); } else slot[v] = 0xFFFFFFFFu;
     }
 }
 __global__ void k_relabel_cols(const u32 *__restrict__ j, u64 nnz, const u32 *__restrict__ slot, u32 *__restrict__ jp) {
@@ -1384,9 +1385,56 @@ __global__ void k_pack_frontier(const u32 *__restrict__ vert, u64 n1, const u64 
     }
 }
 
+// pack + flops + edges + OR-of-everything in one pass over the frontier (fused_prep): the hot set holds every vertex with
+// out-edges, so flops = sum popc(X[v]) * deg(v) and edges = sum [X[v] != 0] * deg(v) over it are the exact totals, and
+// G[w] = OR of word column w is the terminal value the pull kernels vote against.  One thread per packed word.
+template <int W>
+__global__ void __launch_bounds__(256)
+k_pack_flops(const u32 *__restrict__ vert, const u32 *__restrict__ hdeg, u64 n1, const u64 *__restrict__ X, u64 *__restrict__ Xp,
+             u64 *__restrict__ st /* [0] flops [1] edges */, u64 *__restrict__ G) {
+    typedef cub::BlockReduce<u64, 256> Red;
+    __shared__ typename Red::TempStorage ts;
+    __shared__ u64 sG[W];
+    if (threadIdx.x < W) sG[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const u32 gmask = (W >= 32) ? 0xffffffffu : (((1u << W) - 1u) << (lane / W * W));   // the W lanes of one vertex
+    u64 fl = 0, ed = 0, g = 0;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x, total = n1 * W;
+    for (u64 base = t - lane; base < total; base += stride) {       // warp-uniform trip count (ballot inside)
+        const u64 tt = base + lane;
+        u64 x = 0;
+        u32 d = 0;
+        if (tt < total) {
+            const u64 s = tt / W, w = tt % W;
+            x = X[(u64)vert[s] * W + w];
+            d = hdeg[s];
+            Xp[tt] = x;
+        }
+        const u32 nz = __ballot_sync(0xffffffffu, x != 0) & gmask;
+        fl += (u64)__popcll(x) * d;
+        if (nz && (lane % W) == 0) ed += d;
+        g |= x;
+    }
+    // OR across the lanes that hold the same word column (lane % W), then one shared atomic per column and warp
+#pragma unroll
+    for (int o = W; o < 32; o <<= 1) g |= __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane < W && g) atomicOr((unsigned long long *)&sG[lane], g);
+    u64 tf = Red(ts).Sum(fl);
+    __syncthreads();
+    u64 te = Red(ts).Sum(ed);
+    if (threadIdx.x == 0) {
+        if (tf) atomicAdd((unsigned long long *)&st[0], tf);
+        if (te) atomicAdd((unsigned long long *)&st[1], te);
+    }
+    __syncthreads();
+    if (threadIdx.x < W && sG[threadIdx.x]) atomicOr((unsigned long long *)&G[threadIdx.x], sG[threadIdx.x]);
+}
+
 void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
     u64 n = A.nrows;
-    lr.vert.release(); lr.jp.release(); lr.slot.release(); lr.n1 = 0; lr.packed = false;
+    lr.vert.release(); lr.jp.release(); lr.slot.release(); lr.hdeg.release(); lr.n1 = 0; lr.packed = false;
     if (n == 0 || AT.nnz == 0 || n >= 0xFFFFFFFFULL) return;
     DevBuf<u64> keys(n), cnt(1);
     cnt.zero();
@@ -1396,7 +1444,8 @@ void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
     lr.n1 = n1;
     lr.vert.alloc(n1 ? n1 : 1);
     lr.slot.alloc(n);
-    LAUNCH(k_slots_from_keys, grid_for(n, 256, 148 * 16), 256, 0, keys.ptr, n, n1, lr.vert.ptr, lr.slot.ptr);
+    lr.hdeg.alloc(n1 ? n1 : 1);
+    LAUNCH(k_slots_from_keys, grid_for(n, 256, 148 * 16), 256, 0, keys.ptr, n, n1, lr.vert.ptr, lr.slot.ptr, lr.hdeg.ptr);
     lr.packed = true;
 }
 
@@ -1583,7 +1632,17 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     DevBuf<u32> flag(n + 1);
     DevBuf<u64> st(2);
     st.zero();
-    if (n) LAUNCH(k_bits_flops, grid_for(n, 256, 148 * 16), 256, 0, X.w.ptr, (u32)W, n, A.p.ptr, flag.ptr, st.ptr);
+    // fused_prep: when the hot-set tables exist, one pass packs the frontier for the pull AND yields flops / edges / the OR
+    // terminal; the separate flops pass (needed for its per-vertex flags) then only runs if the push direction wins
+    const bool fused = cx.opt_fused_prep && AT && lr && cx.opt_hot_pack && lr->packed && lr->jp.ptr && lr->hdeg.ptr &&
+                       cx.opt_pull_mode != 0 && cx.opt_pull_kernel != 2 && n == m;
+    DevBuf<u64> Xp, Gd;
+    if (fused) {
+        Xp.alloc(lr->n1 * W);
+        Gd.alloc(W);
+        Gd.zero();
+        if (lr->n1) LAUNCH((k_pack_flops<W>), grid_for(lr->n1 * W, 256, 148 * 16), 256, 0, lr->vert.ptr, lr->hdeg.ptr, lr->n1, X.w.ptr, Xp.ptr, st.ptr, Gd.ptr);
+    } else if (n) LAUNCH(k_bits_flops, grid_for(n, 256, 148 * 16), 256, 0, X.w.ptr, (u32)W, n, A.p.ptr, flag.ptr, st.ptr);
     u64 hst[2] = {0, 0};
     d2h(hst, st.ptr, 2);
     sync_stream();
@@ -1599,7 +1658,11 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     const u32 *gj = AT ? AT->j.ptr : nullptr;   // gather index stream
     const u64 *gx = X.w.ptr;                    // gather source
     u64 gn = n;                                 // gather footprint in vertices
-    DevBuf<u64> Xp;
+    if (fused && !pull) {                       // push needs the per-vertex active flags of the classic pass
+        DevBuf<u64> st2(2);
+        st2.zero();
+        LAUNCH(k_bits_flops, grid_for(n, 256, 148 * 16), 256, 0, X.w.ptr, (u32)W, n, A.p.ptr, flag.ptr, st2.ptr);
+    }
     const bool stream_kernel = pull && W <= 4 && cx.opt_pull_kernel == 2;
     if (pull) {   // auxiliary tables are built once per (immutable) matrix, lazily
         if (!lr->packed && cx.opt_hot_pack) build_hot_pack(A, *AT, *lr);
@@ -1626,20 +1689,23 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         return;
     }
     if (pull && cx.opt_hot_pack && lr->packed && lr->jp.ptr) {
-        Xp.alloc(lr->n1 * W);
-        if (lr->n1) LAUNCH((k_pack_frontier<W>), grid_for(lr->n1 * W, 256, 148 * 32), 256, 0, lr->vert.ptr, lr->n1, X.w.ptr, Xp.ptr);
+        if (!fused) {
+            Xp.alloc(lr->n1 * W);
+            if (lr->n1) LAUNCH((k_pack_frontier<W>), grid_for(lr->n1 * W, 256, 148 * 32), 256, 0, lr->vert.ptr, lr->n1, X.w.ptr, Xp.ptr);
+        }
         gj = lr->jp.ptr; gx = Xp.ptr; gn = lr->n1;
     }
-    DevBuf<u64> Gd;
     const u64 *Gp = nullptr;
     // opt_early_exit: 0 never, 1 auto, 2 always.  Measured on B200 (RMAT-24, hop 3): the in-loop vote pays for itself at
     // W = 2 and 4 (hub rows saturate: pull 2.92 -> 2.56 ms and 4.07 -> 3.66 ms), costs more than it saves at W = 1
     // (2.08 -> 3.14 ms, few rows ever hold all 64 bits) and at W >= 8; very dense frontiers always benefit.
     const bool dense_frontier = hst[0] >= (hst[1] * X.nrows) / 4;   // flops/edges = degree-weighted mean popcount of a gathered word
     if (pull && (cx.opt_early_exit == 2 || (cx.opt_early_exit == 1 && (dense_frontier || W == 2 || W == 4)))) {
-        Gd.alloc(W);
-        Gd.zero();
-        if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);
+        if (!(fused && gx == Xp.ptr)) {          // the fused pass already left the OR of the packed frontier in Gd
+            Gd.alloc(W);
+            Gd.zero();
+            if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);
+        }
         Gp = Gd.ptr;
     }
     if (pull && cx.opt_pull_kernel == 1) {

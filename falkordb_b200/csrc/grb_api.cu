@@ -1804,6 +1804,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "fill_kernel") c.opt_fill_kernel = value;
     else if (n == "diag_filter") c.opt_diag_filter = value;
     else if (n == "csr_push") c.opt_csr_push = value;
+    else if (n == "fused_prep") c.opt_fused_prep = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

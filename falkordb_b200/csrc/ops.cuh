@@ -35,7 +35,7 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u32> m_row, m_len; DevBuf<u64> m_start; u64 nm = 0;   // mid rows (SMALL_ROW < len <= LONG_ROW), longest first
     DevBuf<u32> jp;                                    // relabelled col_idx of A' (all rows)
     // hot-set packing: vertices with out-edges, by out-degree descending
-    DevBuf<u32> vert, slot; u64 n1 = 0; bool packed = false;
+    DevBuf<u32> vert, slot, hdeg; u64 n1 = 0; bool packed = false;   // hdeg[s] = out-degree of vert[s]
     // CSR-stream form for the pull kernel: short rows of A' (cols relabelled to slots), window -> first row,
     // and the long rows kept apart; built per frontier word count W
     u32 sW = 0; u64 swin = 0; bool s_packed = false;
@@ -43,7 +43,7 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u32> lrows, jp_l; DevBuf<u64> lrp; u64 nlong = 0, maxlong = 0;
     void clear() {
         built = false; rows.release(); n = 0; maxdeg = 0; choff.release(); nchunks = 0; mp_r.release(); jp.release(); m_row.release(); m_len.release(); m_start.release(); nm = 0;
-        vert.release(); slot.release(); n1 = 0; packed = false;
+        vert.release(); slot.release(); hdeg.release(); n1 = 0; packed = false;
         sW = 0; swin = 0; s_packed = false; rp_s.release(); jp_s.release(); wstart.release(); nwin = 0; nnz_s = 0;
         lrows.release(); jp_l.release(); lrp.release(); nlong = 0; maxlong = 0;
     }
