@@ -417,3 +417,33 @@ def traverse_to_host(sources, A, hops, out_bitmap, sub_batches=None):
     for t in tickets:
         wait_ticket(t)
     return flops
+
+
+def multi_source_reach(sources, A, max_hops=None, include_sources=False):
+    """Reachability from up to 1024 sources at once by level-synchronous mxm -- the multiplicity-insensitive core of a
+    variable-length traversal `-[*1..k]->` with `emit_path = false` (cond_var_len_traverse.rs:196) and of the
+    BFS phase of allShortestPaths (all_shortest_paths.rs:7-25): row i of the result holds every vertex reachable from
+    sources[i] by a walk of 1..max_hops edges (no bound: until no row finds a new vertex).
+    Each level is C<!R, replace> = F*A (matrix.rs:1386: GrB_DESC_RSC, structural complement of the reached set) followed
+    by R = R u F (matrix.rs:1398-1400) -- both stay in device frontier form.  Returns (R, levels run).
+    With `include_sources` the zero-length walk (i, sources[i]) is part of R and never re-discovered."""
+    sources = _u64arr(sources)
+    nsrc, n = len(sources), A.ncols()
+    rows = np.arange(nsrc, dtype=np.uint64)
+    F = Matrix(nsrc, n, bool)
+    F.build(rows, sources)
+    R = Matrix(nsrc, n, bool)
+    if include_sources:
+        R.build(rows, sources)
+    level = 0
+    while max_hops is None or level < max_hops:
+        if R.nvals():
+            F.mxm(F, A, R, Descriptor.RSC)
+        else:
+            F.lmxm(A)
+        if F.nvals() == 0:
+            break
+        R.element_wise_add(None, None, F, None)
+        level += 1
+    return R, level
+

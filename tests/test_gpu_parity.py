@@ -777,3 +777,33 @@ def test_traverse_to_host_sliced_async_hand_off(nsrc, subs):
     fb.wait_ticket(t)
     fb.wait_ticket(t)
     assert np.array_equal(out, bitmap_of(want))
+
+
+@pytest.mark.parametrize("nsrc,max_hops,include", [(64, None, False), (200, 2, False), (300, None, True), (5, 1, False)])
+def test_multi_source_reach_matches_levelwise_oracle(nsrc, max_hops, include):
+    """variable-length reachability from many sources at once: levels of C<!R,replace> = F*A and R = R u F in frontier
+    form against the same loop on the oracle (and, unbounded, against scipy's connected reachability)"""
+    A = orc.rmat_csr(11, 4, 19)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc)
+    src = rng.choice(n, size=nsrc, replace=False)
+    R, levels = fb.multi_source_reach(src, to_dev(A), max_hops, include)
+    rows = np.arange(nsrc)
+    F = orc.build_matrix(nsrc, n, rows, src)
+    Ro = orc.build_matrix(nsrc, n, rows, src) if include else orc.build_matrix(nsrc, n, [], [])
+    lv = 0
+    while max_hops is None or lv < max_hops:
+        F = orc.mxm(F, A, Ro, mask_mode=2) if Ro.nnz else orc.mxm(F, A)
+        if F.nnz == 0:
+            break
+        Ro = orc.ewise_add(Ro, F)
+        lv += 1
+    assert levels == lv
+    R.wait()
+    assert_same(R, Ro, f"reach nsrc={nsrc} max_hops={max_hops} include={include}")
+    if max_hops is None and include:
+        import scipy.sparse.csgraph as cg
+        dist = cg.shortest_path(A.to_scipy(), method="D", unweighted=True, indices=src)
+        want_rows, want_cols = np.nonzero(np.isfinite(dist))
+        gr, gc, _ = from_dev(R).tuples()
+        assert np.array_equal(gr, want_rows.astype(np.uint64)) and np.array_equal(gc, want_cols.astype(np.uint64))
