@@ -183,3 +183,20 @@ def test_host_resident_set_ops_for_multi_edge_store():
     assert ex.nvals() == 5 and ex.contains(K, 7) and not ex.contains(K, 2)
     t = m.transpose()
     assert list(t.iter()) == sorted((c, r) for r, c in m.iter())
+
+
+def test_header_is_plain_c_and_container_layout_matches_the_reference(tmp_path):
+    """include/b200grb.h must be consumable from C (the reference binds it with bindgen); the GxB_Container struct the
+    reference memcpy's into its RDB stream has the size / offsets asserted in mod.rs:14191-14236"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200grb.h")
+    src = tmp_path / "layout.c"
+    src.write_text('#include "%s"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   'int main(void){ printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(struct GxB_Container_struct),'
+                   ' offsetof(struct GxB_Container_struct, format), offsetof(struct GxB_Container_struct, p),'
+                   ' offsetof(struct GxB_Container_struct, Y), offsetof(struct GxB_Container_struct, iso),'
+                   ' offsetof(struct GxB_Container_struct, void_future)); return 0; }\n' % hdr)
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [608, 128, 192, 320, 448, 480]
