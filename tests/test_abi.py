@@ -200,3 +200,65 @@ def test_header_is_plain_c_and_container_layout_matches_the_reference(tmp_path):
     subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert [int(x) for x in out] == [608, 128, 192, 320, 448, 480]
+
+
+@pytest.mark.parametrize("seed,valued", [(1, True), (2, False), (3, True)])
+def test_randomised_host_model_check_with_serialization_in_the_loop(seed, valued):
+    """3,000 random host-only operations (set / remove / get / contains / nvals / wait / dup / resize / clear / ranged
+    iteration / RDB encode-decode round trip) against a dict model -- the same style as the reference's LCG model check
+    of VersionedMatrix (versioned_matrix.rs:1399-1472), one layer down, and runnable without a GPU"""
+    import random
+    from falkordb_b200 import serial
+    rnd = random.Random(seed)
+    nr, nc = 40, 70
+    m = Matrix(nr, nc, "u64" if valued else bool)
+    model = {}
+
+    def check_equal(mm, mod, r, c):
+        assert (mm.nrows(), mm.ncols()) == (r, c)
+        want = sorted((i, j, v) if valued else (i, j) for (i, j), v in mod.items())
+        assert list(mm.iter()) == want
+        assert mm.nvals() == len(mod)
+
+    for step in range(3000):
+        op = rnd.random()
+        i, j = rnd.randrange(nr), rnd.randrange(nc)
+        if op < 0.40:
+            v = rnd.randrange(0, 1 << 40) if valued else True
+            m.set(i, j, v) if valued else m.set(i, j)
+            model[(i, j)] = v
+        elif op < 0.60:
+            m.remove(i, j)
+            model.pop((i, j), None)
+        elif op < 0.75:
+            got = m.get(i, j)
+            assert got == model.get((i, j)), (step, i, j)
+            assert m.contains(i, j) == ((i, j) in model)
+        elif op < 0.80:
+            assert m.nvals() == len(model)
+        elif op < 0.84:
+            m.wait()
+            assert not m.pending()
+        elif op < 0.88:
+            lo = rnd.randrange(nr)
+            hi = rnd.randrange(lo, nr)
+            want = sorted((a, b, v) if valued else (a, b) for (a, b), v in model.items() if lo <= a <= hi)
+            assert list(m.iter(lo, hi)) == want
+        elif op < 0.91:
+            d = m.dup()
+            check_equal(d, model, nr, nc)
+        elif op < 0.94:
+            h2 = serial.decode_matrix(serial.encode_matrix(m.h))        # save / restore in the middle of the history
+            check_equal(Matrix(0, 0, "u64" if valued else bool, _handle=h2), model, nr, nc)
+            check_equal(m, model, nr, nc)
+        elif op < 0.97:
+            nr2, nc2 = rnd.randrange(max(1, nr - 8), nr + 9), rnd.randrange(max(1, nc - 8), nc + 9)
+            m.resize(nr2, nc2)
+            model = {(a, b): v for (a, b), v in model.items() if a < nr2 and b < nc2}
+            nr, nc = nr2, nc2
+        elif op < 0.975:
+            m.clear()
+            model = {}
+        else:
+            check_equal(m, model, nr, nc)
+    check_equal(m, model, nr, nc)
