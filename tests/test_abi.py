@@ -262,3 +262,47 @@ def test_randomised_host_model_check_with_serialization_in_the_loop(seed, valued
         else:
             check_equal(m, model, nr, nc)
     check_equal(m, model, nr, nc)
+
+
+def test_concurrent_callers_on_separate_and_shared_handles():
+    """the reference calls the library from a pool of threads: writers on their own output handles, readers sharing input
+    handles of one snapshot (SURVEY 8b threading).  ctypes drops the GIL inside each call, so these really overlap."""
+    import threading
+    shared = Matrix(200, 200, "u64")
+    for i in range(200):
+        shared.set(i, (i * 13) % 200, i + 1)
+    shared.wait()
+    errors = []
+
+    def worker(t):
+        try:
+            import random
+            rnd = random.Random(t)
+            m = Matrix(64, 64, "u64")
+            model = {}
+            for _ in range(1500):
+                i, j = rnd.randrange(64), rnd.randrange(64)
+                r = rnd.random()
+                if r < 0.5:
+                    m.set(i, j, t * 1000 + i)
+                    model[(i, j)] = t * 1000 + i
+                elif r < 0.7:
+                    m.remove(i, j)
+                    model.pop((i, j), None)
+                elif r < 0.9:
+                    k = rnd.randrange(200)
+                    assert shared.get(k, (k * 13) % 200) == k + 1          # concurrent readers of one handle
+                else:
+                    assert m.nvals() == len(model)
+            assert sorted(model.items()) == [((a, b), v) for a, b, v in m.iter()]
+            d = shared.dup()
+            assert d.nvals() == 200
+        except Exception as ex:      # noqa: BLE001 -- collected and re-raised in the main thread
+            errors.append(repr(ex))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
