@@ -183,3 +183,33 @@ def test_delta_lmxm_equals_materialised_merge():
     want = (orc.mxm(F, m).tuple_set() - mk.tuple_set()) | orc.mxm(F, dp).tuple_set()
     assert got.tuple_set() == want
     assert orc.delta_lmxm(F, eff, orc.CSR.empty(n, n), orc.CSR.empty(n, n)) == orc.mxm(F, eff)
+
+
+def test_bfs_reference_flow_goldens():
+    """known answers of the reference's own query-level BFS tests (tests/flow/test_bfs.py:9-25, 63-175): the graph
+    (a)-[:E1]->(b)-[:E1]->(c), (b)-[:E2]->(d)-[:E1]->(e); `nodes` = every vertex with level >= 1 (0-hop excluded)"""
+    a, b, c, d, e = range(5)
+    E1 = [(a, b), (b, c), (d, e)]
+    E2 = [(b, d)]
+
+    def adj(edges):
+        return orc.build_matrix(5, 5, [s for s, _ in edges], [t for _, t in edges])
+
+    def reached(A, src, max_level=-1):
+        lvl, par = orc.bfs(A, src, max_level)
+        assert lvl[src] == 0 and par[src] == src                      # algo_procedures.rs:1098-1148 convention
+        return sorted(int(v) for v in np.nonzero(lvl >= 1)[0]), lvl, par
+
+    ALL = adj(E1 + E2)
+    nodes, lvl, par = reached(ALL, a)                                  # test01: algo.BFS(a, -1, NULL)
+    assert nodes == [b, c, d, e] and list(lvl) == [0, 1, 2, 2, 3]
+    assert [int(par[v]) for v in (b, c, d, e)] == [a, b, b, d]          # `edges` = the tree edge into each node
+    A1 = adj(E1)
+    assert reached(A1, a)[0] == [b, c]                                 # test02: restricted to E1
+    want3 = {a: [b, c], b: [c], d: [e]}                                # test03: all sources, E1; others yield nothing
+    for src in range(5):
+        assert reached(A1, src)[0] == want3.get(src, [])
+    assert reached(ALL, a, 1)[0] == [b]                                # test04: max depth 1
+    want5 = {a: [b], b: [c, d], d: [e]}                                # test05: all sources, depth 1
+    for src in range(5):
+        assert reached(ALL, src, 1)[0] == want5.get(src, [])
