@@ -213,3 +213,21 @@ def test_bfs_reference_flow_goldens():
     want5 = {a: [b], b: [c, d], d: [e]}                                # test05: all sources, depth 1
     for src in range(5):
         assert reached(ALL, src, 1)[0] == want5.get(src, [])
+
+
+def test_variable_length_reference_flow_goldens():
+    """tests/flow/test_variable_length_traversals.py:3-6, 51-64: on the chain A->B->C->D, MATCH (a)-[*]->(b) returns 6 rows
+    (A reaches 3, B 2, C 1) in either direction.  Paths are unique there, so the pair set equals the level-wise reachability
+    loop falkordb_b200.multi_source_reach runs (C<!R,replace> = F*A ; R = R u F), restated here on the oracle."""
+    A = orc.build_matrix(4, 4, [0, 1, 2], [1, 2, 3])
+    for M_, want in ((A, {(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)}), (orc.transpose(A), {(1, 0), (2, 0), (3, 0), (2, 1), (3, 1), (3, 2)})):
+        F = orc.build_matrix(4, 4, range(4), range(4))
+        R = orc.build_matrix(4, 4, [], [])
+        while True:
+            F = orc.mxm(F, M_, R, mask_mode=2) if R.nnz else orc.mxm(F, M_)
+            if F.nnz == 0:
+                break
+            R = orc.ewise_add(R, F)
+        assert R.tuple_set() == want and R.nnz == 6
+    one_hop = orc.mxm(orc.build_matrix(4, 4, range(4), range(4)), A)      # test01: (a)-[e]->(b): AB, BC, CD
+    assert one_hop.tuple_set() == {(0, 1), (1, 2), (2, 3)}
