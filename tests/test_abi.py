@@ -306,3 +306,16 @@ def test_concurrent_callers_on_separate_and_shared_handles():
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_plain_c_caller_links_and_runs_the_host_only_calls(tmp_path):
+    """examples/c_abi_demo.c: a C11 program against include/b200grb.h + libb200grb.so (element ops, pending work, row
+    iterator, GxB_Container save / restore) -- the calls bindgen's extern block resolves to in the reference"""
+    import subprocess
+    exe = tmp_path / "demo"
+    libdir = os.path.join(ROOT, "falkordb_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lb200grb", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert out == ["nvals 2", "rides: (0,3) (2,5)", "container 6x6 nvals 2 format 2 iso 1", "restored: (0,3) (2,5)"]
