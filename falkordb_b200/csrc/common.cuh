@@ -130,6 +130,7 @@ struct DevBuf {
 // on the copy stream -- and stall the compute stream for milliseconds (prims.cu).
 bool small_read(void *dst, const void *src, size_t bytes);   // false: not taken (too large / no slot), use a memcpy
 void flush_small_reads();                                    // after the stream has been synchronised
+void drop_small_reads();                                     // error paths: pending deliveries are abandoned, not copied
 inline void sync_stream() { CUDA_TRY(cudaStreamSynchronize(stream())); flush_small_reads(); }
 
 template <typename T>

@@ -141,19 +141,25 @@ static std::mutex g_gpu_mu; // serialises GPU submission across caller threads
 
 template <class F>
 static GrB_Info guarded(F &&f) {
+    // an exception may unwind past a small read whose destination lived on the abandoned stack: forget such reads
+    // (drop_small_reads) so that the next sync_stream() does not deliver into dead frames
     try {
         return f();
     } catch (const GrbError &e) {
+        drop_small_reads();
         tl_error = e.what();
         return (GrB_Info)e.info;
     } catch (const CudaError &e) {
+        drop_small_reads();
         tl_error = e.what();
         if (e.code == cudaErrorMemoryAllocation) return GrB_OUT_OF_MEMORY;
         return GxB_GPU_ERROR;
     } catch (const std::bad_alloc &) {
+        drop_small_reads();
         tl_error = "host allocation failed";
         return GrB_OUT_OF_MEMORY;
     } catch (const std::exception &e) {
+        drop_small_reads();
         tl_error = e.what();
         return GrB_PANIC;
     }

@@ -6,7 +6,9 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include <map>
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace b200 {
@@ -40,7 +42,7 @@ void ensure_init() {
 static const size_t SMALL_READ_MAX = 64, SMALL_SLOTS_BYTES = 8192;
 static unsigned char *g_slots_host = nullptr, *g_slots_dev = nullptr;
 static size_t g_slots_used = 0;
-struct SmallPending { void *dst; size_t off, bytes; };
+struct SmallPending { void *dst; size_t off, bytes; std::thread::id owner; };
 static std::vector<SmallPending> g_small_pending;
 static std::mutex g_small_mu;
 __global__ void k_small_read(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src, u32 bytes) {
@@ -58,8 +60,16 @@ bool small_read(void *dst, const void *src, size_t bytes) {
     g_slots_used = off + bytes;
     k_small_read<<<1, 32, 0, stream()>>>(g_slots_dev + off, (const unsigned char *)src, (u32)bytes);
     if (cudaGetLastError() != cudaSuccess) { g_slots_used = off; return false; }
-    g_small_pending.push_back({dst, off, bytes});
+    g_small_pending.push_back({dst, off, bytes, std::this_thread::get_id()});
     return true;
+}
+void drop_small_reads() {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    // only the caller's own reads: another thread's destinations are alive.  Slots stay reserved until the next flush resets
+    // the bump pointer (the kernels may still be in flight).
+    const std::thread::id me = std::this_thread::get_id();
+    g_small_pending.erase(std::remove_if(g_small_pending.begin(), g_small_pending.end(),
+                                         [&](const SmallPending &p) { return p.owner == me; }), g_small_pending.end());
 }
 void flush_small_reads() {
     std::lock_guard<std::mutex> lk(g_small_mu);
