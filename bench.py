@@ -8,8 +8,11 @@ the reference's row iterator walks, cond_traverse.rs:608,644).  TEPS = sum over 
 flops_h = sum_{(i,k) in F_h} deg_A(k)  divided by the step time  (SURVEY.md 8d).
 
   value : device-resident -- F already in HBM when the timed region starts; CUDA-event timed on the library's stream
-  e2e   : the same step through the public C ABI with HOST buffers: GxB_Matrix_build_Scalar from host index arrays
-          (H2D inside), 3x GrB_mxm, GrB_Matrix_wait, B200_Matrix_export_CSR of the result into host memory (D2H inside)
+  e2e   : the same batch host to host through the public API, falkordb_b200.traverse_to_host: per 128-row slice
+          GxB_Matrix_build_Scalar from host index arrays (H2D inside), 3x GrB_mxm, B200_Matrix_export_bitmap_async of the
+          result (packed row-major bitmap, D2H on a second stream, overlapping the next slice's hops), tickets waited at the
+          end.  The bitmap is chosen by Matrix.export_auto's rule on the first batch (result denser than 1/32); the CSR
+          hand-off (GrB_Matrix_wait + B200_Matrix_export_CSR) of the same result is timed next to it at N = 1.
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on a bounded
 sample of the same workload.  Multi-GPU: the batch rows are independent, so ranks shard the sources with A replicated
