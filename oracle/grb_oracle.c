@@ -21,10 +21,11 @@
  *   LAGr_BreadthFirstSearch_Extended          runtime/functions/algo_procedures.rs:1079-1148
  *
  * Parity pinning: the reference has no direct known-answer test for GrB_mxm;
- * this oracle is pinned against (i) every known answer the reference's unit tests hold at
- * this boundary (tests/test_oracle_reference_kats.py transcribes matrix.rs:1617-1775 and
- * versioned_matrix.rs:1278-1523), (ii) scipy.sparse as an independent implementation and
- * (iii) algebraic identities.  For raw mxm on large inputs parity is therefore
+ * this oracle is pinned against (i) every known answer the reference's own tests hold at
+ * this boundary -- transcribed as data in tests/golden/reference_known_answers.json and checked
+ * by tests/test_golden.py and tests/test_oracle.py (matrix.rs:1617-1775, versioned_matrix.rs:
+ * 1278-1330, tests/flow/test_bfs.py, test_variable_length_traversals.py, README.md:85-110) --
+ * (ii) scipy.sparse as an independent implementation and (iii) algebraic identities.  For raw mxm on large inputs parity is therefore
  * "pinned to scipy + identities, unpinned by reference goldens" -- see DESIGN.md.
  *
  * Layout: CSR, rowptr int64[nrows+1], col uint32[nnz] ascending within a row,
