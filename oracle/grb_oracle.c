@@ -185,12 +185,59 @@ int orc_mask_assign(const orc_csr *Cold, const orc_csr *T, const orc_csr *M, int
 
 /* ------------------------------------------------------------------ mxm, ANY_PAIR
  * T = pattern(A*B): T(i,j) present iff exists k with A(i,k) and B(k,j) present; values are
- * never read (ANY_PAIR, matrix.rs:926-947).  Gustavson row-wise with a per-thread stamp
- * workspace, the algorithm family SuiteSparse's saxpy3 uses.  A.ncols == B.nrows.
- * Fused structural mask (mode 0 none, 1 C<M>, 2 C<!M>) drops entries at emission, which with
- * replace is the full semantics of matrix.rs:1386-1394; other combinations go through
- * orc_mask_assign.  flops_out (optional) receives sum_{(i,k) in A} deg_B(k).
+ * never read (ANY_PAIR, matrix.rs:926-947).  Gustavson row-wise, the algorithm family
+ * SuiteSparse's saxpy3 uses, one row of A per task (schedule(dynamic,1): a 512-row frontier
+ * keeps every host thread busy).  Each thread owns a PERSISTENT workspace that survives across
+ * calls: an ncols-bit "seen" bitmap (2 MB at 2^24 columns -- cache resident, unlike a 4-byte
+ * stamp per column) and a short list of first-seen columns.  Sparse rows are emitted by
+ * sorting the list and cleared through it; rows that outgrow the list are emitted by a ctz
+ * scan of the bitmap range [lo, hi] (already sorted) and cleared with one memset of that range.
+ * A.ncols == B.nrows.  Fused structural mask (mode 0 none, 1 C<M>, 2 C<!M>) drops entries at
+ * emission, which with replace is the full semantics of matrix.rs:1386-1394; other combinations
+ * go through orc_mask_assign.  flops_out (optional) receives sum_{(i,k) in A} deg_B(k).
  */
+typedef struct { uint64_t *bits; int64_t nwords; uint32_t *list; } orc_ws;
+typedef struct { int64_t flops, row; } rowwork_t;
+static int cmp_rowwork(const void *a, const void *b) {
+    const rowwork_t *x = a, *y = b;
+    if (x->flops != y->flops) return x->flops > y->flops ? -1 : 1;
+    return (x->row > y->row) - (x->row < y->row);
+}
+#define ORC_LIST_CAP 8192
+static orc_ws *g_ws = NULL;
+static int g_nws = 0;
+static double g_busy_s = 0.0, g_wall_s = 0.0;      /* of the last orc_mxm_anypair / orc_chain */
+static int g_busy_threads = 0, g_team = 1;
+static double now_s(void) {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+static void ws_reserve(int nthreads) {              /* called outside parallel regions */
+    if (nthreads <= g_nws) return;
+    g_ws = realloc(g_ws, sizeof(orc_ws) * (size_t)nthreads);
+    if (!g_ws) abort();
+    for (int t = g_nws; t < nthreads; t++) { g_ws[t].bits = NULL; g_ws[t].nwords = 0; g_ws[t].list = NULL; }
+    g_nws = nthreads;
+}
+static orc_ws *ws_get(int t, int64_t ncols) {       /* thread t's workspace, grown (zeroed) on demand */
+    orc_ws *w = &g_ws[t];
+    int64_t nw = (ncols + 63) / 64 + 1;
+    if (w->nwords < nw) {
+        free(w->bits);
+        w->bits = xmalloc(sizeof(uint64_t) * (size_t)nw);
+        memset(w->bits, 0, sizeof(uint64_t) * (size_t)nw);
+        w->nwords = nw;
+    }
+    if (!w->list) w->list = xmalloc(sizeof(uint32_t) * ORC_LIST_CAP);
+    return w;
+}
+/* how well the last product used the host: busy thread-seconds / (team size * wall seconds) */
+double orc_last_busy_fraction(void) { return (g_wall_s > 0 && g_team > 0) ? g_busy_s / (g_wall_s * g_team) : 0.0; }
+int orc_last_busy_threads(void) { return g_busy_threads; }
+
 int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int mask_mode,
                     orc_csr *out, int64_t *flops_out) {
     int64_t nrows = A->nrows, ncols = B->ncols;
@@ -198,79 +245,157 @@ int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int ma
     int64_t *cnt = xmalloc(sizeof(int64_t) * (size_t)(nrows + 1));
     uint32_t **rows = xmalloc(sizeof(uint32_t *) * (size_t)(nrows ? nrows : 1));
     int64_t flops_total = 0;
-#pragma omp parallel
+    int team = orc_num_threads();
+    ws_reserve(team);
+    double busy_total = 0.0, t_wall = now_s();
+    int busy_threads = 0;
+    /* longest-processing-time-first: rows are handed out in descending flops order so the heavy
+     * rows do not end up as a serial tail */
+    rowwork_t *order = xmalloc(sizeof(rowwork_t) * (size_t)(nrows ? nrows : 1));
+#pragma omp parallel for schedule(static) num_threads(team)
+    for (int64_t i = 0; i < nrows; i++) {
+        int64_t f = 0;
+        for (int64_t a = A->p[i]; a < A->p[i + 1]; a++) f += B->p[A->j[a] + 1] - B->p[A->j[a]];
+        order[i].flops = f; order[i].row = i;
+    }
+    qsort(order, (size_t)nrows, sizeof(rowwork_t), cmp_rowwork);
+#pragma omp parallel num_threads(team)
     {
-        uint32_t *stamp = xmalloc(sizeof(uint32_t) * (size_t)(ncols ? ncols : 1));
-        memset(stamp, 0, sizeof(uint32_t) * (size_t)ncols);
-        uint32_t cur = 0;
-        int64_t lcap = 1024;
-        uint32_t *list = xmalloc(sizeof(uint32_t) * (size_t)lcap);
-        int64_t my_flops = 0;
-#pragma omp for schedule(dynamic, 16)
-        for (int64_t i = 0; i < nrows; i++) {
-            if (++cur == 0) { memset(stamp, 0, sizeof(uint32_t) * (size_t)ncols); cur = 1; }
-            int64_t n = 0;
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num();
+#else
+        const int tid = 0;
+#endif
+        orc_ws *w = ws_get(tid, ncols);
+        uint64_t *bits = w->bits;
+        uint32_t *list = w->list;
+        int64_t my_flops = 0, my_rows = 0;
+        double my_busy = 0.0;
+#pragma omp for schedule(dynamic, 1) nowait
+        for (int64_t oi = 0; oi < nrows; oi++) {
+            const int64_t i = order[oi].row;
+            const double t0 = now_s();
+            int64_t n = 0;               /* distinct columns seen */
             uint32_t lo = UINT32_MAX, hi = 0;
             for (int64_t a = A->p[i]; a < A->p[i + 1]; a++) {
-                uint32_t k = A->j[a];
-                int64_t s = B->p[k], e = B->p[k + 1];
+                const uint32_t k = A->j[a];
+                const int64_t s = B->p[k], e = B->p[k + 1];
                 my_flops += e - s;
-                if (n + (e - s) > lcap) {
-                    while (n + (e - s) > lcap) lcap *= 2;
-                    list = realloc(list, sizeof(uint32_t) * (size_t)lcap);
-                    if (!list) abort();
-                }
                 for (int64_t q = s; q < e; q++) {
-                    uint32_t c = B->j[q];
-                    if (stamp[c] != cur) {
-                        stamp[c] = cur; list[n++] = c;
+                    const uint32_t c = B->j[q];
+                    const uint64_t bit = 1ULL << (c & 63);
+                    uint64_t *wd = &bits[c >> 6];
+                    if (!(*wd & bit)) {
+                        *wd |= bit;
+                        if (n < ORC_LIST_CAP) list[n] = c;
+                        n++;
                         if (c < lo) lo = c;
                         if (c > hi) hi = c;
                     }
                 }
             }
-            /* sorted emission: scan the stamp range when dense enough, else sort the list */
             uint32_t *row = NULL;
             int64_t m = 0;
             if (n > 0) {
                 row = xmalloc(sizeof(uint32_t) * (size_t)n);
-                if ((int64_t)(hi - lo) < 16 * n) {
-                    for (uint32_t c = lo;; c++) { if (stamp[c] == cur) row[m++] = c; if (c == hi) break; }
-                } else {
+                if (n <= ORC_LIST_CAP) {             /* sparse row: sort the list, clear through it */
                     memcpy(row, list, sizeof(uint32_t) * (size_t)n);
                     qsort(row, (size_t)n, sizeof(uint32_t), cmp_u32);
+                    for (int64_t q = 0; q < n; q++) bits[row[q] >> 6] = 0;
                     m = n;
+                } else {                             /* dense row: the bitmap range is the sorted row */
+                    const int64_t w0 = lo >> 6, w1 = hi >> 6;
+                    for (int64_t x = w0; x <= w1; x++) {
+                        uint64_t v = bits[x];
+                        while (v) { row[m++] = (uint32_t)((x << 6) + __builtin_ctzll(v)); v &= v - 1; }
+                    }
+                    memset(bits + w0, 0, sizeof(uint64_t) * (size_t)(w1 - w0 + 1));
                 }
                 if (M && mask_mode) {
-                    int64_t w = 0;
+                    int64_t wq = 0;
                     for (int64_t q = 0; q < m; q++) {
                         int mk = mask_has(M, i, row[q], 1);
                         if (mask_mode == 2) mk = !mk;
-                        if (mk) row[w++] = row[q];
+                        if (mk) row[wq++] = row[q];
                     }
-                    m = w;
+                    m = wq;
                 }
             }
             rows[i] = row; cnt[i + 1] = m;
+            my_busy += now_s() - t0;
+            my_rows++;
         }
-#pragma omp atomic
-        flops_total += my_flops;
-        free(stamp); free(list);
+#pragma omp critical
+        { flops_total += my_flops; busy_total += my_busy; busy_threads += my_rows > 0; }
     }
+    free(order);
     cnt[0] = 0;
     for (int64_t i = 0; i < nrows; i++) cnt[i + 1] += cnt[i];
     out->nrows = nrows; out->ncols = ncols; out->nnz = cnt[nrows];
     out->p = cnt;
     out->j = xmalloc(sizeof(uint32_t) * (size_t)out->nnz);
     out->x = NULL;
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(team)
     for (int64_t i = 0; i < nrows; i++) {
         int64_t m = cnt[i + 1] - cnt[i];
         if (m) memcpy(out->j + cnt[i], rows[i], sizeof(uint32_t) * (size_t)m);
         free(rows[i]);
     }
     free(rows);
+    g_busy_s = busy_total; g_wall_s = now_s() - t_wall; g_busy_threads = busy_threads; g_team = team;
     if (flops_out) *flops_out = flops_total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ k-hop chain, all in C
+ * CondTraverse's expand_batch core (cond_traverse.rs:600-608): F(i, src_i) = 1, then `hops` times
+ * F <- F*A over ANY_PAIR (Matrix::lmxm, matrix.rs:930-947), result materialised as sorted CSR.
+ * Same code path as orc_mxm_anypair; exists so that bench.py can time the CPU arm without the
+ * Python-side copies of multi-GB intermediates.  out may be NULL (the result is digested and freed).
+ * digest[0] = nvals, [1] = sum mix(key), [2] = sum mix(key + GOLD * position): see orc_digest. */
+static inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL; x ^= x >> 33;
+    return x;
+}
+/* Order-sensitive digest of a CSR pattern: key = row << 32 | col, position = index in CSR order.
+ * A result with the same entry set in a different order, or with one entry changed, differs. */
+void orc_digest(const orc_csr *A, uint64_t *digest) {
+    uint64_t s1 = 0, s2 = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : s1, s2)
+    for (int64_t i = 0; i < A->nrows; i++)
+        for (int64_t q = A->p[i]; q < A->p[i + 1]; q++) {
+            const uint64_t key = ((uint64_t)i << 32) | A->j[q];
+            s1 += mix64(key);
+            s2 += mix64(key + 0x9E3779B97F4A7C15ULL * (uint64_t)(q + 1));
+        }
+    digest[0] = (uint64_t)A->nnz; digest[1] = s1; digest[2] = s2;
+}
+int orc_chain(const orc_csr *A, const uint64_t *sources, int64_t nsrc, int hops, orc_csr *out, int64_t *flops_out,
+              uint64_t *digest, double *busy_fraction) {
+    orc_csr F;
+    F.nrows = nsrc; F.ncols = A->nrows; F.nnz = nsrc; F.x = NULL;
+    F.p = xmalloc(sizeof(int64_t) * (size_t)(nsrc + 1));
+    F.j = xmalloc(sizeof(uint32_t) * (size_t)(nsrc ? nsrc : 1));
+    for (int64_t i = 0; i < nsrc; i++) {
+        if (sources[i] >= (uint64_t)A->nrows) { free(F.p); free(F.j); return -4; }
+        F.p[i] = i; F.j[i] = (uint32_t)sources[i];
+    }
+    F.p[nsrc] = nsrc;
+    int64_t flops = 0;
+    double busy = 0.0, wall = 0.0;
+    for (int h = 0; h < hops; h++) {
+        orc_csr T;
+        int64_t fl = 0;
+        int rc = orc_mxm_anypair(&F, A, NULL, 0, &T, &fl);
+        orc_csr_free(&F);
+        if (rc) return rc;
+        F = T; flops += fl;
+        busy += g_busy_s; wall += g_wall_s * g_team;
+    }
+    if (flops_out) *flops_out = flops;
+    if (busy_fraction) *busy_fraction = wall > 0 ? busy / wall : 0.0;
+    if (digest) orc_digest(&F, digest);
+    if (out) *out = F; else orc_csr_free(&F);
     return 0;
 }
 

@@ -44,6 +44,10 @@ def lib():
         L.orc_rmat_edges.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.orc_csr_from_edges.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, P]
         L.orc_csr_free.argtypes = [P]
+        L.orc_chain.argtypes = [P, C.c_void_p, C.c_int64, C.c_int, P, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_double)]
+        L.orc_digest.argtypes = [P, C.c_void_p]
+        L.orc_last_busy_fraction.restype = C.c_double
+        L.orc_last_busy_threads.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
@@ -155,6 +159,35 @@ def mxm(A, B, M=None, mask_mode=0, return_flops=False):
         raise ValueError("GrB_DIMENSION_MISMATCH")
     r = _take(out)
     return (r, fl.value) if return_flops else r
+
+
+def chain(A, sources, hops, keep=True):
+    """CondTraverse's F(i, src_i) = 1; F <- F*A `hops` times (cond_traverse.rs:600-608), entirely in C.
+    Returns (result CSR or None, flops, digest uint64[3], busy fraction of the host threads)."""
+    src = np.ascontiguousarray(sources, dtype=np.uint64)
+    out = _CSR()
+    a = A._c()
+    fl = C.c_int64(0)
+    dg = np.zeros(3, np.uint64)
+    busy = C.c_double(0.0)
+    rc = lib().orc_chain(C.byref(a), _ptr(src), len(src), hops, C.byref(out) if keep else None, C.byref(fl), _ptr(dg),
+                         C.byref(busy))
+    if rc:
+        raise IndexError("GrB_INVALID_INDEX")
+    return (_take(out) if keep else None), fl.value, dg, busy.value
+
+
+def digest(A):
+    """(nvals, sum mix(row << 32 | col), sum mix(key + GOLD * (position + 1))): order-sensitive digest of a CSR pattern;
+    falkordb_b200's B200_Matrix_digest computes the same three numbers on the device."""
+    dg = np.zeros(3, np.uint64)
+    a = A._c()
+    lib().orc_digest(C.byref(a), _ptr(dg))
+    return dg
+
+
+def busy_fraction():
+    return lib().orc_last_busy_fraction()
 
 
 def ewise_add(A, B, keep_values=False):
