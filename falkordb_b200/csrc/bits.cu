@@ -13,9 +13,17 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include <cub/block/block_reduce.cuh>
+#include <algorithm>
+#include <cstring>
 
 namespace b200 {
 
+// how the lanes of a warp share a W-word vertex record: a lane moves at most 32 bytes per instruction (LDG.256 / STG.256)
+template <int W> struct PullCfg {
+    static constexpr int WL = W >= 4 ? 4 : W;      // words per lane
+    static constexpr int SPLIT = W / WL;           // lanes per vertex record
+    static constexpr int VG = 8 / SPLIT;           // vertices gathered per 8-lane group and unroll step
+};
 static const u64 PUSH_CHUNK = 8192;
 static const u64 LONG_ROW = 4096;   // pull: rows longer than this are split over several CTAs
 static const u64 LONG_CHUNK = 8192;
@@ -111,6 +119,75 @@ k_bits_count(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, u32 *__restric
             tc[((u64)w * 64 + tid) * ntiles + tile] = s;
         }
         __syncthreads();
+    }
+}
+
+// Count pass with vertical counters (count_kernel = 1, default).  The counts per (frontier row, tile) are a positional
+// popcount: for each of the 64 bit positions of a word column, how many of the tile's 1024 words have that bit set.  No bit
+// transpose per 32 vertices is needed for that: a lane adds the words of 32 vertices (v = lane, lane + 32, ...) into a
+// carry-save adder tree -- 31 CSAs of two LOP3 per 32-bit half leave six bit-planes (weights 1, 2, .., 32) -- and only the
+// planes are transposed across the warp (12 butterflies per word column instead of 64): ~4x fewer instructions than
+// transposing every word.  One warp per (tile, group of up to 4 word columns); loads are 8*WL contiguous bytes per lane.
+__device__ __forceinline__ void csa(u64 &hi, u64 &lo, u64 a, u64 b, u64 c) {   // a + b + c = 2 * hi + lo, bitwise
+    const u64 u = a ^ b;
+    hi = (a & b) | (u & c);
+    lo = u ^ c;
+}
+template <int WL> __device__ __forceinline__ void ld_part(u64 (&x)[WL], const u64 *p) {
+    if constexpr (WL == 1) { x[0] = __ldg(p); }
+    else if constexpr (WL == 2) { ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p)); x[0] = v.x; x[1] = v.y; }
+    else { u64x4 v = ld_v4(p); x[0] = v.a; x[1] = v.b; x[2] = v.c; x[3] = v.d; }
+}
+template <int W>
+__global__ void __launch_bounds__(128)
+k_bits_count_csa(const u64 *__restrict__ X, u64 n, u64 ntiles, u32 *__restrict__ tc) {
+    constexpr int WL = PullCfg<W>::WL, SPLIT = PullCfg<W>::SPLIT;
+    const u32 lane = threadIdx.x & 31;
+    const u64 wid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 tile = wid / SPLIT;
+    const u32 h = (u32)(wid % SPLIT);
+    if (tile >= ntiles) return;
+    const u64 vbase = tile * TILE_V;
+    // plane[p][w]: bit b = bit p of (number of this lane's 32 words of column w that have bit b set)
+    u64 plane[6][WL];
+    u64 pend[5][WL];            // carry waiting for its partner at level p + 1 (weight 2^(p+1))
+#pragma unroll
+    for (int p = 0; p < 6; p++)
+#pragma unroll
+        for (int w = 0; w < WL; w++) plane[p][w] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {          // 16 pairs of vertices: v = lane + 32 * (2i), lane + 32 * (2i + 1)
+        u64 xa[WL], xb[WL];
+        const u64 va = vbase + lane + 64 * (u64)i, vb_ = va + 32;
+        if (va < n) ld_part<WL>(xa, X + va * W + h * WL); else { for (int w = 0; w < WL; w++) xa[w] = 0; }
+        if (vb_ < n) ld_part<WL>(xb, X + vb_ * W + h * WL); else { for (int w = 0; w < WL; w++) xb[w] = 0; }
+#pragma unroll
+        for (int w = 0; w < WL; w++) {
+            u64 c;
+            csa(c, plane[0][w], plane[0][w], xa[w], xb[w]);      // carry of weight 2
+            // binary counter of pending carries: level L combines two carries of weight 2^L with the running plane
+#pragma unroll
+            for (int L = 1; L < 6; L++) {
+                if ((i >> (L - 1)) & 1) {                        // second carry of this weight: combine, propagate
+                    if (L < 5) { u64 c2; csa(c2, plane[L][w], plane[L][w], pend[L - 1][w], c); c = c2; }
+                    else plane[5][w] ^= 0;                       // (unreachable: i < 16)
+                } else { pend[L - 1][w] = c; break; }
+            }
+            if (i == 15) plane[5][w] = c;                        // the single carry of weight 32
+        }
+    }
+    // planes -> counts: after transpose32 of one half-plane lane b holds bit b of all 32 lanes
+#pragma unroll
+    for (int w = 0; w < WL; w++) {
+        u32 clo = 0, chi = 0;
+#pragma unroll
+        for (int p = 0; p < 6; p++) {
+            clo += __popc(transpose32((u32)plane[p][w], lane)) << p;
+            chi += __popc(transpose32((u32)(plane[p][w] >> 32), lane)) << p;
+        }
+        const u64 col = (u64)(h * WL + w) * 64;
+        tc[(col + lane) * ntiles + tile] = clo;
+        tc[(col + 32 + lane) * ntiles + tile] = chi;
     }
 }
 
@@ -382,6 +459,17 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
     {
         TimedScope ts(TK_BITS_COUNT, 8ULL * W * n + (keep_masks ? 8ULL * W * ntiles * TILE_V : 0));
         if (keep_masks) LAUNCH(k_bits_count_keep, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr, masks.ptr);
+        else if (ctx().opt_count_kernel == 1) {
+            const u64 nwarps = ntiles * (W >= 4 ? W / 4 : 1);
+            const u32 g = (u32)((nwarps + 3) / 4);
+            switch (W) {
+            case 1: LAUNCH((k_bits_count_csa<1>), g, 128, 0, X.w.ptr, n, ntiles, tc.ptr); break;
+            case 2: LAUNCH((k_bits_count_csa<2>), g, 128, 0, X.w.ptr, n, ntiles, tc.ptr); break;
+            case 4: LAUNCH((k_bits_count_csa<4>), g, 128, 0, X.w.ptr, n, ntiles, tc.ptr); break;
+            case 8: LAUNCH((k_bits_count_csa<8>), g, 128, 0, X.w.ptr, n, ntiles, tc.ptr); break;
+            default: LAUNCH((k_bits_count_csa<16>), g, 128, 0, X.w.ptr, n, ntiles, tc.ptr); break;
+            }
+        }
         else LAUNCH(k_bits_count, (u32)ntiles, TILE_THREADS, 0, X.w.ptr, n, W, ntiles, tc.ptr);
     }
     CUDA_TRY(cudaMemsetAsync(tc.ptr + ncnt, 0, sizeof(u32), stream()));
@@ -1207,6 +1295,224 @@ k_bits_pull_long(const u32 *__restrict__ lrows, const u64 *__restrict__ choff, u
     }
 }
 
+// ---------------------------------------------------------------------------- lane-split pull (pull_kernel = 5, default)
+// What bounds a pull is the L1TEX tag stage: one 128-byte line per clock per SM (scripts/ubench/gather*.cu: 281 G lines/s on
+// 148 SMs), and a warp-wide gather with every lane on a different vertex costs 32 of those "wavefronts" per instruction.  A
+// vertex record of W = 8 words is 64 bytes -- one line -- but a lane can fetch at most 32 bytes per instruction (LDG.256),
+// so one-lane-per-vertex spends TWO wavefronts per vertex.  Here SPLIT = W / 4 adjacent lanes share a vertex: lane h of the
+// pair loads words [4h, 4h+4) of the record with one LDG.256, the two requests fall into the same line and coalesce into one
+// wavefront, and the pair never exchanges data (each lane ORs, keeps and finally stores its own 32-byte part of the output row).
+// W = 8 -> half the wavefronts per gathered vertex; W = 16 -> a quarter; W <= 4 is unchanged.
+// Rows longer than LONG_ROW are no longer a separate kernel: they enter the length-sorted list as LONG_ROW-entry segments whose
+// partial results are merged with RED.OR (the small-row kernel zero-fills those rows first).
+template <int WL> __device__ __forceinline__ void store_part(u64 *dst, const u64 (&acc)[WL]) { store_row<WL>(dst, acc); }
+
+static const u32 SEG_ATOMIC = 0x80000000u;
+
+// segments per row: 0 (small), 1 (mid), ceil(len / LONG_ROW) (long)
+__global__ void k_seg_count(const u64 *__restrict__ p, u64 n, u32 *__restrict__ cnt) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; r <= n; r += stride) {
+        if (r == n) { cnt[r] = 0; break; }
+        u64 d = p[r + 1] - p[r];
+        cnt[r] = d <= SMALL_ROW ? 0u : (u32)((d + LONG_ROW - 1) / LONG_ROW);
+    }
+}
+// key = LONG_ROW - seglen (ascending sort = longest first), value = position of the segment: row << 20 | index inside the row
+__global__ void k_seg_emit(const u64 *__restrict__ p, u64 n, const u64 *__restrict__ pos, u64 *__restrict__ keys, u64 *__restrict__ vals) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; r < n; r += stride) {
+        const u64 d = p[r + 1] - p[r];
+        if (d <= SMALL_ROW) continue;
+        u64 o = pos[r];
+        for (u64 s = 0, i = 0; s < d; s += LONG_ROW, i++) {
+            const u64 len = d - s < LONG_ROW ? d - s : LONG_ROW;
+            keys[o] = LONG_ROW - len;
+            vals[o] = (r << 20) | i;
+            o++;
+        }
+    }
+}
+__global__ void k_seg_unpack(const u64 *__restrict__ vals, u64 ns, const u64 *__restrict__ p, u32 *__restrict__ s_row,
+                             u32 *__restrict__ s_len, u64 *__restrict__ s_start) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const u64 v = vals[i];
+    const u32 r = (u32)(v >> 20);
+    const u64 k = v & 0xFFFFFu;
+    const u64 d = p[r + 1] - p[r];
+    const u64 s = k * LONG_ROW;
+    const u64 len = d - s < LONG_ROW ? d - s : LONG_ROW;
+    s_row[i] = r;
+    s_start[i] = p[r] + s;
+    s_len[i] = (u32)len | (d > LONG_ROW ? SEG_ATOMIC : 0u);
+}
+static void build_seg_list(const DevCSR &AT, LongRows &lr) {
+    const u64 n = AT.nrows;
+    lr.ns = 0;
+    lr.s_row.release(); lr.s_len.release(); lr.s_start.release();
+    lr.seg_built = true;
+    if (!n) return;
+    if (lr.maxdeg >= ((u64)LONG_ROW << 20)) throw GrbError(-8, "pull: a row of A' exceeds 2^32 entries");
+    DevBuf<u32> cnt(n + 1);
+    DevBuf<u64> pos(n + 1);
+    LAUNCH(k_seg_count, grid_for(n + 1, 256, 1 << 16), 256, 0, AT.p.ptr, n, cnt.ptr);
+    exclusive_scan_u32_to_u64(cnt.ptr, pos.ptr, n + 1);
+    const u64 ns = read_scalar(pos.ptr + n);
+    lr.ns = ns;
+    if (!ns) return;
+    DevBuf<u64> keys(ns), vals(ns);
+    LAUNCH(k_seg_emit, grid_for(n, 256, 1 << 16), 256, 0, AT.p.ptr, n, pos.ptr, keys.ptr, vals.ptr);
+    sort_pairs_u64(keys.ptr, vals.ptr, ns, 13);          // stable: rows ascending inside one length
+    lr.s_row.alloc(ns); lr.s_len.alloc(ns); lr.s_start.alloc(ns);
+    LAUNCH(k_seg_unpack, grid_for(ns, 256), 256, 0, vals.ptr, ns, AT.p.ptr, lr.s_row.ptr, lr.s_len.ptr, lr.s_start.ptr);
+}
+
+// SPLIT lanes per row, natural order: rows of <= SMALL_ROW entries are finished here, rows longer than LONG_ROW are zero-filled
+// (their segments arrive through RED.OR), everything in between is left to k_pull_seg.
+template <int W, bool HINTS>
+__global__ void __launch_bounds__(256)
+k_pull_small(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
+             u64 *__restrict__ Y, u32 hot_bytes, u32 tot_bytes) {
+    constexpr int WL = PullCfg<W>::WL, SPLIT = PullCfg<W>::SPLIT;
+    const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 h = (u32)(t % SPLIT);
+    const u64 *Xh = X + h * WL;
+    u64 j = t / SPLIT;
+    const u64 stride = ((u64)gridDim.x * blockDim.x) / SPLIT;
+    u64 s = 0, e = 0, s1 = 0, e1 = 0;
+    if (j < n) { s = __ldg(ATp + j); e = __ldg(ATp + j + 1); }
+    if (j + stride < n) { s1 = __ldg(ATp + j + stride); e1 = __ldg(ATp + j + stride + 1); }
+    u32 k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) k[u] = (e - s <= SMALL_ROW && s + u < e) ? __ldg(ATj + s + u) : 0xFFFFFFFFu;
+    for (; j < n; j += stride) {
+        u64 s2 = 0, e2 = 0;
+        if (j + 2 * stride < n) { s2 = __ldg(ATp + j + 2 * stride); e2 = __ldg(ATp + j + 2 * stride + 1); }
+        u32 kn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) kn[u] = (e1 - s1 <= SMALL_ROW && s1 + u < e1) ? __ldg(ATj + s1 + u) : 0xFFFFFFFFu;
+        u64 acc[WL];
+#pragma unroll
+        for (int w = 0; w < WL; w++) acc[w] = 0;
+        if (e - s <= SMALL_ROW) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != 0xFFFFFFFFu) or_words<WL, HINTS>(acc, Xh + (u64)k[u] * W, keep);
+            if (e - s > 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) k[u] = (s + 4 + u < e) ? __ldg(ATj + s + 4 + u) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k[u] != 0xFFFFFFFFu) or_words<WL, HINTS>(acc, Xh + (u64)k[u] * W, keep);
+            }
+        }
+        if (e - s <= SMALL_ROW || e - s > LONG_ROW) store_part<WL>(Y + j * W + h * WL, acc);
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = kn[u];
+        s = s1; e = e1; s1 = s2; e1 = e2;
+    }
+}
+
+// 8 lanes per list entry (a mid row, or one LONG_ROW-entry segment of a long row); entries sorted by length, descending.
+// Same three-stage software pipeline as k_bits_pull_mid (list entry two steps ahead, col_idx batch one step ahead, gathers now);
+// the 8 lanes cover VG vertices x SPLIT record parts per unroll step.
+template <int W, bool HINTS, int U, bool EARLY>
+__global__ void PIPE_BOUNDS
+k_pull_seg(const u32 *__restrict__ s_row, const u64 *__restrict__ s_start, const u32 *__restrict__ s_len, u64 ns,
+           const u32 *__restrict__ ATj, const u64 *__restrict__ X, u64 *__restrict__ Y, const u64 *__restrict__ Gp,
+           u32 hot_bytes, u32 tot_bytes) {
+    constexpr int WL = PullCfg<W>::WL, SPLIT = PullCfg<W>::SPLIT, VG = PullCfg<W>::VG;
+    const u32 lane8 = threadIdx.x & 7;
+    const u32 sub = (threadIdx.x & 31) >> 3;
+    const u32 gmask = 0xFFu << (8 * sub);
+    const u32 vi = lane8 / SPLIT, h = lane8 % SPLIT;
+    const u64 *Xh = X + h * WL;
+    const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0, strm = policy_stream();
+    u64 G[WL];
+#pragma unroll
+    for (int w = 0; w < WL; w++) G[w] = (EARLY && Gp) ? Gp[h * WL + w] : ~0ULL;
+    const u64 ngroups = ((u64)gridDim.x * blockDim.x) >> 3;
+    const u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const u64 steps = (ns + ngroups - 1) / ngroups;
+    auto entry = [&](u64 t) -> u64 { return t * ngroups + ((t & 1) ? ngroups - 1 - g : g); };
+    auto fetch = [&](u64 t, u64 &s, u64 &e) {
+        s = 0; e = 0;
+        if (t < steps) { u64 i = entry(t); if (i < ns) { s = s_start[i]; e = s + (s_len[i] & ~SEG_ATOMIC); } }
+    };
+    u64 s0, e0, s1, e1;
+    fetch(0, s0, e0);
+    fetch(1, s1, e1);
+    u32 k[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { u64 q = s0 + vi + VG * u; k[u] = (q < e0) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+    for (u64 t = 0; t < steps; t++) {
+        u64 s2, e2;
+        fetch(t + 2, s2, e2);
+        u64 acc[WL];
+#pragma unroll
+        for (int w = 0; w < WL; w++) acc[w] = 0;
+        u64 qb = s0;
+        u32 it = 0;
+        while (true) {
+            const bool more = qb + VG * U < e0;
+            const u64 nb = more ? qb + VG * U : s1, ne = more ? e0 : e1;
+            u32 kn[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { u64 q = nb + vi + VG * u; kn[u] = (q < ne) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (k[u] != 0xFFFFFFFFu) or_words<WL, HINTS>(acc, Xh + (u64)k[u] * W, keep);
+#pragma unroll
+            for (int u = 0; u < U; u++) k[u] = kn[u];
+            if (!more) break;
+            if (EARLY) {   // stop once the entry holds the OR monoid's terminal value: cheap per-lane test, exact cross-lane OR every 4th
+                bool full = true;
+                if ((it & 3) == 3) {
+#pragma unroll
+                    for (int w = 0; w < WL; w++) {
+                        u64 a = acc[w];
+#pragma unroll
+                        for (int d = SPLIT; d < 8; d <<= 1) a |= __shfl_xor_sync(gmask, a, d);
+                        acc[w] = a;
+                        full = full && (a == G[w]);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < WL; w++) full = full && (acc[w] == G[w]);
+                }
+                full = __all_sync(gmask, full);
+                if (full) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) { u64 q = s1 + vi + VG * u; k[u] = (q < e1) ? ld_col<HINTS>(ATj + q, strm) : 0xFFFFFFFFu; }
+                    break;
+                }
+            }
+            qb += VG * U;
+            it++;
+        }
+#pragma unroll
+        for (int w = 0; w < WL; w++) {
+            u64 a = acc[w];
+#pragma unroll
+            for (int d = SPLIT; d < 8; d <<= 1) a |= __shfl_xor_sync(gmask, a, d);
+            acc[w] = a;
+        }
+        if (e0 > s0 && vi == 0) {
+            const u64 i = entry(t);
+            u64 *dst = Y + (u64)s_row[i] * W + h * WL;
+            if (s_len[i] & SEG_ATOMIC) {
+#pragma unroll
+                for (int w = 0; w < WL; w++) if (acc[w]) atomicOr((unsigned long long *)(dst + w), acc[w]);
+            } else store_part<WL>(dst, acc);
+        }
+        s0 = s1; e0 = e1; s1 = s2; e1 = e2;
+    }
+}
+
 // ---------------------------------------------------------------------------- pull, merge-path variant
 // Balanced over (rows + nnz) of A' exactly like merge-based CSR SpMV: every CTA takes TILE consecutive items of the
 // merged (row-end, nnz) sequence, so hub rows and runs of empty rows cost what they weigh.  Phase 1 gathers X[col]
@@ -1621,6 +1927,34 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
     LAUNCH(k_mp_coords, grid_for(ndiag, 256), 256, 0, AT.p.ptr, n, AT.nnz, ndiag, lr.mp_r.ptr);
 }
 
+// persisting-L2 access-policy window on the library stream (cudaLimitPersistingL2CacheSize is set at context bring-up)
+static void set_l2_window(const void *base, u64 bytes) {
+    Context &cx = ctx();
+    if (cx.l2_persist_max == 0) return;
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    u64 nb = bytes;
+    if (nb > cx.l2_window_max) nb = cx.l2_window_max;
+    a.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    a.accessPolicyWindow.num_bytes = nb;
+    a.accessPolicyWindow.hitRatio = nb <= cx.l2_persist_max ? 1.0f : (float)((double)cx.l2_persist_max / (double)nb);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CUDA_TRY(cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a));
+}
+static void clear_l2_window() {
+    Context &cx = ctx();
+    if (cx.l2_persist_max == 0) return;
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.num_bytes = 0;
+    a.accessPolicyWindow.hitRatio = 0.0f;
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    CUDA_TRY(cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a));
+    if (cx.opt_l2_reset) CUDA_TRY(cudaCtxResetPersistingL2Cache());
+}
+
 template <int W>
 static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y,
                      u64 *flops_out, int *path_out) {
@@ -1733,7 +2067,36 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
             const u32 hot_bytes = (u64)cx.opt_hot_bytes < tot_bytes ? (u32)cx.opt_hot_bytes : tot_bytes;
             // grid = every CTA resident at once (occupancy x SMs) unless pull_grid overrides it: rows are dealt round-robin to
             // 8-lane groups, so one full wave keeps all SMs busy to the end (measured: 3.41 ms at 16 CTAs/SM, 3.12 ms resident)
-            if (cx.opt_pull_kernel == 4) {
+            if (cx.opt_pull_kernel >= 5) {
+                if (!lr->seg_built) build_seg_list(*AT, *lr);
+                auto occ = [&](auto kern) {
+                    int per_sm = 0;
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+                    if (per_sm < 1) per_sm = 1;
+                    if (cx.opt_pull_grid > 0) per_sm = (int)cx.opt_pull_grid;
+                    return (u32)cx.num_sms * (u32)per_sm;
+                };
+                // keep the hot prefix of the packed frontier L2-resident for the duration of the pull: a persisting access-policy
+                // window on the library stream (no per-instruction hint exists for 256-bit loads)
+                const bool window = cx.opt_l2_window > 0 && gx == Xp.ptr && gn;
+                if (window) set_l2_window(gx, std::min<u64>((u64)cx.opt_l2_window, gn * W * 8));
+                auto small = [&](auto kern) {
+                    LAUNCH(kern, grid_for(m * PullCfg<W>::SPLIT, 256, (u64)cx.num_sms * 32), 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, hot_bytes, tot_bytes);
+                };
+                auto seg = [&](auto kern) {
+                    if (lr->ns) LAUNCH(kern, occ(kern), 256, 0, lr->s_row.ptr, lr->s_start.ptr, lr->s_len.ptr, lr->ns, gj, gx, Y.w.ptr, Gp, hot_bytes, tot_bytes);
+                };
+#define SEG_LAUNCH(H) do { \
+        if (cx.opt_unroll >= 8) { if (early) seg(k_pull_seg<W, H, 8, true>); else seg(k_pull_seg<W, H, 8, false>); } \
+        else if (cx.opt_unroll >= 4) { if (early) seg(k_pull_seg<W, H, 4, true>); else seg(k_pull_seg<W, H, 4, false>); } \
+        else { if (early) seg(k_pull_seg<W, H, 2, true>); else seg(k_pull_seg<W, H, 2, false>); } } while (0)
+                if (cx.opt_hints) { small(k_pull_small<W, true>); SEG_LAUNCH(true); }
+                else { small(k_pull_small<W, false>); SEG_LAUNCH(false); }
+#undef SEG_LAUNCH
+                if (window) clear_l2_window();
+                if (path_out) *path_out = 3;
+                return;
+            } else if (cx.opt_pull_kernel == 4) {
                 auto occ = [&](auto kern) {
                     int per_sm = 0;
                     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));

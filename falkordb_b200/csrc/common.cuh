@@ -52,7 +52,11 @@ struct Context {
     i64 opt_bits_min_flops = 1 << 22;     // auto mode: use bit-frontier when flops >= this
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
-    i64 opt_pull_kernel = 4;       // 0 = 8-lanes-per-row kernel, 1 = merge-path kernel, 2 = CSR-stream (W <= 4), 3 = pipelined 8-lane, 4 = degree-binned (small / mid / long)
+    i64 opt_pull_kernel = 5;       // 5 = lane-split degree-binned (default); 4 = degree-binned, one lane per vertex record; 0..3 = earlier kernels
+    i64 opt_l2_window = 0;         // bytes of the packed frontier's hot prefix kept L2-resident through a persisting access-policy window (0 = off)
+    i64 opt_l2_reset = 0;          // cudaCtxResetPersistingL2Cache after each windowed pull
+    i64 opt_count_kernel = 1;      // materialise count pass: 1 = vertical (carry-save) counters, 0 = transpose + popcount
+    u64 l2_persist_max = 0, l2_window_max = 0;   // device limits (bytes), read at bring-up
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
     i64 opt_hints = 1;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
     i64 opt_hot_bytes = 64 << 20;  // size of that hot prefix

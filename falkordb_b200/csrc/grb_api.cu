@@ -1771,6 +1771,8 @@ uint64_t B200_get_stat(const char *name) {
     if (n == "h2d_bytes") return c.h2d_bytes.load();
     if (n == "d2h_bytes") return c.d2h_bytes.load();
     if (n == "num_sms") return (uint64_t)c.num_sms;
+    if (n == "l2_persist_max") return c.l2_persist_max;
+    if (n == "l2_window_max") return c.l2_window_max;
     return ~0ULL;
 }
 int B200_kernel_stats(const char *name, double *ms, uint64_t *launches, uint64_t *bytes) {
@@ -1811,6 +1813,9 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "diag_filter") c.opt_diag_filter = value;
     else if (n == "csr_push") c.opt_csr_push = value;
     else if (n == "fused_prep") c.opt_fused_prep = value;
+    else if (n == "l2_window") c.opt_l2_window = value;
+    else if (n == "l2_reset") c.opt_l2_reset = value;
+    else if (n == "count_kernel") c.opt_count_kernel = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

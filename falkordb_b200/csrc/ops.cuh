@@ -34,6 +34,9 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u64> mp_r;                                  // merge-path coordinates of every 256th diagonal
     DevBuf<u32> m_row, m_len; DevBuf<u64> m_start; u64 nm = 0;   // mid rows (SMALL_ROW < len <= LONG_ROW), longest first
     DevBuf<u32> jp;                                    // relabelled col_idx of A' (all rows)
+    // lane-split pull (pull_kernel = 5): mid rows and LONG_ROW-entry segments of long rows, longest first; bit 31 of s_len marks a
+    // segment of a long row (merged with RED.OR)
+    DevBuf<u32> s_row, s_len; DevBuf<u64> s_start; u64 ns = 0; bool seg_built = false;
     // hot-set packing: vertices with out-edges, by out-degree descending
     DevBuf<u32> vert, slot, hdeg; u64 n1 = 0; bool packed = false;   // hdeg[s] = out-degree of vert[s]
     // CSR-stream form for the pull kernel: short rows of A' (cols relabelled to slots), window -> first row,
@@ -42,6 +45,7 @@ struct LongRows {   // per-matrix auxiliary data of the pull direction, cached w
     DevBuf<u64> rp_s; DevBuf<u32> jp_s, wstart; u64 nwin = 0, nnz_s = 0;
     DevBuf<u32> lrows, jp_l; DevBuf<u64> lrp; u64 nlong = 0, maxlong = 0;
     void clear() {
+        s_row.release(); s_len.release(); s_start.release(); ns = 0; seg_built = false;
         built = false; rows.release(); n = 0; maxdeg = 0; choff.release(); nchunks = 0; mp_r.release(); jp.release(); m_row.release(); m_len.release(); m_start.release(); nm = 0;
         vert.release(); slot.release(); hdeg.release(); n1 = 0; packed = false;
         sW = 0; swin = 0; s_packed = false; rp_s.release(); jp_s.release(); wstart.release(); nwin = 0; nnz_s = 0;

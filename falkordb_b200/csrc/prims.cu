@@ -35,6 +35,10 @@ void ensure_init() {
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     c.num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    // persisting-L2 carve-out for the frontier's hot prefix (bits.cu: set_l2_window); harmless when no window is ever set
+    c.l2_persist_max = (u64)prop.persistingL2CacheMaxSize;
+    c.l2_window_max = (u64)prop.accessPolicyMaxWindowSize;
+    if (c.l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max) != cudaSuccess) { cudaGetLastError(); c.l2_persist_max = 0; }
     c.ready = true;
 }
 
