@@ -60,6 +60,9 @@ def lib():
         "GrB_Vector_nvals": [C.POINTER(U64), P], "GrB_Vector_setElement_BOOL": [P, C.c_bool, U64],
         "GrB_Vector_extractElement_INT64": [C.POINTER(I64), P, U64], "GrB_Vector_extractElement_BOOL": [C.POINTER(C.c_bool), P, U64],
         "GrB_Vector_extractTuples_INT64": [P, P, C.POINTER(U64), P], "GrB_Vector_extractTuples_BOOL": [P, P, C.POINTER(U64), P],
+        "GrB_Vector_setElement_UINT64": [P, U64, U64], "GrB_Vector_removeElement": [P, U64], "GrB_Vector_clear": [P],
+        "GrB_Vector_wait": [P, C.c_int], "GrB_Vector_resize": [P, U64],
+        "GxB_Vector_Iterator_attach": [P, P, P], "GxB_Vector_Iterator_seek": [P, U64], "GxB_Vector_Iterator_next": [P],
         "GrB_vxm": [P, P, P, P, P, P, P], "GrB_mxv": [P, P, P, P, P, P, P],
         "GxB_Iterator_new": [C.POINTER(P)], "GxB_Iterator_free": [C.POINTER(P)], "GxB_rowIterator_attach": [P, P, P],
         "GxB_rowIterator_seekRow": [P, U64], "GxB_rowIterator_nextRow": [P], "GxB_rowIterator_nextCol": [P],
@@ -84,7 +87,8 @@ def lib():
         f = getattr(L, name)
         f.argtypes = args
         f.restype = C.c_int
-    for name in ("GxB_rowIterator_kount", "GxB_rowIterator_getRowIndex", "GxB_rowIterator_getColIndex", "GxB_Iterator_get_UINT64"):
+    for name in ("GxB_rowIterator_kount", "GxB_rowIterator_getRowIndex", "GxB_rowIterator_getColIndex", "GxB_Iterator_get_UINT64",
+                 "GxB_Vector_Iterator_getpmax", "GxB_Vector_Iterator_getp", "GxB_Vector_Iterator_getIndex"):
         f = getattr(L, name)
         f.argtypes = [P]
         f.restype = U64

@@ -28,7 +28,7 @@ struct GB_BinaryOp_opaque { int code; };
 struct GB_Semiring_opaque { int code; };
 struct GB_Global_opaque { int x; };
 struct GB_Descriptor_opaque { bool t0, t1, comp, structure, replace; };
-struct GB_Scalar_opaque { int type; bool has; uint64_t val; };
+struct GB_Scalar_opaque { int type; bool has; uint64_t val; };   // allocated with the C++ allocator: 24 bytes, short-lived
 
 enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3, T_UINT32 = 4 };
 enum { OP_ANY_BOOL = 1, OP_SECOND_UINT64 = 2, OP_ANY_UINT64 = 3 };
@@ -60,29 +60,76 @@ DESC(RC, 1, 0, 1, 0, 0) DESC(RCT1, 1, 0, 1, 0, 1) DESC(RCT0, 1, 0, 1, 1, 0) DESC
 DESC(RS, 1, 1, 0, 0, 0) DESC(RST1, 1, 1, 0, 0, 1) DESC(RST0, 1, 1, 0, 1, 0) DESC(RST0T1, 1, 1, 0, 1, 1)
 DESC(RSC, 1, 1, 1, 0, 0) DESC(RSCT1, 1, 1, 1, 0, 1) DESC(RSCT0, 1, 1, 1, 1, 0) DESC(RSCT0T1, 1, 1, 1, 1, 1)
 
+// ---- host memory goes through the allocator given to GxB_init (matrix.rs:123-131: Redis' allocator, so that the server's
+// memory accounting and QUERY_MEM_CAPACITY see this library's host footprint).  Every host container of a handle (tuple
+// stores, pending lists, vector payloads, iterator snapshots) and the handles themselves use it; so do the buffers handed
+// to the caller (unloaded arrays, blobs), which the caller frees with the same allocator (vector.rs:171-172).
+static void *(*g_user_malloc)(size_t) = malloc;
+static void *(*g_user_calloc)(size_t, size_t) = calloc;
+static void *(*g_user_realloc)(void *, size_t) = realloc;
+static void (*g_user_free)(void *) = free;
+static std::atomic<uint64_t> g_host_bytes{0}, g_host_allocs{0};     // live bytes / allocation calls through the hooks
+template <class T> struct UAlloc {
+    typedef T value_type;
+    UAlloc() noexcept {}
+    template <class U> UAlloc(const UAlloc<U> &) noexcept {}
+    T *allocate(size_t n) {
+        if (n > (size_t)-1 / sizeof(T)) throw std::bad_alloc();
+        const size_t bytes = n * sizeof(T);
+        void *p = g_user_malloc(bytes > 0 ? bytes : 1);
+        if (!p) throw std::bad_alloc();
+        g_host_bytes += n * sizeof(T); g_host_allocs++;
+        return (T *)p;
+    }
+    void deallocate(T *p, size_t n) noexcept { g_host_bytes -= n * sizeof(T); g_user_free(p); }
+    template <class U> bool operator==(const UAlloc<U> &) const noexcept { return true; }
+    template <class U> bool operator!=(const UAlloc<U> &) const noexcept { return false; }
+};
+template <class T> using uvec = std::vector<T, UAlloc<T>>;
+static void *user_zalloc(size_t bytes) {        // zero-initialised block (the container struct); calloc hook when the caller gave one
+    void *p = g_user_calloc ? g_user_calloc(1, bytes) : g_user_malloc(bytes);
+    if (p && !g_user_calloc) memset(p, 0, bytes);
+    return p;
+}
+static void *user_grow(void *old, size_t old_bytes, size_t new_bytes) {   // realloc hook when given, else malloc + copy + free
+    if (g_user_realloc) return g_user_realloc(old, new_bytes);
+    void *p = g_user_malloc(new_bytes);
+    if (p && old) { memcpy(p, old, old_bytes < new_bytes ? old_bytes : new_bytes); g_user_free(old); }
+    return p;
+}
+// the hooks as the host-side mirror and the tests see them
+extern "C" void *B200_user_realloc(void *p, size_t old_bytes, size_t new_bytes) { return user_grow(p, old_bytes, new_bytes); }
+// handles: operator new / delete through the same hooks
+struct UObject {
+    static void *operator new(size_t n) {
+        void *p = g_user_malloc(n);
+        if (!p) throw std::bad_alloc();
+        g_host_bytes += n; g_host_allocs++;
+        return p;
+    }
+    static void operator delete(void *p, size_t n) noexcept { if (p) { g_host_bytes -= n; g_user_free(p); } }
+};
+
 struct HostStore {
-    std::vector<u64> hrow; // ascending ids of the non-empty rows
-    std::vector<u64> hptr; // hrow.size()+1
-    std::vector<u64> hcol; // ascending inside a row
-    std::vector<u64> hval; // empty for pattern-only (BOOL)
+    uvec<u64> hrow; // ascending ids of the non-empty rows
+    uvec<u64> hptr; // hrow.size()+1
+    uvec<u64> hcol; // ascending inside a row
+    uvec<u64> hval; // empty for pattern-only (BOOL)
     void clear() { hrow.clear(); hptr.assign(1, 0); hcol.clear(); hval.clear(); }
     u64 nnz() const { return hcol.size(); }
 };
 struct PendingOp { u64 i, j, v; u64 seq; bool del; };
 
 static const u32 MAGIC = 0xB200A7u;
-// allocator of buffers that are handed to the caller (set by GxB_init; see the serialization section)
-static void *(*g_user_malloc)(size_t) = malloc;
-static void (*g_user_free)(void *) = free;
 
-struct GB_Matrix_opaque {
+struct GB_Matrix_opaque : UObject {
     u32 magic = MAGIC;
     int type = T_BOOL;
     u64 nrows = 0, ncols = 0;
     std::mutex mu;
     bool host_valid = true;
     HostStore host;
-    std::vector<PendingOp> pending;
+    uvec<PendingOp> pending;
     bool dev_valid = false;
     DevCSR dev;
     bool bits_valid = false;
@@ -99,19 +146,20 @@ struct GB_Matrix_opaque {
     bool valued() const { return type != T_BOOL; }
 };
 
-struct GB_Vector_opaque {
+struct GB_Vector_opaque : UObject {
     u32 magic = MAGIC;
     int type = T_BOOL;
     u64 n = 0;
-    std::vector<u64> idx; // ascending
-    std::vector<i64> val; // same length (bool: 1)
+    uvec<u64> idx; // ascending
+    uvec<i64> val; // same length (bool: 1)
     // full (dense) form of the GxB_Container payload vectors: n entries of `type` in fx (user allocator), idx / val unused
     bool full = false;
     void *fx = nullptr;
     u64 fbytes = 0;
 };
 
-struct GB_Iterator_opaque {
+struct GB_Iterator_opaque : UObject {
+    GrB_Vector V = nullptr;   // vector mode (GxB_Vector_Iterator_*): k = position of the current entry, pmax = nvals
     GrB_Matrix A = nullptr;
     u64 k = 0; // vector (non-empty row) position; the row itself in bitmap mode
     u64 q = 0; // entry position; the column itself in bitmap mode
@@ -120,7 +168,7 @@ struct GB_Iterator_opaque {
     // PCIe instead of a 64-bit column index per entry); same ascending (row, col) order as the sparse walk
     bool bitmap = false;
     u64 wpr = 0, nrows = 0, ncols = 0;
-    std::vector<u64> bm;
+    uvec<u64> bm;
     // first set bit of `row` at column >= from, or ncols
     u64 first_set(u64 row, u64 from) const {
         if (from >= ncols) return ncols;
@@ -169,9 +217,9 @@ static GrB_Info guarded(F &&f) {
                           if ((m)->magic != MAGIC) { tl_error = "invalid matrix: " #m; return GrB_INVALID_OBJECT; } } while (0)
 
 struct MultiLock {
-    std::vector<std::unique_lock<std::mutex>> locks;
+    uvec<std::unique_lock<std::mutex>> locks;
     MultiLock(std::initializer_list<GrB_Matrix> ms) {
-        std::vector<GrB_Matrix> v;
+        uvec<GrB_Matrix> v;
         for (GrB_Matrix m : ms) if (m) v.push_back(m);
         std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());
@@ -232,14 +280,14 @@ static void download_to_host(GrB_Matrix A); // fwd
 static void finish_pending(GrB_Matrix A) {
     if (A->pending.empty()) return;
     if (!A->host_valid) download_to_host(A);
-    std::vector<PendingOp> &p = A->pending;
+    uvec<PendingOp> &p = A->pending;
     std::sort(p.begin(), p.end(), [](const PendingOp &a, const PendingOp &b) {
         if (a.i != b.i) return a.i < b.i;
         if (a.j != b.j) return a.j < b.j;
         return a.seq < b.seq;
     });
     // keep the last op per coordinate
-    std::vector<PendingOp> last;
+    uvec<PendingOp> last;
     last.reserve(p.size());
     for (size_t t = 0; t < p.size(); t++)
         if (t + 1 == p.size() || p[t + 1].i != p[t].i || p[t + 1].j != p[t].j) last.push_back(p[t]);
@@ -425,10 +473,10 @@ static void write_back(GrB_Matrix C, DevCSR &&T, GrB_Matrix M, const Desc &d, bo
 // NOT a fallback: device-capable operands never take this branch (see is_huge), and mxm on such matrices is refused.
 struct HTup { u64 r, c, v; };
 static bool is_huge(GrB_Matrix A) { return A && (A->nrows >= ((u64)1 << 32) || A->ncols >= ((u64)1 << 32)); }
-static std::vector<HTup> host_tuples(GrB_Matrix A) {
+static uvec<HTup> host_tuples(GrB_Matrix A) {
     ensure_host(A);
     const HostStore &h = A->host;
-    std::vector<HTup> t;
+    uvec<HTup> t;
     t.reserve(h.nnz());
     for (u64 k = 0; k < h.hrow.size(); k++)
         for (u64 q = h.hptr[k]; q < h.hptr[k + 1]; q++) t.push_back(HTup{h.hrow[k], h.hcol[q], A->valued() ? h.hval[q] : 1});
@@ -436,7 +484,7 @@ static std::vector<HTup> host_tuples(GrB_Matrix A) {
 }
 static inline bool tup_lt(const HTup &a, const HTup &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; }
 static inline bool tup_eq(const HTup &a, const HTup &b) { return a.r == b.r && a.c == b.c; }
-static void host_store_from(GrB_Matrix C, const std::vector<HTup> &t) {
+static void host_store_from(GrB_Matrix C, const uvec<HTup> &t) {
     HostStore h;
     h.hptr.clear();
     for (const HTup &x : t) {
@@ -448,8 +496,8 @@ static void host_store_from(GrB_Matrix C, const std::vector<HTup> &t) {
     set_empty(C);
     C->host = std::move(h);
 }
-static std::vector<HTup> host_union(const std::vector<HTup> &A, const std::vector<HTup> &B) { // overlap: B's value
-    std::vector<HTup> o;
+static uvec<HTup> host_union(const uvec<HTup> &A, const uvec<HTup> &B) { // overlap: B's value
+    uvec<HTup> o;
     o.reserve(A.size() + B.size());
     size_t i = 0, j = 0;
     while (i < A.size() || j < B.size()) {
@@ -459,8 +507,8 @@ static std::vector<HTup> host_union(const std::vector<HTup> &A, const std::vecto
     }
     return o;
 }
-static std::vector<HTup> host_intersect(const std::vector<HTup> &A, const std::vector<HTup> &B) {
-    std::vector<HTup> o;
+static uvec<HTup> host_intersect(const uvec<HTup> &A, const uvec<HTup> &B) {
+    uvec<HTup> o;
     size_t i = 0, j = 0;
     while (i < A.size() && j < B.size()) {
         if (tup_lt(A[i], B[j])) i++;
@@ -469,8 +517,8 @@ static std::vector<HTup> host_intersect(const std::vector<HTup> &A, const std::v
     }
     return o;
 }
-static std::vector<HTup> host_filter(const std::vector<HTup> &T, const std::vector<HTup> &M, bool comp, bool structural, bool mvalued) {
-    std::vector<HTup> o;
+static uvec<HTup> host_filter(const uvec<HTup> &T, const uvec<HTup> &M, bool comp, bool structural, bool mvalued) {
+    uvec<HTup> o;
     size_t j = 0;
     for (const HTup &x : T) {
         while (j < M.size() && tup_lt(M[j], x)) j++;
@@ -479,17 +527,17 @@ static std::vector<HTup> host_filter(const std::vector<HTup> &T, const std::vect
     }
     return o;
 }
-static void host_write_back(GrB_Matrix C, std::vector<HTup> T, GrB_Matrix M, const Desc &d, bool accum) {
-    std::vector<HTup> Z = accum ? host_union(host_tuples(C), T) : std::move(T);
+static void host_write_back(GrB_Matrix C, uvec<HTup> T, GrB_Matrix M, const Desc &d, bool accum) {
+    uvec<HTup> Z = accum ? host_union(host_tuples(C), T) : std::move(T);
     if (!M) {
         if (d.comp) { if (d.replace) set_empty(C); return; }
         host_store_from(C, Z);
         return;
     }
-    std::vector<HTup> Mt = host_tuples(M);
-    std::vector<HTup> Zm = host_filter(Z, Mt, d.comp, d.structure, M->valued());
+    uvec<HTup> Mt = host_tuples(M);
+    uvec<HTup> Zm = host_filter(Z, Mt, d.comp, d.structure, M->valued());
     if (d.replace) { host_store_from(C, Zm); return; }
-    std::vector<HTup> Ck = host_filter(host_tuples(C), Mt, !d.comp, d.structure, M->valued());
+    uvec<HTup> Ck = host_filter(host_tuples(C), Mt, !d.comp, d.structure, M->valued());
     host_store_from(C, host_union(Ck, Zm));
 }
 
@@ -502,12 +550,16 @@ extern "C" {
 
 const char *B200_last_error(void) { return tl_error.c_str(); }
 
-GrB_Info GxB_init(int mode, void *(*um)(size_t), void *(*)(size_t, size_t), void *(*)(void *, size_t), void (*uf)(void *)) {
+GrB_Info GxB_init(int mode, void *(*um)(size_t), void *(*uc)(size_t, size_t), void *(*ur)(void *, size_t), void (*uf)(void *)) {
     (void)mode;
-    // Internal host containers use the C++ allocator (the hooks only matter for Redis memory accounting in the reference,
-    // matrix.rs:104-107); buffers that are HANDED to the caller (GxB_Vector_unload arrays, GxB_Vector_serialize blobs) come
-    // from the caller's allocator, because the caller frees them with it (vector.rs:171-172).
-    if (um && uf) { g_user_malloc = um; g_user_free = uf; }
+    // Must precede every other call (as in the reference: matrix.rs:123-131 runs once at module load): memory obtained
+    // from one allocator is never released with another.  malloc + free are mandatory (GraphBLAS C API: calloc / realloc may
+    // be NULL and are then emulated).
+    if (um && uf) {
+        if (g_host_bytes.load() != 0) { tl_error = "GxB_init: allocator change with live host objects"; return GrB_INVALID_VALUE; }
+        g_user_malloc = um; g_user_free = uf;
+        g_user_calloc = uc; g_user_realloc = ur;
+    }
     return GrB_SUCCESS; // the CUDA context is created lazily by the first bulk operation
 }
 GrB_Info GrB_init(int mode) { return GxB_init(mode, nullptr, nullptr, nullptr, nullptr); }
@@ -837,7 +889,7 @@ static bool matrix_is_empty(GrB_Matrix C) {
 // host-side build for matrices outside the device-capable range (e.g. Tensor's 2^60 x 2^60 `me`)
 static GrB_Info build_host(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const u64 *X, u64 n) {
     struct T { u64 i, j, v, s; };
-    std::vector<T> t(n);
+    uvec<T> t(n);
     for (u64 k = 0; k < n; k++) {
         if (I[k] >= C->nrows || J[k] >= C->ncols) { tl_error = "build: index out of bounds"; return GrB_INDEX_OUT_OF_BOUNDS; }
         t[k] = T{I[k], J[k], X ? X[k] : 1, k};
@@ -892,7 +944,7 @@ GrB_Info GxB_Matrix_build_Scalar(GrB_Matrix C, const GrB_Index *I, const GrB_Ind
         tl_error = "build_Scalar(false) into a pattern-only BOOL matrix"; return GrB_NOT_IMPLEMENTED;
     }
     if (C && C->magic == MAGIC && C->valued()) {
-        std::vector<u64> X(nvals, scalar->val);
+        uvec<u64> X(nvals, scalar->val);
         return build_common(C, I, J, X.data(), nvals);
     }
     return build_common(C, I, J, nullptr, nvals);
@@ -916,7 +968,7 @@ GrB_Info GrB_Matrix_build_BOOL(GrB_Matrix C, const GrB_Index *I, const GrB_Index
         for (u64 k = 0; k < nvals; k++) if (!X[k]) { tl_error = "stored false in pattern-only BOOL"; return GrB_NOT_IMPLEMENTED; }
         return build_common(C, I, J, nullptr, nvals);
     }
-    std::vector<u64> V(nvals);
+    uvec<u64> V(nvals);
     for (u64 k = 0; k < nvals; k++) V[k] = X[k] ? 1 : 0;
     return build_common(C, I, J, V.data(), nvals);
 }
@@ -1128,7 +1180,7 @@ GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Ma
         if (!C->valued() && A->valued())
             throw GrbError(GrB_NOT_IMPLEMENTED, "transpose: valued -> BOOL typecast is not on the path");
         if (is_huge(C) || is_huge(A)) {
-            std::vector<HTup> T = host_tuples(A);
+            uvec<HTup> T = host_tuples(A);
             if (eff_transpose) {
                 for (HTup &x : T) std::swap(x.r, x.c);
                 std::sort(T.begin(), T.end(), tup_lt);
@@ -1161,7 +1213,7 @@ GrB_Info GrB_Matrix_apply(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB
         check_mask_dims(C, Mask);
         if (is_huge(C)) {
             if (d.t0) throw GrbError(GrB_NOT_IMPLEMENTED, "apply: transposed operand on a host-resident matrix");
-            std::vector<HTup> T = host_tuples(A);
+            uvec<HTup> T = host_tuples(A);
             for (HTup &x : T) x.v = 1;
             host_write_back(C, std::move(T), Mask, d, accum != nullptr);
             return GrB_SUCCESS;
@@ -1269,7 +1321,12 @@ GrB_Index GxB_rowIterator_getColIndex(GxB_Iterator it) {
     if (it->bitmap) return it->q;
     return it->A->host.hcol[it->q];
 }
+static u64 vec_at(GrB_Vector v, u64 k);
 uint64_t GxB_Iterator_get_UINT64(GxB_Iterator it) {
+    if (it && it->V) {
+        if (it->exhausted) return 0;
+        return it->V->full ? vec_at(it->V, it->k) : (uint64_t)it->V->val[it->k];
+    }
     if (!it || !it->A || it->exhausted) return 0;
     if (it->bitmap) return 1;
     return it->A->valued() ? it->A->host.hval[it->q] : 1;
@@ -1287,14 +1344,52 @@ GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n) {
 GrB_Info GrB_Vector_free(GrB_Vector *v) { if (v && *v) { if ((*v)->fx) g_user_free((*v)->fx); delete *v; *v = nullptr; } return GrB_SUCCESS; }
 GrB_Info GrB_Vector_size(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->n; return GrB_SUCCESS; }
 GrB_Info GrB_Vector_nvals(GrB_Index *n, GrB_Vector v) { CHECK_PTR(n); CHECK_PTR(v); *n = v->full ? v->n : v->idx.size(); return GrB_SUCCESS; }
-GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i) {
+// a full (container payload) vector that is written element-wise drops back to the sparse form first
+static void vec_make_sparse(GrB_Vector v);
+static GrB_Info vec_set(GrB_Vector v, i64 x, GrB_Index i) {
     CHECK_PTR(v);
     if (i >= v->n) return GrB_INVALID_INDEX;
-    auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
-    size_t pos = it - v->idx.begin();
-    if (it != v->idx.end() && *it == i) v->val[pos] = x;
-    else { v->idx.insert(it, i); v->val.insert(v->val.begin() + pos, x ? 1 : 0); }
+    return guarded([&]() {
+        vec_make_sparse(v);
+        if (v->idx.empty() || v->idx.back() < i) { v->idx.push_back(i); v->val.push_back(x); return GrB_SUCCESS; }   // ascending fill: O(1)
+        auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
+        size_t pos = it - v->idx.begin();
+        if (it != v->idx.end() && *it == i) v->val[pos] = x;
+        else { v->idx.insert(it, i); v->val.insert(v->val.begin() + pos, x); }
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i) { return vec_set(v, x ? 1 : 0, i); }          // vector.rs:127, 507
+GrB_Info GrB_Vector_setElement_UINT64(GrB_Vector v, uint64_t x, GrB_Index i) { return vec_set(v, (i64)x, i); }     // vector.rs:442
+GrB_Info GrB_Vector_removeElement(GrB_Vector v, GrB_Index i) {                                                       // vector.rs:519
+    CHECK_PTR(v);
+    if (i >= v->n) return GrB_INVALID_INDEX;
+    return guarded([&]() {
+        vec_make_sparse(v);
+        auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
+        if (it != v->idx.end() && *it == i) { v->val.erase(v->val.begin() + (it - v->idx.begin())); v->idx.erase(it); }
+        return GrB_SUCCESS;            // removing an absent entry is not an error (GraphBLAS C API 2.1)
+    });
+}
+GrB_Info GrB_Vector_clear(GrB_Vector v) {                                                                            // vector.rs:98
+    CHECK_PTR(v);
+    v->idx.clear(); v->val.clear();
+    if (v->fx) { g_user_free(v->fx); v->fx = nullptr; }
+    v->full = false; v->fbytes = 0;
     return GrB_SUCCESS;
+}
+GrB_Info GrB_Vector_wait(GrB_Vector v, int) { CHECK_PTR(v); return GrB_SUCCESS; }   // nothing is ever left pending (vector.rs:134)
+GrB_Info GrB_Vector_resize(GrB_Vector v, GrB_Index n) {                                                              // vector.rs:494
+    CHECK_PTR(v);
+    return guarded([&]() {
+        if (n < v->n) {
+            vec_make_sparse(v);
+            size_t keep = std::lower_bound(v->idx.begin(), v->idx.end(), n) - v->idx.begin();
+            v->idx.resize(keep); v->val.resize(keep);
+        } else if (n > v->n && v->full) vec_make_sparse(v);
+        v->n = n;
+        return GrB_SUCCESS;
+    });
 }
 GrB_Info GrB_Vector_extractElement_INT64(int64_t *x, GrB_Vector v, GrB_Index i) {
     CHECK_PTR(x); CHECK_PTR(v);
@@ -1326,6 +1421,36 @@ GrB_Info GrB_Vector_extractTuples_BOOL(GrB_Index *I, bool *X, GrB_Index *nvals, 
     return GrB_SUCCESS;
 }
 
+// ---- vector iterator (vector.rs:553-594): positions 0 .. nvals-1 in ascending index order
+static u64 vec_nvals(GrB_Vector v) { return v->full ? v->n : v->idx.size(); }
+GrB_Info GxB_Vector_Iterator_attach(GxB_Iterator it, GrB_Vector v, GrB_Descriptor) {
+    CHECK_PTR(it); CHECK_PTR(v);
+    it->A = nullptr; it->bitmap = false; it->bm.clear();
+    it->V = v; it->k = 0; it->q = 0;
+    it->exhausted = vec_nvals(v) == 0;
+    return GrB_SUCCESS;
+}
+GrB_Index GxB_Vector_Iterator_getpmax(GxB_Iterator it) { return (it && it->V) ? vec_nvals(it->V) : 0; }
+GrB_Index GxB_Vector_Iterator_getp(GxB_Iterator it) { return (it && it->V) ? it->k : 0; }
+GrB_Info GxB_Vector_Iterator_seek(GxB_Iterator it, GrB_Index p) {
+    if (!it || !it->V) return GrB_NULL_POINTER;
+    const u64 pmax = vec_nvals(it->V);
+    if (p >= pmax) { it->k = pmax; it->exhausted = true; return GxB_EXHAUSTED; }
+    it->k = p; it->exhausted = false;
+    return GrB_SUCCESS;
+}
+GrB_Info GxB_Vector_Iterator_next(GxB_Iterator it) {
+    if (!it || !it->V) return GrB_NULL_POINTER;
+    const u64 pmax = vec_nvals(it->V);
+    if (it->k + 1 >= pmax) { it->k = pmax; it->exhausted = true; return GxB_EXHAUSTED; }
+    it->k++;
+    return GrB_SUCCESS;
+}
+GrB_Index GxB_Vector_Iterator_getIndex(GxB_Iterator it) {
+    if (!it || !it->V || it->exhausted) return 0;
+    return it->V->full ? it->k : it->V->idx[it->k];
+}
+
 // one frontier step w<mask> = u*A (vxm) or A*u (mxv) over ANY_PAIR, run as a 1-row mxm
 static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u,
                               GrB_Matrix A, GrB_Descriptor desc, bool is_mxv) {
@@ -1340,21 +1465,21 @@ static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum,
     GrB_Info info = GrB_Matrix_new(&F, GrB_BOOL, 1, inner);
     if (info) return info;
     GrB_Matrix_new(&Cm, GrB_BOOL, 1, outer);
-    std::vector<u64> zeros(std::max(u->idx.size(), mask ? mask->idx.size() : (size_t)0), 0);
+    uvec<u64> zeros(std::max(u->idx.size(), mask ? mask->idx.size() : (size_t)0), 0);
     GrB_Scalar s; GrB_Scalar_new(&s, GrB_BOOL); GrB_Scalar_setElement_BOOL(s, true);
-    std::vector<u64> uidx;
+    uvec<u64> uidx;
     for (size_t k = 0; k < u->idx.size(); k++) if (u->val[k] != 0 || u->type != T_BOOL) uidx.push_back(u->idx[k]);
     info = GxB_Matrix_build_Scalar(F, zeros.data(), uidx.data(), s, uidx.size());
     if (!info && mask) {
         GrB_Matrix_new(&Mm, GrB_BOOL, 1, outer);
-        std::vector<u64> midx;
+        uvec<u64> midx;
         for (size_t k = 0; k < mask->idx.size(); k++) if (d.structure || mask->val[k] != 0) midx.push_back(mask->idx[k]);
         info = GxB_Matrix_build_Scalar(Mm, zeros.data(), midx.data(), s, midx.size());
     }
     if (!info) {
         // existing w content matters only without replace; seed C with it
         if (mask && !d.replace && !w->idx.empty()) {
-            std::vector<u64> z2(w->idx.size(), 0);
+            uvec<u64> z2(w->idx.size(), 0);
             info = GxB_Matrix_build_Scalar(Cm, z2.data(), w->idx.data(), s, w->idx.size());
         }
     }
@@ -1365,7 +1490,7 @@ static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum,
     if (!info) {
         GrB_Index nv = 0;
         GrB_Matrix_nvals(&nv, Cm);
-        std::vector<u64> I(nv), J(nv);
+        uvec<u64> I(nv), J(nv);
         GrB_Index cap = nv;
         info = GrB_Matrix_extractTuples_BOOL(I.data(), J.data(), nullptr, &cap, Cm);
         if (!info) {
@@ -1446,11 +1571,11 @@ int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGr
     if (!G || !G->A) return GrB_NULL_POINTER;
     if (dest >= 0) { if (msg) snprintf(msg, 256, "dest early-exit is not supported"); return GrB_NOT_IMPLEMENTED; }
     u64 n = G->A->nrows;
-    std::vector<i64> lv(n), pr;
+    uvec<i64> lv(n), pr;
     if (parent) pr.resize(n);
     GrB_Info info = B200_bfs(G->A, src, max_level < 0 ? -1 : max_level, lv.data(), parent ? pr.data() : nullptr, B200_LOC_HOST, nullptr);
     if (info) { if (msg) snprintf(msg, 256, "%s", tl_error.c_str()); return info; }
-    auto fill = [&](GrB_Vector *out, const std::vector<i64> &src_v) {
+    auto fill = [&](GrB_Vector *out, const uvec<i64> &src_v) {
         GrB_Vector v = new GB_Vector_opaque();
         v->type = T_INT64; v->n = n;
         for (u64 i = 0; i < n; i++) if (src_v[i] >= 0) { v->idx.push_back(i); v->val.push_back(src_v[i]); }
@@ -1772,6 +1897,8 @@ uint64_t B200_get_stat(const char *name) {
     if (n == "d2h_bytes") return c.d2h_bytes.load();
     if (n == "num_sms") return (uint64_t)c.num_sms;
     if (n == "l2_persist_max") return c.l2_persist_max;
+    if (n == "host_bytes") return g_host_bytes.load();     // live bytes obtained through the GxB_init allocator hooks
+    if (n == "host_allocs") return g_host_allocs.load();
     if (n == "l2_window_max") return c.l2_window_max;
     return ~0ULL;
 }
@@ -1856,14 +1983,25 @@ static void vec_set_empty(GrB_Vector v) {
 }
 // read entry k of a full integer vector (UINT32 / UINT64 / INT64)
 static bool vec_full_int(GrB_Vector v) { return v && v->full && (v->type == T_UINT32 || v->type == T_UINT64 || v->type == T_INT64); }
-static u64 vec_at(GrB_Vector v, u64 k) { return v->type == T_UINT32 ? (u64)((const u32 *)v->fx)[k] : ((const u64 *)v->fx)[k]; }
+static u64 vec_at(GrB_Vector v, u64 k) {
+    return v->type == T_UINT32 ? (u64)((const u32 *)v->fx)[k] : v->type == T_BOOL ? (u64)((const unsigned char *)v->fx)[k] : ((const u64 *)v->fx)[k];
+}
+static void vec_make_sparse(GrB_Vector v) {
+    if (!v->full) return;
+    uvec<u64> idx(v->n);
+    uvec<i64> val(v->n);
+    for (u64 k = 0; k < v->n; k++) { idx[k] = k; val[k] = v->fx ? (i64)vec_at(v, k) : 0; }
+    if (v->fx) { g_user_free(v->fx); v->fx = nullptr; }
+    v->idx = std::move(idx); v->val = std::move(val);
+    v->full = false; v->fbytes = 0;
+}
 
 extern "C" {
 
 GrB_Info GxB_Container_new(GxB_Container *Container) {
     CHECK_PTR(Container);
     return guarded([&]() {
-        GxB_Container c = (GxB_Container)calloc(1, sizeof(struct GxB_Container_struct));
+        GxB_Container c = (GxB_Container)user_zalloc(sizeof(struct GxB_Container_struct));
         if (!c) throw std::bad_alloc();
         GrB_Vector *vs[5] = {&c->p, &c->h, &c->b, &c->i, &c->x};
         for (GrB_Vector *pv : vs) { *pv = new GB_Vector_opaque(); (*pv)->full = true; (*pv)->n = 0; }
@@ -1878,7 +2016,7 @@ GrB_Info GxB_Container_free(GxB_Container *Container) {
     GrB_Vector *vs[5] = {&c->p, &c->h, &c->b, &c->i, &c->x};
     for (GrB_Vector *pv : vs) GrB_Vector_free(pv);
     if (c->Y) GrB_Matrix_free(&c->Y);
-    free(c);
+    g_user_free(c);
     *Container = nullptr;
     return GrB_SUCCESS;
 }
@@ -1897,14 +2035,14 @@ GrB_Info GxB_unload_Matrix_into_Container(GrB_Matrix A, GxB_Container c, GrB_Des
             vec_set_full(c->p, T_UINT64, h.hptr.data(), nvec + 1);
             vec_set_full(c->h, T_UINT64, h.hrow.data(), nvec);
         } else {
-            std::vector<u64> p(A->nrows + 1, 0);
+            uvec<u64> p(A->nrows + 1, 0);
             for (u64 k = 0; k < nvec; k++) p[h.hrow[k] + 1] = h.hptr[k + 1] - h.hptr[k];
             for (u64 r = 0; r < A->nrows; r++) p[r + 1] += p[r];
             vec_set_full(c->p, T_UINT64, p.data(), A->nrows + 1);
             vec_set_empty(c->h);
         }
         if (A->ncols <= ((u64)1 << 32)) {
-            std::vector<u32> i32(nnz);
+            uvec<u32> i32(nnz);
             for (u64 q = 0; q < nnz; q++) i32[q] = (u32)h.hcol[q];
             vec_set_full(c->i, T_UINT32, i32.data(), nnz);
         } else vec_set_full(c->i, T_UINT64, h.hcol.data(), nnz);
@@ -1964,7 +2102,7 @@ GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container c, GrB_Descr
                 if (xtype != T_BOOL) h.hval[q] = iso ? ((const u64 *)c->x->fx)[0] : ((const u64 *)c->x->fx)[q];
             }
             if (c->jumbled) {   // sort the row by column, values along
-                std::vector<std::pair<u64, u64>> t(e - s);
+                uvec<std::pair<u64, u64>> t(e - s);
                 for (u64 q = s; q < e; q++) t[q - s] = {h.hcol[q], xtype != T_BOOL ? h.hval[q] : 1};
                 std::sort(t.begin(), t.end());
                 for (u64 q = s; q < e; q++) { h.hcol[q] = t[q - s].first; if (xtype != T_BOOL) h.hval[q] = t[q - s].second; }
@@ -1976,9 +2114,9 @@ GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container c, GrB_Descr
         // rows may leave gaps in p (s > previous e): compact so that hptr is contiguous
         {
             u64 w = 0;
-            std::vector<u64> ncol, nval;
+            uvec<u64> ncol, nval;
             ncol.reserve(nnz); if (xtype != T_BOOL) nval.reserve(nnz);
-            std::vector<u64> nptr(1, 0);
+            uvec<u64> nptr(1, 0);
             u64 kk = 0;
             for (u64 k = 0; k < nvec; k++) {
                 const u64 s = vec_at(c->p, k), e = vec_at(c->p, k + 1);
@@ -2008,7 +2146,7 @@ GrB_Info GxB_Vector_unload(GrB_Vector V, void **X, GrB_Type *type, uint64_t *n, 
         if (!V->full) {
             if (V->idx.size() != V->n) throw GrbError(GrB_INVALID_OBJECT, "Vector_unload: the vector is not full (every entry present)");
             // densify a sparse-API vector that happens to be full
-            std::vector<unsigned char> bytes(V->n * type_size(V->type));
+            uvec<unsigned char> bytes(V->n * type_size(V->type));
             for (u64 k = 0; k < V->n; k++) {
                 if (V->type == T_BOOL) bytes[k] = V->val[k] != 0;
                 else ((u64 *)bytes.data())[k] = (u64)V->val[k];
@@ -2046,7 +2184,7 @@ static const u32 BLOB_MAGIC = 0x56473242u; // "B2GV"
 GrB_Info GxB_Vector_serialize(void **blob_handle, GrB_Index *blob_size, GrB_Vector u, GrB_Descriptor) {
     CHECK_PTR(blob_handle); CHECK_PTR(blob_size); CHECK_PTR(u);
     return guarded([&]() {
-        std::vector<u64> idx, val;
+        uvec<u64> idx, val;
         if (u->full) {
             idx.resize(u->n); val.resize(u->n);
             for (u64 k = 0; k < u->n; k++) { idx[k] = k; val[k] = u->type == T_BOOL ? ((const unsigned char *)u->fx)[k] : vec_at(u, k); }

@@ -163,7 +163,20 @@ GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n);
 GrB_Info GrB_Vector_free(GrB_Vector *v);
 GrB_Info GrB_Vector_size(GrB_Index *n, GrB_Vector v);
 GrB_Info GrB_Vector_nvals(GrB_Index *nvals, GrB_Vector v);
-GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i);
+GrB_Info GrB_Vector_setElement_BOOL(GrB_Vector v, bool x, GrB_Index i);     /* vector.rs:127, 507 */
+GrB_Info GrB_Vector_setElement_UINT64(GrB_Vector w, uint64_t x, GrB_Index i); /* mod.rs:9158; vector.rs:442 */
+GrB_Info GrB_Vector_removeElement(GrB_Vector v, GrB_Index i);                 /* mod.rs:9318; vector.rs:519 */
+GrB_Info GrB_Vector_clear(GrB_Vector v);                                      /* mod.rs:8924; vector.rs:98 */
+GrB_Info GrB_Vector_wait(GrB_Vector object, int waitmode);                    /* mod.rs:11072; vector.rs:134 */
+GrB_Info GrB_Vector_resize(GrB_Vector w, GrB_Index nrows_new);                /* mod.rs:14062; vector.rs:494 */
+/* vector iterator: positions 0 .. nvals-1 in ascending index order; seek / next return GxB_EXHAUSTED past the end
+ * (mod.rs:14972-14997; vector.rs:553-594).  GxB_Iterator_get_UINT64 reads the current value. */
+GrB_Info GxB_Vector_Iterator_attach(GxB_Iterator iterator, GrB_Vector v, GrB_Descriptor desc);
+GrB_Index GxB_Vector_Iterator_getpmax(GxB_Iterator iterator);
+GrB_Info GxB_Vector_Iterator_seek(GxB_Iterator iterator, GrB_Index p);
+GrB_Info GxB_Vector_Iterator_next(GxB_Iterator iterator);
+GrB_Index GxB_Vector_Iterator_getp(GxB_Iterator iterator);
+GrB_Index GxB_Vector_Iterator_getIndex(GxB_Iterator iterator);
 GrB_Info GrB_Vector_extractElement_INT64(int64_t *x, GrB_Vector v, GrB_Index i);
 GrB_Info GrB_Vector_extractElement_BOOL(bool *x, GrB_Vector v, GrB_Index i);
 GrB_Info GrB_Vector_extractTuples_INT64(GrB_Index *I, int64_t *X, GrB_Index *nvals, GrB_Vector v);

@@ -319,3 +319,142 @@ def test_plain_c_caller_links_and_runs_the_host_only_calls(tmp_path):
                    check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
     assert out == ["nvals 2", "rides: (0,3) (2,5)", "container 6x6 nvals 2 format 2 iso 1", "restored: (0,3) (2,5)"]
+
+
+# ------------------------------------------------------------------------------------------ link closure
+def test_every_symbol_the_reference_wrappers_link_resolves():
+    """The reference's wrapper layer (matrix.rs, vector.rs, tensor.rs, versioned_matrix.rs, the traversal operators' direct
+    calls, algo.BFS) must link against this library unchanged: every extern "C" function / static those files name
+    (tests/golden/reference_ffi_symbols.json, extracted by tests/golden/make_ffi_symbols.py) is a dynamic symbol here."""
+    import json
+    import subprocess
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_ffi_symbols.json")))
+    assert len(doc["functions"]) >= 70 and len(doc["statics"]) >= 35
+    for must in ("GrB_mxm", "GrB_Vector_clear", "GrB_Vector_wait", "GrB_Vector_setElement_UINT64", "GrB_Vector_resize",
+                 "GrB_Vector_removeElement", "GxB_Vector_Iterator_attach", "GxB_Vector_Iterator_seek",
+                 "GxB_Vector_Iterator_getIndex", "GxB_Vector_Iterator_next", "LAGr_BreadthFirstSearch_Extended"):
+        assert must in doc["functions"], must
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
+    exported = {ln.split()[-1] for ln in nm.splitlines() if ln.strip()}
+    missing = [f"{k} ({v['first_use']})" for k, v in {**doc["functions"], **doc["statics"]}.items() if k not in exported]
+    assert not missing, f"unresolved reference symbols: {missing}"
+    if os.path.isdir("/root/reference/graph/src"):          # in the build container: the fixture is current
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_ffi_symbols.py"))
+        mk = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mk)
+        fn, st = mk.declared()
+        live = set()
+        for rel in mk.WRAPPERS + mk.CALLERS:
+            live |= {k for k in mk.used(rel) if k in fn or k in st}
+        assert live <= set(doc["functions"]) | set(doc["statics"]), sorted(live - set(doc["functions"]) - set(doc["statics"]))
+
+
+def _vec_items(L, v, valued):
+    it = C.c_void_p()
+    fb.check(L.GxB_Iterator_new(C.byref(it)))
+    fb.check(L.GxB_Vector_Iterator_attach(it, v, None))
+    out = []
+    info = L.GxB_Vector_Iterator_seek(it, 0)
+    while info != 7089:                                   # GxB_EXHAUSTED: the loop of vector.rs:553-594
+        i = L.GxB_Vector_Iterator_getIndex(it)
+        out.append((i, L.GxB_Iterator_get_UINT64(it)) if valued else i)
+        info = L.GxB_Vector_Iterator_next(it)
+    L.GxB_Iterator_free(C.byref(it))
+    return out
+
+
+def test_vector_wrapper_calls_like_vector_rs():
+    """Vector<bool> / Vector<u64> as vector.rs drives them: new, set (BOOL / UINT64), wait, iterate in ascending index
+    order, remove, resize (shrinking drops entries), clear (vector.rs:98-134, 422-520, 553-594)."""
+    L = lib()
+    v = C.c_void_p()
+    fb.check(L.GrB_Vector_new(C.byref(v), obj("GrB_BOOL"), 100))
+    for i in (7, 3, 99, 3, 50):
+        fb.check(L.GrB_Vector_setElement_BOOL(v, True, i))
+    fb.check(L.GrB_Vector_wait(v, 1))
+    assert _vec_items(L, v, False) == [3, 7, 50, 99]
+    assert L.GrB_Vector_setElement_BOOL(v, True, 100) == -4            # GrB_INVALID_INDEX
+    fb.check(L.GrB_Vector_removeElement(v, 7))
+    fb.check(L.GrB_Vector_removeElement(v, 8))                           # absent: not an error
+    assert _vec_items(L, v, False) == [3, 50, 99]
+    fb.check(L.GrB_Vector_resize(v, 60))
+    n = C.c_uint64()
+    fb.check(L.GrB_Vector_size(C.byref(n), v))
+    assert n.value == 60 and _vec_items(L, v, False) == [3, 50]
+    fb.check(L.GrB_Vector_resize(v, 1 << 40))
+    fb.check(L.GrB_Vector_setElement_BOOL(v, True, (1 << 40) - 1))
+    assert _vec_items(L, v, False) == [3, 50, (1 << 40) - 1]
+    fb.check(L.GrB_Vector_clear(v))
+    assert _vec_items(L, v, False) == []
+    fb.check(L.GrB_Vector_nvals(C.byref(n), v))
+    assert n.value == 0
+    fb.check(L.GrB_Vector_free(C.byref(v)))
+    u = C.c_void_p()
+    fb.check(L.GrB_Vector_new(C.byref(u), obj("GrB_UINT64"), 10))
+    for i, x in ((4, 40), (1, 2 ** 63 + 5), (4, 41), (9, 0)):
+        fb.check(L.GrB_Vector_setElement_UINT64(u, x, i))
+    assert _vec_items(L, u, True) == [(1, 2 ** 63 + 5), (4, 41), (9, 0)]
+    it = C.c_void_p()
+    fb.check(L.GxB_Iterator_new(C.byref(it)))
+    fb.check(L.GxB_Vector_Iterator_attach(it, u, None))
+    assert L.GxB_Vector_Iterator_getpmax(it) == 3
+    assert L.GxB_Vector_Iterator_seek(it, 2) == 0 and L.GxB_Vector_Iterator_getIndex(it) == 9 and L.GxB_Vector_Iterator_getp(it) == 2
+    assert L.GxB_Vector_Iterator_next(it) == 7089 and L.GxB_Vector_Iterator_seek(it, 3) == 7089
+    L.GxB_Iterator_free(C.byref(it))
+    fb.check(L.GrB_Vector_free(C.byref(u)))
+
+
+def test_gxb_init_allocators_see_the_host_footprint(tmp_path):
+    """GxB_init's allocators (Redis' in the reference, matrix.rs:123-131) must serve the library's host memory: handles,
+    tuple stores, pending lists, vector payloads, container structs, blobs.  Run in a fresh process because the hooks have
+    to be installed before anything is allocated."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from falkordb_b200._lib import lib, obj, check
+L = lib()
+libc = C.CDLL(None)
+libc.malloc.restype = C.c_void_p; libc.malloc.argtypes = [C.c_size_t]
+libc.calloc.restype = C.c_void_p; libc.calloc.argtypes = [C.c_size_t, C.c_size_t]
+libc.realloc.restype = C.c_void_p; libc.realloc.argtypes = [C.c_void_p, C.c_size_t]
+libc.free.argtypes = [C.c_void_p]
+live, calls = {}, {"malloc": 0, "calloc": 0, "free": 0}
+MAL = C.CFUNCTYPE(C.c_void_p, C.c_size_t); CAL = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_size_t)
+REA = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t); FRE = C.CFUNCTYPE(None, C.c_void_p)
+def m(n):
+    p = libc.malloc(n); live[p] = n; calls["malloc"] += 1; return p
+def c(a, b):
+    p = libc.calloc(a, b); live[p] = a * b; calls["calloc"] += 1; return p
+def r(p, n):
+    live.pop(p, None); q = libc.realloc(p, n); live[q] = n; return q
+def f(p):
+    if p: assert p in live, "free of a block the hooks never handed out"; live.pop(p); calls["free"] += 1; libc.free(p)
+cb = (MAL(m), CAL(c), REA(r), FRE(f))
+L.GxB_init.argtypes = [C.c_int, MAL, CAL, REA, FRE]
+check(L.GxB_init(1, *cb))
+A = C.c_void_p(); check(L.GrB_Matrix_new(C.byref(A), obj("GrB_UINT64"), 1000, 1000))
+for k in range(500): check(L.GrB_Matrix_setElement_UINT64(A, k, k, (k * 7) %% 1000))
+check(L.GrB_Matrix_wait(A, 1))
+held = sum(live.values())
+assert calls["malloc"] >= 4 and held >= 500 * 8 * 2, (calls, held)
+assert L.B200_get_stat(b"host_bytes") <= held and L.B200_get_stat(b"host_bytes") >= 500 * 8 * 2
+v = C.c_void_p(); check(L.GrB_Vector_new(C.byref(v), obj("GrB_BOOL"), 64))
+for k in range(0, 64, 3): check(L.GrB_Vector_setElement_BOOL(v, True, k))
+blob = C.c_void_p(); size = C.c_uint64()
+L.GxB_Vector_serialize.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+check(L.GxB_Vector_serialize(C.byref(blob), C.byref(size), v, None))
+assert blob.value in live                      # the caller frees the blob with ITS allocator (vector.rs:171-172)
+f(blob.value)
+cont = C.c_void_p(); L.GxB_Container_new.argtypes = [C.POINTER(C.c_void_p)]; L.GxB_Container_free.argtypes = [C.POINTER(C.c_void_p)]
+check(L.GxB_Container_new(C.byref(cont))); assert calls["calloc"] >= 1
+check(L.GxB_Container_free(C.byref(cont)))
+check(L.GrB_Vector_free(C.byref(v))); check(L.GrB_Matrix_free(C.byref(A)))
+assert not live, "leaked through the hooks: %%r" %% live
+assert L.B200_get_stat(b"host_bytes") == 0
+print("hooks ok", calls)
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "hooks ok" in out.stdout, out.stdout + out.stderr

@@ -814,3 +814,53 @@ def test_multi_source_reach_matches_levelwise_oracle(nsrc, max_hops, include):
         want_rows, want_cols = np.nonzero(np.isfinite(dist))
         gr, gc, _ = from_dev(R).tuples()
         assert np.array_equal(gr, want_rows.astype(np.uint64)) and np.array_equal(gc, want_cols.astype(np.uint64))
+
+
+# ------------------------------------------------------------------------------------------ rmxm / label-restricted matrix
+def diag_csr(n, ids):
+    ids = np.unique(np.asarray(ids, dtype=np.uint64))
+    return orc.build_matrix(n, n, ids, ids)
+
+
+@pytest.mark.parametrize("bits_mode", [-1, 0])
+def test_rmxm_and_label_restricted_relationship_matrix(bits_mode):
+    """Matrix::rmxm (matrix.rs:951-968: C = B*C, C aliases the RIGHT input) and its one caller, Graph::build_relationship_matrix
+    (graph.rs:2564-2630): m = R1 (+) R2; m.rmxm(L_src1 (*) L_src2); m.lmxm(L_dst) with n x n diagonal label matrices --
+    statement for statement, against the oracle composed the same way."""
+    fb.set_option("bits_mode", bits_mode)
+    rng = np.random.default_rng(77)
+    R1 = orc.rmat_csr(12, 8, 5)
+    n = R1.nrows
+    R2 = rand_csr(rng, n, n, 0.001)
+    ls1 = diag_csr(n, rng.choice(n, n // 2, replace=False))
+    ls2 = diag_csr(n, rng.choice(n, n // 2, replace=False))
+    ld = diag_csr(n, rng.choice(n, n // 3, replace=False))
+    # oracle
+    want = orc.ewise_add(R1, R2)
+    src = orc.ewise_mult(ls1, ls2)
+    want = orc.mxm(src, want)                      # rmxm: src on the left
+    want = orc.mxm(want, ld)                       # lmxm: dst labels on the right
+    keep_rows = set(np.nonzero(np.diff(src.p))[0].tolist())
+    assert want.nnz > 0 and all((r in keep_rows) for r in np.nonzero(np.diff(want.p))[0].tolist())
+    # device, through the C ABI, the reference's statements
+    m = to_dev(R1)
+    m.element_wise_add(None, None, to_dev(R2), None)
+    s = to_dev(ls1)
+    s.element_wise_multiply(None, None, to_dev(ls2), None)
+    m.rmxm(s)
+    assert_same(m, orc.mxm(src, orc.ewise_add(R1, R2)), "rmxm with the intersected source-label diagonal")
+    m.lmxm(to_dev(ld))
+    assert_same(m, want, "L_src * R * L_dst")
+    # rmxm with a non-diagonal left operand, result aliasing the right input, rectangular
+    B = rand_csr(rng, 300, 500, 0.02)
+    Cm = rand_csr(rng, 500, 260, 0.03)
+    c = to_dev(Cm)
+    wantc = orc.mxm(B, Cm)
+    c2 = Matrix(300, 260, bool)
+    c2.mxm(to_dev(B), c)
+    assert_same(c2, wantc, "B*C into a fresh output")
+    sq = rand_csr(rng, 400, 400, 0.02)
+    d = to_dev(sq)
+    d.rmxm(to_dev(sq))                             # C = B*C with B == C's old value (A*A through the alias)
+    assert_same(d, orc.mxm(sq, sq), "rmxm aliasing")
+    fb.set_option("bits_mode", -1)
