@@ -79,7 +79,7 @@ enum TimedId { TK_BITS_PULL = 0, TK_BITS_PULL_LONG, TK_BITS_PUSH, TK_HEAVY_ACC, 
                TK_BITMAP_EXPAND, TK_BFS_EXPAND, TK_UNION, TK_FILTER, TK_COUNT_ };
 const char *timed_name(int id);
 void timed_begin(int id);
-void timed_end(int id, u64 algorithmic_bytes);
+void timed_end(int id, u64 algorithmic_bytes) noexcept;
 struct TimedScope {
     int id; u64 bytes;
     TimedScope(int i, u64 b) : id(i), bytes(b) { timed_begin(id); }

@@ -186,6 +186,15 @@ struct GB_Iterator_opaque : UObject {
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string tl_error;
 static std::mutex g_gpu_mu; // serialises GPU submission across caller threads
+// Holds g_gpu_mu for one bulk operation.  If the operation unwinds with an exception, small reads whose destinations lived on
+// the abandoned stack are forgotten BEFORE the mutex is released: once another thread owns the mutex its sync_stream() would
+// otherwise deliver into dead frames.
+struct GpuLock {
+    std::unique_lock<std::mutex> lk;
+    int entry;
+    GpuLock() : lk(g_gpu_mu), entry(std::uncaught_exceptions()) {}
+    ~GpuLock() { if (std::uncaught_exceptions() > entry) drop_small_reads(); }
+};
 
 template <class F>
 static GrB_Info guarded(F &&f) {
@@ -578,10 +587,11 @@ GrB_Info GrB_Matrix_new(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index
     CHECK_PTR(A); CHECK_PTR(type);
     if (nrows > ((u64)1 << 60) || ncols > ((u64)1 << 60)) { tl_error = "dimension > 2^60"; return GrB_INVALID_VALUE; }
     return guarded([&]() {
-        GrB_Matrix m = new GB_Matrix_opaque();
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
         m->type = type->code;
         m->nrows = nrows; m->ncols = ncols;
-        *A = m;
+        *A = mh.release();
         return GrB_SUCCESS;
     });
 }
@@ -590,7 +600,7 @@ GrB_Info GrB_Matrix_free(GrB_Matrix *A) {
     if (!A || !*A) return GrB_SUCCESS;
     if ((*A)->magic != MAGIC) return GrB_INVALID_OBJECT;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         (*A)->magic = 0;
         delete *A;
         *A = nullptr;
@@ -601,9 +611,10 @@ GrB_Info GrB_Matrix_free(GrB_Matrix *A) {
 GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A) {
     CHECK_PTR(C); CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
-        GrB_Matrix m = new GB_Matrix_opaque();
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
         m->type = A->type; m->nrows = A->nrows; m->ncols = A->ncols;
         m->sparsity_control = A->sparsity_control; m->orientation = A->orientation;
         // pending work is copied, not finished (GB_dup; relied on by Matrix::grown, matrix.rs:691-698)
@@ -612,7 +623,7 @@ GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A) {
         if (A->host_valid) m->host = A->host;
         if (A->dev_valid) { csr_copy(A->dev, m->dev, true); m->dev_valid = true; }
         if (A->bits_valid && !A->dev_valid) { bits_copy(A->bits, m->bits); m->bits_valid = true; m->bits_nv = A->bits_nv; }
-        *C = m;
+        *C = mh.release();
         return GrB_SUCCESS;
     });
 }
@@ -620,7 +631,7 @@ GrB_Info GrB_Matrix_dup(GrB_Matrix *C, GrB_Matrix A) {
 GrB_Info GrB_Matrix_clear(GrB_Matrix A) {
     CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         set_empty(A);
         return GrB_SUCCESS;
@@ -631,7 +642,7 @@ GrB_Info GrB_Matrix_resize(GrB_Matrix C, GrB_Index nr, GrB_Index nc) {
     CHECK_MAT(C);
     if (nr > ((u64)1 << 60) || nc > ((u64)1 << 60)) return GrB_INVALID_VALUE;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C};
         bool shrink = nr < C->nrows || nc < C->ncols;
         finish_pending(C);
@@ -681,7 +692,7 @@ GrB_Info GrB_Matrix_ncols(GrB_Index *n, GrB_Matrix A) { CHECK_PTR(n); CHECK_MAT(
 GrB_Info GrB_Matrix_nvals(GrB_Index *n, GrB_Matrix A) {
     CHECK_PTR(n); CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         *n = matrix_nvals(A);
         return GrB_SUCCESS;
@@ -703,7 +714,7 @@ GrB_Info GrB_Matrix_set_INT32(GrB_Matrix A, int32_t value, int field) {
 GrB_Info GrB_Matrix_get_INT32(GrB_Matrix A, int32_t *value, int field) {
     CHECK_MAT(A); CHECK_PTR(value);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         switch (field) {
         case GxB_SPARSITY_CONTROL: *value = A->sparsity_control; return GrB_SUCCESS;
@@ -756,7 +767,7 @@ GrB_Info GxB_Matrix_fprint(GrB_Matrix A, const char *name, int pr, FILE *f) {
 GrB_Info GrB_Matrix_wait(GrB_Matrix A, int waitmode) {
     CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         finish_pending(A);
         if (waitmode == GrB_MATERIALIZE && !A->host_valid && !A->dev_valid && A->bits_valid) ensure_dev(A);
@@ -769,7 +780,7 @@ GrB_Info GrB_Matrix_wait(GrB_Matrix A, int waitmode) {
 static GrB_Info set_element(GrB_Matrix C, u64 v, u64 i, u64 j) {
     if (i >= C->nrows || j >= C->ncols) { tl_error = "setElement index out of bounds"; return GrB_INVALID_INDEX; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C};
         if (!C->host_valid) download_to_host(C);
         PendingOp op{i, j, v, (u64)C->pending.size(), false};
@@ -794,7 +805,7 @@ GrB_Info GrB_Matrix_removeElement(GrB_Matrix C, GrB_Index i, GrB_Index j) {
     CHECK_MAT(C);
     if (i >= C->nrows || j >= C->ncols) return GrB_INVALID_INDEX;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C};
         if (!C->host_valid) download_to_host(C);
         PendingOp op{i, j, 0, (u64)C->pending.size(), true};
@@ -817,7 +828,7 @@ static u64 host_find(const HostStore &h, u64 i, u64 j) {
 static GrB_Info extract_element(u64 *x, GrB_Matrix A, u64 i, u64 j) {
     if (i >= A->nrows || j >= A->ncols) return GrB_INVALID_INDEX;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         if (!A->host_valid || !A->pending.empty()) ensure_host(A);
         u64 q = host_find(A->host, i, j);
@@ -845,7 +856,7 @@ GrB_Info GxB_Matrix_isStoredElement(GrB_Matrix A, GrB_Index i, GrB_Index j) {
 static GrB_Info extract_tuples(GrB_Index *I, GrB_Index *J, void *X, int xkind, GrB_Index *nvals, GrB_Matrix A) {
     CHECK_MAT(A); CHECK_PTR(nvals);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_host(A);
         const HostStore &h = A->host;
@@ -917,7 +928,7 @@ static GrB_Info build_common(GrB_Matrix C, const GrB_Index *I, const GrB_Index *
     CHECK_MAT(C);
     if (n) { CHECK_PTR(I); CHECK_PTR(J); }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C};
         if (!matrix_is_empty(C)) { tl_error = "build: output matrix not empty"; return GrB_OUTPUT_NOT_EMPTY; }
         if (n == 0) return GrB_SUCCESS;
@@ -990,7 +1001,7 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
     if (semiring != GxB_ANY_PAIR_BOOL) { tl_error = "mxm: only GxB_ANY_PAIR_BOOL is on the traversal path"; return GrB_NOT_IMPLEMENTED; }
     if (accum && accum != GxB_ANY_BOOL) { tl_error = "mxm: accum must be NULL or GxB_ANY_BOOL"; return GrB_NOT_IMPLEMENTED; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C, Mask, A, B};
         ensure_init();
         Context &cx = ctx();
@@ -1097,7 +1108,7 @@ GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryO
         tl_error = "eWiseAdd: op must be GxB_ANY_BOOL / GrB_SECOND_UINT64 / GxB_ANY_UINT64"; return GrB_NOT_IMPLEMENTED;
     }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C, Mask, A, B};
         if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
@@ -1141,7 +1152,7 @@ GrB_Info GrB_Matrix_eWiseMult_Semiring(GrB_Matrix C, GrB_Matrix Mask, GrB_Binary
     if (accum) { tl_error = "eWiseMult: accum not on the path"; return GrB_NOT_IMPLEMENTED; }
     if (semiring != GxB_ANY_PAIR_BOOL) { tl_error = "eWiseMult: only GxB_ANY_PAIR_BOOL"; return GrB_NOT_IMPLEMENTED; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C, Mask, A, B};
         if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
@@ -1168,7 +1179,7 @@ GrB_Info GrB_transpose(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Ma
     if (Mask) CHECK_MAT(Mask);
     if (accum) { tl_error = "transpose: accum not on the path"; return GrB_NOT_IMPLEMENTED; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C, Mask, A};
         if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
@@ -1204,7 +1215,7 @@ GrB_Info GrB_Matrix_apply(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB
     if (op != GxB_ONE_BOOL) { tl_error = "apply: only GxB_ONE_BOOL (set_pattern, matrix.rs:906-924)"; return GrB_NOT_IMPLEMENTED; }
     if (accum && accum != GxB_ANY_BOOL) { tl_error = "apply: accum must be NULL or GxB_ANY_BOOL"; return GrB_NOT_IMPLEMENTED; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{C, Mask, A};
         if (!is_huge(C) && !is_huge(A)) ensure_init();   // host-resident operands need no device
         Desc d = get_desc(desc);
@@ -1233,7 +1244,7 @@ GrB_Info GxB_Iterator_free(GxB_Iterator *it) { if (it && *it) { delete *it; *it 
 GrB_Info GxB_rowIterator_attach(GxB_Iterator it, GrB_Matrix A, GrB_Descriptor) {
     CHECK_PTR(it); CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         it->A = A; it->k = 0; it->q = 0; it->exhausted = true;
         it->bitmap = false; it->bm.clear(); it->bm.shrink_to_fit();
@@ -1543,7 +1554,7 @@ GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level
     if (A->nrows != A->ncols) { tl_error = "BFS needs a square adjacency matrix"; return GrB_DIMENSION_MISMATCH; }
     if (src >= A->nrows) return GrB_INVALID_INDEX;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
@@ -1592,9 +1603,10 @@ GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, G
     CHECK_PTR(A); CHECK_PTR(type); CHECK_PTR(Ap);
     if (nrows >= ((u64)1 << 32) || ncols >= ((u64)1 << 32)) return GrB_NOT_IMPLEMENTED;
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         ensure_init();
-        GrB_Matrix m = new GB_Matrix_opaque();
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
         m->type = type->code; m->nrows = nrows; m->ncols = ncols;
         DevCSR d;
         d.nrows = nrows; d.ncols = ncols;
@@ -1615,7 +1627,7 @@ GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, G
         else { h2d(d.j.ptr, (const u32 *)Aj, nnz); if (vals) h2d(d.x.ptr, (const u64 *)Ax, nnz); }
         sync_stream();
         set_dev(m, std::move(d));
-        *A = m;
+        *A = mh.release();
         return GrB_SUCCESS;
     });
 }
@@ -1623,7 +1635,7 @@ GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, G
 GrB_Info B200_Matrix_export_CSR(GrB_Matrix A, uint64_t *Ap, uint32_t *Aj, uint64_t *Ax, int location) {
     CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
@@ -1646,7 +1658,7 @@ GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t wo
     CHECK_MAT(A);
     if (!bits_out) { tl_error = "export_bitmap: null output"; return GrB_NULL_POINTER; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         finish_pending(A);
@@ -1684,7 +1696,7 @@ GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint6
     CHECK_MAT(A);
     if (!bits_out || !ticket) { tl_error = "export_bitmap_async: null argument"; return GrB_NULL_POINTER; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         finish_pending(A);
@@ -1702,17 +1714,26 @@ GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint6
             if (total) CUDA_TRY(cudaMemsetAsync(t->stage.ptr, 0, total * sizeof(u64), stream()));
             csr_to_rowmajor(A->dev, t->stage.ptr, wpr);
         }
-        cudaEvent_t ready;
-        CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(ready, stream()));
-        CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, ready, 0));
-        CUDA_TRY(cudaEventDestroy(ready));                  // released once the wait it feeds has been satisfied
-        if (total) {
-            CUDA_TRY(cudaMemcpyAsync(bits_out, t->stage.ptr, total * sizeof(u64), cudaMemcpyDeviceToHost, g_copy_stream));
-            ctx().d2h_bytes += total * sizeof(u64);
+        // from here on the copy stream may be reading the stage: on any failure drain it before the stage returns to the
+        // (single-stream) pool, and release both events
+        struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } ready, done;
+        try {
+            CUDA_TRY(cudaEventCreateWithFlags(&ready.e, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(ready.e, stream()));
+            CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, ready.e, 0));
+            if (total) {
+                // asynchronous only for page-locked bits_out; a pageable destination makes this call block until the copy is done
+                CUDA_TRY(cudaMemcpyAsync(bits_out, t->stage.ptr, total * sizeof(u64), cudaMemcpyDeviceToHost, g_copy_stream));
+                ctx().d2h_bytes += total * sizeof(u64);
+            }
+            CUDA_TRY(cudaEventCreateWithFlags(&done.e, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(done.e, g_copy_stream));
+        } catch (...) {
+            cudaStreamSynchronize(g_copy_stream);
+            throw;
         }
-        CUDA_TRY(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(t->done, g_copy_stream));
+        t->done = done.e;
+        done.e = nullptr;
         *ticket = t.release();
         return GrB_SUCCESS;
     });
@@ -1726,7 +1747,7 @@ GrB_Info B200_Ticket_wait(B200_Ticket *ticket) {
         cudaError_t e = cudaEventSynchronize(t->done);
         cudaEventDestroy(t->done);
         {
-            std::lock_guard<std::mutex> g(g_gpu_mu);     // the staging block goes back to the (single-stream) pool
+            GpuLock g;     // the staging block goes back to the (single-stream) pool
             t->stage.release();
         }
         delete t;
@@ -1738,7 +1759,7 @@ GrB_Info B200_Ticket_wait(B200_Ticket *ticket) {
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax) {
     CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
@@ -1753,7 +1774,7 @@ GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32
 GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose) {
     CHECK_MAT(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
@@ -1766,15 +1787,17 @@ GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose) {
 GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed) {
     CHECK_PTR(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         ensure_init();
-        GrB_Matrix m = new GB_Matrix_opaque();
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
+        if (scale < 1 || scale > 31) throw GrbError(GrB_INVALID_VALUE, "rmat: scale must be in [1, 31]");
         m->type = T_BOOL; m->nrows = m->ncols = (u64)1 << scale;
         DevCSR d;
         rmat_csr(scale, edge_factor, seed, d);
         sync_stream();
         set_dev(m, std::move(d));
-        *A = m;
+        *A = mh.release();
         return GrB_SUCCESS;
     });
 }
@@ -1785,7 +1808,7 @@ GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_I
     CHECK_MAT(A); CHECK_PTR(found);
     if (n) { CHECK_PTR(I); CHECK_PTR(J); }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
@@ -1806,15 +1829,17 @@ GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_I
 GrB_Info B200_Matrix_rmat_block(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64_t seed, uint64_t lo, uint64_t hi, int by_col) {
     CHECK_PTR(A);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         ensure_init();
-        GrB_Matrix m = new GB_Matrix_opaque();
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
+        if (scale < 1 || scale > 31 || lo > hi || hi > ((u64)1 << scale)) throw GrbError(GrB_INVALID_VALUE, "rmat_block: scale in [1, 31], 0 <= lo <= hi <= 2^scale");
         m->type = T_BOOL; m->nrows = hi - lo; m->ncols = (u64)1 << scale;
         DevCSR d;
         rmat_block_csr(scale, edge_factor, seed, lo, hi, by_col, d);
         sync_stream();
         set_dev(m, std::move(d));
-        *A = m;
+        *A = mh.release();
         return GrB_SUCCESS;
     });
 }
@@ -1824,7 +1849,7 @@ GrB_Info B200_bfs_dist_expand(GrB_Matrix Alocal, uint64_t row_lo, const uint32_t
                               uint64_t *disc, uint64_t nwords, uint64_t *edges_out) {
     CHECK_MAT(Alocal);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{Alocal};
         ensure_init();
         ensure_dev(Alocal);
@@ -1840,7 +1865,7 @@ GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwor
                              uint64_t *frontier_bits) {
     CHECK_PTR(gathered); CHECK_PTR(counters2);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         ensure_init();
         bfs_dist_merge(gathered, nranks, nwords, visited, row_lo, row_hi, level_local, lvl, next_frontier, counters2, frontier_bits);
         return GrB_SUCCESS;
@@ -1850,7 +1875,7 @@ GrB_Info B200_bfs_dist_pull(GrB_Matrix ATlocal, uint64_t row_lo, const uint64_t 
                             uint64_t *disc, uint64_t nwords, uint64_t *scanned_out) {
     CHECK_MAT(ATlocal);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{ATlocal};
         ensure_init();
         ensure_dev(ATlocal);
@@ -1864,7 +1889,7 @@ GrB_Info B200_bfs_dist_pull(GrB_Matrix ATlocal, uint64_t row_lo, const uint64_t 
 GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local) {
     CHECK_MAT(ATlocal);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{ATlocal};
         ensure_init();
         ensure_dev(ATlocal);
@@ -1876,7 +1901,7 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
 
 GrB_Info B200_sync(void) {
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);   // sync_stream also delivers pending small reads: not under a submitter's feet
+        GpuLock g;   // sync_stream also delivers pending small reads: not under a submitter's feet
         if (ctx().ready) sync_stream();
         return GrB_SUCCESS;
     });
@@ -2025,7 +2050,7 @@ GrB_Info GxB_unload_Matrix_into_Container(GrB_Matrix A, GxB_Container c, GrB_Des
     CHECK_MAT(A); CHECK_PTR(c);
     if (!c->p || !c->h || !c->b || !c->i || !c->x) { tl_error = "unload: container vectors missing"; return GrB_NULL_POINTER; }
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         ensure_host(A);
         const HostStore &h = A->host;
@@ -2063,7 +2088,7 @@ GrB_Info GxB_unload_Matrix_into_Container(GrB_Matrix A, GxB_Container c, GrB_Des
 GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container c, GrB_Descriptor) {
     CHECK_MAT(A); CHECK_PTR(c);
     return guarded([&]() {
-        std::lock_guard<std::mutex> g(g_gpu_mu);
+        GpuLock g;
         MultiLock lk{A};
         auto bad = [](const char *m) { throw GrbError(GrB_INVALID_OBJECT, m); };
         if (c->nrows > ((u64)1 << 60) || c->ncols > ((u64)1 << 60)) bad("load: dimensions out of range");
@@ -2083,6 +2108,7 @@ GrB_Info GxB_load_Matrix_from_Container(GrB_Matrix A, GxB_Container c, GrB_Descr
         if (c->x->n < (iso ? (nnz ? 1 : 0) : nnz)) bad("load: x too short");
         if (xtype == T_BOOL && !iso)
             for (u64 q = 0; q < nnz; q++) if (!((const unsigned char *)c->x->fx)[q]) bad("load: explicit false entries are not representable");
+        if (xtype == T_BOOL && iso && nnz && !((const unsigned char *)c->x->fx)[0]) bad("load: an iso `false` pattern is not representable");
         HostStore h;
         h.clear();
         h.hcol.resize(nnz);

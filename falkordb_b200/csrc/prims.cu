@@ -171,14 +171,24 @@ void timed_begin(int id) {
     CUDA_TRY(cudaEventRecord(e, stream()));
     g_open[id] = e;
 }
-void timed_end(int id, u64 bytes) {
+void timed_end(int id, u64 bytes) noexcept {
+    // runs from ~TimedScope, possibly while a CUDA error is unwinding: it must never throw.  A failed record drops the sample.
     if (!ctx().opt_timing) return;
-    std::lock_guard<std::mutex> lk(g_timed_mu);
-    if (!g_open[id]) return;
-    cudaEvent_t e = get_event();
-    CUDA_TRY(cudaEventRecord(e, stream()));
-    g_recs.push_back(TimedRec{id, g_open[id], e, bytes});
-    g_open[id] = nullptr;
+    try {
+        std::lock_guard<std::mutex> lk(g_timed_mu);
+        if (!g_open[id]) return;
+        cudaEvent_t e0 = g_open[id];
+        g_open[id] = nullptr;
+        cudaEvent_t e = get_event();
+        if (cudaEventRecord(e, stream()) != cudaSuccess) {
+            cudaGetLastError();
+            g_event_pool.push_back(e0);
+            g_event_pool.push_back(e);
+            return;
+        }
+        g_recs.push_back(TimedRec{id, e0, e, bytes});
+    } catch (...) {
+    }
 }
 static void drain_locked() {
     if (g_recs.empty()) return;
