@@ -413,4 +413,41 @@ __global__ void k_narrow_u64(const u64 *__restrict__ in, u32 *__restrict__ out, 
 void widen_u32(const u32 *in, u64 *out, u64 n) { if (n) LAUNCH(k_widen_u32, grid_for(n, 256, 148 * 16), 256, 0, in, out, n); }
 void narrow_u64(const u64 *in, u32 *out, u64 n) { if (n) LAUNCH(k_narrow_u64, grid_for(n, 256, 148 * 16), 256, 0, in, out, n); }
 
+
+// ---- order-sensitive digest of a CSR pattern (full-size parity checks: a multi-GB result is compared by three numbers) ----
+// key = row << 32 | col, position q = index in CSR order:  d[0] = nnz, d[1] = sum mix(key), d[2] = sum mix(key + GOLD * (q + 1)).
+// Same arithmetic as oracle/grb_oracle.c: orc_digest (the CPU side hashes the oracle's result).
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL; x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) k_csr_digest(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 nrows, u64 nnz, u64 *__restrict__ d) {
+    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 s1 = 0, s2 = 0;
+    u64 row = 0;                                   // rows only move forward along a thread's ascending positions
+    for (; q < nnz; q += stride) {
+        if (p[row + 1] <= q) {                     // largest row with p[row] <= q, searched in (row, nrows)
+            u64 lo = row + 1, hi = nrows - 1;
+            while (lo < hi) { u64 mid = (lo + hi + 1) >> 1; if (p[mid] <= q) lo = mid; else hi = mid - 1; }
+            row = lo;
+        }
+        const u64 key = (row << 32) | j[q];
+        s1 += mix64(key);
+        s2 += mix64(key + 0x9E3779B97F4A7C15ULL * (q + 1));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd((unsigned long long *)&d[1], s1); atomicAdd((unsigned long long *)&d[2], s2); }
+}
+void csr_digest(const DevCSR &A, u64 *host_out3) {
+    DevBuf<u64> d(3);
+    d.zero();
+    if (A.nnz) LAUNCH(k_csr_digest, grid_for(A.nnz, 256, 148 * 16), 256, 0, A.p.ptr, A.j.ptr, A.nrows, A.nnz, d.ptr);
+    u64 h[3] = {0, 0, 0};
+    d2h(h, d.ptr, 3);
+    sync_stream();
+    host_out3[0] = A.nnz; host_out3[1] = h[1]; host_out3[2] = h[2];
+}
+
 } // namespace b200

@@ -1756,6 +1756,21 @@ GrB_Info B200_Ticket_wait(B200_Ticket *ticket) {
     });
 }
 
+// Order-sensitive digest of A's pattern in CSR order (materialises A on the device first): the full-size parity tests compare
+// multi-GB results through these three numbers against the oracle's digest of its own result (oracle/grb_oracle.c: orc_digest).
+GrB_Info B200_Matrix_digest(GrB_Matrix A, uint64_t *digest3) {
+    CHECK_MAT(A); CHECK_PTR(digest3);
+    return guarded([&]() {
+        GpuLock g;
+        MultiLock lk{A};
+        ensure_init();
+        if (is_huge(A)) throw GrbError(GrB_NOT_IMPLEMENTED, "digest: host-resident matrix");
+        ensure_dev(A);
+        csr_digest(A->dev, digest3);
+        return GrB_SUCCESS;
+    });
+}
+
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax) {
     CHECK_MAT(A);
     return guarded([&]() {
@@ -1899,6 +1914,14 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
     });
 }
 
+// returns every cached device block to the driver (the caching allocator otherwise keeps freed blocks for reuse)
+GrB_Info B200_pool_trim(void) {
+    return guarded([&]() {
+        GpuLock g;
+        if (ctx().ready) pool_trim();
+        return GrB_SUCCESS;
+    });
+}
 GrB_Info B200_sync(void) {
     return guarded([&]() {
         GpuLock g;   // sync_stream also delivers pending small reads: not under a submitter's feet

@@ -82,6 +82,7 @@ void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 ro
                     u32 *next, u64 *host_counters, u64 *frontier_bits);
 void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local);
 
+void csr_digest(const DevCSR &A, u64 *host_out3);   // {nnz, sum mix(key), sum mix(key + GOLD * (pos + 1))}: see oracle orc_digest
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
 
 // hypersparse host form <-> dense device rowptr (ewise.cu)

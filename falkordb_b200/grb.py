@@ -353,6 +353,12 @@ class Matrix:
                                               vals.ctypes.data))
         return found.astype(bool), vals
 
+    def digest(self):
+        """(nvals, sum mix(key), sum mix(key + GOLD * position)) of the pattern in CSR order -- oracle.digest's twin."""
+        d = np.zeros(3, np.uint64)
+        check(lib().B200_Matrix_digest(self.h, d.ctypes.data))
+        return d
+
     def prepare(self, want_transpose=True):
         check(lib().B200_Matrix_prepare(self.h, int(want_transpose)))
         return self

@@ -284,6 +284,9 @@ typedef struct B200_Ticket_opaque *B200_Ticket;
 GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint64_t words_per_row, B200_Ticket *ticket);
 GrB_Info B200_Ticket_wait(B200_Ticket *ticket);
 /* Borrow the device-resident CSR (valid until A is next modified or freed). */
+/* digest3 = { nvals, sum mix(row << 32 | col), sum mix(key + GOLD * (CSR position + 1)) }: a multi-GB result is compared with the
+ * oracle's through three numbers; sensitive to any changed entry and to the order inside a row */
+GrB_Info B200_Matrix_digest(GrB_Matrix A, uint64_t *digest3);
 GrB_Info B200_Matrix_device_view(GrB_Matrix A, const uint64_t **Ap, const uint32_t **Aj, const uint64_t **Ax);
 /* Pre-build the cached transpose mirror used by the pull direction (done lazily otherwise). */
 GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
@@ -313,6 +316,7 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
 GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_Index *J, GrB_Index n, uint8_t *found,
                                    uint64_t *values);
 GrB_Info B200_sync(void);
+GrB_Info B200_pool_trim(void); /* hand the caching allocator's free device blocks back to the driver */
 void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */
 /* stats: "launches", "lib_launches", "last_flops", "total_flops", "last_path", "h2d_bytes", "d2h_bytes" */
 uint64_t B200_get_stat(const char *name);

@@ -486,19 +486,44 @@ int orc_transpose(const orc_csr *A, orc_csr *out) {
 int orc_bfs(const orc_csr *A, int64_t src, int64_t max_level, int64_t *level, int64_t *parent) {
     int64_t n = A->nrows;
     if (src < 0 || src >= n) return -4;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++) { level[i] = -1; if (parent) parent[i] = -1; }
     int64_t *front = xmalloc(sizeof(int64_t) * (size_t)n), *next = xmalloc(sizeof(int64_t) * (size_t)n);
     int64_t nf = 1, lvl = 0;
     front[0] = src; level[src] = 0; if (parent) parent[src] = src;
+    /* level-synchronous, parallel over the frontier: a vertex is claimed by one compare-and-swap on its level (so it
+     * enters `next` once); its parent is the MINIMUM frontier vertex with an edge to it, kept by an atomic-min loop --
+     * the result does not depend on the thread schedule. */
     while (nf > 0 && (max_level < 0 || lvl < max_level)) {
         int64_t nn = 0;
-        for (int64_t f = 0; f < nf; f++) {
-            int64_t u = front[f];
-            for (int64_t q = A->p[u]; q < A->p[u + 1]; q++) {
-                int64_t v = A->j[q];
-                if (level[v] < 0) { level[v] = lvl + 1; if (parent) parent[v] = u; next[nn++] = v; }
-                else if (parent && level[v] == lvl + 1 && u < parent[v]) parent[v] = u;
+#pragma omp parallel
+        {
+            int64_t lcap = 4096, ln = 0;
+            int64_t *loc = xmalloc(sizeof(int64_t) * (size_t)lcap);
+#pragma omp for schedule(dynamic, 256) nowait
+            for (int64_t f = 0; f < nf; f++) {
+                const int64_t u = front[f];
+                for (int64_t q = A->p[u]; q < A->p[u + 1]; q++) {
+                    const int64_t v = A->j[q];
+                    int64_t lv = __atomic_load_n(&level[v], __ATOMIC_RELAXED);
+                    if (lv < 0) {
+                        int64_t expect = -1;
+                        if (__atomic_compare_exchange_n(&level[v], &expect, lvl + 1, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                            if (ln == lcap) { lcap *= 2; loc = realloc(loc, sizeof(int64_t) * (size_t)lcap); if (!loc) abort(); }
+                            loc[ln++] = v;
+                            lv = lvl + 1;
+                        } else lv = expect;
+                    }
+                    if (parent && lv == lvl + 1) {
+                        int64_t cur = __atomic_load_n(&parent[v], __ATOMIC_RELAXED);
+                        while ((cur < 0 || u < cur) &&
+                               !__atomic_compare_exchange_n(&parent[v], &cur, u, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                    }
+                }
             }
+            int64_t at = __atomic_fetch_add(&nn, ln, __ATOMIC_RELAXED);
+            memcpy(next + at, loc, sizeof(int64_t) * (size_t)ln);
+            free(loc);
         }
         int64_t *t = front; front = next; next = t; nf = nn; lvl++;
     }
