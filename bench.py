@@ -53,6 +53,7 @@ def parse():
                     help="chain = the headline 3-hop mxm chain; bfs = 1-D row-partitioned BFS sweep (BASELINE config 5); "
                          "triangles = masked SpGEMM C<L> = L*L on the symmetrised lower triangle (BASELINE config 4)")
     ap.add_argument("--bfs-sources", type=int, default=16)
+    ap.add_argument("--bfs-parity", type=int, default=2, help="sources whose levels / parents are checked against the oracle (0 = none)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
     ap.add_argument("--e2e-format", default="auto", choices=["auto", "csr", "bitmap"],
                     help="result hand-off of the e2e arm: auto = Matrix.export_auto (bitmap when denser than 1/32, else CSR)")
@@ -510,13 +511,15 @@ def run_b200(a):
 
 
 def run_bfs(a):
-    """BASELINE config 5: BFS frontier sweep, adjacency 1-D row-block partitioned over the ranks, one NCCL all-gather of
-    the frontier bitmap per level (falkordb_b200/dist_bfs.py).  TEPS = edges incident to the reached vertices / time
-    (Graph500 convention), summed over sources; time = max over ranks (device events + barrier)."""
+    """BASELINE config 5: BFS frontier sweep, adjacency 1-D row-block partitioned over the ranks; the level loop, the direction
+    switch and the NCCL exchange (bitmap or sparse vertex lists) run inside the library (B200_bfs_partitioned, csrc/bfs_do.cu).
+    TEPS = edges incident to the reached vertices / time (Graph500 convention), summed over sources; time = device
+    events inside the call, max over ranks, plus a wall-clock cross-check.  Parity: the levels and min-id parents of the first
+    --bfs-parity sources are compared bit for bit with the oracle on the same graph (outside the timed region)."""
     import torch
     import torch.distributed as dist
     import falkordb_b200 as fb
-    from falkordb_b200.dist_bfs import GpuBackend, bfs_gpu, partition
+    from falkordb_b200.dist_bfs import PartitionedBfs, partition
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -524,21 +527,27 @@ def run_bfs(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     fb.init()
+    for kv in a.opt:
+        k, v = kv.split("=")
+        fb.set_option(k, int(v))
     n = 1 << a.scale
+
+    def bcast(b):
+        box = [b]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
     t0 = time.time()
-    be = GpuBackend(a.scale, a.edge_factor, a.seed, rank, world, need_parents=True)
+    pb = PartitionedBfs(a.scale, a.edge_factor, a.seed, rank, world, bcast)
     setup_s = time.time() - t0
-    # sources: seeded, restricted to vertices with out-edges; owners publish their degrees through one all-gather
+    # sources: seeded, restricted to vertices with out-edges; owners publish their degrees through one all-reduce
     rng = np.random.default_rng(a.seed * 7919 + 3)
-    cand = rng.choice(n, size=a.bfs_sources * 8, replace=False)
-    p = np.empty(be.hi - be.lo + 1, np.uint64)
-    fb.check(fb.lib().B200_Matrix_export_CSR(be.A, p.ctypes.data, None, None, 0))
-    degl = np.diff(p.astype(np.int64))
-    flag = torch.zeros(len(cand), dtype=torch.int32, device="cuda")
-    mine = (cand >= be.lo) & (cand < be.hi)
+    cand = rng.choice(n, size=(a.bfs_sources + a.warmup) * 8, replace=False)
+    degl = pb.local_degrees()
+    mine = (cand >= pb.lo) & (cand < pb.hi)
     vals = np.zeros(len(cand), np.int32)
-    vals[mine] = (degl[cand[mine] - be.lo] > 0).astype(np.int32)
-    flag.copy_(torch.from_numpy(vals))
+    vals[mine] = (degl[cand[mine] - pb.lo] > 0).astype(np.int32)
+    flag = torch.from_numpy(vals).cuda()
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     srcs = [int(c) for c, f in zip(cand, flag.cpu().numpy()) if f][: a.bfs_sources + a.warmup]
@@ -548,35 +557,85 @@ def run_bfs(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
     for s_ in srcs[: a.warmup]:
-        bfs_gpu(be, s_, want_parents=True)
+        pb.run(s_)
     barrier()
     fb.reset_stats()
+    clocks.mark_begin()
     t0 = time.perf_counter()
-    edges = 0
-    reached = 0
+    edges = reached = 0
+    dev_ms = exch_ms = 0.0
+    agg = {"td_levels": 0, "bu_levels": 0, "sparse_levels": 0, "exchanges": 0, "exchanged_bytes": 0}
     depth = 0
+    keep = []
     for s_ in srcs[a.warmup:]:
-        lv, par, e, d = bfs_gpu(be, s_, want_parents=True)
-        edges += e
-        depth = max(depth, d)
-        reached += int((lv >= 0).sum().item())
+        host = len(keep) < a.bfs_parity               # parity sources come back to the host; the rest stay in HBM
+        lv, par, info = pb.run(s_, on_device=not host)
+        edges += info["edges"]                       # identical on every rank (replicated degree table)
+        depth = max(depth, info["depth"])
+        reached += int((lv >= 0).sum())
+        dev_ms += info["device_ms"]
+        exch_ms += info["exchange_ms"]
+        for k in agg:
+            agg[k] += info[k]
+        if host:
+            keep.append((s_, lv.copy(), par.copy()))
     barrier()
+    clocks.mark_end()
     secs = time.perf_counter() - t0
+    clk = clocks.stop()
     launches = fb.get_stat("launches")
     if world > 1:
-        (secs,), (edges, reached, launches) = reduce_over_ranks([secs], [edges, reached, launches], "cuda")
-    be.close()
+        (secs, dev_ms, exch_ms), (reached, launches) = reduce_over_ranks([secs, dev_ms, exch_ms], [reached, launches], "cuda")
+    # ---- parity (untimed): rank 0 regenerates the whole graph on its GPU, exports it, runs the oracle ----
+    parity = None
+    if a.bfs_parity > 0:
+        good = True
+        full = []
+        for s_, lv, par in keep:
+            if world > 1:
+                block = partition(n, 0, world)[1]
+                pad = torch.full((2, block), -1, dtype=torch.int64, device="cuda")
+                pad[0, : len(lv)] = torch.from_numpy(lv).cuda()
+                pad[1, : len(par)] = torch.from_numpy(par).cuda()
+                out = torch.empty((world, 2, block), dtype=torch.int64, device="cuda")
+                dist.all_gather_into_tensor(out.view(-1), pad.view(-1))
+                full.append((s_, out[:, 0, :].reshape(-1)[:n].cpu().numpy(), out[:, 1, :].reshape(-1)[:n].cpu().numpy()))
+            else:
+                full.append((s_, lv, par))
+        if rank == 0:
+            import oracle as orc
+            orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
+            pb_A = fb.rmat(a.scale, a.edge_factor, a.seed)
+            p_, j_, _ = pb_A.export_csr()
+            del pb_A
+            Ao = orc.CSR(n, n, p_.astype(np.int64), j_)
+            for s_, lv, par in full:
+                wl, wp = orc.bfs(Ao, s_)
+                good = good and bool(np.array_equal(lv, wl) and np.array_equal(par, wp))
+            parity = {"sources_checked": len(full), "levels_and_min_parents_bit_exact": good}
+    pb.close()
     if rank == 0:
         k = len(srcs) - a.warmup
         print(json.dumps({
-            "metric": "traversed edges/sec (BFS sweep, Graph500 TEPS)", "value": edges / secs, "unit": "edges/s", "n_gpus": world,
-            "steps": k, "warmup": a.warmup, "ms_per_step": 1e3 * secs / max(1, k), "higher_is_better": True, "scaling": "strong",
+            "metric": "traversed edges/sec (BFS sweep, Graph500 TEPS)", "value": edges / (dev_ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": k, "warmup": a.warmup, "ms_per_step": dev_ms / max(1, k), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
             "config": {"workload": f"BFS level+parent sweep, RMAT scale-{a.scale} ef{a.edge_factor}, {k} sources", "n": n,
-                       "parallelism": f"1-D row-block partition x{world}, one NCCL all-gather of the n-bit frontier bitmap per level",
+                       "parallelism": f"1-D row-block partition x{world}; per level one NCCL all-gather on the library stream: n-bit bitmaps "
+                                      "(top-down: discovered sets, bottom-up: owned slices) or sentinel-padded vertex lists while the "
+                                      "frontier's out-edges number < n/32",
                        "max_depth": depth, "setup_s": round(setup_s, 2)},
-            "edges_per_bfs": edges / max(1, k), "reached_per_bfs": reached / max(1, k), "gpu_launches": int(launches)}))
+            "wall_ms_per_step": 1e3 * secs / max(1, k), "edges_per_bfs": edges / max(1, k), "reached_per_bfs": reached / max(1, k),
+            "levels": {kk: agg[kk] / max(1, k) for kk in ("td_levels", "bu_levels", "sparse_levels")},
+            "collective": {"name": "ncclAllGather (uint8) on the library stream", "calls_per_bfs": agg["exchanges"] / max(1, k),
+                           "us_per_call": (1e3 * exch_ms / agg["exchanges"]) if agg["exchanges"] else None,
+                           "share_of_bfs_time": exch_ms / dev_ms if dev_ms else None,
+                           "bytes_per_bfs": agg["exchanged_bytes"] / max(1, k)},
+            "parity": parity, "gpu_launches": int(launches), "clocks": clk}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -82,6 +82,9 @@ def lib():
         "B200_bfs_dist_merge": [P, C.c_int, U64, P, U64, U64, P, C.c_int32, P, P, P],
         "B200_bfs_dist_pull": [P, U64, P, P, P, U64, C.POINTER(U64)],
         "B200_bfs_dist_parents": [P, U64, P, P], "B200_bfs": [P, U64, I64, P, P, C.c_int, C.POINTER(U64)],
+        "B200_bfs_ex": [P, U64, I64, I64, P, P, C.c_int, P],
+        "B200_comm_unique_id": [P], "B200_comm_init": [C.POINTER(P), C.c_int, C.c_int, P], "B200_comm_free": [C.POINTER(P)],
+        "B200_bfs_partitioned": [P, P, U64, U64, P, U64, I64, I64, P, P, C.c_int, P],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -103,6 +106,15 @@ def lib():
     L.B200_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+class BfsInfo(C.Structure):
+    """B200_BfsInfo (include/b200grb.h)"""
+    _fields_ = [("depth", U64), ("edges", U64), ("td_levels", U64), ("bu_levels", U64), ("sparse_levels", U64), ("exchanges", U64),
+                ("exchanged_bytes", U64), ("device_ms", C.c_double), ("exchange_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def obj(name):

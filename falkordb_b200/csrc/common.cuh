@@ -56,6 +56,8 @@ struct Context {
     i64 opt_l2_window = 0;         // bytes of the packed frontier's hot prefix kept L2-resident through a persisting access-policy window (0 = off)
     i64 opt_l2_reset = 0;          // cudaCtxResetPersistingL2Cache after each windowed pull
     i64 opt_count_kernel = 1;      // materialise count pass: 1 = vertical (carry-save) counters, 0 = transpose + popcount
+    i64 opt_bfs_direction = 0;     // 0 = direction-optimising, 1 = top-down only, 2 = bottom-up only (test hooks)
+    i64 opt_bfs_sparse_exchange = 1;   // partitioned BFS: ship discovered-vertex lists instead of bitmaps when the frontier is sparse
     u64 l2_persist_max = 0, l2_window_max = 0;   // device limits (bytes), read at bring-up
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
     i64 opt_hints = 1;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)

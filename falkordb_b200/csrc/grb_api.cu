@@ -139,6 +139,7 @@ struct GB_Matrix_opaque : UObject {
     bool devT_valid = false;
     DevCSR devT;
     LongRows lr;
+    DevBuf<u32> bfs_deg; u64 bfs_edges = 0; bool bfs_deg_valid = false;   // out-degree table of the BFS engine (bfs_do.cu)
     int sparsity_control = GxB_HYPERSPARSE | GxB_SPARSE | GxB_BITMAP | GxB_FULL;
     int hyper_hash = 1;
     int orientation = GrB_ROWMAJOR;
@@ -239,6 +240,7 @@ struct MultiLock {
 // ------------------------------------------------------------------------------------------------ form management
 static void invalidate_aux(GrB_Matrix A) {
     A->diag_state = -1;
+    A->bfs_deg.release(); A->bfs_deg_valid = false; A->bfs_edges = 0;
     A->devT_valid = false;
     A->devT.clear();
     A->lr.clear();
@@ -1548,29 +1550,110 @@ int LAGraph_Delete(LAGraph_Graph *G, char *msg) {
     return 0;
 }
 
-GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level, int64_t *parent, int location,
-                  uint64_t *edges_traversed) {
+extern "C" GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
+// Single-GPU BFS.  With the transpose mirror in place (B200_Matrix_prepare(A, 1), or any earlier pull) the direction-optimising
+// engine runs (bfs_do.cu); without it -- one BFS on a fresh matrix, where building A' would cost more than the search -- the
+// top-down kernel of bfs.cu.  Both give level and minimum-id parent.  dest >= 0 stops once that vertex is reached.
+static void bfs_any(GrB_Matrix A, u64 src, i64 max_level, i64 dest, i64 *d_level, i64 *d_parent, u64 *edges, BfsInfo *info) {
+    if (A->devT_valid && ctx().opt_bfs_direction != 3) {
+        if (!A->bfs_deg_valid) { bfs_build_degrees(A->dev, A->nrows, 0, A->nrows, nullptr, A->bfs_deg, &A->bfs_edges); A->bfs_deg_valid = true; }
+        BfsInfo rec;
+        bfs_do(A->dev, A->devT, A->nrows, 0, A->nrows, A->bfs_deg.ptr, A->bfs_edges, nullptr, src, max_level, dest, d_level, d_parent, &rec);
+        if (edges) *edges = rec.edges;
+        if (info) *info = rec;
+    } else {
+        if (dest >= 0) throw GrbError(GrB_NOT_IMPLEMENTED, "BFS with a destination needs the transpose mirror (B200_Matrix_prepare)");
+        u64 e = 0;
+        bfs_run(A->dev, src, max_level, d_level, d_parent, &e);
+        if (edges) *edges = e;
+        if (info) { memset(info, 0, sizeof(*info)); info->edges = e; }
+    }
+}
+GrB_Info B200_bfs_ex(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t dest, int64_t *level, int64_t *parent, int location,
+                     B200_BfsInfo *info_out) {
     CHECK_MAT(A); CHECK_PTR(level);
     if (A->nrows != A->ncols) { tl_error = "BFS needs a square adjacency matrix"; return GrB_DIMENSION_MISMATCH; }
-    if (src >= A->nrows) return GrB_INVALID_INDEX;
+    if (src >= A->nrows || (dest >= 0 && (u64)dest >= A->nrows)) return GrB_INVALID_INDEX;
     return guarded([&]() {
         GpuLock g;
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
         u64 n = A->nrows, edges = 0;
+        BfsInfo rec;
+        memset(&rec, 0, sizeof(rec));
         if (location == B200_LOC_DEVICE) {
-            bfs_run(A->dev, src, max_level, level, parent, &edges);
+            bfs_any(A, src, max_level, dest, level, parent, &edges, &rec);
             sync_stream();
         } else {
             DevBuf<i64> dl(n), dp;
             if (parent) dp.alloc(n);
-            bfs_run(A->dev, src, max_level, dl.ptr, parent ? dp.ptr : nullptr, &edges);
+            bfs_any(A, src, max_level, dest, dl.ptr, parent ? dp.ptr : nullptr, &edges, &rec);
             d2h(level, dl.ptr, n);
             if (parent) d2h(parent, dp.ptr, n);
             sync_stream();
         }
-        if (edges_traversed) *edges_traversed = edges;
+        if (info_out) memcpy(info_out, &rec, sizeof(rec));
+        return GrB_SUCCESS;
+    });
+}
+GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level, int64_t *parent, int location,
+                  uint64_t *edges_traversed) {
+    B200_BfsInfo info;
+    memset(&info, 0, sizeof(info));
+    GrB_Info r = B200_bfs_ex(A, src, max_level, -1, level, parent, location, &info);
+    if (r == GrB_SUCCESS && edges_traversed) *edges_traversed = info.edges;
+    return r;
+}
+
+// ---- NCCL communicator of the partitioned BFS: rank 0 creates the id, the caller ships its 128 bytes to the other ranks by
+// whatever means it has (the tests and bench.py: torch.distributed broadcast), every rank then calls B200_comm_init ----
+GrB_Info B200_comm_unique_id(uint8_t *id128) {
+    CHECK_PTR(id128);
+    return guarded([&]() { ensure_init(); comm_unique_id(id128); return GrB_SUCCESS; });
+}
+GrB_Info B200_comm_init(B200_Comm *comm, int rank, int world, const uint8_t *id128) {
+    CHECK_PTR(comm);
+    if (world > 1) CHECK_PTR(id128);
+    return guarded([&]() { GpuLock g; ensure_init(); *comm = (B200_Comm)comm_init(rank, world, id128); return GrB_SUCCESS; });
+}
+GrB_Info B200_comm_free(B200_Comm *comm) {
+    if (!comm || !*comm) return GrB_SUCCESS;
+    return guarded([&]() { GpuLock g; sync_stream(); comm_free((BfsComm *)*comm); *comm = nullptr; return GrB_SUCCESS; });
+}
+// 1-D row-block partitioned BFS (BASELINE config 5): Alocal = rows [row_lo, row_lo + nrows(Alocal)) of the n x n adjacency
+// matrix, ATlocal = the same rows of its transpose (both with global column ids); row blocks are ceil(n / P) rounded up to 64.
+// level_local / parent_local: int64[nrows(Alocal)] (host or device by `location`).  Collective: every rank calls it.
+GrB_Info B200_bfs_partitioned(GrB_Matrix Alocal, GrB_Matrix ATlocal, uint64_t n, uint64_t row_lo, B200_Comm comm, GrB_Index src,
+                              int64_t max_level, int64_t dest, int64_t *level_local, int64_t *parent_local, int location,
+                              B200_BfsInfo *info_out) {
+    CHECK_MAT(Alocal); CHECK_MAT(ATlocal); CHECK_PTR(level_local);
+    if (Alocal->ncols != n || ATlocal->ncols != n || Alocal->nrows != ATlocal->nrows || row_lo + Alocal->nrows > n) {
+        tl_error = "partitioned BFS: Alocal / ATlocal must be (hi - lo) x n row blocks"; return GrB_DIMENSION_MISMATCH;
+    }
+    if (src >= n || (dest >= 0 && (u64)dest >= n)) return GrB_INVALID_INDEX;
+    return guarded([&]() {
+        GpuLock g;
+        MultiLock lk{Alocal, ATlocal};
+        ensure_init();
+        ensure_dev(Alocal); ensure_dev(ATlocal);
+        BfsComm *c = (BfsComm *)comm;
+        const u64 nloc = Alocal->nrows, hi = row_lo + nloc;
+        if (!Alocal->bfs_deg_valid) { bfs_build_degrees(Alocal->dev, n, row_lo, hi, c, Alocal->bfs_deg, &Alocal->bfs_edges); Alocal->bfs_deg_valid = true; }
+        BfsInfo rec;
+        memset(&rec, 0, sizeof(rec));
+        if (location == B200_LOC_DEVICE) {
+            bfs_do(Alocal->dev, ATlocal->dev, n, row_lo, hi, Alocal->bfs_deg.ptr, Alocal->bfs_edges, c, src, max_level, dest, level_local, parent_local, &rec);
+            sync_stream();
+        } else {
+            DevBuf<i64> dl(nloc ? nloc : 1), dp;
+            if (parent_local) dp.alloc(nloc ? nloc : 1);
+            bfs_do(Alocal->dev, ATlocal->dev, n, row_lo, hi, Alocal->bfs_deg.ptr, Alocal->bfs_edges, c, src, max_level, dest, dl.ptr, parent_local ? dp.ptr : nullptr, &rec);
+            d2h(level_local, dl.ptr, nloc);
+            if (parent_local) d2h(parent_local, dp.ptr, nloc);
+            sync_stream();
+        }
+        if (info_out) memcpy(info_out, &rec, sizeof(rec));
         return GrB_SUCCESS;
     });
 }
@@ -1580,11 +1663,14 @@ int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGr
     (void)many_expected;
     if (msg) msg[0] = 0;
     if (!G || !G->A) return GrB_NULL_POINTER;
-    if (dest >= 0) { if (msg) snprintf(msg, 256, "dest early-exit is not supported"); return GrB_NOT_IMPLEMENTED; }
+    if (dest >= 0) {   // early exit at `dest` (lagraphx_bindings.rs:585-594) runs on the direction-optimising engine: needs A' (LAGraph's cached AT)
+        GrB_Info pi = B200_Matrix_prepare(G->A, 1);
+        if (pi) { if (msg) snprintf(msg, 256, "%s", tl_error.c_str()); return pi; }
+    }
     u64 n = G->A->nrows;
     uvec<i64> lv(n), pr;
     if (parent) pr.resize(n);
-    GrB_Info info = B200_bfs(G->A, src, max_level < 0 ? -1 : max_level, lv.data(), parent ? pr.data() : nullptr, B200_LOC_HOST, nullptr);
+    GrB_Info info = B200_bfs_ex(G->A, src, max_level < 0 ? -1 : max_level, dest, lv.data(), parent ? pr.data() : nullptr, B200_LOC_HOST, nullptr);
     if (info) { if (msg) snprintf(msg, 256, "%s", tl_error.c_str()); return info; }
     auto fill = [&](GrB_Vector *out, const uvec<i64> &src_v) {
         GrB_Vector v = new GB_Vector_opaque();
@@ -1991,6 +2077,8 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "l2_window") c.opt_l2_window = value;
     else if (n == "l2_reset") c.opt_l2_reset = value;
     else if (n == "count_kernel") c.opt_count_kernel = value;
+    else if (n == "bfs_direction") c.opt_bfs_direction = value;
+    else if (n == "bfs_sparse_exchange") c.opt_bfs_sparse_exchange = value;
     else if (n == "timing") { c.opt_timing = value; if (c.ready) timed_reset(); }
     else return GrB_INVALID_VALUE;
     return GrB_SUCCESS;

@@ -83,6 +83,22 @@ void bfs_dist_merge(const u64 *gathered, int P, u64 nwords, u64 *visited, u64 ro
 void bfs_dist_parents(const DevCSR &ATloc, u64 row_lo, const int *level_full, i64 *parent_local);
 
 void csr_digest(const DevCSR &A, u64 *host_out3);   // {nnz, sum mix(key), sum mix(key + GOLD * (pos + 1))}: see oracle orc_digest
+// bfs_do.cu : direction-optimising BFS, single GPU or 1-D row-block partitioned over NCCL
+struct BfsComm;
+struct BfsInfo {          // mirrored by B200_BfsInfo in include/b200grb.h
+    u64 depth, edges, td_levels, bu_levels, sparse_levels, exchanges, exchanged_bytes;
+    double device_ms, exchange_ms;
+};
+void comm_unique_id(unsigned char *id128);
+BfsComm *comm_init(int rank, int world, const unsigned char *id128);
+void comm_free(BfsComm *c);
+int comm_rank(const BfsComm *c);
+int comm_world(const BfsComm *c);
+void comm_allgather(BfsComm *c, const void *send, void *recv, size_t bytes_per_rank);
+void bfs_build_degrees(const DevCSR &Aloc, u64 n, u64 lo, u64 hi, BfsComm *comm, DevBuf<u32> &deg_all, u64 *total_edges);
+void bfs_do(const DevCSR &Aloc, const DevCSR &ATloc, u64 n, u64 lo, u64 hi, const u32 *deg_all, u64 total_edges, BfsComm *comm,
+            u64 src, i64 max_level, i64 dest, i64 *d_level, i64 *d_parent, BfsInfo *info);
+
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
 
 // hypersparse host form <-> dense device rowptr (ewise.cu)

@@ -1,24 +1,23 @@
-"""1-D row-block partitioned BFS over `torch.distributed` (BASELINE config 5).
+"""1-D row-block partitioned BFS (BASELINE config 5): host-side glue around B200_bfs_partitioned.
 
-Rank g owns vertices [lo, hi) and the out-edges of those vertices (a row block of A).  One level =
-  expand : owned part of the frontier  ->  n-bit "discovered" bitmap           (CUDA kernel, bfs.cu)
-  gather : ONE all-gather of the bitmaps over NCCL / NVLink                     (torch.distributed)
-  merge  : OR the P bitmaps, drop visited, assign levels to owned vertices,
-           emit the next owned frontier                                         (CUDA kernel, bfs.cu)
-Every rank keeps the full visited bitmap (n/8 bytes); the loop ends when the merged bitmap is empty, which every rank
-sees identically, so no extra termination collective is needed.  Parents (deterministic minimum id, the rule of the
-single-GPU kernel and of the oracle) come from one all-gather of the int32 levels and a pull over the owned rows of A'.
-
-The level loop is backend-agnostic: `GpuBackend` drives libb200grb.so on device tensors, tests substitute a numpy
-backend under gloo to check the partition / exchange logic on CPU.
+Rank g owns vertices [lo, hi): the out-edges (row block of A) and the in-edges (row block of A') of those vertices.  The level
+loop, the direction switch and the exchange (NCCL all-gather on the library's stream: n-bit bitmaps, or sentinel-padded vertex
+lists while the frontier is sparse) all live in the library (csrc/bfs_do.cu); this module only
+  * builds the row blocks of the synthetic RMAT graph (B200_Matrix_rmat_block regenerates the counter-based edge stream, so the
+    union of the blocks is exactly the single-GPU matrix),
+  * creates the NCCL communicator (rank 0 makes the 128-byte id, torch.distributed ships it),
+  * and offers `reference_levels`, a numpy restatement of the same level loop over any all_gather callable: the gloo /
+    world_size-2 CPU tests run the partition, switch and exchange logic through it.
 """
 import ctypes as C
 
 import numpy as np
 
+ALPHA, BETA = 14, 24          # Beamer's switch constants, as in csrc/bfs_do.cu
+
 
 def partition(n, rank, world):
-    """Contiguous blocks, multiples of 64 vertices so bitmap words never straddle two owners."""
+    """Contiguous blocks of ceil(n / world) rounded up to 64 vertices (bitmap words never straddle two owners)."""
     block = -(-n // world)
     block = (block + 63) // 64 * 64
     lo = min(n, rank * block)
@@ -26,141 +25,159 @@ def partition(n, rank, world):
     return lo, hi
 
 
-def run_levels(backend, n, rank, world, src, all_gather, max_level=-1, pull_threshold=1 / 64):
-    """Level loop.  Returns (levels of owned vertices as int32, out-edges of the owned reached vertices, depth).
-    Direction-optimising: when the previous level discovered more than `pull_threshold * n` vertices the next level runs
-    bottom-up (owned unvisited vertices look for a frontier in-neighbour) if the backend offers it."""
+# ------------------------------------------------------------------------------------------------ numpy restatement
+def _bits_of(idx, nwords):
+    b = np.zeros(nwords, np.uint64)
+    idx = np.asarray(idx, dtype=np.int64)
+    np.bitwise_or.at(b, idx >> 6, np.uint64(1) << (idx & 63).astype(np.uint64))
+    return b
+
+
+def _members(bits, n):
+    return np.nonzero(np.unpackbits(bits.view(np.uint8), bitorder="little")[:n])[0]
+
+
+def reference_levels(Ap, Aj, ATp, ATj, n, rank, world, deg_all, src, all_gather, max_level=-1, dest=-1, sparse_exchange=True):
+    """bfs_do's level loop on host arrays.  Ap/Aj: CSR of the owned row block of A (local rows, global columns); ATp/ATj: the
+    same rows of A'.  all_gather(np.ndarray) -> list of every rank's array (equal shapes).  Returns (level, parent) of the
+    owned vertices (int64, -1 = unreached) and a dict of what happened."""
     lo, hi = partition(n, rank, world)
-    backend.reset(src)
-    nf = 1 if lo <= src < hi else 0
-    lvl, total_new = 0, 1
-    can_pull = hasattr(backend, "expand_pull") and backend.can_pull()
-    while max_level < 0 or lvl < max_level:
-        if can_pull and total_new > pull_threshold * n:
-            backend.expand_pull()
-        else:
-            backend.expand(nf)
-        gathered = all_gather(backend.disc())
-        nf, total_new = backend.merge(gathered, lvl + 1)
-        if total_new == 0:
-            break
+    block = partition(n, 0, world)[1] if world > 1 else n
+    nwl = block // 64 if world > 1 else (n + 63) // 64
+    nw = nwl * world
+    visited = _bits_of([src], nw)
+    frontier = visited.copy()
+    level = np.full(hi - lo, -1, np.int64)
+    parent = np.full(hi - lo, -1, np.int64)
+    if lo <= src < hi:
+        level[src - lo], parent[src - lo] = 0, src
+    total_edges = int(np.asarray(deg_all, dtype=np.int64).sum())
+    nf, mf = 1, int(deg_all[src])
+    explored = mf
+    info = {"td": 0, "bu": 0, "sparse": 0, "dense": 0}
+    bottom_up, lvl = False, 0
+
+    def first_frontier_member(r, fr):
+        nb = ATj[ATp[r]:ATp[r + 1]].astype(np.int64)
+        hit = ((fr[nb >> 6] >> (nb & 63).astype(np.uint64)) & np.uint64(1)).astype(bool)
+        return int(nb[np.argmax(hit)]) if hit.any() else -1
+
+    while nf > 0 and (max_level < 0 or lvl < max_level) and dest != src:
+        unexplored = max(0, total_edges - explored)
+        if not bottom_up:
+            if mf > unexplored // ALPHA:
+                bottom_up = True
+        elif nf < n // BETA:
+            bottom_up = False
         lvl += 1
-    return backend.levels(), backend.reached_edges(), lvl
+        if not bottom_up:
+            mine = [v for v in _members(frontier, n) if lo <= v < hi]
+            tgt = np.concatenate([Aj[Ap[v - lo]:Ap[v - lo + 1]] for v in mine]).astype(np.int64) if mine else np.zeros(0, np.int64)
+            tgt = tgt[((visited[tgt >> 6] >> (tgt & 63).astype(np.uint64)) & np.uint64(1)) == 0]
+            disc = _bits_of(tgt, nw)
+            if world > 1 and sparse_exchange and mf < n // 32:
+                bound = max(1, mf)
+                lst = np.full(bound, 0xFFFFFFFF, np.uint32)
+                mem = _members(disc, n)
+                lst[:len(mem)] = mem
+                allv = np.concatenate(all_gather(lst))
+                allv = allv[allv != 0xFFFFFFFF].astype(np.int64)
+                new = _bits_of(allv, nw) & ~visited
+                info["sparse"] += 1
+            else:
+                parts = all_gather(disc) if world > 1 else [disc]
+                new = np.bitwise_or.reduce(np.stack(parts), axis=0) & ~visited
+                info["dense"] += world > 1
+            for v in _members(new, n):
+                if lo <= v < hi:
+                    level[v - lo] = lvl
+                    parent[v - lo] = first_frontier_member(v - lo, frontier)
+            info["td"] += 1
+        else:
+            new = np.zeros(nw, np.uint64)
+            found = []
+            for r in range(hi - lo):
+                v = lo + r
+                if (visited[v >> 6] >> np.uint64(v & 63)) & np.uint64(1):
+                    continue
+                p = first_frontier_member(r, frontier)
+                if p >= 0:
+                    level[r], parent[r] = lvl, p
+                    found.append(v)
+            new |= _bits_of(found, nw)
+            if world > 1:
+                w0 = rank * nwl
+                parts = all_gather(new[w0:w0 + nwl].copy())
+                new = np.concatenate(parts)
+            info["bu"] += 1
+        mem = _members(new, n)
+        nf, mf = len(mem), int(np.asarray(deg_all, dtype=np.int64)[mem].sum())
+        visited |= new
+        explored += mf
+        if nf == 0:
+            lvl -= 1
+            break
+        frontier = new
+        if dest >= 0 and dest in set(mem.tolist()):
+            break
+    info["depth"] = lvl
+    return level, parent, info
 
 
-class GpuBackend:
-    """Device-resident state in torch tensors; kernels through the C ABI on raw device pointers."""
+# ------------------------------------------------------------------------------------------------ GPU
+class PartitionedBfs:
+    """Row blocks of the RMAT graph on this rank's GPU + the NCCL communicator; `run` is one collective BFS."""
 
-    def __init__(self, scale, edge_factor, seed, rank, world, need_parents=True):
-        import torch
+    def __init__(self, scale, edge_factor, seed, rank, world, broadcast_bytes=None):
+        """broadcast_bytes(bytes or None) -> bytes: ships rank 0's 128-byte NCCL id to every rank (torch.distributed in
+        bench.py and the tests); not needed for world == 1."""
         from ._lib import lib, check, P
-        self.torch, self.L, self.check = torch, lib(), check
+        self.L, self.check = lib(), check
         self.n = 1 << scale
         self.rank, self.world = rank, world
         self.lo, self.hi = partition(self.n, rank, world)
-        self.nwords = (self.n + 63) // 64
-        h = P()
-        check(self.L.B200_Matrix_rmat_block(C.byref(h), scale, edge_factor, seed, self.lo, self.hi, 0))
-        self.A = h
-        self.AT = None
-        if need_parents:
-            ht = P()
-            check(self.L.B200_Matrix_rmat_block(C.byref(ht), scale, edge_factor, seed, self.lo, self.hi, 1))
-            self.AT = ht
-        dev = torch.device("cuda", torch.cuda.current_device())
-        nloc = max(1, self.hi - self.lo)
-        self.visited = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
-        self._disc = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
-        self.frontier_bits = torch.zeros(self.nwords, dtype=torch.int64, device=dev)
-        self.level = torch.full((nloc,), -1, dtype=torch.int32, device=dev)
+        self.A, self.AT = P(), P()
+        check(self.L.B200_Matrix_rmat_block(C.byref(self.A), scale, edge_factor, seed, self.lo, self.hi, 0))
+        check(self.L.B200_Matrix_rmat_block(C.byref(self.AT), scale, edge_factor, seed, self.lo, self.hi, 1))
+        self.comm = P()
+        ident = None
+        if world > 1:
+            buf = (C.c_uint8 * 128)()
+            if rank == 0:
+                check(self.L.B200_comm_unique_id(buf))
+            ident = broadcast_bytes(bytes(buf) if rank == 0 else None)
+            buf = (C.c_uint8 * 128).from_buffer_copy(ident)
+            check(self.L.B200_comm_init(C.byref(self.comm), rank, world, buf))
+        else:
+            check(self.L.B200_comm_init(C.byref(self.comm), 0, 1, None))
+
+    def local_degrees(self):
         p = np.empty(self.hi - self.lo + 1, np.uint64)
-        check(self.L.B200_Matrix_export_CSR(self.A, p.ctypes.data, None, None, 0))
-        self.deg = torch.from_numpy(np.diff(p.astype(np.int64))).to(dev)
-        self.fa = torch.zeros(nloc, dtype=torch.int32, device=dev)
-        self.fb = torch.zeros(nloc, dtype=torch.int32, device=dev)
-        self.cnt = np.zeros(2, np.uint64)
+        self.check(self.L.B200_Matrix_export_CSR(self.A, p.ctypes.data, None, None, 0))
+        return np.diff(p.astype(np.int64))
 
-    def reset(self, src):
-        t = self.torch
-        self.visited.zero_()
-        self.level.fill_(-1)
-        w, b = src >> 6, src & 63
-        self.visited[w] = (1 << b) if b < 63 else -(1 << 63)
-        if self.lo <= src < self.hi:
-            self.level[src - self.lo] = 0
-            self.fa[0] = src if src < (1 << 31) else src - (1 << 32)
-        t.cuda.synchronize()
-
-    def expand(self, nf):
-        e = C.c_uint64(0)
-        self.check(self.L.B200_bfs_dist_expand(self.A, self.lo, self.fa.data_ptr(), nf, self.visited.data_ptr(),
-                                               self._disc.data_ptr(), self.nwords, C.byref(e)))
-        return e.value
-
-    def can_pull(self):
-        return self.AT is not None
-
-    def expand_pull(self):
-        sc = C.c_uint64(0)
-        self.check(self.L.B200_bfs_dist_pull(self.AT, self.lo, self.frontier_bits.data_ptr(), self.visited.data_ptr(),
-                                             self._disc.data_ptr(), self.nwords, C.byref(sc)))
-        return sc.value
-
-    def reached_edges(self):
-        """Graph500 edge count: out-edges of the owned vertices that were reached."""
-        lv = self.level[: self.hi - self.lo]
-        return int(self.deg[lv >= 0].sum().item()) if self.hi > self.lo else 0
-
-    def disc(self):
-        return self._disc
-
-    def merge(self, gathered, lvl):
-        self.torch.cuda.synchronize()                     # NCCL ran on torch's stream; the library has its own
-        self.check(self.L.B200_bfs_dist_merge(gathered.data_ptr(), self.world, self.nwords, self.visited.data_ptr(), self.lo,
-                                              self.hi, self.level.data_ptr(), lvl, self.fb.data_ptr(), self.cnt.ctypes.data,
-                                              self.frontier_bits.data_ptr()))
-        self.fa, self.fb = self.fb, self.fa
-        return int(self.cnt[0]), int(self.cnt[1])
-
-    def levels(self):
-        return self.level[: self.hi - self.lo]
-
-    def parents(self, level_full):
-        """level_full: int32[n] on the device (all-gathered).  Returns int64 parents of the owned vertices."""
-        par = self.torch.full((max(1, self.hi - self.lo),), -1, dtype=self.torch.int64, device=self.level.device)
-        self.torch.cuda.synchronize()
-        self.check(self.L.B200_bfs_dist_parents(self.AT, self.lo, level_full.data_ptr(), par.data_ptr()))
-        return par[: self.hi - self.lo]
+    def run(self, src, max_level=-1, dest=-1, want_parents=True, on_device=False):
+        """Returns (level_local int64[hi-lo], parent_local or None, info dict).  Collective: every rank calls it.
+        on_device: the results stay in HBM (torch tensors) instead of being copied to host arrays."""
+        from ._lib import BfsInfo
+        nloc = self.hi - self.lo
+        info = BfsInfo()
+        if on_device:
+            import torch
+            level = torch.empty(max(1, nloc), dtype=torch.int64, device="cuda")
+            parent = torch.empty(max(1, nloc), dtype=torch.int64, device="cuda") if want_parents else None
+            lp, pp, loc = level.data_ptr(), (None if parent is None else parent.data_ptr()), 1
+        else:
+            level = np.empty(max(1, nloc), np.int64)
+            parent = np.empty(max(1, nloc), np.int64) if want_parents else None
+            lp, pp, loc = level.ctypes.data, (None if parent is None else parent.ctypes.data), 0
+        self.check(self.L.B200_bfs_partitioned(self.A, self.AT, self.n, self.lo, self.comm, int(src), int(max_level), int(dest),
+                                               lp, pp, loc, C.byref(info)))
+        return level[:nloc], (None if parent is None else parent[:nloc]), info.as_dict()
 
     def close(self):
+        if self.comm.value:
+            self.L.B200_comm_free(C.byref(self.comm))
         for h in (self.A, self.AT):
-            if h is not None and h.value:
+            if h.value:
                 self.L.GrB_Matrix_free(C.byref(h))
-
-
-def bfs_gpu(backend, src, max_level=-1, want_parents=True):
-    """Whole distributed BFS on the GPU backend.  Returns (level_local, parent_local or None, edges_local, depth)."""
-    import torch
-    import torch.distributed as dist
-    world = backend.world
-
-    def all_gather(disc):
-        if world == 1:
-            return disc
-        out = torch.empty(world * disc.numel(), dtype=disc.dtype, device=disc.device)
-        dist.all_gather_into_tensor(out, disc)
-        return out
-
-    lv, edges, depth = run_levels(backend, backend.n, backend.rank, world, src, all_gather, max_level)
-    par = None
-    if want_parents:
-        block = partition(backend.n, 0, world)[1]
-        if world == 1:
-            full = lv
-        else:
-            pad = torch.full((block,), -1, dtype=torch.int32, device=lv.device)
-            pad[: lv.numel()] = lv
-            full = torch.empty(world * block, dtype=torch.int32, device=lv.device)
-            dist.all_gather_into_tensor(full, pad)
-        par = backend.parents(full.contiguous())
-    return lv, par, edges, depth

@@ -332,6 +332,26 @@ const char *B200_last_error(void);
 /* single-source BFS straight into caller buffers (int64 level/parent per vertex, -1 = unreached) */
 GrB_Info B200_bfs(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t *level, int64_t *parent, int location,
                   uint64_t *edges_traversed);
+/* what one BFS did: levels by direction, exchange volume / time of the partitioned form (device-event timed) */
+typedef struct {
+    uint64_t depth, edges, td_levels, bu_levels, sparse_levels, exchanges, exchanged_bytes;
+    double device_ms, exchange_ms;
+} B200_BfsInfo;
+/* BFS with the `dest` early exit of LAGr_BreadthFirstSearch_Extended (lagraphx_bindings.rs:585-594; -1 = none).  Runs the
+ * direction-optimising engine when the transpose mirror exists (B200_Matrix_prepare(A, 1)), else the top-down kernel. */
+GrB_Info B200_bfs_ex(GrB_Matrix A, GrB_Index src, int64_t max_level, int64_t dest, int64_t *level, int64_t *parent, int location,
+                     B200_BfsInfo *info);
+/* 1-D row-block partitioned BFS over NCCL (BASELINE config 5).  Rank 0 obtains the 128-byte id, the caller ships it
+ * to the other ranks, every rank calls B200_comm_init; world == 1 needs no id.  NCCL is resolved with dlopen at run time. */
+typedef struct B200_Comm_opaque *B200_Comm;
+GrB_Info B200_comm_unique_id(uint8_t *id128);
+GrB_Info B200_comm_init(B200_Comm *comm, int rank, int world, const uint8_t *id128);
+GrB_Info B200_comm_free(B200_Comm *comm);
+/* Alocal / ATlocal: rows [row_lo, row_lo + nloc) of the n x n adjacency matrix and of its transpose (global column ids); blocks
+ * are ceil(n / world) rounded up to a multiple of 64.  level_local / parent_local: int64[nloc].  Collective over `comm`. */
+GrB_Info B200_bfs_partitioned(GrB_Matrix Alocal, GrB_Matrix ATlocal, uint64_t n, uint64_t row_lo, B200_Comm comm, GrB_Index src,
+                              int64_t max_level, int64_t dest, int64_t *level_local, int64_t *parent_local, int location,
+                              B200_BfsInfo *info);
 
 #ifdef __cplusplus
 }
