@@ -2,9 +2,10 @@
 # round 2, call A: parity of the new pull / count kernels, then A/B bench lines of the chain with kernel options
 set -x
 mkdir -p gpurun_out
+make -C falkordb_b200/csrc -j16 -s 2>&1 | tail -3; make -C oracle -s
 nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/r2a_smi.txt 2>&1
 nproc >> gpurun_out/r2a_smi.txt; free -g >> gpurun_out/r2a_smi.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_full_size.py > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
 tail -5 gpurun_out/r2a_pytest.log
 B="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-format csr"
 for v in "pull_kernel=4" "pull_kernel=5" "pull_kernel=5 --opt unroll=8" "pull_kernel=5 --opt l2_window=67108864" "pull_kernel=5 --opt l2_window=67108864 --opt l2_reset=1" "pull_kernel=5 --opt l2_window=33554432" "pull_kernel=5 --opt l2_window=134217728" "pull_kernel=5 --opt count_kernel=0" "pull_kernel=5 --opt pull_grid=3" "pull_kernel=5 --opt pull_grid=6" "pull_kernel=5 --opt hints=0"; do
@@ -36,3 +37,8 @@ PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_pull_seg|k_pull_small|k_bits_count_csa" -c 6 -o gpurun_out/r2a_prof_pull python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=0 > gpurun_out/r2a_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"k_pull_seg" -c 2 -o gpurun_out/r2a_prof_pull_win python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=67108864 > gpurun_out/r2a_ncu2.log 2>&1
 ls -la gpurun_out | tail -5
+# BFS engine: single GPU, scale 24 and 26
+timeout 600 python bench.py --workload bfs --scale 24 --bfs-sources 8 --warmup 2 > gpurun_out/r2a_bfs_s24.json 2> gpurun_out/r2a_bfs_s24.err; tail -1 gpurun_out/r2a_bfs_s24.json | cut -c1-1200
+timeout 900 python bench.py --workload bfs --scale 26 --bfs-sources 8 --warmup 2 > gpurun_out/r2a_bfs_s26.json 2> gpurun_out/r2a_bfs_s26.err; tail -1 gpurun_out/r2a_bfs_s26.json | cut -c1-1200
+# full-size parity
+( time timeout 2400 python -m pytest tests/test_full_size.py -m gpu -x -q --durations=0 ) > gpurun_out/r2a_fullsize.log 2>&1; tail -25 gpurun_out/r2a_fullsize.log
