@@ -2000,6 +2000,94 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
     });
 }
 
+// ---- the coalesced traversal as ONE C call (CondTraverseOp's batch coalescing, cond_traverse.rs:600-608, 1264-1285) ----
+// F(i, sources[i]) = 1;  F <- F * hops[0] * ... * hops[nhops-1] over GxB_ANY_PAIR_BOOL;  result rows to HOST memory.
+//   B200_OUT_BITMAP : out_bits[row * words_per_row + (col >> 6)], one bit per slot.  The batch is processed in 128-row slices and
+//                     slice k's device-to-host copy (second stream) overlaps slice k+1's hops; page-locked out_bits makes the
+//                     copies asynchronous.
+//   B200_OUT_CSR    : out_p[nsrc + 1], out_j[<= out_j_capacity]; GrB_INSUFFICIENT_SPACE (with *nvals_out = entries needed) when the
+//                     buffer is too small.
+//   B200_OUT_AUTO   : bitmap when the result holds more than one entry per 32 slots (fewer bytes over PCIe), else CSR; the choice
+//                     is reported in *format_out.  Needs both output buffers.
+// Composed from the public entry points (each takes the submission lock for its own duration), so other threads' calls interleave.
+GrB_Info B200_traverse_batch(const GrB_Index *sources, GrB_Index nsrc, const GrB_Matrix *hops, int nhops, int format,
+                             uint64_t *out_bits, uint64_t words_per_row, uint64_t *out_p, uint32_t *out_j, uint64_t out_j_capacity,
+                             uint64_t *nvals_out, uint64_t *flops_out, int *format_out) {
+    CHECK_PTR(hops);
+    if (nsrc) CHECK_PTR(sources);
+    if (nhops < 1) { tl_error = "traverse_batch: nhops < 1"; return GrB_INVALID_VALUE; }
+    for (int h = 0; h < nhops; h++) CHECK_MAT(hops[h]);
+    if (format != B200_OUT_BITMAP && format != B200_OUT_CSR && format != B200_OUT_AUTO) { tl_error = "traverse_batch: unknown format"; return GrB_INVALID_VALUE; }
+    if ((format != B200_OUT_CSR && !out_bits) || (format != B200_OUT_BITMAP && (!out_p || (!out_j && out_j_capacity)))) {
+        tl_error = "traverse_batch: output buffer missing for the requested format"; return GrB_NULL_POINTER;
+    }
+    const u64 inner = hops[0]->nrows, ncols = hops[nhops - 1]->ncols;
+    const u64 wpr = (ncols + 63) / 64;
+    if (format != B200_OUT_CSR && words_per_row != wpr) { tl_error = "traverse_batch: words_per_row must be ceil(ncols / 64)"; return GrB_DIMENSION_MISMATCH; }
+    GrB_Scalar one = nullptr;
+    GrB_Info info = GrB_Scalar_new(&one, GrB_BOOL);
+    if (info) return info;
+    GrB_Scalar_setElement_BOOL(one, true);
+    u64 flops = 0, nvals = 0;
+    int chosen = format;
+    std::vector<B200_Ticket> tickets;
+    auto run_hops = [&](GrB_Matrix F, u64 r0, u64 r1) -> GrB_Info {
+        uvec<u64> rows(r1 - r0);
+        for (u64 i = 0; i < r1 - r0; i++) rows[i] = i;
+        GrB_Info e = GxB_Matrix_build_Scalar(F, rows.data(), sources + r0, one, r1 - r0);
+        for (int h = 0; h < nhops && !e; h++) {
+            e = GrB_mxm(F, nullptr, nullptr, GxB_ANY_PAIR_BOOL, F, hops[h], nullptr);
+            if (!e) flops += ctx().last_flops.load();
+            if (!e && h + 1 < nhops && F->ncols != hops[h + 1]->nrows) { tl_error = "traverse_batch: hop dimensions do not chain"; e = GrB_DIMENSION_MISMATCH; }
+        }
+        return e;
+    };
+    auto fresh = [&](GrB_Matrix *F, u64 rows) -> GrB_Info {
+        // the frontier's column dimension follows the hops: n0 x n1 x ... (rectangular label ranges are n x n in the reference)
+        return GrB_Matrix_new(F, GrB_BOOL, rows, inner);
+    };
+    // GrB_mxm(C = F, A = F, B) needs C's dimensions to match the product: a chain over square n x n operands (what the reference
+    // stores, graph.rs:1191, 1211) keeps them; rectangular chains are rejected up front
+    for (int h = 0; h < nhops; h++)
+        if (hops[h]->nrows != inner || hops[h]->ncols != inner) { GrB_Scalar_free(&one); tl_error = "traverse_batch: operands must be square and equally sized"; return GrB_DIMENSION_MISMATCH; }
+    if (format == B200_OUT_AUTO || format == B200_OUT_CSR) {
+        // density is known only after the hops: run the whole batch once, then pick the hand-off
+        GrB_Matrix F = nullptr;
+        info = fresh(&F, nsrc);
+        if (!info) info = run_hops(F, 0, nsrc);
+        if (!info) info = GrB_Matrix_nvals(&nvals, F);
+        if (!info) {
+            if (format == B200_OUT_AUTO) chosen = (nvals * 32 > nsrc * ncols) ? B200_OUT_BITMAP : B200_OUT_CSR;
+            if (chosen == B200_OUT_BITMAP) info = B200_Matrix_export_bitmap(F, out_bits, wpr, nullptr, B200_LOC_HOST);
+            else if (nvals > out_j_capacity) { tl_error = "traverse_batch: out_j too small"; info = GrB_INSUFFICIENT_SPACE; }
+            else {
+                info = GrB_Matrix_wait(F, GrB_MATERIALIZE);
+                if (!info) info = B200_Matrix_export_CSR(F, out_p, out_j, nullptr, B200_LOC_HOST);
+            }
+        }
+        GrB_Matrix_free(&F);
+    } else {
+        const u64 per = 128;
+        for (u64 r0 = 0; r0 < nsrc && !info; r0 += per) {
+            const u64 r1 = std::min<u64>(nsrc, r0 + per);
+            GrB_Matrix F = nullptr;
+            info = fresh(&F, r1 - r0);
+            if (!info) info = run_hops(F, r0, r1);
+            B200_Ticket t = nullptr;
+            if (!info) info = B200_Matrix_export_bitmap_async(F, out_bits + r0 * wpr, wpr, &t);
+            if (!info) tickets.push_back(t);
+            GrB_Matrix_free(&F);
+        }
+        for (B200_Ticket &t : tickets) { GrB_Info e = B200_Ticket_wait(&t); if (!info) info = e; }
+        nvals = ~0ULL;       // not counted on this path (a popcount pass per slice would only serve this number)
+    }
+    GrB_Scalar_free(&one);
+    if (nvals_out) *nvals_out = nvals;
+    if (flops_out) *flops_out = flops;
+    if (format_out) *format_out = chosen;
+    return info;
+}
+
 // returns every cached device block to the driver (the caching allocator otherwise keeps freed blocks for reuse)
 GrB_Info B200_pool_trim(void) {
     return guarded([&]() {

@@ -401,28 +401,32 @@ def wait_ticket(ticket):
     check(lib().B200_Ticket_wait(C.byref(ticket)))
 
 
-def traverse_to_host(sources, A, hops, out_bitmap, sub_batches=None):
-    """The batched traversal an operator runs (cond_traverse.rs:600-608), host to host: F(i, sources[i]) = 1, `hops` x
-    F <- F*A, result rows into `out_bitmap` (pinned uint64[len(sources), ceil(n/64)], packed row-major bitmap).
-    The batch is processed in `sub_batches` row slices (multiples of 64 rows; default: 128-row slices, the measured sweet
-    spot on B200): while slice k's bitmap crosses PCIe on the copy stream, slice k+1's hops run -- the result transfer,
-    not the GPU, is what bounds this call.
-    Returns the flops (edges traversed).  For dense results; sparse ones are cheaper through Matrix.export_auto."""
+OUT_AUTO, OUT_BITMAP, OUT_CSR = 0, 1, 2
+
+
+def traverse_batch(sources, hop_matrices, fmt=OUT_AUTO, out_bitmap=None, out_p=None, out_j=None):
+    """B200_traverse_batch: the batched traversal an operator runs (cond_traverse.rs:600-608), host to host, as ONE C call.
+    F(i, sources[i]) = 1, F <- F * hop_matrices[0] * ... ; the result lands in `out_bitmap` (uint64[nsrc, ceil(n/64)], pinned for
+    overlapped copies) and / or (`out_p` uint64[nsrc+1], `out_j` uint32[capacity]).  Returns (flops, nvals or None, format)."""
     sources = _u64arr(sources)
-    nsrc, n = len(sources), A.ncols()
-    per = 128 if not sub_batches else max(64, -(-nsrc // max(1, sub_batches)) + 63 & ~63)
-    tickets, flops = [], 0
-    for r0 in range(0, nsrc, per):
-        r1 = min(nsrc, r0 + per)
-        F = Matrix(r1 - r0, n, bool)
-        F.build(np.arange(r1 - r0, dtype=np.uint64), sources[r0:r1])
-        for _ in range(hops):
-            F.lmxm(A)
-            flops += get_stat("last_flops")
-        tickets.append(F.export_bitmap_async(out_bitmap[r0:r1]))
-    for t in tickets:
-        wait_ticket(t)
-    return flops
+    hs = (C.c_void_p * len(hop_matrices))(*[m.h for m in hop_matrices])
+    nv, fl, chosen = U64(0), U64(0), C.c_int(0)
+    wpr = out_bitmap.shape[1] if out_bitmap is not None else 0
+    info = lib().B200_traverse_batch(sources.ctypes.data, len(sources), hs, len(hop_matrices), fmt,
+                                     None if out_bitmap is None else out_bitmap.ctypes.data, wpr,
+                                     None if out_p is None else out_p.ctypes.data, None if out_j is None else out_j.ctypes.data,
+                                     0 if out_j is None else len(out_j), C.byref(nv), C.byref(fl), C.byref(chosen))
+    if info == -103:                     # GrB_INSUFFICIENT_SPACE: nv holds the entries needed
+        raise BufferError(f"out_j holds {0 if out_j is None else len(out_j)} entries, the result has {nv.value}")
+    check(info)
+    return fl.value, (None if nv.value == 2 ** 64 - 1 else nv.value), chosen.value
+
+
+def traverse_to_host(sources, A, hops, out_bitmap, sub_batches=None):
+    """Dense-result form of traverse_batch: `hops` times the same matrix, bitmap hand-off in 128-row slices whose device-to-host
+    copies overlap the next slice's hops (the result transfer, not the GPU, bounds this call).  Returns the flops."""
+    del sub_batches                      # the slicing lives in the library now
+    return traverse_batch(sources, [A] * hops, OUT_BITMAP, out_bitmap=out_bitmap)[0]
 
 
 def multi_source_reach(sources, A, max_hops=None, include_sources=False):

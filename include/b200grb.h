@@ -315,6 +315,15 @@ GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_
  * for a whole 1024-row batch in one device call; host arrays in, host arrays out. */
 GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_Index *J, GrB_Index n, uint8_t *found,
                                    uint64_t *values);
+/* The coalesced traversal of CondTraverseOp::expand_batch as one call (cond_traverse.rs:600-608, 1264-1285): F(i, sources[i]) = 1,
+ * F <- F * hops[0] * ... * hops[nhops-1] over GxB_ANY_PAIR_BOOL (square, equally sized operands), result rows to host memory as a
+ * packed row-major bitmap (128-row slices, copies overlapped with the next slice's hops), as CSR, or whichever moves fewer bytes. */
+#define B200_OUT_AUTO 0
+#define B200_OUT_BITMAP 1
+#define B200_OUT_CSR 2
+GrB_Info B200_traverse_batch(const GrB_Index *sources, GrB_Index nsrc, const GrB_Matrix *hops, int nhops, int format,
+                             uint64_t *out_bits, uint64_t words_per_row, uint64_t *out_p, uint32_t *out_j, uint64_t out_j_capacity,
+                             uint64_t *nvals_out, uint64_t *flops_out, int *format_out);
 GrB_Info B200_sync(void);
 GrB_Info B200_pool_trim(void); /* hand the caching allocator's free device blocks back to the driver */
 void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */

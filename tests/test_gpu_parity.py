@@ -786,6 +786,43 @@ def test_traverse_to_host_sliced_async_hand_off(nsrc, subs):
     assert np.array_equal(out, bitmap_of(want))
 
 
+@pytest.mark.parametrize("nsrc,hops", [(200, 3), (64, 1), (300, 2)])
+def test_traverse_batch_c_entry_formats(nsrc, hops):
+    """B200_traverse_batch: the coalesced traversal as one C call -- CSR hand-off, bitmap hand-off and the automatic choice
+    (bitmap iff denser than one entry per 32 slots), a too-small CSR buffer, and a chain over two different matrices"""
+    A = orc.rmat_csr(11, 8, 17)
+    B = orc.rmat_csr(11, 4, 18)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc + hops)
+    src = rng.choice(n, size=nsrc, replace=False)
+    dA, dB = to_dev(A), to_dev(B)
+    ops_dev, ops_orc = [dA, dB, dA][:hops], [A, B, A][:hops]
+    want = orc.build_matrix(nsrc, n, np.arange(nsrc), src)
+    wfl = 0
+    for M_ in ops_orc:
+        wfl += int(np.diff(M_.p)[want.j].sum())
+        want = orc.mxm(want, M_)
+    wpr = (n + 63) // 64
+    bm = np.zeros((nsrc, wpr), np.uint64)
+    p_, j_ = np.zeros(nsrc + 1, np.uint64), np.zeros(want.nnz + 5, np.uint32)
+    fl, nv, fmt = fb.traverse_batch(src, ops_dev, fb.OUT_CSR, out_p=p_, out_j=j_)
+    assert (fl, nv, fmt) == (wfl, want.nnz, fb.OUT_CSR)
+    assert np.array_equal(p_.astype(np.int64), want.p) and np.array_equal(j_[:want.nnz], want.j)
+    fl, nv, fmt = fb.traverse_batch(src, ops_dev, fb.OUT_BITMAP, out_bitmap=bm)
+    assert fl == wfl and fmt == fb.OUT_BITMAP and np.array_equal(bm, bitmap_of(want))
+    bm[:] = 0
+    p_[:] = 0
+    fl, nv, fmt = fb.traverse_batch(src, ops_dev, fb.OUT_AUTO, out_bitmap=bm, out_p=p_, out_j=j_)
+    assert fmt == (fb.OUT_BITMAP if want.nnz * 32 > nsrc * n else fb.OUT_CSR) and nv == want.nnz
+    if fmt == fb.OUT_BITMAP:
+        assert np.array_equal(bm, bitmap_of(want))
+    else:
+        assert np.array_equal(p_.astype(np.int64), want.p) and np.array_equal(j_[:want.nnz], want.j)
+    if want.nnz > 1:
+        with pytest.raises(BufferError):
+            fb.traverse_batch(src, ops_dev, fb.OUT_CSR, out_p=p_, out_j=j_[: want.nnz - 1])
+
+
 @pytest.mark.parametrize("nsrc,max_hops,include", [(64, None, False), (200, 2, False), (300, None, True), (5, 1, False)])
 def test_multi_source_reach_matches_levelwise_oracle(nsrc, max_hops, include):
     """variable-length reachability from many sources at once: levels of C<!R,replace> = F*A and R = R u F in frontier
