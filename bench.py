@@ -132,6 +132,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads (and therefore the first-touch placement of its pinned host buffers) to the NUMA node its GPU
+    hangs off: with 8 ranks each streaming ~1 GB per step to the host, buffers on the far socket halve the D2H rate."""
+    try:
+        out = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], text=True).strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def pick_sources(deg, nbatches, nsrc, seed, rank):
     """Seeded batches of distinct source vertices with non-zero out-degree."""
     rng = np.random.default_rng(seed * 1000003 + rank)
@@ -149,50 +173,61 @@ def cpu_chain(orc, A, src, hops):
     return F, flops
 
 
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def workload_name(a):
+    return f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}"
+
+
 def run_reference(a):
     """The reference's CPU implementation of the path.  SuiteSparse:GraphBLAS is not vendored under /root/reference and
-    cannot be built here (cmake + generated code), so this arm times the oracle port (kind="port") with every host
-    thread OpenMP gives it.  Each step = a bounded sample (--cpu-sources sources) of the b200 arm's workload."""
+    cannot be built here (cmake + generated code), so this arm times the oracle port (kind="port"): row-task Gustavson with
+    thread-persistent bitmap workspaces on every host thread (oracle/grb_oracle.c: orc_chain), the whole chain in C.
+    Each step = one batch of the b200 arm's workload -- the same --sources per step when the run then fits in ~4 minutes
+    (a 64-source probe decides), else the largest multiple of the thread count that does."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle as orc
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # torchrun pins OMP_NUM_THREADS=1 per rank; this arm runs on rank 0 alone and is entitled to every host core
-        orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    cores = host_threads()
+    orc.lib().orc_set_num_threads(cores)       # torchrun pins OMP_NUM_THREADS=1 per rank; this arm owns the host
     t0 = time.time()
     A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
     gen_s = time.time() - t0
     deg = np.diff(A.p)
-    cores = orc.num_threads()
     S = a.cpu_sources
-    if S <= 0:  # calibrate: one untimed chain with one source per thread, then size a step to ~5 s of CPU work
-        probe = pick_sources(deg, 1, max(8, cores), a.seed + 17, 0)[0]
+    if S <= 0:
+        probe = pick_sources(deg, 2, min(64, a.sources), a.seed + 17, 0)
+        orc.chain(A, probe[0], a.hops, keep=False)                   # allocates the per-thread workspaces
         t0 = time.perf_counter()
-        cpu_chain(orc, A, probe, a.hops)
-        per_src = (time.perf_counter() - t0) / len(probe)       # wall seconds per source with every thread busy
-        # one source per thread keeps the OpenMP team busy; then bound the whole run (warm-up + K steps) to ~150 s
-        S = int(min(256, max(8, min(max(cores, round(5.0 / max(per_src, 1e-6))),
-                                   round(150.0 / ((a.steps + a.warmup) * max(per_src, 1e-6)))))))
-    a.cpu_sources = S
-    batches = pick_sources(deg, a.steps + a.warmup, a.cpu_sources, a.seed, 0)
+        orc.chain(A, probe[1], a.hops, keep=False)
+        per_src = (time.perf_counter() - t0) / len(probe[1])
+        budget = 240.0 / max(1, a.steps + a.warmup)
+        S = a.sources if per_src * a.sources <= budget else max(cores, int(budget / per_src) // cores * cores)
+        S = min(S, a.sources)
+    batches = pick_sources(deg, a.steps + a.warmup, S, a.seed, 0)
     for b in batches[:a.warmup]:
-        cpu_chain(orc, A, b, a.hops)
-    flops, t = 0, 0.0
+        orc.chain(A, b, a.hops, keep=False)
+    flops, t, busy = 0, 0.0, []
     for b in batches[a.warmup:]:
         t0 = time.perf_counter()
-        _, fl = cpu_chain(orc, A, b, a.hops)
+        _, fl, _, bz = orc.chain(A, b, a.hops, keep=False)
         t += time.perf_counter() - t0
         flops += fl
+        busy.append(bz)
     teps = flops / t
-    sample = f"{a.hops}-hop chain, {a.cpu_sources} sources/step, RMAT-{a.scale} ef{a.edge_factor}, {a.steps} steps"
+    sample = f"{a.hops}-hop chain, {S} sources/step, RMAT-{a.scale} ef{a.edge_factor}, {a.steps} steps"
     print(json.dumps({
         "impl": "reference", "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": teps,
         "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
-        "config": {"workload": f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}",
-                   "sources_per_step": a.cpu_sources, "graph_build_s": round(gen_s, 1)},
-        "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(a), "n": A.nrows, "nnz_A": A.nnz, "sources_per_gpu_per_step": S},
+        "graph_build_s": round(gen_s, 1), "result_format": "CSR (sorted rows, the form the reference's iterator walks)",
+        "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
+                         "threads_busy_fraction": float(np.mean(busy)) if busy else None,
+                         "algorithm": "Gustavson, one frontier row per task (LPT order), per-thread persistent n-bit accumulators"},
         "e2e": {"value": teps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -220,6 +255,8 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    all_cpus = set(os.sched_getaffinity(0))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = lib()
@@ -327,9 +364,16 @@ def run_b200(a):
     def e2e_step(i, fmt):
         """host sources in -> host result out through the public API; returns (flops, nvals, d2h bytes, format)"""
         nonlocal out_j
-        if fmt == "bitmap_sliced":             # dense result known from the warm-up: sliced, overlapped hand-off
-            fl = fb.traverse_to_host(src_pin[i], A, a.hops, bm_pin, a.e2e_subbatches or None)   # H2D of the sources inside its builds
+        if fmt == "bitmap_sliced":             # dense result known from the warm-up: sliced, overlapped hand-off, ONE C call
+            fl, _, _ = fb.traverse_batch(src_pin[i], [A] * a.hops, fb.OUT_BITMAP, out_bitmap=bm_pin)   # H2D of the sources inside
             return fl, 0, bm_pin.nbytes, "bitmap"
+        if fmt == "csr_c":                     # B200_traverse_batch with the CSR hand-off
+            try:
+                fl, nv, _ = fb.traverse_batch(src_pin[i], [A] * a.hops, fb.OUT_CSR, out_p=out_p, out_j=out_j)
+            except BufferError:
+                out_j = torch.empty(int(len(out_j) * 1.5) + 1024, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                fl, nv, _ = fb.traverse_batch(src_pin[i], [A] * a.hops, fb.OUT_CSR, out_p=out_p, out_j=out_j)
+            return fl, nv, 8 * (a.sources + 1) + 4 * nv, "csr"
         F = Matrix(a.sources, n, bool)
         F.build(rows_pin, src_pin[i])          # H2D of the step's inputs inside GxB_Matrix_build_Scalar
         if fmt != "csr":
@@ -371,14 +415,14 @@ def run_b200(a):
         # Matrix.export_auto's rule decides the format on the first batch; a dense result then goes through the sliced call
         if e2e_fmt == "bitmap" or e2e_step(0, "auto")[3] == "bitmap":
             e2e_fmt = "bitmap_sliced"
-    e2e_ms, e2e_wall_ms, e2e_flops, e2e_nnz, e2e_d2h, e2e_kind = e2e_run(e2e_fmt, a.warmup, nb)
+    e2e_ms, e2e_wall_ms, e2e_flops, e2e_nnz, e2e_d2h, e2e_kind = e2e_run("csr_c" if e2e_fmt == "csr" else e2e_fmt, a.warmup, nb)
     # secondary: the same arm with a CSR hand-off (3 steps), so both interchange formats are on record
     # (N = 1 only: it pins a multi-GB host buffer per rank and is a side note, not a scaling measurement)
     csr_steps = min(a.steps, 3)
     if a.e2e_format == "csr":
         csr_ms, csr_flops, csr_d2h = e2e_ms, e2e_flops, e2e_d2h
     elif world == 1:
-        csr_ms, _, csr_flops, _, csr_d2h, _ = e2e_run("csr", a.warmup, a.warmup + csr_steps)
+        csr_ms, _, csr_flops, _, csr_d2h, _ = e2e_run("csr_c", a.warmup, a.warmup + csr_steps)
     else:
         csr_ms, csr_flops, csr_d2h, csr_steps = 0.0, 0, 0, 0
     if a.e2e_format == "csr":
@@ -463,23 +507,30 @@ def run_b200(a):
         try:
             import oracle as orc
             from oracle import CSR
+            os.sched_setaffinity(0, all_cpus)
+            cores = host_threads()
+            orc.lib().orc_set_num_threads(cores)
             pj = np.empty(nnzA, np.uint32)
             fb.check(L.B200_Matrix_export_CSR(A.h, p.ctypes.data, pj.ctypes.data, None, 0))
             Ao = CSR(n, n, p.astype(np.int64), pj)
-            ncpu = a.cpu_sources if a.cpu_sources > 0 else min(a.sources, max(8, orc.num_threads()))
+            ncpu = a.cpu_sources if a.cpu_sources > 0 else a.sources
             b = batches[a.warmup][:ncpu]
+            orc.chain(Ao, b[: min(len(b), cores)], a.hops, keep=False)          # untimed: allocates the per-thread workspaces
             t0 = time.perf_counter()
-            Fo, cfl = cpu_chain(orc, Ao, b, a.hops)
+            _, cfl, cdg, busy = orc.chain(Ao, b, a.hops, keep=False)
             ct = time.perf_counter() - t0
-            # parity spot-check at FULL size: the same sources through the GPU path must give identical rows
+            # parity at FULL size, every row of the batch: the same sources through the GPU path, compared by digest
+            # (nvals, sum mix(row, col), sum mix(row, col, CSR position)) -- B200_Matrix_digest vs orc_digest
             G = Matrix(len(b), n, bool)
             G.build(np.arange(len(b), dtype=np.uint64), b)
-            chain(G)
-            gp, gj, _ = G.export_csr()
-            parity = bool(np.array_equal(gp, Fo.p) and np.array_equal(gj, Fo.j))
-            cpu = {"value": cfl / ct, "unit": "edges/s", "cores": orc.num_threads(), "kind": "port",
-                   "sample": f"{a.hops}-hop chain for the first {len(b)} sources of the first timed batch ({cfl} flops, {ct:.1f} s)",
-                   "full_size_parity_bit_exact": parity}
+            gfl = chain(G)
+            parity = bool(np.array_equal(G.digest(), cdg) and gfl == cfl)
+            del G
+            cpu = {"value": cfl / ct, "unit": "edges/s", "cores": cores, "kind": "port",
+                   "sample": f"{a.hops}-hop chain for the {len(b)} sources of the first timed batch ({cfl} flops, {ct:.1f} s)",
+                   "threads_busy_fraction": busy,
+                   "algorithm": "Gustavson, one frontier row per task (LPT order), per-thread persistent n-bit accumulators",
+                   "full_size_parity_bit_exact": parity, "parity_rows": len(b), "result_digest": [int(x) for x in cdg]}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "error": repr(ex)}
 
@@ -489,17 +540,17 @@ def run_b200(a):
         "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": flops / (ms * 1e-3), "unit": "edges/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
-        "config": {"workload": f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}",
+        "config": {"workload": workload_name(a),
                    "n": n, "nnz_A": nnzA, "sources_per_gpu_per_step": a.sources, "parallelism": f"replicated A, sources sharded x{world}",
+                   "numa_node_bound": numa,
                    "l2_policy": "inputs larger than L2 (A col_idx %.2f GB) and a fresh random source batch every step" % (4 * nnzA / 1e9),
                    "bits_mode": a.bits_mode, "pull_mode": a.pull_mode, "setup_s": round(setup_s, 2)},
         "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz_out / a.steps,
         "e2e": {"value": e2e_flops / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": e2e_wall_ms / a.steps, "result_format": e2e_kind,
-                "api": ("falkordb_b200.traverse_to_host: per row slice (%d slices) " % (a.e2e_subbatches or -(-a.sources // 128)) if e2e_fmt == "bitmap_sliced" else "")
-                       + "GrB_Matrix_new + GxB_Matrix_build_Scalar (host sources) -> 3 x GrB_mxm -> "
-                       + ("B200_Matrix_export_bitmap_async + B200_Ticket_wait" if e2e_fmt == "bitmap_sliced" else
-                          "B200_Matrix_export_bitmap" if e2e_kind == "bitmap" else "B200_Matrix_export_CSR") + " (host result)",
+                "api": ("B200_traverse_batch (one C-ABI call per batch: host sources in, host result out; %s)"
+                        % ("packed bitmap, 128-row slices, D2H overlapped with the next slice's hops" if e2e_fmt == "bitmap_sliced"
+                           else "CSR hand-off" if e2e_kind == "csr" else "bitmap hand-off")),
                 "csr_handoff": ({"value": csr_flops / (csr_ms * 1e-3), "unit": "edges/s", "steps": csr_steps,
                                  "ms_per_step": csr_ms / csr_steps, "d2h_bytes_per_step": int(csr_d2h / csr_steps)}
                                 if csr_steps and csr_ms > 0 else None)},

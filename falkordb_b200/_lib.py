@@ -63,6 +63,11 @@ def lib():
         "GrB_Vector_setElement_UINT64": [P, U64, U64], "GrB_Vector_removeElement": [P, U64], "GrB_Vector_clear": [P],
         "GrB_Vector_wait": [P, C.c_int], "GrB_Vector_resize": [P, U64],
         "GxB_Vector_Iterator_attach": [P, P, P], "GxB_Vector_Iterator_seek": [P, U64], "GxB_Vector_Iterator_next": [P],
+        "GrB_Vector_setElement_FP64": [P, C.c_double, U64], "GrB_Vector_extractElement_FP64": [C.POINTER(C.c_double), P, U64],
+        "GrB_Vector_extractTuples_FP64": [P, P, C.POINTER(U64), P],
+        "GrB_Matrix_build_FP64": [P, P, P, P, U64, P], "GrB_Matrix_extractTuples_FP64": [P, P, P, C.POINTER(U64), P],
+        "LAGraph_Cached_AT": [P, C.c_char_p], "LAGraph_Cached_OutDegree": [P, C.c_char_p],
+        "LAGr_PageRank": [C.POINTER(P), C.POINTER(C.c_int), P, C.c_float, C.c_float, C.c_int, C.c_char_p],
         "GrB_vxm": [P, P, P, P, P, P, P], "GrB_mxv": [P, P, P, P, P, P, P],
         "GxB_Iterator_new": [C.POINTER(P)], "GxB_Iterator_free": [C.POINTER(P)], "GxB_rowIterator_attach": [P, P, P],
         "GxB_rowIterator_seekRow": [P, U64], "GxB_rowIterator_nextRow": [P], "GxB_rowIterator_nextCol": [P],

@@ -78,7 +78,7 @@ inline cudaStream_t stream() { return ctx().stream; }
 
 // ---- optional per-kernel timing (CUDA events on the launch stream; B200_set_option("timing",1)) ----
 enum TimedId { TK_BITS_PULL = 0, TK_BITS_PULL_LONG, TK_BITS_PUSH, TK_HEAVY_ACC, TK_SMALL_ROWS, TK_BITS_FILL, TK_BITS_COUNT,
-               TK_BITMAP_EXPAND, TK_BFS_EXPAND, TK_UNION, TK_FILTER, TK_COUNT_ };
+               TK_BITMAP_EXPAND, TK_BFS_EXPAND, TK_UNION, TK_FILTER, TK_MXV, TK_MASKED, TK_TRANSPOSE, TK_COUNT_ };
 const char *timed_name(int id);
 void timed_begin(int id);
 void timed_end(int id, u64 algorithmic_bytes) noexcept;

@@ -30,20 +30,21 @@ struct GB_Global_opaque { int x; };
 struct GB_Descriptor_opaque { bool t0, t1, comp, structure, replace; };
 struct GB_Scalar_opaque { int type; bool has; uint64_t val; };   // allocated with the C++ allocator: 24 bytes, short-lived
 
-enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3, T_UINT32 = 4 };
-enum { OP_ANY_BOOL = 1, OP_SECOND_UINT64 = 2, OP_ANY_UINT64 = 3 };
+enum { T_BOOL = 1, T_UINT64 = 2, T_INT64 = 3, T_UINT32 = 4, T_FP64 = 5 };   // FP64 values travel as IEEE-754 bit patterns in the u64 arrays
+enum { OP_ANY_BOOL = 1, OP_SECOND_UINT64 = 2, OP_ANY_UINT64 = 3, OP_PLUS_FP64 = 4 };
+enum { SR_ANY_PAIR = 1, SR_PLUS_TIMES_FP64 = 2, SR_PLUS_SECOND_FP64 = 3 };
 
 static GB_Type_opaque t_bool = {T_BOOL, 1, "bool"}, t_u64 = {T_UINT64, 8, "uint64_t"}, t_i64 = {T_INT64, 8, "int64_t"},
-                      t_u32 = {T_UINT32, 4, "uint32_t"};
-static GB_Semiring_opaque s_any_pair = {1};
-static GB_BinaryOp_opaque b_any_bool = {OP_ANY_BOOL}, b_second_u64 = {OP_SECOND_UINT64}, b_any_u64 = {OP_ANY_UINT64};
+                      t_u32 = {T_UINT32, 4, "uint32_t"}, t_f64 = {T_FP64, 8, "double"};
+static GB_Semiring_opaque s_any_pair = {SR_ANY_PAIR}, s_plus_times_f64 = {SR_PLUS_TIMES_FP64}, s_plus_second_f64 = {SR_PLUS_SECOND_FP64};
+static GB_BinaryOp_opaque b_any_bool = {OP_ANY_BOOL}, b_second_u64 = {OP_SECOND_UINT64}, b_any_u64 = {OP_ANY_UINT64}, b_plus_f64 = {OP_PLUS_FP64};
 static GB_UnaryOp_opaque u_one_bool = {1};
 static GB_Global_opaque g_global = {0};
 
 extern "C" {
-GrB_Type GrB_BOOL = &t_bool, GrB_UINT64 = &t_u64, GrB_INT64 = &t_i64, GrB_UINT32 = &t_u32;
-GrB_Semiring GxB_ANY_PAIR_BOOL = &s_any_pair;
-GrB_BinaryOp GxB_ANY_BOOL = &b_any_bool, GrB_SECOND_UINT64 = &b_second_u64, GxB_ANY_UINT64 = &b_any_u64;
+GrB_Type GrB_BOOL = &t_bool, GrB_UINT64 = &t_u64, GrB_INT64 = &t_i64, GrB_UINT32 = &t_u32, GrB_FP64 = &t_f64;
+GrB_Semiring GxB_ANY_PAIR_BOOL = &s_any_pair, GrB_PLUS_TIMES_SEMIRING_FP64 = &s_plus_times_f64, GxB_PLUS_SECOND_FP64 = &s_plus_second_f64;
+GrB_BinaryOp GxB_ANY_BOOL = &b_any_bool, GrB_SECOND_UINT64 = &b_second_u64, GxB_ANY_UINT64 = &b_any_u64, GrB_PLUS_FP64 = &b_plus_f64;
 GrB_UnaryOp GxB_ONE_BOOL = &u_one_bool;
 const GrB_Global GrB_GLOBAL = &g_global;
 }
@@ -253,7 +254,7 @@ static void set_dev(GrB_Matrix A, DevCSR &&d) {
     if (!A->valued()) A->dev.x.release();
     else if (!A->dev.has_values()) {
         A->dev.x.alloc(A->dev.nnz);
-        fill_u64(A->dev.x.ptr, 1, A->dev.nnz); // typecast of `true`
+        fill_u64(A->dev.x.ptr, A->type == T_FP64 ? 0x3FF0000000000000ULL : 1ULL, A->dev.nnz); // typecast of `true` (1 / 1.0)
     }
     A->dev_valid = true;
     A->host_valid = false;
@@ -742,7 +743,7 @@ GrB_Info GrB_Matrix_get_INT32(GrB_Matrix A, int32_t *value, int field) {
 
 GrB_Info GxB_Matrix_type(GrB_Type *type, GrB_Matrix A) {
     CHECK_PTR(type); CHECK_MAT(A);
-    *type = A->type == T_BOOL ? GrB_BOOL : (A->type == T_UINT64 ? GrB_UINT64 : GrB_INT64);
+    *type = A->type == T_BOOL ? GrB_BOOL : A->type == T_UINT64 ? GrB_UINT64 : A->type == T_FP64 ? GrB_FP64 : GrB_INT64;
     return GrB_SUCCESS;
 }
 GrB_Info GxB_Matrix_iso(bool *iso, GrB_Matrix A) { CHECK_PTR(iso); CHECK_MAT(A); *iso = (A->type == T_BOOL); return GrB_SUCCESS; }
@@ -984,6 +985,27 @@ GrB_Info GrB_Matrix_build_BOOL(GrB_Matrix C, const GrB_Index *I, const GrB_Index
     uvec<u64> V(nvals);
     for (u64 k = 0; k < nvals; k++) V[k] = X[k] ? 1 : 0;
     return build_common(C, I, J, V.data(), nvals);
+}
+
+// FP64 matrices (weighted paths: GrB_PLUS_TIMES_SEMIRING_FP64): values are stored as their IEEE-754 bit patterns
+GrB_Info GrB_Matrix_build_FP64(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const double *X, GrB_Index nvals, GrB_BinaryOp dup) {
+    (void)dup;   // duplicates: the first tuple of a run wins (GxB_ANY-like, deterministic); the reference builds from distinct edges
+    if (nvals) CHECK_PTR(X);
+    CHECK_MAT(C);
+    if (C->type != T_FP64) { tl_error = "build_FP64 into a non-FP64 matrix"; return GrB_DOMAIN_MISMATCH; }
+    static_assert(sizeof(double) == sizeof(u64), "FP64 travels in the u64 value arrays");
+    return build_common(C, I, J, reinterpret_cast<const u64 *>(X), nvals);
+}
+GrB_Info GrB_Matrix_extractTuples_FP64(GrB_Index *I, GrB_Index *J, double *X, GrB_Index *nvals, GrB_Matrix A) {
+    CHECK_MAT(A);
+    if (A->type != T_FP64) {     // typecast from the integer / pattern types
+        CHECK_PTR(nvals);
+        uvec<u64> V(X ? *nvals : 0);
+        GrB_Info r = extract_tuples(I, J, X ? V.data() : nullptr, 2, nvals, A);
+        if (r == GrB_SUCCESS && X) for (u64 k = 0; k < *nvals; k++) X[k] = A->type == T_INT64 ? (double)(i64)V[k] : (double)V[k];
+        return r;
+    }
+    return extract_tuples(I, J, X, 2, nvals, A);      // the stored bit patterns ARE the doubles
 }
 
 // ---------------------------------------------------------------------------------------------- mxm
@@ -1464,6 +1486,92 @@ GrB_Index GxB_Vector_Iterator_getIndex(GxB_Iterator it) {
     return it->V->full ? it->k : it->V->idx[it->k];
 }
 
+// ---- FP64 vectors (values as bit patterns in `val` / as doubles in a full payload) ----
+static inline i64 f64_bits(double x) { i64 b; memcpy(&b, &x, 8); return b; }
+static inline double bits_f64(i64 b) { double x; memcpy(&x, &b, 8); return x; }
+static double vec_value_f64(GrB_Vector v, u64 k) {       // k-th stored entry as a double (typecast from the integer types)
+    if (v->full) {
+        if (v->type == T_FP64) return ((const double *)v->fx)[k];
+        return v->type == T_INT64 ? (double)(i64)vec_at(v, k) : (double)vec_at(v, k);
+    }
+    return v->type == T_FP64 ? bits_f64(v->val[k]) : (double)v->val[k];
+}
+GrB_Info GrB_Vector_setElement_FP64(GrB_Vector v, double x, GrB_Index i) {
+    CHECK_PTR(v);
+    if (v->type != T_FP64) { tl_error = "setElement_FP64 into a non-FP64 vector"; return GrB_DOMAIN_MISMATCH; }
+    return vec_set(v, f64_bits(x), i);
+}
+GrB_Info GrB_Vector_extractElement_FP64(double *x, GrB_Vector v, GrB_Index i) {
+    CHECK_PTR(x); CHECK_PTR(v);
+    if (i >= v->n) return GrB_INVALID_INDEX;
+    if (v->full) { *x = vec_value_f64(v, i); return GrB_SUCCESS; }
+    auto it = std::lower_bound(v->idx.begin(), v->idx.end(), i);
+    if (it == v->idx.end() || *it != i) return GrB_NO_VALUE;
+    *x = vec_value_f64(v, it - v->idx.begin());
+    return GrB_SUCCESS;
+}
+// the call algo.pageRank reads its result through (algo_procedures.rs: extract_vector_f64)
+GrB_Info GrB_Vector_extractTuples_FP64(GrB_Index *I, double *X, GrB_Index *nvals, GrB_Vector v) {
+    CHECK_PTR(nvals); CHECK_PTR(v);
+    const u64 nv = v->full ? v->n : v->idx.size();
+    if (*nvals < nv) return GrB_INSUFFICIENT_SPACE;
+    for (u64 k = 0; k < nv; k++) { if (I) I[k] = v->full ? k : v->idx[k]; if (X) X[k] = vec_value_f64(v, k); }
+    *nvals = nv;
+    return GrB_SUCCESS;
+}
+
+// w = A*u (mxv) or u*A (vxm) over PLUS_TIMES_FP64 / PLUS_SECOND_FP64: dense device vectors, sparse semantics kept through a
+// presence byte per entry (w(i) exists iff some A(i,k) meets an existing u(k)).  accum: NULL or GrB_PLUS_FP64; no mask.
+static GrB_Info mxv_fp64_entry(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u, GrB_Matrix A,
+                               GrB_Descriptor desc, bool is_mxv) {
+    CHECK_PTR(w); CHECK_PTR(u); CHECK_MAT(A);
+    if (mask) { tl_error = "FP64 mxv/vxm: masks are not on this path"; return GrB_NOT_IMPLEMENTED; }
+    if (accum && accum != GrB_PLUS_FP64) { tl_error = "FP64 mxv/vxm: accum must be NULL or GrB_PLUS_FP64"; return GrB_NOT_IMPLEMENTED; }
+    if (w->type != T_FP64) { tl_error = "FP64 mxv/vxm: the output vector must be GrB_FP64"; return GrB_DOMAIN_MISMATCH; }
+    const bool times = semiring->code == SR_PLUS_TIMES_FP64;
+    if (times && A->type != T_FP64) { tl_error = "PLUS_TIMES_FP64 needs a GrB_FP64 matrix"; return GrB_DOMAIN_MISMATCH; }
+    Desc d = get_desc(desc);
+    const bool a_transposed = is_mxv ? d.t0 : !d.t1;          // rows of the operand we stream = output indices
+    const u64 outer = a_transposed ? A->ncols : A->nrows, inner = a_transposed ? A->nrows : A->ncols;
+    if (u->n != inner || w->n != outer) return GrB_DIMENSION_MISMATCH;
+    return guarded([&]() {
+        GpuLock g;
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        const DevCSR *Ad = &A->dev;
+        DevCSR T;
+        if (a_transposed) {
+            if (times) { transpose_csr(A->dev, T, true); Ad = &T; }      // valued transpose (the cached mirror is pattern-only)
+            else { ensure_devT(A); Ad = &A->devT; }
+        }
+        // u -> dense
+        uvec<double> hx(inner, 0.0);
+        uvec<unsigned char> hp(inner, 0);
+        const u64 unv = u->full ? u->n : u->idx.size();
+        for (u64 k = 0; k < unv; k++) { const u64 i = u->full ? k : u->idx[k]; hx[i] = vec_value_f64(u, k); hp[i] = 1; }
+        DevBuf<double> dx(inner ? inner : 1), dy(outer ? outer : 1);
+        DevBuf<unsigned char> dp(inner ? inner : 1), dyp(outer ? outer : 1);
+        h2d(dx.ptr, hx.data(), inner); h2d(dp.ptr, hp.data(), inner);
+        uvec<double> hy(outer, 0.0);
+        uvec<unsigned char> hw(outer, 0);
+        if (accum) {
+            const u64 wnv = w->full ? w->n : w->idx.size();
+            for (u64 k = 0; k < wnv; k++) { const u64 i = w->full ? k : w->idx[k]; hy[i] = vec_value_f64(w, k); hw[i] = 1; }
+            h2d(dy.ptr, hy.data(), outer);
+        }
+        mxv_fp64(*Ad, times, dx.ptr, unv == inner ? nullptr : dp.ptr, dy.ptr, dyp.ptr, 0.0, accum != nullptr);
+        uvec<unsigned char> hyp(outer, 0);
+        d2h(hy.data(), dy.ptr, outer); d2h(hyp.data(), dyp.ptr, outer);
+        sync_stream();
+        vec_make_sparse(w);
+        w->idx.clear(); w->val.clear();
+        for (u64 i = 0; i < outer; i++)
+            if (hyp[i] || (accum && hw[i])) { w->idx.push_back(i); w->val.push_back(f64_bits(hy[i])); }
+        return GrB_SUCCESS;
+    });
+}
+
 // one frontier step w<mask> = u*A (vxm) or A*u (mxv) over ANY_PAIR, run as a 1-row mxm
 static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u,
                               GrB_Matrix A, GrB_Descriptor desc, bool is_mxv) {
@@ -1517,10 +1625,14 @@ static GrB_Info frontier_step(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum,
 }
 GrB_Info GrB_vxm(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u, GrB_Matrix A,
                  GrB_Descriptor desc) {
+    CHECK_PTR(semiring);
+    if (semiring->code != SR_ANY_PAIR) return mxv_fp64_entry(w, mask, accum, semiring, u, A, desc, false);
     return frontier_step(w, mask, accum, semiring, u, A, desc, false);
 }
 GrB_Info GrB_mxv(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Vector u,
                  GrB_Descriptor desc) {
+    CHECK_PTR(semiring);
+    if (semiring->code != SR_ANY_PAIR) return mxv_fp64_entry(w, mask, accum, semiring, u, A, desc, true);
     return frontier_step(w, mask, accum, semiring, u, A, desc, true);
 }
 
@@ -1551,6 +1663,47 @@ int LAGraph_Delete(LAGraph_Graph *G, char *msg) {
 }
 
 extern "C" GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose);
+// LAGraph's cached properties the reference asks for before PageRank (algo_procedures.rs:748-749): the transpose mirror lives
+// inside the matrix handle here, out-degrees are read off A's row pointers -- both calls only make sure the mirror exists.
+int LAGraph_Cached_AT(LAGraph_Graph G, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G || !G->A) return GrB_NULL_POINTER;
+    return B200_Matrix_prepare(G->A, 1);
+}
+int LAGraph_Cached_OutDegree(LAGraph_Graph G, char *msg) {
+    if (msg) msg[0] = 0;
+    return (!G || !G->A) ? GrB_NULL_POINTER : GrB_SUCCESS;
+}
+// LAGr_PageRank (lagraph_bindings.rs:549-558; call site algo_procedures.rs:744-752).  Computed in FP64 on the device (algo.cu);
+// centrality is a full GrB_FP64 vector, read by the reference through GrB_Vector_extractTuples_FP64.
+int LAGr_PageRank(GrB_Vector *centrality, int *iters, LAGraph_Graph G, float damping, float tol, int itermax, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G || !G->A || !centrality || !iters) return GrB_NULL_POINTER;
+    GrB_Matrix A = G->A;
+    if (A->magic != MAGIC) return GrB_INVALID_OBJECT;
+    if (A->nrows != A->ncols) return GrB_DIMENSION_MISMATCH;
+    GrB_Info info = guarded([&]() {
+        GpuLock g;
+        MultiLock lk{A};
+        ensure_init();
+        ensure_devT(A);
+        const u64 n = A->nrows;
+        DevBuf<double> r(n ? n : 1);
+        *iters = pagerank(A->dev, A->devT, (double)damping, (double)tol, itermax, r.ptr);
+        std::unique_ptr<GB_Vector_opaque> v(new GB_Vector_opaque());
+        v->type = T_FP64; v->n = n; v->full = true; v->fbytes = n * sizeof(double);
+        if (n) {
+            v->fx = g_user_malloc(v->fbytes);
+            if (!v->fx) throw std::bad_alloc();
+            CUDA_TRY(cudaMemcpyAsync(v->fx, r.ptr, v->fbytes, cudaMemcpyDeviceToHost, stream()));
+            sync_stream();
+        }
+        *centrality = v.release();
+        return GrB_SUCCESS;
+    });
+    if (info && msg) snprintf(msg, 256, "%s", tl_error.c_str());
+    return info;
+}
 // Single-GPU BFS.  With the transpose mirror in place (B200_Matrix_prepare(A, 1), or any earlier pull) the direction-optimising
 // engine runs (bfs_do.cu); without it -- one BFS on a fresh matrix, where building A' would cost more than the search -- the
 // top-down kernel of bfs.cu.  Both give level and minimum-id parent.  dest >= 0 stops once that vertex is reached.
@@ -2187,7 +2340,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
 // because the caller releases them with its own allocator (vector.rs:171-172).
 // ====================================================================================================================
 static size_t type_size(int code) { return code == T_BOOL ? 1 : code == T_UINT32 ? 4 : 8; }
-static GrB_Type type_of(int code) { return code == T_BOOL ? GrB_BOOL : code == T_UINT32 ? GrB_UINT32 : code == T_INT64 ? GrB_INT64 : GrB_UINT64; }
+static GrB_Type type_of(int code) { return code == T_BOOL ? GrB_BOOL : code == T_UINT32 ? GrB_UINT32 : code == T_INT64 ? GrB_INT64 : code == T_FP64 ? GrB_FP64 : GrB_UINT64; }
 
 // replace the content of a container vector with a full (dense) array copied from `src`
 static void vec_set_full(GrB_Vector v, int type, const void *src, u64 n) {

@@ -99,6 +99,11 @@ void bfs_build_degrees(const DevCSR &Aloc, u64 n, u64 lo, u64 hi, BfsComm *comm,
 void bfs_do(const DevCSR &Aloc, const DevCSR &ATloc, u64 n, u64 lo, u64 hi, const u32 *deg_all, u64 total_edges, BfsComm *comm,
             u64 src, i64 max_level, i64 dest, i64 *d_level, i64 *d_parent, BfsInfo *info);
 
+// algo.cu : FP64 mxv (PLUS_TIMES / PLUS_SECOND) and PageRank
+void mxv_fp64(const DevCSR &A, bool use_values, const double *x, const unsigned char *present, double *y, unsigned char *ypresent,
+              double init, bool accum);
+int pagerank(const DevCSR &A, const DevCSR &AT, double damping, double tol, int itermax, double *r);
+
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
 
 // hypersparse host form <-> dense device rowptr (ewise.cu)

@@ -155,7 +155,7 @@ static u64 g_n[TK_COUNT_], g_bytes[TK_COUNT_];
 
 const char *timed_name(int id) {
     static const char *names[] = {"bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "small_rows", "bits_fill",
-                                  "bits_count", "bitmap_expand", "bfs_expand", "union", "filter"};
+                                  "bits_count", "bitmap_expand", "bfs_expand", "union", "filter", "mxv_fp64", "spgemm_masked", "transpose"};
     return (id >= 0 && id < TK_COUNT_) ? names[id] : "?";
 }
 static cudaEvent_t get_event() {

@@ -87,9 +87,11 @@ typedef struct GB_Global_opaque *GrB_Global;         /* mod.rs:370 */
 typedef struct GB_Iterator_opaque *GxB_Iterator;     /* mod.rs:383 */
 
 /* exported data symbols (mod.rs:430-544, 721, 1301, 1547, 1643, 3001, 6852) */
-extern GrB_Type GrB_BOOL, GrB_UINT64, GrB_INT64;
+extern GrB_Type GrB_BOOL, GrB_UINT64, GrB_INT64, GrB_FP64;
 extern GrB_Semiring GxB_ANY_PAIR_BOOL;
-extern GrB_BinaryOp GxB_ANY_BOOL, GrB_SECOND_UINT64, GxB_ANY_UINT64;
+/* the weighted / ranking corner of the path (north_star: "a stated fp tolerance for PLUS_TIMES weighted paths"): FP64 mxv / vxm */
+extern GrB_Semiring GrB_PLUS_TIMES_SEMIRING_FP64, GxB_PLUS_SECOND_FP64;
+extern GrB_BinaryOp GxB_ANY_BOOL, GrB_SECOND_UINT64, GxB_ANY_UINT64, GrB_PLUS_FP64;
 extern GrB_UnaryOp GxB_ONE_BOOL;
 extern const GrB_Global GrB_GLOBAL;
 /* the 31 predefined descriptors: T0/T1 = transpose input 0/1, C = complement mask,
@@ -181,7 +183,13 @@ GrB_Info GrB_Vector_extractElement_INT64(int64_t *x, GrB_Vector v, GrB_Index i);
 GrB_Info GrB_Vector_extractElement_BOOL(bool *x, GrB_Vector v, GrB_Index i);
 GrB_Info GrB_Vector_extractTuples_INT64(GrB_Index *I, int64_t *X, GrB_Index *nvals, GrB_Vector v);
 GrB_Info GrB_Vector_extractTuples_BOOL(GrB_Index *I, bool *X, GrB_Index *nvals, GrB_Vector v);
-/* w<mask> = u*A / A*u over ANY_PAIR: one frontier step (mod.rs:11173, 11184) */
+GrB_Info GrB_Vector_setElement_FP64(GrB_Vector w, double x, GrB_Index i);
+GrB_Info GrB_Vector_extractElement_FP64(double *x, GrB_Vector v, GrB_Index i);
+GrB_Info GrB_Vector_extractTuples_FP64(GrB_Index *I, double *X, GrB_Index *nvals, GrB_Vector v);  /* algo_procedures.rs: extract_vector_f64 */
+GrB_Info GrB_Matrix_build_FP64(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const double *X, GrB_Index nvals, GrB_BinaryOp dup);
+GrB_Info GrB_Matrix_extractTuples_FP64(GrB_Index *I, GrB_Index *J, double *X, GrB_Index *nvals, GrB_Matrix A);
+/* w<mask> = u*A / A*u: one frontier step over ANY_PAIR (mod.rs:11173, 11184); over GrB_PLUS_TIMES_SEMIRING_FP64 / GxB_PLUS_SECOND_FP64
+ * the FP64 mxv (no mask; accum NULL or GrB_PLUS_FP64; fixed summation order, rel 1e-12 against the sequential oracle) */
 GrB_Info GrB_vxm(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Vector u, GrB_Matrix A,
                  GrB_Descriptor desc);
 GrB_Info GrB_mxv(GrB_Vector w, GrB_Vector mask, GrB_BinaryOp accum, GrB_Semiring semiring, GrB_Matrix A, GrB_Vector u,
@@ -261,6 +269,10 @@ int LAGraph_New(LAGraph_Graph *G, GrB_Matrix *A, LAGraph_Kind kind, char *msg);
 int LAGraph_Delete(LAGraph_Graph *G, char *msg);
 int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGraph_Graph G, GrB_Index src,
                                      int64_t max_level, int64_t dest, bool many_expected, char *msg);
+/* algo.pageRank (algo_procedures.rs:744-752; lagraph_bindings.rs:549-558): FP64 on the device, centrality = full GrB_FP64 vector */
+int LAGraph_Cached_AT(LAGraph_Graph G, char *msg);
+int LAGraph_Cached_OutDegree(LAGraph_Graph G, char *msg);
+int LAGr_PageRank(GrB_Vector *centrality, int *iters, LAGraph_Graph G, float damping, float tol, int itermax, char *msg);
 
 /* ---- B200 extensions ---- */
 #define B200_LOC_HOST 0

@@ -531,6 +531,73 @@ int orc_bfs(const orc_csr *A, int64_t src, int64_t max_level, int64_t *level, in
     return 0;
 }
 
+/* ------------------------------------------------------------------ PLUS_TIMES / PLUS_SECOND, FP64
+ * y = A*x over GrB_PLUS_TIMES_SEMIRING_FP64 (A valued: x_bits holds IEEE doubles) or GxB_PLUS_SECOND_FP64 (A's values are not
+ * read: "second" returns x(k)) -- the mxv LAGraph's PageRank is built on (LAGr_PageRank.c: r += AT*w over plus_second; PreJIT
+ * evidence build/graphblas/PreJIT/GB_jit__AxB_saxpy3__e3f4410b0b2b0b65.c; call site algo_procedures.rs:744).  Dense x and y;
+ * `present` (optional, one byte per entry of x) marks which entries of x exist, ypresent (optional) receives which entries of y
+ * do: y(i) exists iff some A(i,k) meets an existing x(k).  Rows are summed in ascending column order (sequential, one
+ * rounding per term); the CUDA kernel sums the same terms in a fixed tree order, so the two agree to ~1e-15 relative per term --
+ * SURVEY 8(d) states rel 1e-12. */
+void orc_mxv_fp64(const orc_csr *A, int use_values, const double *x, const unsigned char *present, double *y,
+                  unsigned char *ypresent) {
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < A->nrows; i++) {
+        double acc = 0.0;
+        int any = 0;
+        for (int64_t q = A->p[i]; q < A->p[i + 1]; q++) {
+            const uint32_t k = A->j[q];
+            if (present && !present[k]) continue;
+            double a = 1.0;
+            if (use_values) memcpy(&a, &A->x[q], sizeof(double));
+            acc += use_values ? a * x[k] : x[k];
+            any = 1;
+        }
+        y[i] = acc;
+        if (ypresent) ypresent[i] = (unsigned char)any;
+    }
+}
+
+/* ------------------------------------------------------------------ PageRank
+ * LAGr_PageRank as the reference calls it (algo_procedures.rs:744-752: damping 0.85, tol 1e-4, itermax 100), restated from
+ * LAGraph v1.x src/algorithm/LAGr_PageRank.c (third-party, not vendored: graphblas.sh:73):
+ *     d = max(out_degree / damping, 1 / damping);  r = 1/n;  sink = vertices without out-edges
+ *     repeat (while iters < itermax and rdiff > tol):
+ *         teleport = (1 - damping) / n  +  (damping / n) * sum of r over the sinks
+ *         t <- r;  w = t ./ d;  r = teleport + AT * w  (plus_second);  rdiff = sum |t - r|
+ * LAGraph runs this in FP32; this restatement and the CUDA path run it in FP64 (the reference reads the result through
+ * extract_vector_f64, and its own tests only need sum = 1 within 1e-4: tests/flow/test_pagerank.py:94-96).
+ * AT = transpose of the adjacency pattern (rows = in-neighbours).  Returns the iteration count. */
+int orc_pagerank(const orc_csr *AT, const int64_t *out_degree, double damping, double tol, int itermax, double *r) {
+    const int64_t n = AT->nrows;
+    if (n == 0) return 0;
+    double *t = xmalloc(sizeof(double) * (size_t)n), *w = xmalloc(sizeof(double) * (size_t)n), *d = xmalloc(sizeof(double) * (size_t)n);
+    const double dmin = 1.0 / damping, scaled = (1.0 - damping) / (double)n, damping_over_n = damping / (double)n;
+    for (int64_t i = 0; i < n; i++) {
+        const double di = (double)out_degree[i] / damping;
+        d[i] = di > dmin ? di : dmin;
+        r[i] = 1.0 / (double)n;
+    }
+    double rdiff = 1.0;
+    int iters = 0;
+    for (; iters < itermax && rdiff > tol; iters++) {
+        double sink = 0.0;
+        for (int64_t i = 0; i < n; i++) if (out_degree[i] == 0) sink += r[i];
+        const double teleport = scaled + damping_over_n * sink;
+        for (int64_t i = 0; i < n; i++) { t[i] = r[i]; w[i] = t[i] / d[i]; }
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < n; i++) {
+            double acc = 0.0;
+            for (int64_t q = AT->p[i]; q < AT->p[i + 1]; q++) acc += w[AT->j[q]];
+            r[i] = teleport + acc;
+        }
+        rdiff = 0.0;
+        for (int64_t i = 0; i < n; i++) { const double e = t[i] - r[i]; rdiff += e < 0 ? -e : e; }
+    }
+    free(t); free(w); free(d);
+    return iters;
+}
+
 /* ------------------------------------------------------------------ RMAT generator
  * Graph500-style Kronecker edges (a,b,c,d = .57,.19,.19,.05), counter-based so the CUDA
  * generator (falkordb_b200/csrc/rmat.cuh) produces the identical edge list: edge e, level l

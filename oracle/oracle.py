@@ -46,6 +46,9 @@ def lib():
         L.orc_csr_free.argtypes = [P]
         L.orc_chain.argtypes = [P, C.c_void_p, C.c_int64, C.c_int, P, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_double)]
         L.orc_digest.argtypes = [P, C.c_void_p]
+        L.orc_mxv_fp64.argtypes = [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pagerank.argtypes = [P, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.orc_pagerank.restype = C.c_int
         L.orc_last_busy_fraction.restype = C.c_double
         L.orc_last_busy_threads.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
@@ -240,6 +243,27 @@ def rmat_csr(scale, edge_factor=16, seed=1):
     out = _CSR()
     lib().orc_csr_from_edges(n, len(I), _ptr(I), _ptr(J), C.byref(out))
     return _take(out)
+
+
+def mxv_fp64(A, x, use_values=True, present=None):
+    """y = A*x over PLUS_TIMES (A.x = IEEE-754 bit patterns of doubles) or PLUS_SECOND (use_values=False).  Returns (y, ypresent)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    pr = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+    y = np.zeros(A.nrows, np.float64)
+    yp = np.zeros(A.nrows, np.uint8)
+    a = A._c()
+    lib().orc_mxv_fp64(C.byref(a), int(use_values), _ptr(x), _ptr(pr), _ptr(y), _ptr(yp))
+    return y, yp.astype(bool)
+
+
+def pagerank(A, damping=0.85, tol=1e-4, itermax=100):
+    """LAGr_PageRank on the pattern of A (directed; rank flows along out-edges).  Returns (scores float64[n], iterations)."""
+    AT = transpose(pattern(A))
+    deg = np.ascontiguousarray(np.diff(A.p), dtype=np.int64)
+    r = np.zeros(A.nrows, np.float64)
+    at = AT._c()
+    it = lib().orc_pagerank(C.byref(at), _ptr(deg), damping, tol, itermax, _ptr(r))
+    return r, it
 
 
 def num_threads():
