@@ -37,8 +37,3 @@ PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_pull_seg|k_pull_small|k_bits_count_csa" -c 6 -o gpurun_out/r2a_prof_pull python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=0 > gpurun_out/r2a_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"k_pull_seg" -c 2 -o gpurun_out/r2a_prof_pull_win python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=67108864 > gpurun_out/r2a_ncu2.log 2>&1
 ls -la gpurun_out | tail -5
-# BFS engine: single GPU, scale 24 and 26
-timeout 600 python bench.py --workload bfs --scale 24 --bfs-sources 8 --warmup 2 > gpurun_out/r2a_bfs_s24.json 2> gpurun_out/r2a_bfs_s24.err; tail -1 gpurun_out/r2a_bfs_s24.json | cut -c1-1200
-timeout 900 python bench.py --workload bfs --scale 26 --bfs-sources 8 --warmup 2 > gpurun_out/r2a_bfs_s26.json 2> gpurun_out/r2a_bfs_s26.err; tail -1 gpurun_out/r2a_bfs_s26.json | cut -c1-1200
-# full-size parity
-( time timeout 2400 python -m pytest tests/test_full_size.py -m gpu -x -q --durations=0 ) > gpurun_out/r2a_fullsize.log 2>&1; tail -25 gpurun_out/r2a_fullsize.log
