@@ -2,7 +2,6 @@
 # round 2, call B: the BFS engine, small to large, every step bounded in time and host memory
 set -x
 mkdir -p gpurun_out
-ulimit -v 600000000        # 600 GB of address space: a runaway host allocation fails instead of taking the box down
 make -C falkordb_b200/csrc -j16 -s 2>&1 | tail -3; make -C oracle -s
 timeout 300 python -m pytest tests/test_dist_bfs.py tests/test_fp64.py -m gpu -x -q > gpurun_out/r2b_pytest.log 2>&1; tail -3 gpurun_out/r2b_pytest.log
 for sc in 20 22 24; do

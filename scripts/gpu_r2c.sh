@@ -2,7 +2,6 @@
 # round 2, call C: full-size parity, one test per process, bounded in time and host memory
 set -x
 mkdir -p gpurun_out
-ulimit -v 900000000
 make -C falkordb_b200/csrc -j16 -s 2>&1 | tail -3; make -C oracle -s
 : > gpurun_out/r2c_fullsize.log
 for t in "test_chain_rmat24_all_rows" "test_config3_ldbc_sf10_shaped_chain" "test_config4_masked_triangles_rmat24" "test_config2_single_mxm_rmat22" "test_config5_bfs_rmat26_levels_and_parents"; do
