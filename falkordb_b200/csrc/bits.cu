@@ -1928,16 +1928,23 @@ void build_long_rows(const DevCSR &AT, LongRows &lr) {
 }
 
 // persisting-L2 access-policy window on the library stream (cudaLimitPersistingL2CacheSize is set at context bring-up)
+static u64 g_l2_carved = 0;        // bytes of L2 currently set aside for persisting accesses
+static void carve_l2(u64 bytes) {
+    if (bytes == g_l2_carved) return;
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    g_l2_carved = bytes;
+}
 static void set_l2_window(const void *base, u64 bytes) {
     Context &cx = ctx();
     if (cx.l2_persist_max == 0) return;
+    carve_l2(std::min<u64>(bytes, cx.l2_persist_max));
     cudaStreamAttrValue a;
     memset(&a, 0, sizeof(a));
     u64 nb = bytes;
     if (nb > cx.l2_window_max) nb = cx.l2_window_max;
     a.accessPolicyWindow.base_ptr = const_cast<void *>(base);
     a.accessPolicyWindow.num_bytes = nb;
-    a.accessPolicyWindow.hitRatio = nb <= cx.l2_persist_max ? 1.0f : (float)((double)cx.l2_persist_max / (double)nb);
+    a.accessPolicyWindow.hitRatio = nb <= g_l2_carved ? 1.0f : (float)((double)g_l2_carved / (double)nb);
     a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     CUDA_TRY(cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a));
@@ -1953,6 +1960,7 @@ static void clear_l2_window() {
     a.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     CUDA_TRY(cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a));
     if (cx.opt_l2_reset) CUDA_TRY(cudaCtxResetPersistingL2Cache());
+    if (cx.opt_l2_reset >= 2) carve_l2(0);       // hand the set-aside back to the other kernels until the next pull
 }
 
 template <int W>

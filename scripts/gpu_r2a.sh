@@ -8,7 +8,7 @@ nproc >> gpurun_out/r2a_smi.txt; free -g >> gpurun_out/r2a_smi.txt
 timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_full_size.py > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
 tail -5 gpurun_out/r2a_pytest.log
 B="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-format csr"
-for v in "pull_kernel=4" "pull_kernel=5" "pull_kernel=5 --opt unroll=8" "pull_kernel=5 --opt l2_window=67108864" "pull_kernel=5 --opt l2_window=67108864 --opt l2_reset=1" "pull_kernel=5 --opt l2_window=33554432" "pull_kernel=5 --opt l2_window=134217728" "pull_kernel=5 --opt count_kernel=0" "pull_kernel=5 --opt pull_grid=3" "pull_kernel=5 --opt pull_grid=6" "pull_kernel=5 --opt hints=0"; do
+for v in "pull_kernel=4" "pull_kernel=5" "pull_kernel=5 --opt unroll=8" "pull_kernel=5 --opt l2_window=67108864" "pull_kernel=5 --opt l2_window=33554432" "pull_kernel=5 --opt l2_window=33554432 --opt l2_reset=2" "pull_kernel=5 --opt l2_window=67108864 --opt l2_reset=2" "pull_kernel=5 --opt hints=0" "pull_kernel=5 --opt early_exit=2"; do
   tag=$(echo "$v" | tr -d ' ' | tr '=' '_' | tr -d '-')
   timeout 300 $B --opt $v > gpurun_out/r2a_bench_$tag.json 2> gpurun_out/r2a_bench_$tag.err
   python - "$tag" <<'PY'
@@ -24,16 +24,17 @@ done
 # W=4 (256 sources) sanity
 timeout 300 $B --sources 256 --opt pull_kernel=5 > gpurun_out/r2a_bench_s256.json 2> gpurun_out/r2a_bench_s256.err
 timeout 300 $B --sources 1024 --opt pull_kernel=5 > gpurun_out/r2a_bench_s1024.json 2> gpurun_out/r2a_bench_s1024.err
-timeout 300 $B --sources 1024 --opt pull_kernel=4 > gpurun_out/r2a_bench_s1024_k4.json 2> gpurun_out/r2a_bench_s1024_k4.err
 python - <<'PY'
 import json
-for t in ('s256','s1024','s1024_k4'):
+for t in ('s256','s1024'):
     try:
         d=json.loads(open(f'gpurun_out/r2a_bench_{t}.json').read().strip().splitlines()[-1]); k=d['kernels']
         print(t, 'TTEPS %.3f ms %.2f'%(d['value']/1e12,d['ms_per_step']), {n:round(v['ms']/v['launches'],3) for n,v in k.items()})
     except Exception as e: print(t,'ERR',e)
 PY
-# ncu of the new kernels (one chain)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_pull_seg|k_pull_small|k_bits_count_csa" -c 6 -o gpurun_out/r2a_prof_pull python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=0 > gpurun_out/r2a_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_pull_seg" -c 2 -o gpurun_out/r2a_prof_pull_win python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-format csr --opt l2_window=67108864 > gpurun_out/r2a_ncu2.log 2>&1
-ls -la gpurun_out | tail -5
+grep -h "l2_persist" gpurun_out/*.err | head -2
+python -c "
+import falkordb_b200 as fb
+fb.init(); A=fb.rmat(10,8,1); A.prepare(True)
+print('l2_persist_max', fb.get_stat('l2_persist_max'), 'l2_window_max', fb.get_stat('l2_window_max'))
+"

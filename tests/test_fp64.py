@@ -160,7 +160,10 @@ def _pagerank_dev(L, A_dev_handle, n, damping=0.85, tol=1e-4, itermax=100):
 def test_lagr_pagerank_against_the_oracle_and_the_reference_flow_tests():
     fb.init()
     L = lib()
-    from tests.test_gpu_parity import to_dev
+    from falkordb_b200.grb import Matrix
+
+    def to_dev(c):
+        return Matrix.import_csr(c.nrows, c.ncols, c.p.astype(np.uint64), c.j, None, bool)
     names = "ABCDEF"
     idx = {c: i for i, c in enumerate(names)}
     edges = [("A", "B"), ("B", "C"), ("C", "F"), ("F", "E"), ("E", "D"), ("D", "A"), ("E", "B")]
