@@ -49,10 +49,11 @@ def parse():
     ap.add_argument("--bits-mode", type=int, default=-1)
     ap.add_argument("--pull-mode", type=int, default=-1)
     ap.add_argument("--pull-kernel", type=int, default=-1, help="-1 library default, 0 = 8-lanes-per-row, 1 = merge-path")
-    ap.add_argument("--workload", default="chain", choices=["chain", "bfs", "triangles"],
+    ap.add_argument("--workload", default="chain", choices=["chain", "bfs", "triangles", "delta", "pagerank"],
                     help="chain = the headline 3-hop mxm chain; bfs = 1-D row-partitioned BFS sweep (BASELINE config 5); "
                          "triangles = masked SpGEMM C<L> = L*L on the symmetrised lower triangle (BASELINE config 4)")
     ap.add_argument("--bfs-sources", type=int, default=16)
+    ap.add_argument("--tri-parity", type=int, default=1, help="triangles: check every rank's result block against the oracle (0 = skip)")
     ap.add_argument("--bfs-parity", type=int, default=2, help="sources whose levels / parents are checked against the oracle (0 = none)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (B200_set_option), repeatable")
     ap.add_argument("--e2e-format", default="auto", choices=["auto", "csr", "bitmap"],
@@ -716,7 +717,22 @@ def run_triangles(a):
     h = P()
     check(L_.B200_Matrix_rmat_block(C.byref(h), a.scale, a.edge_factor, a.seed, 0, n, 2))
     Lfull = Matrix(0, 0, bool, _handle=h)
-    lo, hi = partition(n, rank, world)
+    # row blocks of equal WORK, not equal rows: tril(L) is heavily skewed
+    # (equal-row blocks gave 43 % strong-scaling efficiency at N = 4); every rank derives the same split from the replicated L
+    lp, lj, _ = Lfull.export_csr()
+    lp = lp.astype(np.int64)
+    degL = np.diff(lp)
+    # what a pair (i,k) costs the kernel: the shorter of B(k,:) and M(i,:) drives (ewise.cu: k_masked_pairs), plus a fixed part
+    rows_of = np.repeat(np.arange(n, dtype=np.int64), degL)
+    work = np.minimum(degL[lj], degL[rows_of]) + 8
+    del rows_of
+    csum = np.concatenate([[0], np.cumsum(work, dtype=np.int64)])
+    rowwork_cum = csum[lp]                                     # work of rows [0, i)
+    total_w = int(rowwork_cum[-1])
+    cuts = [int(np.searchsorted(rowwork_cum, total_w * g // world, side="left")) for g in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    lo, hi = cuts[rank], cuts[rank + 1]
+    del lj, csum, work
     if world > 1:
         hb = P()
         check(L_.B200_Matrix_rmat_block(C.byref(hb), a.scale, a.edge_factor, a.seed, lo, hi, 2))
@@ -730,15 +746,19 @@ def run_triangles(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step():
         Cm = Matrix(hi - lo, n, bool)
         Cm.mxm(Lblk, Lfull, Lblk, Descriptor.RS)
         fl = fb.get_stat("last_flops")
+        last["C"] = Cm
         return fl, Cm.nvals()
 
     for _ in range(a.warmup):
         step()
     barrier()
+    fb.set_option("timing", 1)
     fb.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -751,18 +771,181 @@ def run_triangles(a):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = fb.get_stat("launches")
+    peak, peak_src = peaks()
+    roofs = kernel_rooflines(L_, ("spgemm_masked", "filter"), peak)
+    fb.set_option("timing", 0)
+    my_ms = ms
+    # parity at full size (untimed): this rank's block of the result against the oracle's masked product of the same rows
+    parity = None
+    if a.tri_parity:
+        import oracle as orc
+        orc.lib().orc_set_num_threads(max(1, host_threads() // world))
+        Lo = orc.CSR(n, n, lp, Lfull.export_csr()[1])
+        pb_, jb_ = lp[lo:hi + 1] - lp[lo], Lo.j[lp[lo]:lp[hi]]
+        Lb = orc.CSR(hi - lo, n, pb_, jb_)
+        want, wfl = orc.mxm(Lb, Lo, Lb, 1, return_flops=True)
+        ok = bool(np.array_equal(last["C"].digest(), orc.digest(want)) and wfl * a.steps == flops)
+        del want
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"digest_and_flops_bit_exact_every_rank": bool(flag.item())}
     if world > 1:
         (ms,), (flops, nnz, launches) = reduce_over_ranks([ms], [flops, nnz, launches], "cuda")
     if rank == 0:
         print(json.dumps({
+            "parity": parity, "kernels_rank0": roofs, "peak_gbs": peak, "rank0_ms_per_step": my_ms / a.steps,
+            "row_cuts": cuts if world <= 8 else None,
             "metric": "traversed edges/sec (masked mxm TEPS, C<L> = L*L)", "value": flops / (ms * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
             "config": {"workload": f"masked SpGEMM C<L,struct> = L*L, L = tril(A u A'), RMAT scale-{a.scale} ef{a.edge_factor}",
-                       "n": n, "nnz_L": Lfull.nvals(), "parallelism": f"row blocks of L x{world}, L replicated, no exchange"},
+                       "n": n, "nnz_L": Lfull.nvals(), "parallelism": f"row blocks of L with equal intersection work x{world}, L replicated, no exchange"},
             "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz / a.steps, "gpu_launches": int(launches)}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_rooflines(L, names, peak):
+    """per kernel family: event-timed ms / launches / algorithmic bytes (B200_kernel_stats) -> achieved GB/s and fraction of peak"""
+    out = {}
+    for name in names:
+        m, nl, by = C.c_double(), C.c_uint64(), C.c_uint64()
+        if L.B200_kernel_stats(name.encode(), C.byref(m), C.byref(nl), C.byref(by)) == 0 and nl.value:
+            ach = by.value / (m.value * 1e-3) / 1e9 if m.value > 0 else 0.0
+            out[name] = {"ms_per_launch": m.value / nl.value, "launches": nl.value, "algorithmic_bytes_per_launch": by.value / nl.value,
+                         "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak}
+    return out
+
+
+def run_delta(a):
+    """Delta-matrix sync (fold formulas versioned_matrix.rs:909-926) at fold sizes: base m = RMAT scale-S
+    adjacency (S = --scale, default 23: 1.3e8 entries), dp = 1e6 fresh entries, dm = 1e6 tombstones sampled from m.
+      fold      : C<!dm, replace> = m (+) dp           GrB_Matrix_eWiseAdd_BinaryOp with GrB_DESC_RC      (matrix.rs:852-874)
+      select    : C<!dm, replace> = m                  GrB_transpose(.., GrB_DESC_RCT0)                  (matrix.rs:824-845)
+      tombstone : C = dm (*) m                          GrB_Matrix_eWiseMult_Semiring                     (matrix.rs:876-896)
+      transpose : C = m'                                GrB_transpose                                     (matrix.rs:633-662)
+    Each is bit-exact against the oracle on a scale-16 instance of the same construction before the timed runs."""
+    import torch
+    import falkordb_b200 as fb
+    import oracle as orc
+    from falkordb_b200._lib import lib
+    from falkordb_b200.grb import Matrix, Descriptor
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    fb.init()
+    L = lib()
+    peak, peak_src = peaks()
+
+    def make(scale, ndelta, seed):
+        A = fb.rmat(scale, a.edge_factor, seed)
+        n = 1 << scale
+        p, j, _ = A.export_csr()
+        rng = np.random.default_rng(seed + 99)
+        pick = np.sort(rng.choice(len(j), size=min(ndelta, len(j)), replace=False))
+        rows = (np.searchsorted(p.astype(np.int64), pick, side="right") - 1).astype(np.uint64)
+        dm = Matrix(n, n, bool)
+        dm.build(rows, j[pick].astype(np.uint64))
+        dp = Matrix(n, n, bool)
+        dp.build(rng.integers(0, n, ndelta).astype(np.uint64), rng.integers(0, n, ndelta).astype(np.uint64))
+        for M_ in (A, dm, dp):
+            M_.wait()
+        return A, dp, dm, n, (p, j)
+
+    def ops(A, dp, dm, n):
+        C1 = Matrix(n, n, bool); C1.element_wise_add(dm, A, dp, Descriptor.RC)
+        C2 = Matrix(n, n, bool); C2.select(dm, A)
+        C3 = Matrix(n, n, bool); C3.element_wise_multiply(None, dm, A, None)
+        C4 = A.transpose()
+        return C1, C2, C3, C4
+
+    # parity first (small instance, same construction)
+    A, dp, dm, n, (p, j) = make(16, 4000, a.seed)
+    Ao = orc.CSR(n, n, p.astype(np.int64), j)
+    pd, jd, _ = dp.export_csr(); pm, jm, _ = dm.export_csr()
+    dpo, dmo = orc.CSR(n, n, pd.astype(np.int64), jd), orc.CSR(n, n, pm.astype(np.int64), jm)
+    got = ops(A, dp, dm, n)
+    want = (orc.mask_assign(None, orc.ewise_add(Ao, dpo), dmo, comp=True, structural=False, replace=True),
+            orc.mask_assign(None, Ao, dmo, comp=True, structural=False, replace=True), orc.ewise_mult(dmo, Ao), orc.transpose(Ao))
+    parity = all(np.array_equal(g.digest(), orc.digest(w)) for g, w in zip(got, want))
+    del A, dp, dm, got
+    # timed
+    scale = a.scale if a.scale != 24 else 23
+    A, dp, dm, n, _ = make(scale, 1_000_000, a.seed)
+    for _ in range(a.warmup):
+        ops(A, dp, dm, n)
+    fb.set_option("timing", 1)
+    fb.reset_stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ops(A, dp, dm, n)
+    fb.sync()
+    secs = time.perf_counter() - t0
+    roofs = kernel_rooflines(L, ("union", "filter", "transpose"), peak)
+    fb.set_option("timing", 0)
+    print(json.dumps({"metric": "delta-sync kernels: achieved GB/s on SURVEY 8(d) algorithmic bytes", "value": max((r["achieved_gbs"] for r in roofs.values()), default=0.0),
+                      "unit": "GB/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
+                      "dtype": "bool/u32 index", "data": "synthetic",
+                      "config": {"workload": f"fold / select / tombstone / transpose, m = RMAT scale-{scale} ef{a.edge_factor} ({A.nvals()} entries), |dp| = |dm| = 1e6"},
+                      "kernels": roofs, "peak_gbs": peak, "peak_source": peak_src, "parity_bit_exact_scale16": parity,
+                      "gpu_launches": int(fb.get_stat("launches"))}))
+
+
+def run_pagerank(a):
+    """algo.pageRank's LAGr_PageRank (algo_procedures.rs:744-752: damping 0.85, tol 1e-4, itermax 100) on the RMAT graph; the FP64
+    plus_second mxv is the kernel; scores against the oracle (rel 1e-9) at --scale <= 22."""
+    import ctypes as CT
+    import torch
+    import falkordb_b200 as fb
+    import oracle as orc
+    from falkordb_b200._lib import lib, P
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    fb.init()
+    L = lib()
+    peak, peak_src = peaks()
+    scale = a.scale if a.scale != 24 else 22
+    A = fb.rmat(scale, a.edge_factor, a.seed)
+    n = 1 << scale
+    p, j, _ = A.export_csr()
+    G, h = P(), P(A.h.value)
+    A.h = P()
+    assert L.LAGraph_New(CT.byref(G), CT.byref(h), 1, None) == 0
+    L.LAGraph_Cached_AT(G, None)
+
+    def once():
+        cen, it = P(), CT.c_int(0)
+        assert L.LAGr_PageRank(CT.byref(cen), CT.byref(it), G, 0.85, 1e-4, 100, None) == 0
+        return cen, it.value
+
+    for _ in range(a.warmup):
+        c, _ = once(); L.GrB_Vector_free(CT.byref(c))
+    fb.set_option("timing", 1)
+    fb.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cen, iters = once()
+        if _ + 1 < a.steps:
+            L.GrB_Vector_free(CT.byref(cen))
+    secs = time.perf_counter() - t0
+    roofs = kernel_rooflines(L, ("mxv_fp64",), peak)
+    fb.set_option("timing", 0)
+    nv = CT.c_uint64(n)
+    X = np.empty(n, np.float64)
+    fb.check(L.GrB_Vector_extractTuples_FP64(None, X.ctypes.data, CT.byref(nv), cen))
+    Ao = orc.CSR(n, n, p.astype(np.int64), j)
+    orc.lib().orc_set_num_threads(host_threads())
+    t0 = time.perf_counter()
+    want, wit = orc.pagerank(Ao, float(np.float32(0.85)), float(np.float32(1e-4)), 100)
+    cpu_s = time.perf_counter() - t0
+    rel = float(np.max(np.abs(X - want) / np.maximum(np.abs(want), 1e-300)))
+    nnz = int(p[-1])
+    print(json.dumps({"metric": "PageRank edges/sec (nnz * iterations / time)", "value": nnz * iters / (secs / a.steps), "unit": "edges/s", "n_gpus": 1,
+                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"LAGr_PageRank(0.85, 1e-4, 100) on RMAT scale-{scale} ef{a.edge_factor}", "n": n, "nnz": nnz, "iterations": iters},
+                      "kernels": roofs, "peak_gbs": peak, "peak_source": peak_src,
+                      "parity": {"max_rel_err_vs_oracle": rel, "tolerance": 1e-9, "iterations_equal": iters == wit, "ok": bool(rel < 1e-9 and iters == wit)},
+                      "cpu_baseline": {"value": nnz * wit / cpu_s, "unit": "edges/s", "cores": host_threads(), "kind": "port"},
+                      "gpu_launches": int(fb.get_stat("launches"))}))
 
 
 if __name__ == "__main__":
@@ -773,5 +956,9 @@ if __name__ == "__main__":
         run_bfs(args)
     elif args.workload == "triangles":
         run_triangles(args)
+    elif args.workload == "delta":
+        run_delta(args)
+    elif args.workload == "pagerank":
+        run_pagerank(args)
     else:
         run_b200(args)

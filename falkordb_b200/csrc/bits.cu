@@ -1371,12 +1371,14 @@ static void build_seg_list(const DevCSR &AT, LongRows &lr) {
 }
 
 // SPLIT lanes per row, natural order: rows of <= SMALL_ROW entries are finished here, rows longer than LONG_ROW are zero-filled
-// (their segments arrive through RED.OR), everything in between is left to k_pull_seg.
-template <int W, bool HINTS>
+// (their segments arrive through RED.OR), everything in between is left to k_pull_seg.  This kernel is latency-bound, not
+// L1TEX-bound (l1tex 17 %, issue 17 %: profiles/r2a): splitting the record across lanes halves the bytes each warp keeps in
+// flight and was slower (0.90 vs 0.52 ms at W = 8), so by default one lane owns the whole record here (small_split = 0).
+template <int W, bool HINTS, int SPLIT>
 __global__ void __launch_bounds__(256)
 k_pull_small(const u64 *__restrict__ ATp, const u32 *__restrict__ ATj, u64 n, const u64 *__restrict__ X,
              u64 *__restrict__ Y, u32 hot_bytes, u32 tot_bytes) {
-    constexpr int WL = PullCfg<W>::WL, SPLIT = PullCfg<W>::SPLIT;
+    constexpr int WL = W / SPLIT;                  // words per lane: SPLIT = PullCfg<W>::SPLIT (one 32-byte load per record part) or 1
     const u64 keep = HINTS ? policy_range(X, hot_bytes, tot_bytes) : 0;
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 h = (u32)(t % SPLIT);
@@ -2088,9 +2090,10 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
                 // window on the library stream (no per-instruction hint exists for 256-bit loads)
                 const bool window = cx.opt_l2_window > 0 && gx == Xp.ptr && gn;
                 if (window) set_l2_window(gx, std::min<u64>((u64)cx.opt_l2_window, gn * W * 8));
-                auto small = [&](auto kern) {
-                    LAUNCH(kern, grid_for(m * PullCfg<W>::SPLIT, 256, (u64)cx.num_sms * 32), 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, hot_bytes, tot_bytes);
+                auto small = [&](auto kern, u64 split) {
+                    LAUNCH(kern, grid_for(m * split, 256, (u64)cx.num_sms * 32), 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, hot_bytes, tot_bytes);
                 };
+                constexpr int SP = PullCfg<W>::SPLIT;
                 auto seg = [&](auto kern) {
                     if (lr->ns) LAUNCH(kern, occ(kern), 256, 0, lr->s_row.ptr, lr->s_start.ptr, lr->s_len.ptr, lr->ns, gj, gx, Y.w.ptr, Gp, hot_bytes, tot_bytes);
                 };
@@ -2098,8 +2101,10 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         if (cx.opt_unroll >= 8) { if (early) seg(k_pull_seg<W, H, 8, true>); else seg(k_pull_seg<W, H, 8, false>); } \
         else if (cx.opt_unroll >= 4) { if (early) seg(k_pull_seg<W, H, 4, true>); else seg(k_pull_seg<W, H, 4, false>); } \
         else { if (early) seg(k_pull_seg<W, H, 2, true>); else seg(k_pull_seg<W, H, 2, false>); } } while (0)
-                if (cx.opt_hints) { small(k_pull_small<W, true>); SEG_LAUNCH(true); }
-                else { small(k_pull_small<W, false>); SEG_LAUNCH(false); }
+#define SMALL_LAUNCH(H) do { if (cx.opt_small_split && SP > 1) small(k_pull_small<W, H, SP>, SP); else small(k_pull_small<W, H, 1>, 1); } while (0)
+                if (cx.opt_hints) { SMALL_LAUNCH(true); SEG_LAUNCH(true); }
+                else { SMALL_LAUNCH(false); SEG_LAUNCH(false); }
+#undef SMALL_LAUNCH
 #undef SEG_LAUNCH
                 if (window) clear_l2_window();
                 if (path_out) *path_out = 3;

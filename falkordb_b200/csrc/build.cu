@@ -142,6 +142,8 @@ __global__ void k_transpose_keys(const u64 *__restrict__ p, const u32 *__restric
 void transpose_csr(const DevCSR &A, DevCSR &out, bool keep_values) {
     u64 n = A.nnz;
     if (n == 0) { csr_from_sorted_keys(nullptr, 0, A.ncols, A.nrows, nullptr, nullptr, out); return; }
+    // SURVEY 8(d) bytes_transpose = 2 * (4 * nnz + 4 * (n + 1)) (+ 2 * 8 * nnz if valued); the radix sort inside moves more
+    TimedScope ts(TK_TRANSPOSE, 2 * (4 * n + 8 * (A.nrows + 1)) + ((keep_values && A.has_values()) ? 16 * n : 0));
     DevBuf<u64> keys(n);
     LAUNCH(k_transpose_keys, grid_for(A.nrows * 32, 256, 1 << 16), 256, 0, A.p.ptr, A.j.ptr, A.nrows, keys.ptr);
     int eb = key_bits(A.ncols);

@@ -53,6 +53,7 @@ struct Context {
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
     i64 opt_pull_kernel = 5;       // 5 = lane-split degree-binned (default); 4 = degree-binned, one lane per vertex record; 0..3 = earlier kernels
+    i64 opt_small_split = 0;       // small-row pull kernel: 1 = split the vertex record across lanes like the segment kernel, 0 = one lane per record
     i64 opt_l2_window = 0;         // bytes of the packed frontier's hot prefix kept L2-resident through a persisting access-policy window (0 = off)
     i64 opt_l2_reset = 0;          // cudaCtxResetPersistingL2Cache after each windowed pull
     i64 opt_count_kernel = 1;      // materialise count pass: 1 = vertical (carry-save) counters, 0 = transpose + popcount

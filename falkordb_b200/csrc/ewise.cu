@@ -107,6 +107,7 @@ static void rowfilter(const DevCSR &T, Pred pred, u64 out_nrows, u64 out_ncols, 
     if (T.nnz == 0 || rows == 0) { out.p.zero(); out.nnz = 0; return; }
     DevBuf<u32> cnt(out_nrows + 1);
     cnt.zero();
+    timed_begin(TK_FILTER);
     LAUNCH((k_rowfilter_count<Pred>), grid_for(rows * 32, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr, rows, pred, cnt.ptr);
     exclusive_scan_u32_to_u64(cnt.ptr, out.p.ptr, out_nrows + 1);
     u64 nnz = read_scalar(out.p.ptr + out_nrows);
@@ -117,6 +118,9 @@ static void rowfilter(const DevCSR &T, Pred pred, u64 out_nrows, u64 out_ncols, 
     if (nnz)
         LAUNCH((k_rowfilter_fill<Pred>), grid_for(rows * 32, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr,
                vals ? T.x.ptr : (const u64 *)nullptr, rows, pred, out.p.ptr, out.j.ptr, vals ? out.x.ptr : (u64 *)nullptr);
+    // SURVEY 8(d) bytes_ewise: the operand once, the result once, row pointers of both (+ 8 B per carried value); the probed
+    // side (mask / larger operand) is touched by binary searches only and is not counted
+    timed_end(TK_FILTER, 4 * (T.nnz + nnz) + 8 * (rows + out_nrows + 2) + (vals ? 8 * (T.nnz + nnz) : 0));
 }
 
 void filter_by_mask(const DevCSR &T, const DevCSR &M, bool comp, bool structural, DevCSR &out) {
@@ -215,7 +219,9 @@ void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool struc
     flag.zero();
     LAUNCH(k_row_ids, grid_for(A.nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.nrows, rid.ptr);
     {
-        TimedScope ts(TK_FILTER, 0);
+        // SURVEY 8(d) bytes_mxm with the mask term: A's entries + their row ids, B's and M's row-pointer pairs per (i,k), the
+        // B segments (4 B per flop is the row-wise bound; the kernel reads min(|B(k,:)|, |M(i,:)|) per pair), M once, flags
+        TimedScope ts(TK_MASKED, 8 * A.nnz + 32 * A.nnz + 4 * M.nnz + M.nnz / 8);
         LAUNCH(k_masked_pairs, grid_for(A.nnz * 32, 256, 148 * 64), 256, 0, rid.ptr, A.j.ptr, A.nnz, B.p.ptr, B.j.ptr, M.p.ptr,
                M.j.ptr, flag.ptr);
     }
@@ -315,6 +321,7 @@ void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out
     if (nrows == 0 || (A.nnz == 0 && B.nnz == 0)) { out.p.zero(); out.nnz = 0; return; }
     DevBuf<u32> cnt(nrows + 1);
     CUDA_TRY(cudaMemsetAsync(cnt.ptr + nrows, 0, sizeof(u32), stream()));
+    timed_begin(TK_UNION);
     LAUNCH(k_union_count, grid_for(nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr, B.p.ptr, B.j.ptr, nrows, cnt.ptr);
     exclusive_scan_u32_to_u64(cnt.ptr, out.p.ptr, nrows + 1);
     u64 nnz = read_scalar(out.p.ptr + nrows);
@@ -327,6 +334,8 @@ void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out
                A.has_values() ? A.x.ptr : (const u64 *)nullptr, B.p.ptr, B.j.ptr,
                B.has_values() ? B.x.ptr : (const u64 *)nullptr, nrows, out.p.ptr, out.j.ptr,
                vals ? out.x.ptr : (u64 *)nullptr);
+    // SURVEY 8(d) bytes_ewise = 4 * (nnz(A) + nnz(B) + nnz(C)) + row pointers (+ 8 B per valued entry read / written)
+    timed_end(TK_UNION, 4 * (A.nnz + B.nnz + nnz) + 8 * 3 * (nrows + 1) + (vals ? 8 * (A.nnz + B.nnz + nnz) : 0));
 }
 
 

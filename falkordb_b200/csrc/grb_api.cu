@@ -2316,6 +2316,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "csr_push") c.opt_csr_push = value;
     else if (n == "fused_prep") c.opt_fused_prep = value;
     else if (n == "l2_window") c.opt_l2_window = value;
+    else if (n == "small_split") c.opt_small_split = value;
     else if (n == "l2_reset") c.opt_l2_reset = value;
     else if (n == "count_kernel") c.opt_count_kernel = value;
     else if (n == "bfs_direction") c.opt_bfs_direction = value;

@@ -233,7 +233,7 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
                                   {"pull_kernel": 5}, {"pull_kernel": 5, "early_exit": 2}, {"pull_kernel": 5, "early_exit": 0, "hints": 0},
                                   {"pull_kernel": 5, "unroll": 8, "early_exit": 2}, {"pull_kernel": 5, "unroll": 2, "hot_pack": 0},
                                   {"pull_kernel": 5, "l2_window": 1 << 20}, {"pull_kernel": 5, "l2_window": 1 << 30, "l2_reset": 1},
-                                  {"count_kernel": 0}, {"count_kernel": 1}])
+                                  {"count_kernel": 0}, {"count_kernel": 1}, {"pull_kernel": 5, "small_split": 1}])
 def test_bit_frontier_kernel_variants(opts):
     """every selectable kernel variant (direct-write materialise, hot-set packing on/off, merge-path pull, L2 hints)"""
     fb.set_option("bits_mode", 1)
@@ -256,7 +256,7 @@ def test_bit_frontier_kernel_variants(opts):
             assert_same(F, want, f"variant {opts} nsrc={nsrc}")
     finally:
         for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 5), ("hints", 1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 1), ("fused_prep", 1),
-                     ("l2_window", 0), ("l2_reset", 0), ("count_kernel", 1)):
+                     ("l2_window", 0), ("l2_reset", 0), ("count_kernel", 1), ("small_split", 0)):
             fb.set_option(k, v)
 
 
@@ -557,7 +557,7 @@ def test_row_iterator_walks_dense_chain_result_from_bitmap(materialise_first):
 @pytest.mark.parametrize("opts", [{"pull_kernel": 4}, {"pull_kernel": 4, "early_exit": 2}, {"pull_kernel": 4, "early_exit": 0, "hot_pack": 0},
                                   {"pull_kernel": 3}, {"pull_kernel": 0, "early_exit": 2}, {"pull_kernel": 1},
                                   {"pull_kernel": 5}, {"pull_kernel": 5, "early_exit": 2}, {"pull_kernel": 5, "early_exit": 0, "hot_pack": 0},
-                                  {"pull_kernel": 5, "unroll": 8}, {"pull_kernel": 5, "l2_window": 4 << 20}])
+                                  {"pull_kernel": 5, "unroll": 8}, {"pull_kernel": 5, "l2_window": 4 << 20}, {"pull_kernel": 5, "small_split": 1}])
 def test_pull_bins_small_mid_long_rows(opts):
     """a graph whose transpose has empty, small (<= 8), mid and long (> 4096 entries) rows, so every bin of the
     degree-binned pull (and the long-row chunk table) is exercised; W = 1, 8 and 16 word columns"""
@@ -594,7 +594,7 @@ def test_pull_bins_small_mid_long_rows(opts):
             F.wait()
             assert_same(F, want, f"binned pull {opts} nsrc={nsrc}")
     finally:
-        for k, v in (("hot_pack", 1), ("pull_kernel", 5), ("early_exit", 1), ("pull_mode", -1), ("bits_mode", -1), ("unroll", 4), ("l2_window", 0)):
+        for k, v in (("hot_pack", 1), ("pull_kernel", 5), ("early_exit", 1), ("pull_mode", -1), ("bits_mode", -1), ("unroll", 4), ("l2_window", 0), ("small_split", 0)):
             fb.set_option(k, v)
 
 
