@@ -2102,7 +2102,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         else if (cx.opt_unroll >= 4) { if (early) seg(k_pull_seg<W, H, 4, true>); else seg(k_pull_seg<W, H, 4, false>); } \
         else { if (early) seg(k_pull_seg<W, H, 2, true>); else seg(k_pull_seg<W, H, 2, false>); } } while (0)
 #define SMALL_LAUNCH(H) do { if (cx.opt_small_split && SP > 1) small(k_pull_small<W, H, SP>, SP); else small(k_pull_small<W, H, 1>, 1); } while (0)
-                if (cx.opt_hints) { SMALL_LAUNCH(true); SEG_LAUNCH(true); }
+                if (cx.opt_hints > 0 || (cx.opt_hints < 0 && W <= 2)) { SMALL_LAUNCH(true); SEG_LAUNCH(true); }
                 else { SMALL_LAUNCH(false); SEG_LAUNCH(false); }
 #undef SMALL_LAUNCH
 #undef SEG_LAUNCH
@@ -2125,7 +2125,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         if (cx.opt_unroll >= 8) { if (early) mid(k_bits_pull_mid<W, H, 8, true>); else mid(k_bits_pull_mid<W, H, 8, false>); } \
         else if (cx.opt_unroll >= 4) { if (early) mid(k_bits_pull_mid<W, H, 4, true>); else mid(k_bits_pull_mid<W, H, 4, false>); } \
         else { if (early) mid(k_bits_pull_mid<W, H, 2, true>); else mid(k_bits_pull_mid<W, H, 2, false>); } } while (0)
-                if (cx.opt_hints) { small(k_bits_pull_small<W, true>); MID_LAUNCH(true); }
+                if (cx.opt_hints > 0 || (cx.opt_hints < 0 && W <= 2)) { small(k_bits_pull_small<W, true>); MID_LAUNCH(true); }
                 else { small(k_bits_pull_small<W, false>); MID_LAUNCH(false); }
 #undef MID_LAUNCH
             } else {
@@ -2140,7 +2140,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
 #define PULL_LAUNCH(H, UU) do { \
         if (cx.opt_pull_kernel == 0) { if (early) go(k_bits_pull<W, H, UU, true>); else go(k_bits_pull<W, H, UU, false>); } \
         else { if (early) go(k_bits_pull_pipe<W, H, UU, true>); else go(k_bits_pull_pipe<W, H, UU, false>); } } while (0)
-            if (cx.opt_hints) {
+            if (cx.opt_hints > 0 || (cx.opt_hints < 0 && W <= 2)) {
                 if (cx.opt_unroll >= 4) PULL_LAUNCH(true, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(true, 2); else PULL_LAUNCH(true, 1);
             } else {
                 if (cx.opt_unroll >= 4) PULL_LAUNCH(false, 4); else if (cx.opt_unroll >= 2) PULL_LAUNCH(false, 2); else PULL_LAUNCH(false, 1);

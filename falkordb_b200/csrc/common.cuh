@@ -61,7 +61,7 @@ struct Context {
     i64 opt_bfs_sparse_exchange = 1;   // partitioned BFS: ship discovered-vertex lists instead of bitmaps when the frontier is sparse
     u64 l2_persist_max = 0, l2_window_max = 0;   // device limits (bytes), read at bring-up
     i64 opt_early_exit = 1;        // stop a pull row once it holds the OR monoid's terminal value (exact)
-    i64 opt_hints = 1;             // L2 createpolicy hints in the pull kernel (hot prefix of packed X evict_last)
+    i64 opt_hints = -1;            // L2 createpolicy hints in the pull kernels: -1 = auto (on for W <= 2, where the gathers take a cache-hint operand; measured slower at W = 8: 2.27 vs 2.17 ms), 0 / 1 = off / on
     i64 opt_hot_bytes = 64 << 20;  // size of that hot prefix
     i64 opt_hot_pack = 1;          // gather through the degree-sorted, sink-free relabelling of the frontier
     i64 opt_fill_cap = 0;          // 0 = auto; >0 forces the materialise staging capacity (test hook)

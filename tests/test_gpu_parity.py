@@ -230,7 +230,7 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
                                   {"pull_kernel": 4}, {"pull_kernel": 4, "hints": 0, "early_exit": 0}, {"pull_kernel": 4, "early_exit": 2, "pull_grid": 2},
                                   {"pull_kernel": 4, "hot_pack": 0}, {"fused_prep": 0}, {"fused_prep": 0, "early_exit": 2}, {"fused_prep": 1, "early_exit": 2},
                                   {"fused_prep": 1, "pull_kernel": 3}, {"fused_prep": 1, "pull_kernel": 1},
-                                  {"pull_kernel": 5}, {"pull_kernel": 5, "early_exit": 2}, {"pull_kernel": 5, "early_exit": 0, "hints": 0},
+                                  {"pull_kernel": 5}, {"pull_kernel": 5, "early_exit": 2}, {"pull_kernel": 5, "early_exit": 0, "hints": 0}, {"pull_kernel": 5, "hints": 1},
                                   {"pull_kernel": 5, "unroll": 8, "early_exit": 2}, {"pull_kernel": 5, "unroll": 2, "hot_pack": 0},
                                   {"pull_kernel": 5, "l2_window": 1 << 20}, {"pull_kernel": 5, "l2_window": 1 << 30, "l2_reset": 1},
                                   {"count_kernel": 0}, {"count_kernel": 1}, {"pull_kernel": 5, "small_split": 1}])
@@ -255,7 +255,7 @@ def test_bit_frontier_kernel_variants(opts):
             F.wait()
             assert_same(F, want, f"variant {opts} nsrc={nsrc}")
     finally:
-        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 5), ("hints", 1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 1), ("fused_prep", 1),
+        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 5), ("hints", -1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 1), ("fused_prep", 1),
                      ("l2_window", 0), ("l2_reset", 0), ("count_kernel", 1), ("small_split", 0)):
             fb.set_option(k, v)
 
