@@ -258,6 +258,92 @@ k_bits_fill_rows(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles, const u64 
     }
 }
 
+// Row-per-warp materialise over 2048-vertex tiles (fill_kernel = 3, default).  Same two phases as k_bits_fill_rows; what changed is
+// the bookkeeping per emitted entry, which is what bounds this kernel (issue-active 81 %, profiles/r1f): a (row, tile) pass now
+// covers 2048 vertices (each lane owns a 64-bit mask), a warp scans the counts of its rows in PAIRS (two 16-bit fields per
+// shuffle), the four output offsets of a word column are fetched before the scans so their latency overlaps, and the staged ids
+// keep only their low 16 bits -- the high half is merged with one PRMT on the way out.  ~1.0 instructions per entry against 1.6.
+static const u32 F3_TILE = 2048, F3_THREADS = 512, F3_STRIDE = 66, F3_LIST = F3_TILE + 8;
+static const size_t F3_SMEM = 2 * 64 * F3_STRIDE * sizeof(u32) + (F3_THREADS / 32) * F3_LIST * sizeof(unsigned short);
+__global__ void __launch_bounds__(F3_THREADS, 2)
+k_bits_fill_v3(const u64 *__restrict__ X, u64 n, u32 W, u64 ntiles1k, const u64 *__restrict__ off, u32 *__restrict__ Cj) {
+    extern __shared__ __align__(16) unsigned char f3_smem[];
+    u32 *T = reinterpret_cast<u32 *>(f3_smem);                                      // [2][64][F3_STRIDE]
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned short *L = reinterpret_cast<unsigned short *>(f3_smem + 2 * 64 * F3_STRIDE * sizeof(u32)) + warp * F3_LIST;
+    constexpr u32 NW = F3_THREADS / 32, RPW = 64 / NW;                              // 16 warps, 4 rows per warp and word column
+    const u64 strm = policy_stream();
+    const u64 tile = blockIdx.x;
+    const u64 vbase = tile * F3_TILE;
+    const u32 lo16base = (u32)(vbase & 0xFFFFu), vbhi = (u32)(vbase >> 16);
+    for (u32 w = 0; w < W; w++) {
+        u32 *Tw = T + (w & 1) * 64 * F3_STRIDE;
+        // offsets of this warp's rows: issued first, consumed after the scans
+        u64 g0[RPW];
+#pragma unroll
+        for (u32 i = 0; i < RPW; i++) g0[i] = off[((u64)w * 64 + warp + NW * i) * ntiles1k + 2 * tile];
+#pragma unroll
+        for (u32 g = 0; g < 4; g++) {
+            const u64 v = vbase + (u64)warp * 128 + g * 32 + lane;
+            const u64 word = (v < n) ? X[v * W + w] : 0ULL;
+            u32 tl = 0, th = 0;
+            if (__ballot_sync(0xffffffffu, word != 0ULL)) {
+                tl = transpose32((u32)word, lane);
+                th = transpose32((u32)(word >> 32), lane);
+            }
+            Tw[lane * F3_STRIDE + 4 * warp + g] = tl;
+            Tw[(lane + 32) * F3_STRIDE + 4 * warp + g] = th;
+        }
+        __syncthreads();
+        u64 m[RPW];
+        u32 c[RPW];
+#pragma unroll
+        for (u32 i = 0; i < RPW; i++) {
+            m[i] = *reinterpret_cast<const u64 *>(Tw + (warp + NW * i) * F3_STRIDE + 2 * lane);
+            c[i] = __popcll(m[i]);
+        }
+        u32 pk[RPW / 2];
+#pragma unroll
+        for (u32 h = 0; h < RPW / 2; h++) pk[h] = c[2 * h] | (c[2 * h + 1] << 16);     // prefixes stay below 2^16 (tile = 2048)
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (u32 h = 0; h < RPW / 2; h++) { const u32 t = __shfl_up_sync(0xffffffffu, pk[h], d); if (lane >= d) pk[h] += t; }
+        }
+#pragma unroll
+        for (u32 i = 0; i < RPW; i++) {
+            const u32 field = (i & 1) ? (pk[i / 2] >> 16) : (pk[i / 2] & 0xFFFFu);
+            const u32 cnt = __shfl_sync(0xffffffffu, field, 31);
+            if (cnt == 0) continue;
+            const u32 a = (u32)(g0[i] & 3);
+            u32 o = a + field - c[i];
+            u32 idb = lo16base + lane * 64;
+            u32 lo = (u32)m[i], hi = (u32)(m[i] >> 32);
+            while (lo) { const u32 bit = __ffs(lo) - 1; L[o++] = (unsigned short)(idb + bit); lo &= lo - 1; }
+            idb += 32;
+            while (hi) { const u32 bit = __ffs(hi) - 1; L[o++] = (unsigned short)(idb + bit); hi &= hi - 1; }
+            __syncwarp();
+            u32 *dst = Cj + (g0[i] - a);                    // 16-byte aligned; dst[k] <-> L[k] for k in [a, a + cnt)
+            const u32 total = a + cnt;
+            const u32 head_end = a ? (total < 4 ? total : 4) : 0;
+            if (lane >= a && lane < head_end) st_u32_stream(dst + lane, (vbhi << 16) | L[lane], strm);
+            const u32 nfull = total >> 2;
+            const uint2 *L2 = reinterpret_cast<const uint2 *>(L);
+            uint4 *dv = reinterpret_cast<uint4 *>(dst);
+            for (u32 k = (a ? 1 : 0) + lane; k < nfull; k += 32) {
+                const uint2 p = L2[k];
+                uint4 q;
+                q.x = __byte_perm(p.x, vbhi, 0x5410); q.y = __byte_perm(p.x, vbhi, 0x5432);
+                q.z = __byte_perm(p.y, vbhi, 0x5410); q.w = __byte_perm(p.y, vbhi, 0x5432);
+                __stcs(dv + k, q);
+            }
+            const u32 tail = nfull * 4 > head_end ? nfull * 4 : head_end;
+            if (tail + lane < total) st_u32_stream(dst + tail + lane, (vbhi << 16) | L[tail + lane], strm);
+            __syncwarp();
+        }
+    }
+}
+
 // Materialise with the transposed masks kept (fill_kernel = 2, default).  k_bits_count_keep counts like k_bits_count and also
 // writes the 64 x 32 row masks of every (word column, tile) to global memory, coalesced (8 KB per tile); k_bits_fill_masks is
 // then phase B of k_bits_fill_rows alone: a warp reads one row's 32 mask words with one 128-byte load -- no second transpose,
@@ -483,11 +569,14 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
         if (!attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_bits_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * TILE_V * sizeof(unsigned short))));
             CUDA_TRY(cudaFuncSetAttribute(k_bits_fill_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILL2_SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(k_bits_fill_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F3_SMEM));
             attr_set = true;
         }
         TimedScope ts(TK_BITS_FILL, 8ULL * W * n + 4 * nnz);
         if (keep_masks) {
             LAUNCH(k_bits_fill_masks, (u32)ctx().num_sms * 8, FILLM_WARPS * 32, 0, masks.ptr, W, ntiles, off.ptr, C.j.ptr);
+        } else if (ctx().opt_fill_kernel == 3 && ctx().opt_fill_cap <= 0) {
+            LAUNCH(k_bits_fill_v3, (u32)((n + F3_TILE - 1) / F3_TILE), F3_THREADS, F3_SMEM, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
         } else if (ctx().opt_fill_kernel == 1 && ctx().opt_fill_cap <= 0) {
             LAUNCH(k_bits_fill_rows, (u32)ntiles, TILE_THREADS, FILL2_SMEM, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
         } else {

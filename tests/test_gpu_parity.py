@@ -226,7 +226,7 @@ def test_mxm_chain_bit_frontier_matches_oracle(nsrc, pull):
 @pytest.mark.parametrize("opts", [{"fill_cap": 64}, {"hot_pack": 0}, {"pull_kernel": 0, "hot_pack": 0}, {"pull_kernel": 0, "unroll": 1},
                                   {"pull_kernel": 1}, {"pull_kernel": 0, "hints": 0, "unroll": 2}, {"pull_kernel": 2}, {"early_exit": 0}, {"early_exit": 2},
                                   {"pull_kernel": 3}, {"pull_kernel": 3, "early_exit": 2, "unroll": 2}, {"pull_kernel": 3, "early_exit": 0, "hints": 0},
-                                  {"pull_kernel": 3, "pull_grid": 1}, {"pull_kernel": 0, "pull_grid": 16}, {"fill_kernel": 0}, {"fill_kernel": 2},
+                                  {"pull_kernel": 3, "pull_grid": 1}, {"pull_kernel": 0, "pull_grid": 16}, {"fill_kernel": 0}, {"fill_kernel": 2}, {"fill_kernel": 1}, {"fill_kernel": 3},
                                   {"pull_kernel": 4}, {"pull_kernel": 4, "hints": 0, "early_exit": 0}, {"pull_kernel": 4, "early_exit": 2, "pull_grid": 2},
                                   {"pull_kernel": 4, "hot_pack": 0}, {"fused_prep": 0}, {"fused_prep": 0, "early_exit": 2}, {"fused_prep": 1, "early_exit": 2},
                                   {"fused_prep": 1, "pull_kernel": 3}, {"fused_prep": 1, "pull_kernel": 1},
@@ -255,7 +255,7 @@ def test_bit_frontier_kernel_variants(opts):
             F.wait()
             assert_same(F, want, f"variant {opts} nsrc={nsrc}")
     finally:
-        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 5), ("hints", -1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 1), ("fused_prep", 1),
+        for k, v in (("fill_cap", 0), ("hot_pack", 1), ("unroll", 4), ("pull_kernel", 5), ("hints", -1), ("early_exit", 1), ("pull_grid", 0), ("fill_kernel", 3), ("fused_prep", 1),
                      ("l2_window", 0), ("l2_reset", 0), ("count_kernel", 1), ("small_split", 0)):
             fb.set_option(k, v)
 
