@@ -28,6 +28,8 @@ static const u64 PUSH_CHUNK = 8192;
 static const u64 LONG_ROW = 4096;   // pull: rows longer than this are split over several CTAs
 static const u64 LONG_CHUNK = 8192;
 
+static void require_natural(const DevBits &X, const char *what);
+
 u32 bits_words_for(u64 nrows) {
     if (nrows == 0) return 1;
     u64 w = (nrows + 63) / 64;
@@ -529,6 +531,7 @@ __global__ void k_bits_rowptr(const u64 *__restrict__ off, u64 nrows, u64 ntiles
 }
 
 void bits_to_csr(const DevBits &X, DevCSR &C) {
+    require_natural(X, "bits_to_csr");
     u64 n = X.ncols;
     u32 W = X.W;
     C.clear();
@@ -630,6 +633,7 @@ k_bits_diag(const u64 *__restrict__ X, const u64 *__restrict__ Ap, u64 n, u32 W,
     if (threadIdx.x == 0 && tot) atomicAdd((unsigned long long *)flops, tot);
 }
 void bits_diag(const DevBits &X, const DevCSR &A, DevBits &Y, u64 *flops_out) {
+    require_natural(X, "bits_diag");
     if (X.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
     Y.clear();
     Y.nrows = X.nrows; Y.ncols = A.ncols; Y.W = X.W;
@@ -679,6 +683,7 @@ k_bits_rowmajor(const u64 *__restrict__ X, u64 n, u32 W, u64 nrows, u64 wpr, u64
 }
 
 void bits_to_rowmajor(const DevBits &X, u64 *out, u64 wpr) {
+    require_natural(X, "bits_to_rowmajor");
     u64 n = X.ncols;
     if (!n || !X.nrows) return;
     u64 ntiles = (n + TILE_V - 1) / TILE_V;
@@ -817,7 +822,7 @@ __global__ void k_csr_entry_info(const u64 *__restrict__ Fp, const u32 *__restri
 template <int W>
 __global__ void __launch_bounds__(256)
 k_csr_push(const u32 *__restrict__ erow, const u32 *__restrict__ Fj, const u64 *__restrict__ cum, u64 nent, u64 total,
-           const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, u64 *__restrict__ Y) {
+           const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, u64 *__restrict__ Y, const u32 *__restrict__ perm) {
     __shared__ u64 s_e0, s_e1;
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     u64 lo = (u64)blockIdx.x * PUSH_CHUNK, hi = lo + PUSH_CHUNK;
@@ -834,20 +839,21 @@ k_csr_push(const u32 *__restrict__ erow, const u32 *__restrict__ Fj, const u64 *
         if (t < hi) {
             while (e < e1 && cum[e + 1] <= t) e++;
             const u32 i = erow[e];
-            const u32 col = Aj[Ap[Fj[e]] + (t - cum[e])];
+            u32 col = Aj[Ap[Fj[e]] + (t - cum[e])];
+            if (perm) col = __ldg(perm + col);          // hot-set order: hubs of the next gather become neighbours (64 MB table, L2)
             atomicOr((unsigned long long *)&Y[(u64)col * W + (i >> 6)], 1ULL << (i & 63));
         }
     }
 }
 template <int W>
-static void csr_push_impl(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 flops, const u32 *erow, const u64 *cum) {
+static void csr_push_impl(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 flops, const u32 *erow, const u64 *cum, const u32 *perm) {
     u64 nchunks = (flops + PUSH_CHUNK - 1) / PUSH_CHUNK;
     TimedScope ts(TK_BITS_PUSH, 4 * flops + 16 * F.nnz + 8 * flops);
-    LAUNCH((k_csr_push<W>), (u32)nchunks, 256, 0, erow, F.j.ptr, cum, F.nnz, flops, A.p.ptr, A.j.ptr, Y.w.ptr);
+    LAUNCH((k_csr_push<W>), (u32)nchunks, 256, 0, erow, F.j.ptr, cum, F.nnz, flops, A.p.ptr, A.j.ptr, Y.w.ptr, perm);
 }
 // Y = F * A from the CSR form of F.  Returns false (nothing done) when the expansion is large enough that the
 // direction-optimising bit-matrix hop should take it: flops * 4 > nnz(A), the same switch bits_hop applies to edges.
-bool bits_push_from_csr(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 *flops_out) {
+bool bits_push_from_csr(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 *flops_out, const LongRows *lr) {
     if (F.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
     const u32 W = bits_words_for(F.nrows);
     u64 flops = 0;
@@ -865,15 +871,41 @@ bool bits_push_from_csr(const DevCSR &F, const DevCSR &A, DevBits &Y, u64 *flops
     Y.w.alloc(A.ncols * W);
     Y.w.zero();
     if (flops_out) *flops_out = flops;
+    // a square operand with pull tables: write the result in its hot-set order, the form the next pull gathers from directly
+    const u32 *perm = nullptr;
+    if (lr && ctx().opt_perm_push && lr->perm_tag && lr->pperm && A.nrows == A.ncols && lr->pperm->n == A.ncols) {
+        perm = lr->pperm->ptr;
+        Y.pvert = lr->pvert;
+        Y.perm_tag = lr->perm_tag;
+    }
     if (flops == 0) return true;
     switch (W) {
-    case 1: csr_push_impl<1>(F, A, Y, flops, erow.ptr, cum.ptr); break;
-    case 2: csr_push_impl<2>(F, A, Y, flops, erow.ptr, cum.ptr); break;
-    case 4: csr_push_impl<4>(F, A, Y, flops, erow.ptr, cum.ptr); break;
-    case 8: csr_push_impl<8>(F, A, Y, flops, erow.ptr, cum.ptr); break;
-    default: csr_push_impl<16>(F, A, Y, flops, erow.ptr, cum.ptr); break;
+    case 1: csr_push_impl<1>(F, A, Y, flops, erow.ptr, cum.ptr, perm); break;
+    case 2: csr_push_impl<2>(F, A, Y, flops, erow.ptr, cum.ptr, perm); break;
+    case 4: csr_push_impl<4>(F, A, Y, flops, erow.ptr, cum.ptr, perm); break;
+    case 8: csr_push_impl<8>(F, A, Y, flops, erow.ptr, cum.ptr, perm); break;
+    default: csr_push_impl<16>(F, A, Y, flops, erow.ptr, cum.ptr, perm); break;
     }
     return true;
+}
+
+// permuted form -> natural order: Xn[pvert[s]] = X[s], one thread per word
+__global__ void k_unpermute(const u64 *__restrict__ X, const u32 *__restrict__ pvert, u64 n, u32 W, u64 *__restrict__ out) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x, total = n * W;
+    for (; t < total; t += stride) { const u64 s = t / W, w = t - s * W; out[(u64)pvert[s] * W + w] = X[t]; }
+}
+void bits_naturalise(DevBits &X) {
+    if (!X.permuted()) return;
+    const u64 n = X.ncols;
+    DevBuf<u64> out(n * X.W);
+    if (n) LAUNCH(k_unpermute, grid_for(n * X.W, 256, 148 * 32), 256, 0, X.w.ptr, X.pvert->ptr, n, X.W, out.ptr);
+    X.w = std::move(out);
+    X.pvert.reset();
+    X.perm_tag = 0;
+}
+static void require_natural(const DevBits &X, const char *what) {
+    if (X.permuted()) throw GrbError(-101, std::string(what) + ": frontier is in permuted form (internal error: bits_naturalise was not called)");
 }
 
 // ---------------------------------------------------------------------------- pull
@@ -1767,6 +1799,11 @@ __global__ void k_slots_from_keys(const u64 *__restrict__ keys, u64 n, u64 n1, u
         if (s < n1) { vert[s] = v; slot[v] = (u32)s; hdeg[s] = 0xFFFFFFFFu - (u32)(keys[s] >> 32); } else slot[v] = 0xFFFFFFFFu;
     }
 }
+__global__ void k_full_order(const u64 *__restrict__ keys, u64 n, u32 *__restrict__ pvert, u32 *__restrict__ pperm) {
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; s < n; s += stride) { const u32 v = (u32)(keys[s] & 0xFFFFFFFFULL); pvert[s] = v; pperm[v] = (u32)s; }
+}
 __global__ void k_relabel_cols(const u32 *__restrict__ j, u64 nnz, const u32 *__restrict__ slot, u32 *__restrict__ jp) {
     u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 stride = (u64)gridDim.x * blockDim.x;
@@ -1829,6 +1866,44 @@ k_pack_flops(const u32 *__restrict__ vert, const u32 *__restrict__ hdeg, u64 n1,
     if (threadIdx.x < W && sG[threadIdx.x]) atomicOr((unsigned long long *)&G[threadIdx.x], sG[threadIdx.x]);
 }
 
+// the same totals for a frontier that already IS in hot-set order (permuted form): nothing to gather, nothing to write
+template <int W>
+__global__ void __launch_bounds__(256)
+k_ordered_flops(const u32 *__restrict__ hdeg, u64 n1, const u64 *__restrict__ Xp, u64 *__restrict__ st, u64 *__restrict__ G) {
+    typedef cub::BlockReduce<u64, 256> Red;
+    __shared__ typename Red::TempStorage ts;
+    __shared__ u64 sG[W];
+    if (threadIdx.x < W) sG[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const u32 gmask = (W >= 32) ? 0xffffffffu : (((1u << W) - 1u) << (lane / W * W));
+    u64 fl = 0, ed = 0, g = 0;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x, total = n1 * W;
+    for (u64 base = t - lane; base < total; base += stride) {
+        const u64 tt = base + lane;
+        u64 x = 0;
+        u32 d = 0;
+        if (tt < total) { x = Xp[tt]; d = hdeg[tt / W]; }
+        const u32 nz = __ballot_sync(0xffffffffu, x != 0) & gmask;
+        fl += (u64)__popcll(x) * d;
+        if (nz && (lane % W) == 0) ed += d;
+        g |= x;
+    }
+#pragma unroll
+    for (int o = W; o < 32; o <<= 1) g |= __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane < W && g) atomicOr((unsigned long long *)&sG[lane], g);
+    u64 tf = Red(ts).Sum(fl);
+    __syncthreads();
+    u64 te = Red(ts).Sum(ed);
+    if (threadIdx.x == 0) {
+        if (tf) atomicAdd((unsigned long long *)&st[0], tf);
+        if (te) atomicAdd((unsigned long long *)&st[1], te);
+    }
+    __syncthreads();
+    if (threadIdx.x < W && sG[threadIdx.x]) atomicOr((unsigned long long *)&G[threadIdx.x], sG[threadIdx.x]);
+}
+
 void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
     u64 n = A.nrows;
     lr.vert.release(); lr.jp.release(); lr.slot.release(); lr.hdeg.release(); lr.n1 = 0; lr.packed = false;
@@ -1843,6 +1918,12 @@ void build_hot_pack(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
     lr.slot.alloc(n);
     lr.hdeg.alloc(n1 ? n1 : 1);
     LAUNCH(k_slots_from_keys, grid_for(n, 256, 148 * 16), 256, 0, keys.ptr, n, n1, lr.vert.ptr, lr.slot.ptr, lr.hdeg.ptr);
+    // the order over ALL vertices (the sort already put the sinks last, by id): frontiers may be stored in it (permuted form)
+    lr.pvert = std::make_shared<DevBuf<u32>>(n);
+    lr.pperm = std::make_shared<DevBuf<u32>>(n);
+    LAUNCH(k_full_order, grid_for(n, 256, 148 * 16), 256, 0, keys.ptr, n, lr.pvert->ptr, lr.pperm->ptr);
+    static std::atomic<u64> next_tag{1};
+    lr.perm_tag = next_tag.fetch_add(1);
     lr.packed = true;
 }
 
@@ -2055,10 +2136,18 @@ static void clear_l2_window() {
 }
 
 template <int W>
-static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y,
+static void hop_impl(const DevBits &Xin, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y,
                      u64 *flops_out, int *path_out) {
     Context &cx = ctx();
     u64 n = A.nrows, m = A.ncols;
+    // X in permuted form: usable as it stands only by the pull through the tables it was ordered for; anything else works on a
+    // natural-order copy (cannot happen on the bench path: the caller orders a frontier only for the operand it is pushed through)
+    DevBits Xnat;
+    const bool ordered = Xin.permuted() && AT && lr && lr->packed && Xin.perm_tag == lr->perm_tag && lr->jp.ptr && lr->hdeg.ptr &&
+                         cx.opt_pull_mode != 0 && cx.opt_hot_pack && cx.opt_pull_kernel >= 4 && n == m;
+    const DevBits *Xuse = &Xin;
+    if (Xin.permuted() && !ordered) { bits_copy(Xin, Xnat); bits_naturalise(Xnat); Xuse = &Xnat; }
+    const DevBits &X = *Xuse;
     Y.clear();
     Y.nrows = X.nrows; Y.ncols = m; Y.W = W;
     Y.w.alloc(m * W);
@@ -2070,7 +2159,11 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     const bool fused = cx.opt_fused_prep && AT && lr && cx.opt_hot_pack && lr->packed && lr->jp.ptr && lr->hdeg.ptr &&
                        cx.opt_pull_mode != 0 && cx.opt_pull_kernel != 2 && n == m;
     DevBuf<u64> Xp, Gd;
-    if (fused) {
+    if (ordered) {            // already in gather order: totals only
+        Gd.alloc(W);
+        Gd.zero();
+        if (lr->n1) LAUNCH((k_ordered_flops<W>), grid_for(lr->n1 * W, 256, 148 * 16), 256, 0, lr->hdeg.ptr, lr->n1, X.w.ptr, st.ptr, Gd.ptr);
+    } else if (fused) {
         Xp.alloc(lr->n1 * W);
         Gd.alloc(W);
         Gd.zero();
@@ -2091,7 +2184,14 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     const u32 *gj = AT ? AT->j.ptr : nullptr;   // gather index stream
     const u64 *gx = X.w.ptr;                    // gather source
     u64 gn = n;                                 // gather footprint in vertices
-    if (fused && !pull) {                       // push needs the per-vertex active flags of the classic pass
+    if (ordered && !pull) {                     // the push direction works on natural order: undo the frontier's order and start over
+        DevBits Xn;
+        bits_copy(Xin, Xn);
+        bits_naturalise(Xn);
+        hop_impl<W>(Xn, A, AT, lr, Y, flops_out, path_out);
+        return;
+    }
+    if (fused && !ordered && !pull) {           // push needs the per-vertex active flags of the classic pass
         DevBuf<u64> st2(2);
         st2.zero();
         LAUNCH(k_bits_flops, grid_for(n, 256, 148 * 16), 256, 0, X.w.ptr, (u32)W, n, A.p.ptr, flag.ptr, st2.ptr);
@@ -2121,7 +2221,9 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
         if (path_out) *path_out = 5;
         return;
     }
-    if (pull && cx.opt_hot_pack && lr->packed && lr->jp.ptr) {
+    if (ordered) {                              // the frontier already is the packed gather source (its first n1 records)
+        gj = lr->jp.ptr; gx = X.w.ptr; gn = lr->n1;
+    } else if (pull && cx.opt_hot_pack && lr->packed && lr->jp.ptr) {
         if (!fused) {
             Xp.alloc(lr->n1 * W);
             if (lr->n1) LAUNCH((k_pack_frontier<W>), grid_for(lr->n1 * W, 256, 148 * 32), 256, 0, lr->vert.ptr, lr->n1, X.w.ptr, Xp.ptr);
@@ -2134,7 +2236,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     // (2.08 -> 3.14 ms, few rows ever hold all 64 bits) and at W >= 8; very dense frontiers always benefit.
     const bool dense_frontier = hst[0] >= (hst[1] * X.nrows) / 4;   // flops/edges = degree-weighted mean popcount of a gathered word
     if (pull && (cx.opt_early_exit == 2 || (cx.opt_early_exit == 1 && (dense_frontier || W == 2 || W == 4)))) {
-        if (!(fused && gx == Xp.ptr)) {          // the fused pass already left the OR of the packed frontier in Gd
+        if (!((fused && gx == Xp.ptr) || ordered)) {   // the fused / ordered pass already left the OR of the packed frontier in Gd
             Gd.alloc(W);
             Gd.zero();
             if (gn) LAUNCH((k_or_all<W>), grid_for(gn, 256, 148 * 8), 256, 0, gx, gn, Gd.ptr);
@@ -2177,7 +2279,7 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
                 };
                 // keep the hot prefix of the packed frontier L2-resident for the duration of the pull: a persisting access-policy
                 // window on the library stream (no per-instruction hint exists for 256-bit loads)
-                const bool window = cx.opt_l2_window > 0 && gx == Xp.ptr && gn;
+                const bool window = cx.opt_l2_window > 0 && (gx == Xp.ptr || ordered) && gn;
                 if (window) set_l2_window(gx, std::min<u64>((u64)cx.opt_l2_window, gn * W * 8));
                 auto small = [&](auto kern, u64 split) {
                     LAUNCH(kern, grid_for(m * split, 256, (u64)cx.num_sms * 32), 256, 0, AT->p.ptr, gj, m, gx, Y.w.ptr, hot_bytes, tot_bytes);
@@ -2263,6 +2365,15 @@ static void hop_impl(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRo
     }
 }
 
+// builds every per-matrix table of the pull direction now (B200_Matrix_prepare) instead of inside the first hop that pulls
+void bits_prepare_pull(const DevCSR &A, const DevCSR &AT, LongRows &lr) {
+    if (A.nrows != A.ncols || !AT.nnz) return;
+    Context &cx = ctx();
+    if (!lr.packed && cx.opt_hot_pack) build_hot_pack(A, AT, lr);
+    if (!lr.built || (lr.packed && !lr.jp.ptr)) build_long_rows(AT, lr);
+    if (cx.opt_pull_kernel >= 5 && !lr.seg_built) build_seg_list(AT, lr);
+}
+
 void bits_hop(const DevBits &X, const DevCSR &A, const DevCSR *AT, LongRows *lr, DevBits &Y, u64 *flops_out,
               int *path_out) {
     if (X.ncols != A.nrows) throw GrbError(-6, "mxm: inner dimensions differ");
@@ -2288,11 +2399,13 @@ __global__ void k_bits_or(u64 *__restrict__ y, const u64 *__restrict__ z, u64 n)
     for (; t < n; t += stride) y[t] |= z[t];
 }
 void bits_andnot(DevBits &Y, const DevBits &M) {
+    require_natural(Y, "bits_andnot"); require_natural(M, "bits_andnot");
     if (Y.W != M.W || Y.ncols != M.ncols) throw GrbError(-6, "bits_andnot: shape mismatch");
     u64 n = Y.ncols * Y.W;
     if (n) LAUNCH(k_bits_andnot, grid_for(n, 256, 148 * 16), 256, 0, Y.w.ptr, M.w.ptr, n);
 }
 void bits_or(DevBits &Y, const DevBits &Z) {
+    require_natural(Y, "bits_or"); require_natural(Z, "bits_or");
     if (Y.W != Z.W || Y.ncols != Z.ncols) throw GrbError(-6, "bits_or: shape mismatch");
     u64 n = Y.ncols * Y.W;
     if (n) LAUNCH(k_bits_or, grid_for(n, 256, 148 * 16), 256, 0, Y.w.ptr, Z.w.ptr, n);
@@ -2302,6 +2415,7 @@ void bits_copy(const DevBits &X, DevBits &Y) {
     Y.nrows = X.nrows; Y.ncols = X.ncols; Y.W = X.W;
     Y.w.alloc(X.ncols * X.W);
     d2d(Y.w.ptr, X.w.ptr, X.ncols * X.W);
+    Y.pvert = X.pvert; Y.perm_tag = X.perm_tag;       // a copy keeps the vertex order of its source
 }
 
 } // namespace b200

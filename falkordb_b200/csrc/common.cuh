@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <memory>
 #include <cstdio>
 
 namespace b200 {
@@ -53,6 +54,7 @@ struct Context {
     i64 opt_sync_after_op = 0;
     i64 opt_timing = 0;
     i64 opt_pull_kernel = 5;       // 5 = lane-split degree-binned (default); 4 = degree-binned, one lane per vertex record; 0..3 = earlier kernels
+    i64 opt_perm_push = 1;         // a CSR frontier pushed through a prepared matrix lands in that matrix's hot-set order (no packing pass before the next pull)
     i64 opt_small_split = 0;       // small-row pull kernel: 1 = split the vertex record across lanes like the segment kernel, 0 = one lane per record
     i64 opt_l2_window = 0;         // bytes of the packed frontier's hot prefix kept L2-resident through a persisting access-policy window (0 = off)
     i64 opt_l2_reset = 0;          // cudaCtxResetPersistingL2Cache after each windowed pull
@@ -195,8 +197,14 @@ struct DevBits {
     u64 nrows = 0, ncols = 0;
     u32 W = 0;
     DevBuf<u64> w;
+    // Permuted form (bits.cu, "hot-set order"): the words of vertex v live at position pos(v) instead of v, pos = the degree-sorted
+    // gather order of the matrix this frontier is about to be multiplied by (LongRows::pperm), so the pull of the next hop gathers
+    // straight from it with no packing pass.  pvert[position] = vertex undoes it; perm_tag names the permutation (0 = natural).
+    std::shared_ptr<DevBuf<u32>> pvert;
+    u64 perm_tag = 0;
     bool valid() const { return w.ptr != nullptr; }
-    void clear() { w.release(); W = 0; }
+    bool permuted() const { return perm_tag != 0; }
+    void clear() { w.release(); W = 0; pvert.reset(); perm_tag = 0; }
 };
 
 // ---- L2 residency hints (createpolicy descriptors; sm_80+) ---------------------------------------

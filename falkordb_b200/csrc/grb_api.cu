@@ -277,6 +277,12 @@ static void set_bits(GrB_Matrix A, DevBits &&b) {
     invalidate_aux(A);
 }
 
+// a frontier kept in another matrix's hot-set order (bits.cu: permuted form) goes back to natural vertex order before anything
+// but the pull it was ordered for looks at it
+static void natural_bits(GrB_Matrix A) {
+    if (A->bits_valid && A->bits.permuted()) bits_naturalise(A->bits);
+}
+
 static void set_empty(GrB_Matrix A) {
     A->host.clear();
     A->host_valid = true;
@@ -372,6 +378,7 @@ static void ensure_dev(GrB_Matrix A) {
     finish_pending(A);
     if (A->dev_valid) return;
     if (A->bits_valid) {
+        natural_bits(A);
         DevCSR d;
         bits_to_csr(A->bits, d);
         A->dev = std::move(d);
@@ -412,7 +419,7 @@ static void ensure_host(GrB_Matrix A) {
 
 static void ensure_bits(GrB_Matrix A) {
     finish_pending(A);
-    if (A->bits_valid) return;
+    if (A->bits_valid) { natural_bits(A); return; }
     ensure_dev(A);
     DevBits b;
     bits_from_csr(A->dev, b);
@@ -1059,11 +1066,11 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
                 // (only worth probing for a small CSR: its preparation is O(nnz(F)); an expansion already known to be large skips it)
                 const bool from_csr = cx.opt_csr_push && A->dev_valid && !A->bits_valid && cx.opt_pull_mode != 1 &&
                                       A->dev.nnz <= ((u64)1 << 20) && (known_flops == ~0ULL || known_flops * 4 <= B->dev.nnz) &&
-                                      !(B->diag_state == 1 && cx.opt_diag_filter) && bits_push_from_csr(A->dev, B->dev, Y, &fl);
+                                      !(B->diag_state == 1 && cx.opt_diag_filter) && bits_push_from_csr(A->dev, B->dev, Y, &fl, (B->devT_valid && !Mask) ? &B->lr : (const LongRows *)nullptr);
                 if (from_csr) path = 7;
-                else ensure_bits(A);
+                else if (!(A->bits_valid && A->pending.empty())) ensure_bits(A);   // an existing frontier keeps its vertex order for the hop
                 if (from_csr) {}
-                else if (B->diag_state == 1 && cx.opt_diag_filter) { bits_diag(A->bits, B->dev, Y, &fl); path = 5; }
+                else if (B->diag_state == 1 && cx.opt_diag_filter) { natural_bits(A); bits_diag(A->bits, B->dev, Y, &fl); path = 5; }
                 else {
                     if (cx.opt_pull_mode != 0) ensure_devT(B);
                     bits_hop(A->bits, B->dev, B->devT_valid ? &B->devT : nullptr, B->devT_valid ? &B->lr : (LongRows *)nullptr, Y, &fl, &path);
@@ -1154,6 +1161,7 @@ GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryO
             ((A->bits_valid && !A->dev_valid && !A->host_valid) || (B->bits_valid && !B->dev_valid && !B->host_valid))) {
             ensure_bits(A); ensure_bits(B);
             DevBits Y;
+            natural_bits(A); natural_bits(B);
             bits_copy(A->bits, Y);
             bits_or(Y, B->bits);
             set_bits(C, std::move(Y));
@@ -1274,6 +1282,7 @@ GrB_Info GxB_rowIterator_attach(GxB_Iterator it, GrB_Matrix A, GrB_Descriptor) {
         it->bitmap = false; it->bm.clear(); it->bm.shrink_to_fit();
         if (A->pending.empty() && !A->host_valid && A->bits_valid && A->bits.nrows == A->nrows && !A->valued() && !is_huge(A)) {
             ensure_init();
+            natural_bits(A);
             const u64 nv = A->dev_valid ? A->dev.nnz : bits_nvals(A->bits);
             if (A->nrows && A->ncols && nv > (A->nrows * A->ncols) / 32) {   // denser than one entry per 32 slots
                 const u64 wpr = (A->ncols + 63) / 64;
@@ -1906,7 +1915,7 @@ GrB_Info B200_Matrix_export_bitmap(GrB_Matrix A, uint64_t *bits_out, uint64_t wo
         if (A->nrows && wpr > (1ULL << 36) / A->nrows) throw GrbError(GrB_OUT_OF_MEMORY, "export_bitmap: bitmap larger than 512 GiB");
         const u64 total = A->nrows * wpr;
         const bool from_bits = A->bits_valid && A->bits.nrows == A->nrows;
-        if (!from_bits) ensure_dev(A);
+        if (!from_bits) ensure_dev(A); else natural_bits(A);
         DevBuf<u64> stage;
         u64 *dst = (u64 *)bits_out;
         if (location != B200_LOC_DEVICE) { stage.alloc(total); dst = stage.ptr; }
@@ -1944,7 +1953,7 @@ GrB_Info B200_Matrix_export_bitmap_async(GrB_Matrix A, uint64_t *bits_out, uint6
         if (A->nrows && wpr > (1ULL << 36) / A->nrows) throw GrbError(GrB_OUT_OF_MEMORY, "export_bitmap_async: bitmap larger than 512 GiB");
         const u64 total = A->nrows * wpr;
         const bool from_bits = A->bits_valid && A->bits.nrows == A->nrows;
-        if (!from_bits) ensure_dev(A);
+        if (!from_bits) ensure_dev(A); else natural_bits(A);
         if (!g_copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
         std::unique_ptr<B200_Ticket_opaque> t(new B200_Ticket_opaque());
         t->stage.alloc(total);
@@ -2032,7 +2041,10 @@ GrB_Info B200_Matrix_prepare(GrB_Matrix A, int want_transpose) {
         MultiLock lk{A};
         ensure_init();
         ensure_dev(A);
-        if (want_transpose) ensure_devT(A);
+        if (want_transpose) {
+            ensure_devT(A);
+            bits_prepare_pull(A->dev, A->devT, A->lr);     // hot-set order, degree bins, segment list: off the first query's path
+        }
         sync_stream();
         return GrB_SUCCESS;
     });
@@ -2317,6 +2329,7 @@ GrB_Info B200_set_option(const char *name, int64_t value) {
     else if (n == "fused_prep") c.opt_fused_prep = value;
     else if (n == "l2_window") c.opt_l2_window = value;
     else if (n == "small_split") c.opt_small_split = value;
+    else if (n == "perm_push") c.opt_perm_push = value;
     else if (n == "l2_reset") c.opt_l2_reset = value;
     else if (n == "count_kernel") c.opt_count_kernel = value;
     else if (n == "bfs_direction") c.opt_bfs_direction = value;
