@@ -8,15 +8,19 @@ the reference's row iterator walks, cond_traverse.rs:608,644).  TEPS = sum over 
 flops_h = sum_{(i,k) in F_h} deg_A(k)  divided by the step time  (SURVEY.md 8d).
 
   value : device-resident -- F already in HBM when the timed region starts; CUDA-event timed on the library's stream
-  e2e   : the same batch host to host through the public API, falkordb_b200.traverse_to_host: per 128-row slice
-          GxB_Matrix_build_Scalar from host index arrays (H2D inside), 3x GrB_mxm, B200_Matrix_export_bitmap_async of the
-          result (packed row-major bitmap, D2H on a second stream, overlapping the next slice's hops), tickets waited at the
-          end.  The bitmap is chosen by Matrix.export_auto's rule on the first batch (result denser than 1/32); the CSR
-          hand-off (GrB_Matrix_wait + B200_Matrix_export_CSR) of the same result is timed next to it at N = 1.
+  e2e   : the same batch host to host through ONE C-ABI call per batch, B200_traverse_batch: host source ids in (H2D inside),
+          3 hops, the result in host memory as a packed row-major bitmap (128-row slices, D2H on a second stream overlapping
+          the next slice's hops) -- the hand-off Matrix.export_auto's rule picks for a result denser than 1/32; the CSR
+          hand-off of the same call is timed next to it at N = 1.
+  roofline : the dominant kernel family's algorithmic bytes / its event-timed duration against the measured HBM peak, every
+          family in `families`, and for the hop what really bounds it (`hop_gather_ceiling`: L1TEX wavefronts per second).
+  cpu_baseline : the whole first timed batch on the host (oracle port, all threads) + digest parity of all its rows vs the GPU.
 
---impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on a bounded
-sample of the same workload.  Multi-GPU: the batch rows are independent, so ranks shard the sources with A replicated
-and no data-path collective (weak scaling: fixed sources per rank).
+--impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on the same
+batches.  Multi-GPU: the batch rows are independent, so ranks shard the sources with A replicated and no data-path
+collective (weak scaling: fixed sources per rank); ranks bind to their GPU's NUMA node.
+Other workloads (--workload): bfs (config 5: partitioned direction-optimising BFS over NCCL), triangles (config 4), delta
+(delta-matrix sync kernels at fold sizes), pagerank (FP64 mxv).
 """
 import argparse
 import ctypes as C
@@ -336,7 +340,7 @@ def run_b200(a):
     ms = e0.elapsed_time(e1)
     launches = fb.get_stat("launches")
     kstats = {}
-    for name in ("bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "bits_fill", "bits_count"):
+    for name in ("bits_pull", "bits_pull_long", "bits_push", "heavy_accumulate", "bits_fill", "bits_count", "small_rows"):
         m, nl, by = C.c_double(), C.c_uint64(), C.c_uint64()
         if L.B200_kernel_stats(name.encode(), C.byref(m), C.byref(nl), C.byref(by)) == 0 and nl.value:
             kstats[name] = {"ms": m.value, "launches": nl.value, "bytes": by.value}
@@ -473,8 +477,9 @@ def run_b200(a):
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         traffic = None
         try:   # dram__bytes_read+write per launch from the committed ncu --set full captures of this configuration
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1f_traffic.json")))
-            fam = {"bits_pull": ("k_bits_pull_mid", "k_bits_pull_small"), "bits_fill": ("k_bits_fill_rows",)}
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            fam = {"bits_pull": ("k_pull_seg", "k_pull_small"), "bits_fill": ("k_bits_fill_v3",), "bits_push": ("k_csr_push",),
+                   "bits_count": ("k_bits_count_csa",)}
             if (tj["config"]["scale"] == a.scale and tj["config"]["sources"] == a.sources and tj["config"]["edge_factor"] == a.edge_factor
                     and dom in fam and not a.opt):
                 traffic = int(sum(tj["dram_bytes_by_kernel"][k] for k in fam[dom]))
@@ -485,18 +490,32 @@ def run_b200(a):
                 "share_of_step": ks["ms"] / ms,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
                 "basis": "bytes this kernel family must move per launch (DESIGN.md 4.1), not SURVEY 8(d)'s row-wise figure"}
-        if dom == "bits_pull" and pull_flops[1]:
+        # every timed family, same arithmetic (the dominant one above is repeated here)
+        roof["families"] = {k: {"ms_per_launch": v["ms"] / v["launches"], "achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
+                                "frac": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak) if v["ms"] > 0 else 0.0,
+                                "share_of_step": v["ms"] / ms} for k, v in kstats.items()}
+        if "bits_pull" in kstats and pull_flops[1]:
+            kp = kstats["bits_pull"]
+            pl_ms = kp["ms"] / kp["launches"]
             # SURVEY 8(d) bytes_mxm for the same launches: 4 B per flop (A's col_idx segment re-read for every frontier row) is
             # the dominant term.  The bit-matrix kernel serves 64*W frontier rows per pass over A, so it never moves these bytes.
             sb = 4.0 * pull_flops[0] / pull_flops[1]
-            roof["survey_8d"] = {"bytes_per_launch": sb, "achieved": sb / (per_launch_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                 "frac": sb / (per_launch_ms * 1e-3) / 1e9 / peak}
-            # what actually bounds it: random 32-byte gathers through L1TEX/L2 (one per edge of A'), against the rate the
-            # gather micro-benchmark sustains on this access pattern with every lane busy (profiles/r1c_ubench_gather.txt)
-            tl = ks["ms"] + kstats.get("bits_pull_long", {"ms": 0.0})["ms"]
-            gps = nnzA * ks["launches"] / (tl * 1e-3) / 1e9
-            roof["gather_bound"] = {"gathers_per_launch": nnzA, "achieved_ggathers_per_s": gps, "ceiling_ggathers_per_s": 240.0,
-                                    "frac": gps / 240.0, "time_ms_incl_long_rows": tl / ks["launches"]}
+            roof["hop_survey_8d"] = {"bytes_per_launch": sb, "achieved": sb / (pl_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                     "frac": sb / (pl_ms * 1e-3) / 1e9 / peak}
+            # what actually bounds the hop: one L1TEX wavefront (a 128-byte line through the tag stage) per gathered vertex
+            # record -- SPLIT lanes share a record -- against one line per clock per SM at the SM clock sampled during the run
+            W = max(1, -(-a.sources // 64))
+            Wp = 1
+            while Wp < W:
+                Wp <<= 1
+            parts = max(1, Wp // 4)                      # 32-byte parts per record
+            lanes_per_record = parts                      # lane-split kernels: the parts of a record coalesce into ONE wavefront
+            wavefronts = nnzA * 1.0 + nnzA * 4.0 / 128.0  # gathers + the coalesced col_idx stream
+            ceiling = 148 * (clk.get("sm_mhz") or 1965.0) * 1e6
+            roof["hop_gather_ceiling"] = {"wavefronts_per_launch": wavefronts, "achieved_wavefronts_per_s": wavefronts / (pl_ms * 1e-3),
+                                          "ceiling_wavefronts_per_s": ceiling, "frac": wavefronts / (pl_ms * 1e-3) / ceiling,
+                                          "lanes_per_record": lanes_per_record,
+                                          "note": "L1TEX tag stage: one 128-byte line per clock per SM (scripts/ubench/gather*.cu)"}
     # SURVEY 8d's row-wise formula (4 B per flop dominant) for the whole step, for reference: a frontier kernel that
     # serves 64*W rows per pass over A reads far fewer bytes than this, so this fraction may exceed 1.
     survey_bytes = 4 * flops + 4 * nnz_out
