@@ -578,9 +578,11 @@ void bits_to_csr(const DevBits &X, DevCSR &C) {
         TimedScope ts(TK_BITS_FILL, 8ULL * W * n + 4 * nnz);
         if (keep_masks) {
             LAUNCH(k_bits_fill_masks, (u32)ctx().num_sms * 8, FILLM_WARPS * 32, 0, masks.ptr, W, ntiles, off.ptr, C.j.ptr);
-        } else if (ctx().opt_fill_kernel == 3 && ctx().opt_fill_cap <= 0) {
+        } else if (ctx().opt_fill_kernel == 3 && ctx().opt_fill_cap <= 0 && W <= 8) {
+            // (at W = 16 the 2048-vertex tile's 128 KB of frontier words per CTA no longer survives in L1 next to 100 KB of shared
+            // memory and the word columns are re-fetched from L2: 8.7 vs 6.2 ms -- the 1024-vertex kernel below takes W = 16)
             LAUNCH(k_bits_fill_v3, (u32)((n + F3_TILE - 1) / F3_TILE), F3_THREADS, F3_SMEM, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
-        } else if (ctx().opt_fill_kernel == 1 && ctx().opt_fill_cap <= 0) {
+        } else if ((ctx().opt_fill_kernel == 1 || ctx().opt_fill_kernel == 3) && ctx().opt_fill_cap <= 0) {
             LAUNCH(k_bits_fill_rows, (u32)ntiles, TILE_THREADS, FILL2_SMEM, X.w.ptr, n, W, ntiles, off.ptr, C.j.ptr);
         } else {
             // staging capacity from the average (tile, word) population, 1.5x headroom, 8K-entry steps: sparse frontiers

@@ -196,7 +196,38 @@ int orc_mask_assign(const orc_csr *Cold, const orc_csr *T, const orc_csr *M, int
  * emission, which with replace is the full semantics of matrix.rs:1386-1394; other combinations
  * go through orc_mask_assign.  flops_out (optional) receives sum_{(i,k) in A} deg_B(k).
  */
-typedef struct { uint64_t *bits; int64_t nwords; uint32_t *list; } orc_ws;
+/* rows are staged in thread-local bump arenas that persist across calls: a 512-row frontier produces multi-MB rows, and a malloc /
+ * free pair per row means an mmap, a page-fault storm and an munmap per row, serialised on the process's mm lock with 128 threads */
+#define ORC_ARENA_CHUNK ((size_t)64 << 20)
+typedef struct { char **chunk; size_t *cap; int nchunks, cur; size_t used; } orc_arena;
+typedef struct { uint64_t *bits; int64_t nwords; uint32_t *list; orc_arena ar; } orc_ws;
+static void arena_reset(orc_arena *a) { a->cur = 0; a->used = 0; }
+static void *arena_alloc(orc_arena *a, size_t bytes) {
+    bytes = (bytes + 63) & ~(size_t)63;
+    while (1) {
+        if (a->cur < a->nchunks && a->used + bytes <= a->cap[a->cur]) { void *p = a->chunk[a->cur] + a->used; a->used += bytes; return p; }
+        if (a->cur + 1 < a->nchunks && a->used > 0) { a->cur++; a->used = 0; continue; }           /* next retained chunk */
+        if (a->cur < a->nchunks && a->used == 0 && bytes > a->cap[a->cur]) {                       /* retained chunk too small: replace */
+            free(a->chunk[a->cur]);
+            a->cap[a->cur] = bytes;
+            a->chunk[a->cur] = malloc(bytes);
+            if (!a->chunk[a->cur]) abort();
+            continue;
+        }
+        if (a->cur >= a->nchunks || a->used > 0) {                                                 /* grow the chunk table */
+            const size_t cap = bytes > ORC_ARENA_CHUNK ? bytes : ORC_ARENA_CHUNK;
+            a->chunk = realloc(a->chunk, sizeof(char *) * (size_t)(a->nchunks + 1));
+            a->cap = realloc(a->cap, sizeof(size_t) * (size_t)(a->nchunks + 1));
+            if (!a->chunk || !a->cap) abort();
+            a->chunk[a->nchunks] = malloc(cap);
+            if (!a->chunk[a->nchunks]) abort();
+            a->cap[a->nchunks] = cap;
+            a->cur = a->nchunks;
+            a->nchunks++;
+            a->used = 0;
+        }
+    }
+}
 typedef struct { int64_t flops, row; } rowwork_t;
 static int cmp_rowwork(const void *a, const void *b) {
     const rowwork_t *x = a, *y = b;
@@ -219,7 +250,7 @@ static void ws_reserve(int nthreads) {              /* called outside parallel r
     if (nthreads <= g_nws) return;
     g_ws = realloc(g_ws, sizeof(orc_ws) * (size_t)nthreads);
     if (!g_ws) abort();
-    for (int t = g_nws; t < nthreads; t++) { g_ws[t].bits = NULL; g_ws[t].nwords = 0; g_ws[t].list = NULL; }
+    for (int t = g_nws; t < nthreads; t++) { g_ws[t].bits = NULL; g_ws[t].nwords = 0; g_ws[t].list = NULL; memset(&g_ws[t].ar, 0, sizeof(orc_arena)); }
     g_nws = nthreads;
 }
 static orc_ws *ws_get(int t, int64_t ncols) {       /* thread t's workspace, grown (zeroed) on demand */
@@ -269,6 +300,7 @@ int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int ma
         orc_ws *w = ws_get(tid, ncols);
         uint64_t *bits = w->bits;
         uint32_t *list = w->list;
+        arena_reset(&w->ar);
         int64_t my_flops = 0, my_rows = 0;
         double my_busy = 0.0;
 #pragma omp for schedule(dynamic, 1) nowait
@@ -277,7 +309,12 @@ int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int ma
             const double t0 = now_s();
             int64_t n = 0;               /* distinct columns seen */
             uint32_t lo = UINT32_MAX, hi = 0;
-            for (int64_t a = A->p[i]; a < A->p[i + 1]; a++) {
+            const int64_t a_end = A->p[i + 1];
+            for (int64_t a = A->p[i]; a < a_end; a++) {
+                /* the rows of B a frontier row touches are short and scattered: fetch the row pointers 8 entries ahead and
+                 * the first line of the column list 4 ahead, so the misses overlap instead of serialising */
+                if (a + 8 < a_end) __builtin_prefetch(&B->p[A->j[a + 8]], 0, 1);
+                if (a + 4 < a_end) __builtin_prefetch(&B->j[B->p[A->j[a + 4]]], 0, 1);
                 const uint32_t k = A->j[a];
                 const int64_t s = B->p[k], e = B->p[k + 1];
                 my_flops += e - s;
@@ -297,7 +334,7 @@ int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int ma
             uint32_t *row = NULL;
             int64_t m = 0;
             if (n > 0) {
-                row = xmalloc(sizeof(uint32_t) * (size_t)n);
+                row = arena_alloc(&w->ar, sizeof(uint32_t) * (size_t)n);
                 if (n <= ORC_LIST_CAP) {             /* sparse row: sort the list, clear through it */
                     memcpy(row, list, sizeof(uint32_t) * (size_t)n);
                     qsort(row, (size_t)n, sizeof(uint32_t), cmp_u32);
@@ -339,9 +376,8 @@ int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int ma
     for (int64_t i = 0; i < nrows; i++) {
         int64_t m = cnt[i + 1] - cnt[i];
         if (m) memcpy(out->j + cnt[i], rows[i], sizeof(uint32_t) * (size_t)m);
-        free(rows[i]);
     }
-    free(rows);
+    free(rows);                          /* the rows themselves live in the thread arenas (kept for the next call) */
     g_busy_s = busy_total; g_wall_s = now_s() - t_wall; g_busy_threads = busy_threads; g_team = team;
     if (flops_out) *flops_out = flops_total;
     return 0;
