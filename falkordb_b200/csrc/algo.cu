@@ -122,4 +122,62 @@ int pagerank(const DevCSR &A, const DevCSR &AT, double damping, double tol, int 
     return iters;
 }
 
+
+// ---- weakly connected components (algo.WCC -> LAGr_ConnectedComponents, algo_procedures.rs:838-846) ------------------------
+// LAGraph's FastSV returns, for every vertex, the representative of its component; with min-hooking that is the smallest vertex id
+// of the component, which is what this gives (deterministic).  A must have a symmetric pattern (the reference builds
+// build_symmetric_adjacency_matrix and sets is_symmetric_structure).  Rounds of: hook every edge's larger root under the smaller
+// (atomicMin), then full pointer jumping; O(log n) rounds, each one streaming pass over the CSR (4 B per entry + 8 B gathers).
+__global__ void k_cc_init(u64 *__restrict__ parent, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) parent[i] = i;
+}
+__global__ void __launch_bounds__(256)
+k_cc_hook(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 n, u64 *__restrict__ parent, u32 *__restrict__ changed) {
+    const u32 lane8 = threadIdx.x & 7;
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const u64 ng = ((u64)gridDim.x * blockDim.x) >> 3;
+    bool ch = false;
+    for (u64 u = g; u < n; u += ng) {
+        const u64 s = p[u], e = p[u + 1];
+        if (s == e) continue;
+        const u64 ru = parent[u];
+        for (u64 q = s + lane8; q < e; q += 8) {
+            const u64 rv = parent[j[q]];
+            if (rv == ru) continue;
+            const u64 hi = ru > rv ? ru : rv, lo = ru > rv ? rv : ru;
+            atomicMin((unsigned long long *)&parent[hi], (unsigned long long)lo);
+            ch = true;
+        }
+    }
+    if (ch) *changed = 1;
+}
+__global__ void k_cc_jump(u64 *__restrict__ parent, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 r = parent[i];
+        while (true) { const u64 rr = parent[r]; if (rr == r) break; r = rr; }
+        parent[i] = r;
+    }
+}
+int connected_components(const DevCSR &A, u64 *d_comp) {
+    const u64 n = A.nrows;
+    if (!n) return 0;
+    const u32 g = grid_for(n, 256, 148 * 16);
+    LAUNCH(k_cc_init, g, 256, 0, d_comp, n);
+    DevBuf<u32> changed(1);
+    int rounds = 0;
+    while (true) {
+        changed.zero();
+        LAUNCH(k_cc_hook, grid_for(n * 8, 256, (u64)ctx().num_sms * 32), 256, 0, A.p.ptr, A.j.ptr, n, d_comp, changed.ptr);
+        LAUNCH(k_cc_jump, g, 256, 0, d_comp, n);
+        rounds++;
+        if (!read_scalar(changed.ptr)) break;
+        if (rounds > 64) throw GrbError(-101, "connected components did not converge");
+    }
+    return rounds;
+}
+
 } // namespace b200

@@ -1450,11 +1450,18 @@ GrB_Info GrB_Vector_extractElement_BOOL(bool *x, GrB_Vector v, GrB_Index i) {
     if (r == GrB_SUCCESS) *x = t != 0;
     return r;
 }
+static u64 vec_at(GrB_Vector v, u64 k);
+static inline double bits_as_double(i64 b) { double x; memcpy(&x, &b, 8); return x; }
 GrB_Info GrB_Vector_extractTuples_INT64(GrB_Index *I, int64_t *X, GrB_Index *nvals, GrB_Vector v) {
     CHECK_PTR(nvals); CHECK_PTR(v);
-    if (*nvals < v->idx.size()) return GrB_INSUFFICIENT_SPACE;
-    for (size_t k = 0; k < v->idx.size(); k++) { if (I) I[k] = v->idx[k]; if (X) X[k] = v->val[k]; }
-    *nvals = v->idx.size();
+    const u64 nv = v->full ? v->n : v->idx.size();
+    if (*nvals < nv) return GrB_INSUFFICIENT_SPACE;
+    for (u64 k = 0; k < nv; k++) {
+        if (I) I[k] = v->full ? k : v->idx[k];
+        if (X) X[k] = v->full ? (v->type == T_FP64 ? (int64_t)((const double *)v->fx)[k] : (int64_t)vec_at(v, k))
+                              : (v->type == T_FP64 ? (int64_t)bits_as_double(v->val[k]) : v->val[k]);
+    }
+    *nvals = nv;
     return GrB_SUCCESS;
 }
 GrB_Info GrB_Vector_extractTuples_BOOL(GrB_Index *I, bool *X, GrB_Index *nvals, GrB_Vector v) {
@@ -1708,6 +1715,41 @@ int LAGr_PageRank(GrB_Vector *centrality, int *iters, LAGraph_Graph G, float dam
             sync_stream();
         }
         *centrality = v.release();
+        return GrB_SUCCESS;
+    });
+    if (info && msg) snprintf(msg, 256, "%s", tl_error.c_str());
+    return info;
+}
+// LAGr_ConnectedComponents (lagraph_bindings.rs:521-526; call site algo_procedures.rs:838-846): component(i) = the smallest vertex
+// id of i's component, a full (dense) GrB_UINT64 vector as LAGraph documents.  The pattern must be symmetric (the reference passes
+// build_symmetric_adjacency_matrix and sets is_symmetric_structure); a directed graph is refused like LAGraph does (-1005).
+int LAGr_ConnectedComponents(GrB_Vector *component, LAGraph_Graph G, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G || !G->A || !component) return GrB_NULL_POINTER;
+    GrB_Matrix A = G->A;
+    if (A->magic != MAGIC) return GrB_INVALID_OBJECT;
+    if (A->nrows != A->ncols) return GrB_DIMENSION_MISMATCH;
+    if (G->kind != LAGraph_ADJACENCY_UNDIRECTED && G->is_symmetric_structure != 1) {
+        if (msg) snprintf(msg, 256, "G->A must be known to be symmetric");
+        return -1005;       // LAGRAPH_SYMMETRIC_STRUCTURE_REQUIRED
+    }
+    GrB_Info info = guarded([&]() {
+        GpuLock g;
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        const u64 n = A->nrows;
+        DevBuf<u64> comp(n ? n : 1);
+        connected_components(A->dev, comp.ptr);
+        std::unique_ptr<GB_Vector_opaque> v(new GB_Vector_opaque());
+        v->type = T_UINT64; v->n = n; v->full = true; v->fbytes = n * sizeof(u64);
+        if (n) {
+            v->fx = g_user_malloc(v->fbytes);
+            if (!v->fx) throw std::bad_alloc();
+            CUDA_TRY(cudaMemcpyAsync(v->fx, comp.ptr, v->fbytes, cudaMemcpyDeviceToHost, stream()));
+            sync_stream();
+        }
+        *component = v.release();
         return GrB_SUCCESS;
     });
     if (info && msg) snprintf(msg, 256, "%s", tl_error.c_str());

@@ -109,6 +109,7 @@ void bfs_do(const DevCSR &Aloc, const DevCSR &ATloc, u64 n, u64 lo, u64 hi, cons
 void mxv_fp64(const DevCSR &A, bool use_values, const double *x, const unsigned char *present, double *y, unsigned char *ypresent,
               double init, bool accum);
 int pagerank(const DevCSR &A, const DevCSR &AT, double damping, double tol, int itermax, double *r);
+int connected_components(const DevCSR &A, u64 *d_comp);     // symmetric pattern; d_comp[v] = smallest vertex id of v's component
 
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
 

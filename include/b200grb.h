@@ -273,6 +273,8 @@ int LAGr_BreadthFirstSearch_Extended(GrB_Vector *level, GrB_Vector *parent, LAGr
 int LAGraph_Cached_AT(LAGraph_Graph G, char *msg);
 int LAGraph_Cached_OutDegree(LAGraph_Graph G, char *msg);
 int LAGr_PageRank(GrB_Vector *centrality, int *iters, LAGraph_Graph G, float damping, float tol, int itermax, char *msg);
+/* algo.WCC (algo_procedures.rs:838-846; lagraph_bindings.rs:521-526): component(i) = smallest vertex id of i's component (dense) */
+int LAGr_ConnectedComponents(GrB_Vector *component, LAGraph_Graph G, char *msg);
 
 /* ---- B200 extensions ---- */
 #define B200_LOC_HOST 0

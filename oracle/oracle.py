@@ -266,6 +266,17 @@ def pagerank(A, damping=0.85, tol=1e-4, itermax=100):
     return r, it
 
 
+def wcc(A):
+    """LAGr_ConnectedComponents as algo.WCC consumes it (algo_procedures.rs:838-846): component(i) = representative of i's
+    component; FastSV's min-hooking makes that the SMALLEST vertex id of the component.  A: symmetric pattern.  Restated with
+    scipy's connected_components (an independent implementation) + a min per label."""
+    import scipy.sparse.csgraph as cg
+    ncomp, lab = cg.connected_components(A.to_scipy(), directed=False)
+    rep = np.full(ncomp, A.nrows, np.int64)
+    np.minimum.at(rep, lab, np.arange(A.nrows, dtype=np.int64))
+    return rep[lab]
+
+
 def num_threads():
     return lib().orc_num_threads()
 
