@@ -926,7 +926,9 @@ def test_frontier_in_hot_set_order_between_push_and_pull(nsrc):
         fb.set_option("pull_mode", -1)  # a forced pull would bypass the CSR push
         F = Matrix(nsrc, n, bool)
         F.build(np.arange(nsrc), src)
+        fb.set_option("bits_mode", 0)   # hop 1 row-wise (a CSR result), as the auto mode does for a one-entry-per-row frontier
         F.lmxm(dA)
+        fb.set_option("bits_mode", 1)
         F.lmxm(dA)                      # CSR push while the expansion is small: the result is in dA's order when perm_push is on
         pushed.append(fb.get_stat("last_path") == 7)
         fb.set_option("pull_mode", 1)
