@@ -210,7 +210,7 @@ k_masked_pairs(const u32 *__restrict__ Arid, const u32 *__restrict__ Aj, u64 nnz
     }
 }
 
-void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out) {
+void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out, u64 flops) {
     if (A.ncols != B.nrows || M.nrows != A.nrows || M.ncols != B.ncols) throw GrbError(-6, "masked mxm: dimension mismatch");
     out.clear();
     out.nrows = M.nrows; out.ncols = M.ncols;
@@ -219,9 +219,10 @@ void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool struc
     flag.zero();
     LAUNCH(k_row_ids, grid_for(A.nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.nrows, rid.ptr);
     {
-        // SURVEY 8(d) bytes_mxm with the mask term: A's entries + their row ids, B's and M's row-pointer pairs per (i,k), the
-        // B segments (4 B per flop is the row-wise bound; the kernel reads min(|B(k,:)|, |M(i,:)|) per pair), M once, flags
-        TimedScope ts(TK_MASKED, 8 * A.nnz + 32 * A.nnz + 4 * M.nnz + M.nnz / 8);
+        // SURVEY 8(d) bytes_mxm with the mask term: F's entries and row pointers, A's row-pointer pair per F entry, 4 B per flop (the
+        // row-wise bound on the B segments; this kernel reads min(|B(k,:)|, |M(i,:)|) per pair and probes the other side), the mask;
+        // the output (a subset of M) is written by the compaction that follows
+        TimedScope ts(TK_MASKED, 4 * A.nnz + 4 * (A.nrows + 1) + 8 * A.nnz + 4 * flops + 4 * M.nnz + 4 * (M.nrows + 1));
         LAUNCH(k_masked_pairs, grid_for(A.nnz * 32, 256, 148 * 64), 256, 0, rid.ptr, A.j.ptr, A.nnz, B.p.ptr, B.j.ptr, M.p.ptr,
                M.j.ptr, flag.ptr);
     }

@@ -1096,7 +1096,7 @@ GrB_Info GrB_mxm(GrB_Matrix C, GrB_Matrix Mask, GrB_BinaryOp accum, GrB_Semiring
             ensure_dev(Mask);
             u64 fl = spgemm_flops(*Ad, *Bd);
             DevCSR Zm;
-            spgemm_masked(*Ad, *Bd, Mask->dev, d.structure, Zm);
+            spgemm_masked(*Ad, *Bd, Mask->dev, d.structure, Zm, fl);
             cx.last_flops = fl; cx.total_flops += fl; cx.last_path = 6;
             if (d.replace) set_dev(C, std::move(Zm));
             else {

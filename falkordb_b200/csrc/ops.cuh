@@ -76,7 +76,7 @@ void ewise_intersect(const DevCSR &A, const DevCSR &B, DevCSR &out);            
 void filter_by_mask(const DevCSR &T, const DevCSR &M, bool comp, bool structural, DevCSR &out);
 void csr_resize(const DevCSR &A, u64 nrows, u64 ncols, DevCSR &out); // grow/shrink dims (drops out-of-range)
 // Z = pattern(A*B) restricted to M's structure (valued mask: entries of M with value 0 excluded unless structural)
-void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out);
+void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool structural, DevCSR &out, u64 flops = 0);
 
 // bfs.cu
 void bfs_run(const DevCSR &A, u64 src, i64 max_level, i64 *d_level, i64 *d_parent, u64 *edges_traversed);
