@@ -74,4 +74,28 @@ inline ExpandResult expand_batch(const std::vector<uint64_t> &src_ids, const std
     return out;
 }
 
+// The batch boundary on the way out (graph/src/runtime/batch.rs:81, 274-287, 832): the (parent row, destination) pairs leave the
+// operator re-packed into batches of <= BATCH_SIZE rows -- a `Column::NodeIds` with the destinations plus a selection vector
+// (`Vec<u16>`: index of the parent row in the INPUT batch) that `Batch::gather` uses to copy the parent's columns next to it.
+// Pairs arrive in ascending (row, dest) order (the iterator contract), so every output batch is a contiguous, ordered slice.
+struct OutBatch {
+    std::vector<uint64_t> node_ids;    // Column::NodeIds(Vec<NodeId>)  (graph.rs:139: NodeId(u64))
+    std::vector<uint16_t> selection;   // parent row per output row; input batches hold <= BATCH_SIZE rows, so u16 suffices
+};
+inline std::vector<OutBatch> repack(const ExpandResult &r, size_t batch = BATCH_SIZE) {
+    std::vector<OutBatch> out;
+    for (size_t i = 0; i < r.dest.size(); i += batch) {
+        const size_t e = std::min(r.dest.size(), i + batch);
+        OutBatch b;
+        b.node_ids.assign(r.dest.begin() + i, r.dest.begin() + e);
+        b.selection.reserve(e - i);
+        for (size_t k = i; k < e; k++) {
+            if (r.row_idx[k] >= BATCH_SIZE) throw std::runtime_error("repack: parent row outside a BATCH_SIZE input batch");
+            b.selection.push_back((uint16_t)r.row_idx[k]);
+        }
+        out.push_back(std::move(b));
+    }
+    return out;
+}
+
 } // namespace fdb

@@ -313,6 +313,28 @@ static void t_batch_can_demote_and_then_empty_the_same_pair() {  // tensor.rs:15
 }
 // CondTraverse over a relationship tensor (TraversalMatrix::U64, cond_traverse.rs:83): the u64 edge ids -- including
 // id 0 and the MULTI_EDGE sentinel -- are never read by ANY_PAIR; only the pattern matters.
+// batch boundary (batch.rs:81, 274-287): <= 1024 rows per output batch, NodeIds + u16 selection vector, order preserved
+static void t_repack_output_batches() {
+    const uint64_t n = 4096;
+    VersionedMatrix star(n, n);
+    for (uint64_t j = 1; j <= 2500; j++) star.set(0, j);          // one parent with 2500 destinations
+    for (uint64_t j = 10; j < 40; j++) star.set(3, j);            // another with 30
+    star.wait();
+    ExpandResult r = expand_batch({0, 7, 2, 3}, {TraversalMatrix(&star)}, {}, {});
+    REQUIRE(r.dest.size() == 2530, "expand_batch pair count");
+    std::vector<OutBatch> b = repack(r);
+    REQUIRE(b.size() == 3 && b[0].node_ids.size() == 1024 && b[1].node_ids.size() == 1024 && b[2].node_ids.size() == 482, "batches of <= 1024 rows");
+    size_t k = 0;
+    for (const OutBatch &ob : b) {
+        REQUIRE(ob.node_ids.size() == ob.selection.size(), "one selection entry per row");
+        for (size_t t = 0; t < ob.node_ids.size(); t++, k++) {
+            REQUIRE(ob.node_ids[t] == r.dest[k] && ob.selection[t] == r.row_idx[k], "order and parent rows preserved");
+            REQUIRE(ob.selection[t] == 0 || ob.selection[t] == 3, "parents are input rows 0 and 3");
+        }
+    }
+    REQUIRE(repack(ExpandResult{}).empty(), "nothing in, nothing out");
+}
+
 static void t_traverse_over_tensor_operand() {
     uint64_t n = 64;
     Tensor t(n, n);
@@ -348,6 +370,7 @@ static TestEntry TESTS[] = {
     {"batch_demote_leaves_every_survivor_inline", t_batch_demote_leaves_every_survivor_inline},
     {"batch_can_demote_and_then_empty_the_same_pair", t_batch_can_demote_and_then_empty_the_same_pair},
     {"traverse_over_tensor_operand", t_traverse_over_tensor_operand},
+    {"repack_output_batches", t_repack_output_batches},
 };
 
 extern "C" {
