@@ -139,70 +139,15 @@ __global__ void k_transpose_keys(const u64 *__restrict__ p, const u32 *__restric
     }
 }
 
-// The rows of A are already in ascending row order, so a STABLE sort by column alone yields A' with ascending rows inside each
-// column: 32-bit keys (the column, log2(ncols) significant bits: 3 radix passes at scale 24) carrying 32-bit payloads, instead of
-// the 64-bit (col << 32 | row) keys of round 1 (8 passes of twice the bytes: 11.7 ms for 1.3e8 entries, 0.015 of the HBM roofline).
-__global__ void k_transpose_pairs(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 nrows, u32 *__restrict__ keys,
-                                  u32 *__restrict__ vals, int positions) {
-    const u32 l8 = threadIdx.x & 7;
-    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const u64 ng = ((u64)gridDim.x * blockDim.x) >> 3;
-    for (u64 r = g; r < nrows; r += ng) {
-        const u64 s = p[r], e = p[r + 1];
-        for (u64 q = s + l8; q < e; q += 8) { keys[q] = j[q]; vals[q] = positions ? (u32)q : (u32)r; }
-    }
-}
-// p[c] = first position whose key >= c
-__global__ void k_ptr_from_u32_keys(const u32 *__restrict__ keys, u64 n, u64 ncols, u64 *__restrict__ p) {
-    u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 stride = (u64)gridDim.x * blockDim.x;
-    for (; c <= ncols; c += stride) {
-        u64 lo = 0, hi = n;
-        while (lo < hi) { u64 mid = (lo + hi) >> 1; if ((u64)keys[mid] < c) lo = mid + 1; else hi = mid; }
-        p[c] = lo;
-    }
-}
-// through the sort's permutation: out.j[d] = row of A's entry perm[d], out.x[d] = its value
-__global__ void k_transpose_gather(const u32 *__restrict__ perm, u64 n, const u64 *__restrict__ Ap, u64 nrows, const u64 *__restrict__ Ax,
-                                   u32 *__restrict__ outj, u64 *__restrict__ outx) {
-    u64 d = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 stride = (u64)gridDim.x * blockDim.x;
-    for (; d < n; d += stride) {
-        const u64 q = perm[d];
-        u64 lo = 0, hi = nrows - 1;                  // largest r with Ap[r] <= q
-        while (lo < hi) { u64 mid = (lo + hi + 1) >> 1; if (Ap[mid] <= q) lo = mid; else hi = mid - 1; }
-        outj[d] = (u32)lo;
-        outx[d] = Ax[q];
-    }
-}
 void transpose_csr(const DevCSR &A, DevCSR &out, bool keep_values) {
     u64 n = A.nnz;
     if (n == 0) { csr_from_sorted_keys(nullptr, 0, A.ncols, A.nrows, nullptr, nullptr, out); return; }
     // SURVEY 8(d) bytes_transpose = 2 * (4 * nnz + 4 * (n + 1)) (+ 2 * 8 * nnz if valued); the radix sort inside moves more
     TimedScope ts(TK_TRANSPOSE, 2 * (4 * n + 8 * (A.nrows + 1)) + ((keep_values && A.has_values()) ? 16 * n : 0));
-    const bool valued = keep_values && A.has_values();
-    if (n <= 0x7fffffffULL) {
-        int bits = 1;
-        while (bits < 32 && ((u64)1 << bits) < A.ncols) bits++;
-        DevBuf<u32> keys(n), vals(n);
-        LAUNCH(k_transpose_pairs, grid_for(A.nrows * 8, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr, A.nrows, keys.ptr, vals.ptr, valued ? 1 : 0);
-        sort_pairs_u32(keys.ptr, vals.ptr, n, bits);
-        out.clear();
-        out.nrows = A.ncols; out.ncols = A.nrows; out.nnz = n;
-        out.p.alloc(A.ncols + 1);
-        LAUNCH(k_ptr_from_u32_keys, grid_for(A.ncols + 1, 256, 1 << 16), 256, 0, keys.ptr, n, A.ncols, out.p.ptr);
-        if (valued) {
-            out.j.alloc(n); out.x.alloc(n);
-            LAUNCH(k_transpose_gather, grid_for(n, 256, 148 * 32), 256, 0, vals.ptr, n, A.p.ptr, A.nrows, A.x.ptr, out.j.ptr, out.x.ptr);
-        } else {
-            out.j = std::move(vals);                 // the payloads ARE the row ids, already in A' order
-        }
-        return;
-    }
     DevBuf<u64> keys(n);
     LAUNCH(k_transpose_keys, grid_for(A.nrows * 32, 256, 1 << 16), 256, 0, A.p.ptr, A.j.ptr, A.nrows, keys.ptr);
     int eb = key_bits(A.ncols);
-    if (valued) {
+    if (keep_values && A.has_values()) {
         DevBuf<u64> perm(n);
         LAUNCH(k_iota_u64, grid_for(n, 256, 1 << 20), 256, 0, perm.ptr, n);
         sort_pairs_u64(keys.ptr, perm.ptr, n, eb);

@@ -254,7 +254,6 @@ void exclusive_scan_u64(const u64 *in, u64 *out, size_t n);           // out[i] 
 void exclusive_scan_u32_to_u64(const u32 *in, u64 *out, size_t n);
 void sort_keys_u64(u64 *keys_in_out, size_t n, int end_bit);            // ascending, in place (uses temp)
 void sort_pairs_u64(u64 *keys_in_out, u64 *vals_in_out, size_t n, int end_bit); // stable
-void sort_pairs_u32(u32 *keys_in_out, u32 *vals_in_out, size_t n, int end_bit); // stable
 u64 reduce_sum_u64(const u64 *in, size_t n);
 
 } // namespace b200

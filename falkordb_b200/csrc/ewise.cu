@@ -53,56 +53,43 @@ struct FlagPred {
     }
 };
 
-// Rows of the stored matrices are short (RMAT-23: 16 entries on average) and there are millions of them: with a warp per row the
-// kernels were bound by the number of dependent row-pointer -> entry -> probe chains in flight (union 0.06, filter 0.02 of the HBM
-// roofline at fold sizes, profiles/r2f).  Now 8 lanes own a row, four rows per warp step; ballots are taken warp-wide and each
-// group reads its own byte of the result, the trip count is the longest of the four rows (__reduce_max_sync).
-struct Grp8 {
-    u32 lane, sub, l8, shift, lt8;
-    __device__ Grp8() {
-        lane = threadIdx.x & 31; sub = lane >> 3; l8 = lane & 7; shift = 8 * sub; lt8 = (1u << l8) - 1u;
-    }
-    __device__ u32 mine(u32 ballot) const { return (ballot >> shift) & 0xFFu; }      // this group's 8 votes
-};
 template <class Pred>
-__global__ void __launch_bounds__(256)
-k_rowfilter_count(const u64 *__restrict__ Tp, const u32 *__restrict__ Tj, u64 nrows, Pred pred, u32 *__restrict__ cnt) {
-    const Grp8 g;
-    const u64 grp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngrp = ((u64)gridDim.x * blockDim.x) >> 3;
-    for (u64 base = grp - g.sub; base < nrows; base += ngrp) {
-        const u64 i = base + g.sub;
-        const bool ok = i < nrows;
-        const u64 s = ok ? Tp[i] : 0, e = ok ? Tp[i + 1] : 0;
-        const u32 steps = (__reduce_max_sync(0xffffffffu, (u32)(e - s)) + 7) >> 3;
+__global__ void k_rowfilter_count(const u64 *__restrict__ Tp, const u32 *__restrict__ Tj, u64 nrows, Pred pred,
+                                  u32 *__restrict__ cnt) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 i = warp; i < nrows; i += nwarps) {
+        u64 s = Tp[i], e = Tp[i + 1];
         u32 c = 0;
-        for (u32 t = 0; t < steps; t++) {
-            const u64 q = s + 8ull * t + g.l8;
-            const bool keep = (q < e) && pred(i, Tj[q], q);
-            c += __popc(g.mine(__ballot_sync(0xffffffffu, keep)));
+        for (u64 q0 = s; q0 < e; q0 += 32) {
+            u64 q = q0 + lane;
+            bool keep = (q < e) && pred(i, Tj[q], q);
+            c += __popc(__ballot_sync(0xffffffffu, keep));
         }
-        if (ok && g.l8 == 0) cnt[i] = c;
+        if (lane == 0) cnt[i] = c;
     }
 }
 
 template <class Pred>
-__global__ void __launch_bounds__(256)
-k_rowfilter_fill(const u64 *__restrict__ Tp, const u32 *__restrict__ Tj, const u64 *__restrict__ Tx,
-                 u64 nrows, Pred pred, const u64 *__restrict__ Cp, u32 *__restrict__ Cj, u64 *__restrict__ Cx) {
-    const Grp8 g;
-    const u64 grp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngrp = ((u64)gridDim.x * blockDim.x) >> 3;
-    for (u64 base = grp - g.sub; base < nrows; base += ngrp) {
-        const u64 i = base + g.sub;
-        const bool ok = i < nrows;
-        u64 s = 0, e = 0, o = 0;
-        if (ok) { s = Tp[i]; e = Tp[i + 1]; o = Cp[i]; if (Cp[i + 1] == o) e = s; }      // nothing survives in this row: skip its entries
-        const u32 steps = (__reduce_max_sync(0xffffffffu, (u32)(e - s)) + 7) >> 3;
-        for (u32 t = 0; t < steps; t++) {
-            const u64 q = s + 8ull * t + g.l8;
-            const u32 col = (q < e) ? Tj[q] : 0u;
-            const bool keep = (q < e) && pred(i, col, q);
-            const u32 m = g.mine(__ballot_sync(0xffffffffu, keep));
+__global__ void k_rowfilter_fill(const u64 *__restrict__ Tp, const u32 *__restrict__ Tj, const u64 *__restrict__ Tx,
+                                 u64 nrows, Pred pred, const u64 *__restrict__ Cp, u32 *__restrict__ Cj,
+                                 u64 *__restrict__ Cx) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    u32 lt = (1u << lane) - 1u;
+    for (u64 i = warp; i < nrows; i += nwarps) {
+        u64 s = Tp[i], e = Tp[i + 1];
+        u64 o = Cp[i];
+        if (Cp[i + 1] == o) continue;
+        for (u64 q0 = s; q0 < e; q0 += 32) {
+            u64 q = q0 + lane;
+            u32 col = (q < e) ? Tj[q] : 0u;
+            bool keep = (q < e) && pred(i, col, q);
+            u32 m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
-                const u64 d = o + __popc(m & g.lt8);
+                u64 d = o + __popc(m & lt);
                 Cj[d] = col;
                 if (Cx) Cx[d] = Tx ? Tx[q] : 1ULL;
             }
@@ -121,7 +108,7 @@ static void rowfilter(const DevCSR &T, Pred pred, u64 out_nrows, u64 out_ncols, 
     DevBuf<u32> cnt(out_nrows + 1);
     cnt.zero();
     timed_begin(TK_FILTER);
-    LAUNCH((k_rowfilter_count<Pred>), grid_for(rows * 8, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr, rows, pred, cnt.ptr);
+    LAUNCH((k_rowfilter_count<Pred>), grid_for(rows * 32, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr, rows, pred, cnt.ptr);
     exclusive_scan_u32_to_u64(cnt.ptr, out.p.ptr, out_nrows + 1);
     u64 nnz = read_scalar(out.p.ptr + out_nrows);
     out.nnz = nnz;
@@ -129,7 +116,7 @@ static void rowfilter(const DevCSR &T, Pred pred, u64 out_nrows, u64 out_ncols, 
     bool vals = keep_values && T.has_values();
     if (vals) out.x.alloc(nnz);
     if (nnz)
-        LAUNCH((k_rowfilter_fill<Pred>), grid_for(rows * 8, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr,
+        LAUNCH((k_rowfilter_fill<Pred>), grid_for(rows * 32, 256, 148 * 32), 256, 0, T.p.ptr, T.j.ptr,
                vals ? T.x.ptr : (const u64 *)nullptr, rows, pred, out.p.ptr, out.j.ptr, vals ? out.x.ptr : (u64 *)nullptr);
     // SURVEY 8(d) bytes_ewise: the operand once, the result once, row pointers of both (+ 8 B per carried value); the probed
     // side (mask / larger operand) is touched by binary searches only and is not counted
@@ -244,78 +231,70 @@ void spgemm_masked(const DevCSR &A, const DevCSR &B, const DevCSR &M, bool struc
 }
 
 // ---- union ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_union_count(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *__restrict__ Bp,
-              const u32 *__restrict__ Bj, u64 nrows, u32 *__restrict__ cnt) {
-    const Grp8 g;
-    const u64 grp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngrp = ((u64)gridDim.x * blockDim.x) >> 3;
-    for (u64 base = grp - g.sub; base < nrows; base += ngrp) {
-        const u64 i = base + g.sub;
-        const bool ok = i < nrows;
-        u64 as = 0, ae = 0, bs = 0, be = 0;
-        if (ok) { as = Ap[i]; ae = Ap[i + 1]; bs = Bp[i]; be = Bp[i + 1]; }
-        // probe the shorter row into the longer one; an empty side means no common elements and nothing to probe
-        const bool a_short = (ae - as) <= (be - bs);
-        const u32 *Sj = a_short ? Aj : Bj;
-        const u32 *Lj = a_short ? Bj : Aj;
-        u64 ss = a_short ? as : bs, se = a_short ? ae : be;
-        const u64 ls = a_short ? bs : as, le = a_short ? be : ae;
-        if (ae == as || be == bs) se = ss;
-        const u32 steps = (__reduce_max_sync(0xffffffffu, (u32)(se - ss)) + 7) >> 3;
+__global__ void k_union_count(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *__restrict__ Bp,
+                              const u32 *__restrict__ Bj, u64 nrows, u32 *__restrict__ cnt) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    for (u64 i = warp; i < nrows; i += nwarps) {
+        u64 as = Ap[i], ae = Ap[i + 1], bs = Bp[i], be = Bp[i + 1];
         u32 common = 0;
-        for (u32 t = 0; t < steps; t++) {
-            const u64 q = ss + 8ull * t + g.l8;
-            bool hit = false;
-            if (q < se) {
-                const u32 c = Sj[q];
-                const u64 r = lower_bound_u32(Lj, ls, le, c);
-                hit = (r < le && Lj[r] == c);
+        if (ae > as && be > bs) {
+            // probe the shorter row into the longer one
+            bool a_short = (ae - as) <= (be - bs);
+            const u32 *Sj = a_short ? Aj : Bj;
+            const u32 *Lj = a_short ? Bj : Aj;
+            u64 ss = a_short ? as : bs, se = a_short ? ae : be, ls = a_short ? bs : as, le = a_short ? be : ae;
+            for (u64 q0 = ss; q0 < se; q0 += 32) {
+                u64 q = q0 + lane;
+                bool hit = false;
+                if (q < se) {
+                    u32 c = Sj[q];
+                    u64 r = lower_bound_u32(Lj, ls, le, c);
+                    hit = (r < le && Lj[r] == c);
+                }
+                common += __popc(__ballot_sync(0xffffffffu, hit));
             }
-            common += __popc(g.mine(__ballot_sync(0xffffffffu, hit)));
         }
-        if (ok && g.l8 == 0) cnt[i] = (u32)((ae - as) + (be - bs) - common);
+        if (lane == 0) cnt[i] = (u32)((ae - as) + (be - bs) - common);
     }
 }
 
 // pos(a_i) = i + lb_B(a_i) - #{common < a_i};   pos(b_j, b_j not in A) = j + lb_A(b_j) - #{common < b_j}
 // value on overlap = B's (SECOND, matrix.rs:277-281)
-__global__ void __launch_bounds__(256)
-k_union_fill(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *__restrict__ Ax,
-             const u64 *__restrict__ Bp, const u32 *__restrict__ Bj, const u64 *__restrict__ Bx,
-             u64 nrows, const u64 *__restrict__ Cp, u32 *__restrict__ Cj, u64 *__restrict__ Cx) {
-    const Grp8 g;
-    const u64 grp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngrp = ((u64)gridDim.x * blockDim.x) >> 3;
-    for (u64 base = grp - g.sub; base < nrows; base += ngrp) {
-        const u64 i = base + g.sub;
-        const bool ok = i < nrows;
-        u64 as = 0, ae = 0, bs = 0, be = 0, o = 0;
-        if (ok) { as = Ap[i]; ae = Ap[i + 1]; bs = Bp[i]; be = Bp[i + 1]; o = Cp[i]; }
-        u32 steps = (__reduce_max_sync(0xffffffffu, (u32)(ae - as)) + 7) >> 3;
+__global__ void k_union_fill(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *__restrict__ Ax,
+                             const u64 *__restrict__ Bp, const u32 *__restrict__ Bj, const u64 *__restrict__ Bx,
+                             u64 nrows, const u64 *__restrict__ Cp, u32 *__restrict__ Cj, u64 *__restrict__ Cx) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    u32 lt = (1u << lane) - 1u;
+    for (u64 i = warp; i < nrows; i += nwarps) {
+        u64 as = Ap[i], ae = Ap[i + 1], bs = Bp[i], be = Bp[i + 1];
+        u64 o = Cp[i];
         u64 run = 0; // common elements seen so far along a
-        for (u32 t = 0; t < steps; t++) {
-            const u64 q = as + 8ull * t + g.l8;
-            const bool valid = q < ae;
-            bool hit = false;
+        for (u64 q0 = as; q0 < ae; q0 += 32) {
+            u64 q = q0 + lane;
+            bool valid = q < ae, hit = false;
             u32 c = 0;
             u64 r = bs;
             if (valid) {
                 c = Aj[q];
-                if (be > bs) { r = lower_bound_u32(Bj, bs, be, c); hit = (r < be && Bj[r] == c); }
+                r = lower_bound_u32(Bj, bs, be, c);
+                hit = (r < be && Bj[r] == c);
             }
-            const u32 m = g.mine(__ballot_sync(0xffffffffu, hit));
+            u32 m = __ballot_sync(0xffffffffu, hit);
             if (valid) {
-                const u64 d = o + (q - as) + (r - bs) - (run + __popc(m & g.lt8));
+                u64 d = o + (q - as) + (r - bs) - (run + __popc(m & lt));
                 Cj[d] = c;
                 if (Cx) Cx[d] = hit ? (Bx ? Bx[r] : 1ULL) : (Ax ? Ax[q] : 1ULL);
             }
             run += __popc(m);
         }
-        steps = (__reduce_max_sync(0xffffffffu, (u32)(be - bs)) + 7) >> 3;
         run = 0; // common elements seen so far along b
-        for (u32 t = 0; t < steps; t++) {
-            const u64 q = bs + 8ull * t + g.l8;
-            const bool valid = q < be;
-            bool hit = false;
+        for (u64 q0 = bs; q0 < be; q0 += 32) {
+            u64 q = q0 + lane;
+            bool valid = q < be, hit = false;
             u32 c = 0;
             u64 r = as;
             if (valid) {
@@ -323,9 +302,9 @@ k_union_fill(const u64 *__restrict__ Ap, const u32 *__restrict__ Aj, const u64 *
                 r = lower_bound_u32(Aj, as, ae, c);
                 hit = (r < ae && Aj[r] == c);
             }
-            const u32 m = g.mine(__ballot_sync(0xffffffffu, hit));
+            u32 m = __ballot_sync(0xffffffffu, hit);
             if (valid && !hit) {
-                const u64 d = o + (q - bs) + (r - as) - (run + __popc(m & g.lt8));
+                u64 d = o + (q - bs) + (r - as) - (run + __popc(m & lt));
                 Cj[d] = c;
                 if (Cx) Cx[d] = Bx ? Bx[q] : 1ULL;
             }
@@ -344,7 +323,7 @@ void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out
     DevBuf<u32> cnt(nrows + 1);
     CUDA_TRY(cudaMemsetAsync(cnt.ptr + nrows, 0, sizeof(u32), stream()));
     timed_begin(TK_UNION);
-    LAUNCH(k_union_count, grid_for(nrows * 8, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr, B.p.ptr, B.j.ptr, nrows, cnt.ptr);
+    LAUNCH(k_union_count, grid_for(nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr, B.p.ptr, B.j.ptr, nrows, cnt.ptr);
     exclusive_scan_u32_to_u64(cnt.ptr, out.p.ptr, nrows + 1);
     u64 nnz = read_scalar(out.p.ptr + nrows);
     out.nnz = nnz;
@@ -352,7 +331,7 @@ void ewise_union(const DevCSR &A, const DevCSR &B, bool keep_values, DevCSR &out
     bool vals = keep_values && (A.has_values() || B.has_values());
     if (vals) out.x.alloc(nnz);
     if (nnz)
-        LAUNCH(k_union_fill, grid_for(nrows * 8, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr,
+        LAUNCH(k_union_fill, grid_for(nrows * 32, 256, 148 * 32), 256, 0, A.p.ptr, A.j.ptr,
                A.has_values() ? A.x.ptr : (const u64 *)nullptr, B.p.ptr, B.j.ptr,
                B.has_values() ? B.x.ptr : (const u64 *)nullptr, nrows, out.p.ptr, out.j.ptr,
                vals ? out.x.ptr : (u64 *)nullptr);

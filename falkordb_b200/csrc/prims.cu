@@ -250,20 +250,6 @@ void sort_keys_u64(u64 *keys, size_t n, int end_bit) {
     ctx().lib_launches += 8;
 }
 
-void sort_pairs_u32(u32 *keys, u32 *vals, size_t n, int end_bit) {      // stable, ascending, bits [0, end_bit) of the key
-    if (n <= 1) return;
-    if ((u64)n > 0x7fffffffULL) throw GrbError(-8, "sort_pairs_u32: more than 2^31-1 keys not supported yet");
-    DevBuf<u32> altk(n), altv(n);
-    cub::DoubleBuffer<u32> dk(keys, altk.ptr), dv(vals, altv.ptr);
-    size_t tb = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n, 0, end_bit, stream()));
-    DevBuf<char> tmp(tb);
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.ptr, tb, dk, dv, (int)n, 0, end_bit, stream()));
-    if (dk.Current() != keys) d2d(keys, dk.Current(), n);
-    if (dv.Current() != vals) d2d(vals, dv.Current(), n);
-    ctx().lib_launches += 8;
-}
-
 void sort_pairs_u64(u64 *keys, u64 *vals, size_t n, int end_bit) {
     if (n <= 1) return;
     if ((u64)n > 0x7fffffffULL) throw GrbError(-8, "sort_pairs_u64: more than 2^31-1 keys not supported yet");
