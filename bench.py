@@ -490,32 +490,35 @@ def run_b200(a):
                 "share_of_step": ks["ms"] / ms,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
                 "basis": "bytes this kernel family must move per launch (DESIGN.md 4.1), not SURVEY 8(d)'s row-wise figure"}
-        # every timed family, same arithmetic (the dominant one above is repeated here)
-        roof["families"] = {k: {"ms_per_launch": v["ms"] / v["launches"], "achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
-                                "frac": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak) if v["ms"] > 0 else 0.0,
-                                "share_of_step": v["ms"] / ms} for k, v in kstats.items()}
-        if "bits_pull" in kstats and pull_flops[1]:
-            kp = kstats["bits_pull"]
-            pl_ms = kp["ms"] / kp["launches"]
-            # SURVEY 8(d) bytes_mxm for the same launches: 4 B per flop (A's col_idx segment re-read for every frontier row) is
-            # the dominant term.  The bit-matrix kernel serves 64*W frontier rows per pass over A, so it never moves these bytes.
-            sb = 4.0 * pull_flops[0] / pull_flops[1]
-            roof["hop_survey_8d"] = {"bytes_per_launch": sb, "achieved": sb / (pl_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                     "frac": sb / (pl_ms * 1e-3) / 1e9 / peak}
-            # what actually bounds the hop: one L1TEX wavefront (a 128-byte line through the tag stage) per gathered vertex
-            # record -- SPLIT lanes share a record -- against one line per clock per SM at the SM clock sampled during the run
-            W = max(1, -(-a.sources // 64))
-            Wp = 1
-            while Wp < W:
-                Wp <<= 1
-            parts = max(1, Wp // 4)                      # 32-byte parts per record
-            lanes_per_record = parts                      # lane-split kernels: the parts of a record coalesce into ONE wavefront
-            wavefronts = nnzA * 1.0 + nnzA * 4.0 / 128.0  # gathers + the coalesced col_idx stream
-            ceiling = 148 * (clk.get("sm_mhz") or 1965.0) * 1e6
-            roof["hop_gather_ceiling"] = {"wavefronts_per_launch": wavefronts, "achieved_wavefronts_per_s": wavefronts / (pl_ms * 1e-3),
-                                          "ceiling_wavefronts_per_s": ceiling, "frac": wavefronts / (pl_ms * 1e-3) / ceiling,
-                                          "lanes_per_record": lanes_per_record,
-                                          "note": "L1TEX tag stage: one 128-byte line per clock per SM (scripts/ubench/gather*.cu)"}
+        try:   # explanatory extras: must never take the bench line down
+            # every timed family, same arithmetic (the dominant one above is repeated here)
+            roof["families"] = {k: {"ms_per_launch": v["ms"] / v["launches"], "achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
+                                    "frac": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak) if v["ms"] > 0 else 0.0,
+                                    "share_of_step": v["ms"] / ms} for k, v in kstats.items()}
+            if "bits_pull" in kstats and pull_flops[1]:
+                kp = kstats["bits_pull"]
+                pl_ms = kp["ms"] / kp["launches"]
+                # SURVEY 8(d) bytes_mxm for the same launches: 4 B per flop (A's col_idx segment re-read for every frontier row) is
+                # the dominant term.  The bit-matrix kernel serves 64*W frontier rows per pass over A, so it never moves these bytes.
+                sb = 4.0 * pull_flops[0] / pull_flops[1]
+                roof["hop_survey_8d"] = {"bytes_per_launch": sb, "achieved": sb / (pl_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                         "frac": sb / (pl_ms * 1e-3) / 1e9 / peak}
+                # what actually bounds the hop: one L1TEX wavefront (a 128-byte line through the tag stage) per gathered vertex
+                # record -- SPLIT lanes share a record -- against one line per clock per SM at the SM clock sampled during the run
+                W = max(1, -(-a.sources // 64))
+                Wp = 1
+                while Wp < W:
+                    Wp <<= 1
+                parts = max(1, Wp // 4)                      # 32-byte parts per record
+                lanes_per_record = parts                      # lane-split kernels: the parts of a record coalesce into ONE wavefront
+                wavefronts = nnzA * 1.0 + nnzA * 4.0 / 128.0  # gathers + the coalesced col_idx stream
+                ceiling = 148 * (clk.get("sm_mhz") or 1965.0) * 1e6
+                roof["hop_gather_ceiling"] = {"wavefronts_per_launch": wavefronts, "achieved_wavefronts_per_s": wavefronts / (pl_ms * 1e-3),
+                                              "ceiling_wavefronts_per_s": ceiling, "frac": wavefronts / (pl_ms * 1e-3) / ceiling,
+                                              "lanes_per_record": lanes_per_record,
+                                              "note": "L1TEX tag stage: one 128-byte line per clock per SM (scripts/ubench/gather*.cu)"}
+        except Exception as ex:
+            roof["extras_error"] = repr(ex)
     # SURVEY 8d's row-wise formula (4 B per flop dominant) for the whole step, for reference: a frontier kernel that
     # serves 64*W rows per pass over A reads far fewer bytes than this, so this fraction may exceed 1.
     survey_bytes = 4 * flops + 4 * nnz_out

@@ -269,10 +269,85 @@ static orc_ws *ws_get(int t, int64_t ncols) {       /* thread t's workspace, gro
 double orc_last_busy_fraction(void) { return (g_wall_s > 0 && g_team > 0) ? g_busy_s / (g_wall_s * g_team) : 0.0; }
 int orc_last_busy_threads(void) { return g_busy_threads; }
 
+int orc_transpose(const orc_csr *A, orc_csr *out);
+/* C<M, struct> = A*B, dot formulation: C(i,j) for (i,j) in M exists iff A(i,:) and B(:,j) share a column -- what SuiteSparse itself
+ * picks for a masked product (dot3).  Nothing outside the mask is ever formed: the saxpy form below would materialise whole unmasked
+ * rows first (for the triangle pattern on RMAT-24 that is ~1e11 entries, hundreds of GB -- it took the test box down).  Row i's
+ * columns are marked in the thread's bitmap; for every mask entry the SHORTER of A(i,:) and B'(j,:) drives: scan B'(j,:) against the
+ * bitmap, or binary-search A(i,:)'s entries in the sorted B'(j,:). */
+static int mxm_masked_dot(const orc_csr *A, const orc_csr *B, const orc_csr *M, orc_csr *out, int64_t *flops_out) {
+    const int64_t nrows = A->nrows;
+    orc_csr BT;
+    orc_csr Bp = *B;
+    Bp.x = NULL;
+    orc_transpose(&Bp, &BT);
+    unsigned char *keep = xmalloc((size_t)(M->nnz ? M->nnz : 1));
+    int64_t *cnt = xmalloc(sizeof(int64_t) * (size_t)(nrows + 1));
+    int64_t flops_total = 0;
+    int team = orc_num_threads();
+    ws_reserve(team);
+    double t_wall = now_s();
+#pragma omp parallel num_threads(team) reduction(+ : flops_total)
+    {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num();
+#else
+        const int tid = 0;
+#endif
+        orc_ws *w = ws_get(tid, A->ncols);
+        uint64_t *bits = w->bits;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < nrows; i++) {
+            const int64_t as = A->p[i], ae = A->p[i + 1];
+            int64_t c = 0;
+            for (int64_t a = as; a < ae; a++) { const uint32_t k = A->j[a]; flops_total += B->p[k + 1] - B->p[k]; bits[k >> 6] |= 1ULL << (k & 63); }
+            for (int64_t q = M->p[i]; q < M->p[i + 1]; q++) {
+                const uint32_t j = M->j[q];
+                const int64_t bs = BT.p[j], be = BT.p[j + 1];
+                int hit = 0;
+                if (be - bs <= (ae - as) * 4) {
+                    for (int64_t t = bs; t < be && !hit; t++) { const uint32_t k = BT.j[t]; hit = (int)((bits[k >> 6] >> (k & 63)) & 1ULL); }
+                } else {
+                    for (int64_t a = as; a < ae && !hit; a++) {
+                        const uint32_t k = A->j[a];
+                        int64_t lo = bs, hi = be;
+                        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (BT.j[mid] < k) lo = mid + 1; else hi = mid; }
+                        hit = (lo < be && BT.j[lo] == k);
+                    }
+                }
+                keep[q] = (unsigned char)hit;
+                c += hit;
+            }
+            for (int64_t a = as; a < ae; a++) bits[A->j[a] >> 6] = 0;
+            cnt[i + 1] = c;
+        }
+    }
+    cnt[0] = 0;
+    for (int64_t i = 0; i < nrows; i++) cnt[i + 1] += cnt[i];
+    out->nrows = nrows; out->ncols = B->ncols; out->nnz = cnt[nrows];
+    out->p = cnt;
+    out->j = xmalloc(sizeof(uint32_t) * (size_t)(out->nnz ? out->nnz : 1));
+    out->x = NULL;
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(team)
+    for (int64_t i = 0; i < nrows; i++) {
+        int64_t o = cnt[i];
+        for (int64_t q = M->p[i]; q < M->p[i + 1]; q++) if (keep[q]) out->j[o++] = M->j[q];
+    }
+    free(keep);
+    orc_csr_free(&BT);
+    g_busy_s = 0; g_wall_s = now_s() - t_wall; g_busy_threads = team; g_team = team;
+    if (flops_out) *flops_out = flops_total;
+    return 0;
+}
+
 int orc_mxm_anypair(const orc_csr *A, const orc_csr *B, const orc_csr *M, int mask_mode,
                     orc_csr *out, int64_t *flops_out) {
     int64_t nrows = A->nrows, ncols = B->ncols;
     if (A->ncols != B->nrows) return -6; /* GrB_DIMENSION_MISMATCH */
+    if (M && mask_mode == 1) {
+        if (M->nrows != nrows || M->ncols != ncols) return -6;
+        return mxm_masked_dot(A, B, M, out, flops_out);
+    }
     int64_t *cnt = xmalloc(sizeof(int64_t) * (size_t)(nrows + 1));
     uint32_t **rows = xmalloc(sizeof(uint32_t *) * (size_t)(nrows ? nrows : 1));
     int64_t flops_total = 0;

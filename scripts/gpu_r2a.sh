@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 make -C falkordb_b200/csrc -j16 -s 2>&1 | tail -3; make -C oracle -s
 nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/r2a_smi.txt 2>&1
 nproc >> gpurun_out/r2a_smi.txt; free -g >> gpurun_out/r2a_smi.txt
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_full_size.py > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_full_size.py > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
 tail -5 gpurun_out/r2a_pytest.log
 B="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-format csr"
 for v in "pull_kernel=4" "pull_kernel=5" "pull_kernel=5 --opt unroll=8" "pull_kernel=5 --opt l2_window=67108864" "pull_kernel=5 --opt l2_window=33554432" "pull_kernel=5 --opt l2_window=33554432 --opt l2_reset=2" "pull_kernel=5 --opt l2_window=67108864 --opt l2_reset=2" "pull_kernel=5 --opt hints=0" "pull_kernel=5 --opt early_exit=2"; do

@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 make -C falkordb_b200/csrc -j16 -s 2>&1 | tail -3; make -C oracle -s
-timeout 1200 python -m pytest tests -m gpu -x -q --deselect tests/test_full_size.py > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.log
+timeout 1200 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_full_size.py > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.log
 tail -5 gpurun_out/r2d_pytest.log
 B="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-format csr"
 for v in "fill_kernel=3" "fill_kernel=1" "perm_push=0" "small_split=1" "fill_kernel=1 --opt perm_push=0"; do

@@ -186,41 +186,3 @@ def _detach(m):
     h = P(m.h.value)
     m.h = P()
     return h
-
-
-@pytest.mark.gpu
-def test_lagr_connected_components_min_id_representatives():
-    """algo.WCC's LAGr_ConnectedComponents: dense component vector, representative = smallest vertex id of the component, on a
-    symmetrised RMAT graph with many isolated vertices, a path, a star and a pair; a directed graph handle is refused"""
-    fb.init()
-    L = lib()
-    from falkordb_b200.grb import Matrix
-    A = orc.rmat_csr(13, 2, 21)                       # sparse: hundreds of components
-    n = A.nrows
-    extra_r = np.array([5000, 5001, 5002, 7000, 7000, 7000, 8100], np.uint64)     # path 5000-5001-5002-5003, star at 7000, pair
-    extra_c = np.array([5001, 5002, 5003, 7001, 7002, 7003, 8101], np.uint64)
-    r, c, _ = A.tuples()
-    rows = np.concatenate([r, c, extra_r, extra_c]).astype(np.uint64)
-    cols = np.concatenate([c, r, extra_c, extra_r]).astype(np.uint64)
-    S = orc.build_matrix(n, n, rows, cols)
-    want = orc.wcc(S)
-    m = Matrix.import_csr(n, n, S.p.astype(np.uint64), S.j, None, bool)
-    G, h = P(), P(m.h.value)
-    m.h = P()
-    assert L.LAGraph_New(C.byref(G), C.byref(h), 0, None) == 0           # LAGraph_ADJACENCY_UNDIRECTED
-    comp = P()
-    assert L.LAGr_ConnectedComponents(C.byref(comp), G, None) == 0
-    nv = C.c_uint64(n)
-    I, X = np.empty(n, np.uint64), np.empty(n, np.int64)
-    check(L.GrB_Vector_extractTuples_INT64(I.ctypes.data, X.ctypes.data, C.byref(nv), comp))     # extract_vector_i64
-    assert nv.value == n and np.array_equal(I, np.arange(n)), "the component vector is dense"
-    assert np.array_equal(X, want), "representatives differ from the smallest id of each component"
-    assert len(np.unique(X)) > 100 and X[5003] == min(X[5000], 5000) and X[7003] == X[7000] and X[8101] == X[8100]
-    L.GrB_Vector_free(C.byref(comp))
-    L.LAGraph_Delete(C.byref(G), None)
-    d = Matrix.import_csr(n, n, A.p.astype(np.uint64), A.j, None, bool)
-    G2, h2 = P(), P(d.h.value)
-    d.h = P()
-    assert L.LAGraph_New(C.byref(G2), C.byref(h2), 1, None) == 0          # directed, symmetry unknown
-    assert L.LAGr_ConnectedComponents(C.byref(comp), G2, None) == -1005
-    L.LAGraph_Delete(C.byref(G2), None)

@@ -33,7 +33,6 @@ def test_tensor_multi_edge_bookkeeping(name):
     "batch_demote_leaves_every_survivor_inline",      # tensor.rs:1548-1571
     "batch_can_demote_and_then_empty_the_same_pair",  # tensor.rs:1573-1615
     "traverse_over_tensor_operand",                   # cond_traverse.rs:83 (TraversalMatrix::U64)
-    "repack_output_batches",                          # batch.rs:81, 274-287 (<= 1024 rows, NodeIds + u16 selection vector)
 ])
 def test_tensor_on_device(name):
     run(name)

@@ -2,7 +2,13 @@
 Multi-GB results are compared through an order-sensitive digest computed on both sides (B200_Matrix_digest on the device,
 orc_digest on the host: nvals, sum mix(row << 32 | col), sum mix(key + GOLD * CSR position)) plus exact flops; BFS levels and
 parents are compared element for element.  The graph is generated on the device and exported once, so both sides read the
-same CSR.  Each test skips only when the box lacks the memory it needs (free HBM / host RAM probe), never by default."""
+same CSR.  Each test skips only when the box lacks the memory it needs (free HBM / host RAM probe), never by default.
+
+The module sorts last on purpose (pytest -x): these are the longest tests, and the only ones not yet run on hardware in the form
+committed here -- the session that wrote them lost its GPU access when the first version of the config-4 oracle (saxpy form: every
+unmasked row materialised, ~1e11 entries on RMAT-24) exhausted a test box's RAM.  The oracle now evaluates masked products in dot
+form (oracle/grb_oracle.c: mxm_masked_dot, a few GB), every test states its host-memory need up front (`need`), and
+tests/conftest.py runs a resident-set watchdog that kills the test process long before the host is in danger."""
 import os
 import time
 
@@ -60,6 +66,21 @@ def same_digest(dev, want_digest, what):
     assert np.array_equal(got, want_digest), f"{what}: digests differ (same nvals): {got} vs {want_digest}"
 
 
+def rows_of(Ao, rows):
+    """F = A(rows, :) as an oracle CSR (len(rows) x n)"""
+    deg = np.diff(Ao.p)[rows]
+    p = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum(deg, out=p[1:])
+    j = np.empty(int(p[-1]), np.uint32)
+    for k, r in enumerate(rows):             # rows is sorted; slices are contiguous copies
+        j[p[k]:p[k + 1]] = Ao.j[Ao.p[r]:Ao.p[r + 1]]
+    return orc.CSR(len(rows), Ao.ncols, p, j)
+
+
+def dev_of(c):
+    return Matrix.import_csr(c.nrows, c.ncols, c.p.astype(np.uint64), c.j, None, bool)
+
+
 # ------------------------------------------------------------------------------------------ headline: 3-hop chain, RMAT-24
 @pytest.mark.parametrize("nsrc", [512, 1000])
 def test_chain_rmat24_all_rows(nsrc):
@@ -95,48 +116,52 @@ def test_chain_rmat24_all_rows(nsrc):
     assert np.array_equal(np.bitwise_count(bm).sum(axis=1).astype(np.int64), np.diff(p.astype(np.int64)))
 
 
-# ------------------------------------------------------------------------------------------ config 2: single mxm, RMAT-22
-def rows_of(Ao, rows):
-    """F = A(rows, :) as an oracle CSR (len(rows) x n)"""
-    deg = np.diff(Ao.p)[rows]
-    p = np.zeros(len(rows) + 1, np.int64)
-    np.cumsum(deg, out=p[1:])
-    j = np.empty(int(p[-1]), np.uint32)
-    for k, r in enumerate(rows):             # rows is sorted; slices are contiguous copies
-        j[p[k]:p[k + 1]] = Ao.j[Ao.p[r]:Ao.p[r + 1]]
-    return orc.CSR(len(rows), Ao.ncols, p, j)
+# ------------------------------------------------------------------------------------------ config 5: BFS, RMAT-26
+def test_config5_bfs_rmat26_levels_and_parents():
+    """BASELINE config 5's graph on one GPU: BFS level (bit-exact) and min-id parent vectors from 4 random sources with out-edges
+    on RMAT scale-26 (n = 67.1 M, ~1.05e9 edges) against the oracle; algo.BFS's conventions (algo_procedures.rs:1098-1148)."""
+    need(90, 40)
+    A, Ao = rmat_both(26)
+    deg = np.diff(Ao.p)
+    rng = np.random.default_rng(3)
+    srcs = rng.choice(np.nonzero(deg > 0)[0], size=4, replace=False)
+    for s in srcs:
+        lvl, par, edges = fb.bfs(A, int(s))
+        wl, wp = orc.bfs(Ao, int(s))
+        assert np.array_equal(lvl, wl), f"levels differ from the oracle (source {s})"
+        assert np.array_equal(par, wp), f"min-id parents differ from the oracle (source {s})"
+        assert edges == int(deg[wl >= 0].sum()), "edges traversed (Graph500 convention) differ"
+    _GRAPHS.clear()
 
 
-def dev_of(c):
-    return Matrix.import_csr(c.nrows, c.ncols, c.p.astype(np.uint64), c.j, None, bool)
-
-
-@pytest.mark.parametrize("variant", ["frontier_2e18", "F_eq_A_row_block"])
-def test_config2_single_mxm_rmat22(variant):
-    """BASELINE config 2 at its stated size: one GrB_mxm over ANY_PAIR on RMAT scale-22 through the row-wise SpGEMM.
-    frontier_2e18: F = the rows of A for a random 2^18-vertex frontier (seed 2).  F_eq_A_row_block: F = A, evaluated for one
-    2^17-row block -- the whole product A*A has ~7.8e10 entries (312 GB of column indices; measured growth x7.8 per two
-    scales: 1.28e9 at scale 18), more than one GPU's HBM, so the F = A variant is checked block-wise."""
-    need(60, 80)
-    A, Ao = rmat_both(22)
-    n = Ao.nrows
-    rng = np.random.default_rng(2)
-    if variant == "frontier_2e18":
-        rows = np.sort(rng.choice(n, size=1 << 18, replace=False))
-    else:
-        lo = int(rng.integers(0, n - (1 << 17)))
-        rows = np.arange(lo, lo + (1 << 17))
-    F = rows_of(Ao, rows)
-    want, flops = orc.mxm(F, Ao, return_flops=True)
+# ------------------------------------------------------------------------------------------ config 4: masked triangles, RMAT-24
+def test_config4_masked_triangles_rmat24():
+    """BASELINE config 4 at its stated size: C<L, struct, replace> = L*L over ANY_PAIR with L = tril(A u A') of RMAT-24: which
+    edges close a wedge.  The oracle evaluates the product row by row and drops what the mask excludes."""
+    need(40, 24)          # host: L (1.3 GB) + L' + one byte per mask entry + the result; the dot-form oracle forms nothing unmasked
+    import ctypes as C
+    from falkordb_b200._lib import lib, check, P as VP
+    _GRAPHS.clear()
+    scale = 24
+    n = 1 << scale
+    h = VP()
+    check(lib().B200_Matrix_rmat_block(C.byref(h), scale, 16, 1, 0, n, 2))
+    L = Matrix(0, 0, bool, _handle=h)
+    p, j, _ = L.export_csr()
+    Lo = orc.CSR(n, n, p.astype(np.int64), j)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(Lo.p))
+    assert np.all(Lo.j.astype(np.int64) < rows), "L must be strictly lower triangular"
+    del rows
+    want, flops = orc.mxm(Lo, Lo, Lo, 1, return_flops=True)
     dg = orc.digest(want)
     nnz_want = want.nnz
     del want
-    C_ = Matrix(F.nrows, n, bool)
-    C_.mxm(dev_of(F), A)
-    C_.wait()
-    assert fb.get_stat("last_flops") == flops == int(np.diff(Ao.p)[F.j].sum())
-    assert C_.nvals() == nnz_want
-    same_digest(C_, dg, f"config 2 {variant}: {F.nrows} x {n}, flops {flops}, nnz(C) {nnz_want}")
+    fb.set_option("bits_mode", 0)
+    Cm = Matrix(n, n, bool)
+    Cm.mxm(L, L, L, Descriptor.RS)
+    assert fb.get_stat("last_flops") == flops
+    assert Cm.nvals() == nnz_want
+    same_digest(Cm, dg, f"config 4: nnz(L) {Lo.nnz}, flops {flops}, closed wedges {nnz_want}")
 
 
 # ------------------------------------------------------------------------------------------ config 3: LDBC SF10-shaped chain
@@ -186,49 +211,30 @@ def test_config3_ldbc_sf10_shaped_chain():
         same_digest(F, orc.digest(want), f"config 3 ({rows} rows): {counts}")
 
 
-# ------------------------------------------------------------------------------------------ config 4: masked triangles, RMAT-24
-def test_config4_masked_triangles_rmat24():
-    """BASELINE config 4 at its stated size: C<L, struct, replace> = L*L over ANY_PAIR with L = tril(A u A') of RMAT-24: which
-    edges close a wedge.  The oracle evaluates the product row by row and drops what the mask excludes."""
-    need(40, 60)
-    import ctypes as C
-    from falkordb_b200._lib import lib, check, P as VP
-    _GRAPHS.clear()
-    scale = 24
-    n = 1 << scale
-    h = VP()
-    check(lib().B200_Matrix_rmat_block(C.byref(h), scale, 16, 1, 0, n, 2))
-    L = Matrix(0, 0, bool, _handle=h)
-    p, j, _ = L.export_csr()
-    Lo = orc.CSR(n, n, p.astype(np.int64), j)
-    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(Lo.p))
-    assert np.all(Lo.j.astype(np.int64) < rows), "L must be strictly lower triangular"
-    del rows
-    want, flops = orc.mxm(Lo, Lo, Lo, 1, return_flops=True)
+# ------------------------------------------------------------------------------------------ config 2: single mxm, RMAT-22
+@pytest.mark.parametrize("variant", ["frontier_2e18", "F_eq_A_row_block"])
+def test_config2_single_mxm_rmat22(variant):
+    """BASELINE config 2 at its stated size: one GrB_mxm over ANY_PAIR on RMAT scale-22 through the row-wise SpGEMM.
+    frontier_2e18: F = the rows of A for a random 2^18-vertex frontier (seed 2).  F_eq_A_row_block: F = A, evaluated for one
+    2^17-row block -- the whole product A*A has ~7.8e10 entries (312 GB of column indices; measured growth x7.8 per two
+    scales: 1.28e9 at scale 18), more than one GPU's HBM, so the F = A variant is checked block-wise."""
+    need(60, 120)         # host: the oracle's rows (~5e9 entries at 2^18 frontier rows: 20 GB) three times over (arena, result, numpy copy)
+    A, Ao = rmat_both(22)
+    n = Ao.nrows
+    rng = np.random.default_rng(2)
+    if variant == "frontier_2e18":
+        rows = np.sort(rng.choice(n, size=1 << 18, replace=False))
+    else:
+        lo = int(rng.integers(0, n - (1 << 17)))
+        rows = np.arange(lo, lo + (1 << 17))
+    F = rows_of(Ao, rows)
+    want, flops = orc.mxm(F, Ao, return_flops=True)
     dg = orc.digest(want)
     nnz_want = want.nnz
     del want
-    fb.set_option("bits_mode", 0)
-    Cm = Matrix(n, n, bool)
-    Cm.mxm(L, L, L, Descriptor.RS)
-    assert fb.get_stat("last_flops") == flops
-    assert Cm.nvals() == nnz_want
-    same_digest(Cm, dg, f"config 4: nnz(L) {Lo.nnz}, flops {flops}, closed wedges {nnz_want}")
-
-
-# ------------------------------------------------------------------------------------------ config 5: BFS, RMAT-26
-def test_config5_bfs_rmat26_levels_and_parents():
-    """BASELINE config 5's graph on one GPU: BFS level (bit-exact) and min-id parent vectors from 4 random sources with out-edges
-    on RMAT scale-26 (n = 67.1 M, ~1.05e9 edges) against the oracle; algo.BFS's conventions (algo_procedures.rs:1098-1148)."""
-    need(90, 40)
-    A, Ao = rmat_both(26)
-    deg = np.diff(Ao.p)
-    rng = np.random.default_rng(3)
-    srcs = rng.choice(np.nonzero(deg > 0)[0], size=4, replace=False)
-    for s in srcs:
-        lvl, par, edges = fb.bfs(A, int(s))
-        wl, wp = orc.bfs(Ao, int(s))
-        assert np.array_equal(lvl, wl), f"levels differ from the oracle (source {s})"
-        assert np.array_equal(par, wp), f"min-id parents differ from the oracle (source {s})"
-        assert edges == int(deg[wl >= 0].sum()), "edges traversed (Graph500 convention) differ"
-    _GRAPHS.clear()
+    C_ = Matrix(F.nrows, n, bool)
+    C_.mxm(dev_of(F), A)
+    C_.wait()
+    assert fb.get_stat("last_flops") == flops == int(np.diff(Ao.p)[F.j].sum())
+    assert C_.nvals() == nnz_want
+    same_digest(C_, dg, f"config 2 {variant}: {F.nrows} x {n}, flops {flops}, nnz(C) {nnz_want}")
