@@ -1,5 +1,5 @@
 """GPU tests written after round 2's last hardware session (gpurun closed before they could run on a B200): the module sorts
-after every hardware-verified one so that `pytest -x` reports those first.  What is here:
+after every hardware-verified one -- and after the full-size parity module -- so that `pytest -x` reports those first.  What is here:
   * hot-set-ordered frontiers (bits.cu: permuted form): every observer of an ordered intermediate -- the 3-hop chain through this
     path IS hardware-verified (bench.py's all-rows digest parity, profiles/r2_summary.md); this test adds the other observers
   * LAGr_ConnectedComponents (algo.cu) against scipy's connected components
