@@ -2,6 +2,10 @@
 // cond_traverse.hpp) so tests/ can drive it with ctypes, plus transcriptions of the reference's own unit tests
 // at this boundary (graph/src/graph/graphblas/versioned_matrix.rs:1278-1523).  Links against libb200grb.so only.
 #include "cond_traverse.hpp"
+#include "cond_var_len_traverse.hpp"
+#include <functional>
+#include <map>
+#include <set>
 #include <cstring>
 #include <set>
 #include <sstream>
@@ -335,6 +339,87 @@ static void t_repack_output_batches() {
     REQUIRE(repack(ExpandResult{}).empty(), "nothing in, nothing out");
 }
 
+// CondVarLenTraverse's trail enumerator (cond_var_len_traverse.rs:152-386) against a brute-force enumeration of every trail:
+// a small multigraph with a cycle, a multi-edge pair, a self-loop and a dead end; outgoing, incoming and bidirectional expansion,
+// min/max hop windows, a fixed destination, and the emission order inside one frame (adjacency order).  Run twice: over a plain
+// in-memory adjacency in tensor storage order (host only: the DFS logic) and over a Tensor through the C ABI (row iterators).
+static const std::vector<uint64_t> VL_S{0, 0, 1, 2, 2, 3, 1, 4, 0}, VL_D{1, 1, 2, 0, 3, 3, 4, 5, 6}, VL_I{10, 11, 12, 13, 14, 15, 16, 17, 18};
+// edges (src, dst, id):  0->1 (10), 0->1 (11) multi-edge, 1->2 (12), 2->0 (13) closes a cycle, 2->3 (14), 3->3 (15) self-loop,
+//                        1->4 (16), 4->5 (17), 0->6 (18) dead end
+struct PlainAdjacency {       // what node_relationships returns for the same graph: out by (dst, id), in by (src, id)
+    std::vector<Edge> operator()(uint64_t node, EdgeDirection dir) const {
+        std::vector<Edge> out, in;
+        for (size_t e = 0; e < VL_S.size(); e++) {
+            if (VL_S[e] == node) out.push_back({VL_S[e], VL_D[e], VL_I[e]});
+            if (VL_D[e] == node && !(dir == EdgeDirection::Both && VL_S[e] == node)) in.push_back({VL_S[e], VL_D[e], VL_I[e]});
+        }
+        std::sort(out.begin(), out.end(), [](const Edge &a, const Edge &b) { return a.dst != b.dst ? a.dst < b.dst : a.id < b.id; });
+        std::sort(in.begin(), in.end(), [](const Edge &a, const Edge &b) { return a.src != b.src ? a.src < b.src : a.id < b.id; });
+        std::vector<Edge> r;
+        if (dir != EdgeDirection::Incoming) r = out;
+        if (dir != EdgeDirection::Outgoing) r.insert(r.end(), in.begin(), in.end());
+        return r;
+    }
+};
+static std::multiset<std::pair<uint64_t, uint64_t>> vl_brute(uint64_t start, uint64_t lo, uint64_t hi, int mode /*0 out 1 in 2 both*/, int64_t dest) {
+    std::multiset<std::pair<uint64_t, uint64_t>> out;
+    if (lo == 0 && (dest < 0 || (uint64_t)dest == start)) out.insert({start, start});
+    std::function<void(uint64_t, std::set<uint64_t> &, uint64_t)> go = [&](uint64_t cur, std::set<uint64_t> &used, uint64_t depth) {
+        if (depth == hi) return;
+        for (size_t e = 0; e < VL_S.size(); e++) {
+            if (used.count(VL_I[e])) continue;
+            uint64_t nb;
+            if ((mode == 0 || mode == 2) && VL_S[e] == cur) nb = VL_D[e];
+            else if ((mode == 1 || mode == 2) && VL_D[e] == cur) nb = VL_S[e];
+            else continue;
+            used.insert(VL_I[e]);
+            if (depth + 1 >= lo && (dest < 0 || (uint64_t)dest == nb)) out.insert(mode == 1 ? std::make_pair(nb, start) : std::make_pair(start, nb));
+            go(nb, used, depth + 1);
+            used.erase(VL_I[e]);
+        }
+    };
+    std::set<uint64_t> used;
+    go(start, used, 0);
+    return out;
+}
+template <class MakeIter>
+static void vl_check(MakeIter make) {
+    for (int mode = 0; mode < 3; mode++)
+        for (uint64_t start : {0ull, 1ull, 2ull, 3ull, 5ull, 6ull})
+            for (auto win : std::vector<std::pair<uint64_t, uint64_t>>{{1, 1}, {1, 3}, {0, 2}, {2, 5}, {3, 3}, {1, 9}})
+                for (int64_t dest : {(int64_t)-1, (int64_t)0, (int64_t)3}) {
+                    auto it = make(win.first, win.second, mode == 1, mode == 2, dest);
+                    it.begin_start_node(start);
+                    std::multiset<std::pair<uint64_t, uint64_t>> got;
+                    VarLenResult r;
+                    while (it.next(r)) {
+                        got.insert({r.from, r.to});
+                        std::set<uint64_t> uniq(r.edges.begin(), r.edges.end());
+                        REQUIRE(uniq.size() == r.edges.size(), "a trail repeats an edge");
+                        REQUIRE(r.edges.size() >= win.first && r.edges.size() <= win.second, "trail length outside the hop window");
+                    }
+                    REQUIRE(got == vl_brute(start, win.first, win.second, mode, dest),
+                            "trails differ: mode " << mode << " start " << start << " hops " << win.first << ".." << win.second << " dest " << dest);
+                }
+    // emission order inside the first frame = adjacency order: (0,1) via edge 10, (0,1) via edge 11, (0,6)
+    auto it = make(1, 1, false, false, -1);
+    it.begin_start_node(0);
+    std::vector<uint64_t> order;
+    VarLenResult r;
+    while (it.next(r)) order.push_back(r.edges[0]);
+    REQUIRE((order == std::vector<uint64_t>{10, 11, 18}), "first-frame emissions must come out in adjacency order");
+}
+static void t_var_len_trails_logic() {      // host only: no GraphBLAS call
+    vl_check([](uint64_t lo, uint64_t hi, bool rev, bool bi, int64_t dest) { return VarLenIterT<PlainAdjacency>(PlainAdjacency(), lo, hi, rev, bi, dest, true); });
+}
+static void t_var_len_trails() {            // the same over a Tensor: adjacency through the row iterators of the C ABI
+    Tensor t(16, 16);
+    t.set_all_from_slices(VL_S, VL_D, VL_I);
+    t.wait();
+    t.rebuild_backward();
+    vl_check([&](uint64_t lo, uint64_t hi, bool rev, bool bi, int64_t dest) { return VarLenIter(t, lo, hi, rev, bi, dest, true); });
+}
+
 static void t_traverse_over_tensor_operand() {
     uint64_t n = 64;
     Tensor t(n, n);
@@ -371,6 +456,8 @@ static TestEntry TESTS[] = {
     {"batch_can_demote_and_then_empty_the_same_pair", t_batch_can_demote_and_then_empty_the_same_pair},
     {"traverse_over_tensor_operand", t_traverse_over_tensor_operand},
     {"repack_output_batches", t_repack_output_batches},
+    {"var_len_trails", t_var_len_trails},
+    {"var_len_trails_logic", t_var_len_trails_logic},
 };
 
 extern "C" {

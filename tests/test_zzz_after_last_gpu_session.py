@@ -3,7 +3,8 @@ after every hardware-verified one -- and after the full-size parity module -- so
   * hot-set-ordered frontiers (bits.cu: permuted form): every observer of an ordered intermediate -- the 3-hop chain through this
     path IS hardware-verified (bench.py's all-rows digest parity, profiles/r2_summary.md); this test adds the other observers
   * LAGr_ConnectedComponents (algo.cu) against scipy's connected components
-  * the output batch re-pack of the host mirror (cond_traverse.hpp: repack)"""
+  * the output batch re-pack of the host mirror (cond_traverse.hpp: repack)
+  * the trail enumerator over a Tensor (cond_var_len_traverse.hpp; its DFS logic alone is CPU-tested in test_host_varlen.py)"""
 import ctypes as C
 
 import numpy as np
@@ -146,3 +147,8 @@ def test_lagr_connected_components_min_id_representatives():
 def test_repack_output_batches_host_mirror():
     """batch.rs:81, 274-287: <= 1024 rows per output batch, NodeIds + u16 selection vector, order preserved"""
     run_host_test("repack_output_batches")
+
+
+def test_var_len_trails_over_a_tensor():
+    """cond_var_len_traverse.rs:152-386 with the adjacency fetched from a relationship Tensor through the row iterators"""
+    run_host_test("var_len_trails")
