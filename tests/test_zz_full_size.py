@@ -122,6 +122,7 @@ def test_config5_bfs_rmat26_levels_and_parents():
     on RMAT scale-26 (n = 67.1 M, ~1.05e9 edges) against the oracle; algo.BFS's conventions (algo_procedures.rs:1098-1148)."""
     need(90, 40)
     A, Ao = rmat_both(26)
+    A.prepare(True)               # the transpose mirror: B200_bfs then runs the direction-optimising engine (bfs_do.cu)
     deg = np.diff(Ao.p)
     rng = np.random.default_rng(3)
     srcs = rng.choice(np.nonzero(deg > 0)[0], size=3, replace=False)

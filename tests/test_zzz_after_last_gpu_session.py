@@ -100,8 +100,11 @@ def test_frontier_in_hot_set_order_between_push_and_pull(nsrc):
             F = two_hops()
             wr = np.repeat(np.arange(nsrc), np.diff(F2.p))
             assert list(F.iter()) == list(zip(wr.tolist(), F2.j.tolist())), "row iterator over an ordered frontier"
+        # the CSR push takes a hop iff its expansion is small against A (flops * 4 <= nnz(A), bits.cu: bits_push_from_csr)
+        expect_push = int(np.diff(A.p)[F1.j].sum()) * 4 <= A.nnz
+        assert all(p == expect_push for p in pushed), (expect_push, pushed)
         if nsrc <= 6:
-            assert all(pushed), "the small case must take the CSR push (the ordered form is what this test is about)"
+            assert expect_push, "the small case is meant to exercise the ordered form"
     finally:
         for k, v in (("bits_mode", -1), ("pull_mode", -1), ("perm_push", 1)):
             fb.set_option(k, v)
