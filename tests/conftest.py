@@ -1,11 +1,15 @@
 import os
 import sys
+import time
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+
+SESSION_T0 = time.time()
 
 
 def pytest_configure(config):
