@@ -68,6 +68,7 @@ def lib():
         "GrB_Matrix_build_FP64": [P, P, P, P, U64, P], "GrB_Matrix_extractTuples_FP64": [P, P, P, C.POINTER(U64), P],
         "LAGraph_Cached_AT": [P, C.c_char_p], "LAGraph_Cached_OutDegree": [P, C.c_char_p],
         "LAGr_ConnectedComponents": [C.POINTER(P), P, C.c_char_p],
+        "LAGraph_cdlp": [C.POINTER(P), P, C.c_int, C.c_char_p],
         "LAGr_PageRank": [C.POINTER(P), C.POINTER(C.c_int), P, C.c_float, C.c_float, C.c_int, C.c_char_p],
         "GrB_vxm": [P, P, P, P, P, P, P], "GrB_mxv": [P, P, P, P, P, P, P],
         "GxB_Iterator_new": [C.POINTER(P)], "GxB_Iterator_free": [C.POINTER(P)], "GxB_rowIterator_attach": [P, P, P],

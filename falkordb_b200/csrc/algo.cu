@@ -180,4 +180,72 @@ int connected_components(const DevCSR &A, u64 *d_comp) {
     return rounds;
 }
 
+// ---- LAGraph_cdlp: community detection by synchronous label propagation (LDBC Graphalytics CDLP; algo_procedures.rs:1232) -------
+// L0(v) = v; every round each vertex takes the most frequent label among its neighbours, the SMALLEST such label on ties; a vertex
+// without neighbours keeps its label; stop after itermax rounds or at a fixed point.  One round = one key per entry
+// (row << 32 | label of the neighbour), one radix sort over 32 + bits(n) bits -- the row field keeps every row's keys inside its
+// own CSR segment [p[r], p[r+1]) -- and one pass that walks each sorted segment for its first longest run (ascending order makes
+// the first longest run the minimum label).  8 B written + 8 B read per entry per pass; the sort's passes dominate.
+__global__ void __launch_bounds__(256)
+k_cdlp_keys(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 n, const u64 *__restrict__ L, u64 *__restrict__ keys) {
+    const u32 lane8 = threadIdx.x & 7;
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const u64 ng = ((u64)gridDim.x * blockDim.x) >> 3;
+    for (u64 u = g; u < n; u += ng) {
+        const u64 s = p[u], e = p[u + 1];
+        for (u64 q = s + lane8; q < e; q += 8) keys[q] = (u << 32) | L[j[q]];
+    }
+}
+__global__ void __launch_bounds__(256)
+k_cdlp_pick(const u64 *__restrict__ p, const u64 *__restrict__ keys, u64 n, const u64 *__restrict__ L, u64 *__restrict__ Lnew,
+            u32 *__restrict__ changed) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    bool ch = false;
+    for (; u < n; u += stride) {
+        const u64 s = p[u], e = p[u + 1];
+        u64 best = L[u];
+        if (s < e) {
+            u64 cur = keys[s] & 0xFFFFFFFFull, run = 1, best_run = 0;
+            best = cur;
+            for (u64 q = s + 1; q < e; ++q) {
+                const u64 l = keys[q] & 0xFFFFFFFFull;
+                if (l == cur) { ++run; continue; }
+                if (run > best_run) { best_run = run; best = cur; }
+                cur = l; run = 1;
+            }
+            if (run > best_run) best = cur;
+        }
+        Lnew[u] = best;
+        ch |= best != L[u];
+    }
+    if (ch) *changed = 1;
+}
+int cdlp(const DevCSR &A, int itermax, u64 *d_label) {
+    const u64 n = A.nrows;
+    if (!n) return 0;
+    if (n > (1ull << 32)) throw GrbError(-8, "cdlp: more than 2^32 vertices not supported");
+    const u32 g = grid_for(n, 256, 148 * 16);
+    LAUNCH(k_cc_init, g, 256, 0, d_label, n);                 // L0(v) = v
+    if (!A.nnz) return 0;
+    int bits_n = 1;
+    while ((1ull << bits_n) < n) ++bits_n;
+    DevBuf<u64> keys(A.nnz), next(n);
+    DevBuf<u32> changed(1);
+    u64 *cur = d_label, *nxt = next.ptr;
+    int rounds = 0;
+    for (; rounds < itermax; ) {
+        changed.zero();
+        LAUNCH(k_cdlp_keys, grid_for(n * 8, 256, (u64)ctx().num_sms * 32), 256, 0, A.p.ptr, A.j.ptr, n, cur, keys.ptr);
+        sort_keys_u64(keys.ptr, A.nnz, 32 + bits_n);
+        LAUNCH(k_cdlp_pick, g, 256, 0, A.p.ptr, keys.ptr, n, cur, nxt, changed.ptr);
+        ++rounds;
+        u64 *t = cur; cur = nxt; nxt = t;
+        if (!read_scalar(changed.ptr)) break;
+    }
+    if (cur != d_label) CUDA_TRY(cudaMemcpyAsync(d_label, cur, n * sizeof(u64), cudaMemcpyDeviceToDevice, stream()));
+    sync_stream();                                              // `next` is released on return
+    return rounds;
+}
+
 } // namespace b200

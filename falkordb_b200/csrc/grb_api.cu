@@ -1755,6 +1755,42 @@ int LAGr_ConnectedComponents(GrB_Vector *component, LAGraph_Graph G, char *msg) 
     if (info && msg) snprintf(msg, 256, "%s", tl_error.c_str());
     return info;
 }
+// LAGraph_cdlp (lagraphx_bindings.rs:218-223; call site algo_procedures.rs:1232-1237): label(i) after at most `itermax` rounds of
+// synchronous label propagation from label(i) = i, a full GrB_UINT64 vector.  The reference always passes the symmetric adjacency
+// (build_symmetric_adjacency_matrix, kind UNDIRECTED), so "neighbours" are the entries of row i; a directed graph is refused.
+int LAGraph_cdlp(GrB_Vector *CDLP_handle, LAGraph_Graph G, int itermax, char *msg) {
+    if (msg) msg[0] = 0;
+    if (!G || !G->A || !CDLP_handle) return GrB_NULL_POINTER;
+    GrB_Matrix A = G->A;
+    if (A->magic != MAGIC) return GrB_INVALID_OBJECT;
+    if (A->nrows != A->ncols) return GrB_DIMENSION_MISMATCH;
+    if (itermax < 0) return GrB_INVALID_VALUE;
+    if (G->kind != LAGraph_ADJACENCY_UNDIRECTED && G->is_symmetric_structure != 1) {
+        if (msg) snprintf(msg, 256, "G->A must be known to be symmetric");
+        return -1005;       // LAGRAPH_SYMMETRIC_STRUCTURE_REQUIRED
+    }
+    GrB_Info info = guarded([&]() {
+        GpuLock g;
+        MultiLock lk{A};
+        ensure_init();
+        ensure_dev(A);
+        const u64 n = A->nrows;
+        DevBuf<u64> lab(n ? n : 1);
+        cdlp(A->dev, itermax, lab.ptr);
+        std::unique_ptr<GB_Vector_opaque> v(new GB_Vector_opaque());
+        v->type = T_UINT64; v->n = n; v->full = true; v->fbytes = n * sizeof(u64);
+        if (n) {
+            v->fx = g_user_malloc(v->fbytes);
+            if (!v->fx) throw std::bad_alloc();
+            CUDA_TRY(cudaMemcpyAsync(v->fx, lab.ptr, v->fbytes, cudaMemcpyDeviceToHost, stream()));
+            sync_stream();
+        }
+        *CDLP_handle = v.release();
+        return GrB_SUCCESS;
+    });
+    if (info && msg) snprintf(msg, 256, "%s", tl_error.c_str());
+    return info;
+}
 // Single-GPU BFS.  With the transpose mirror in place (B200_Matrix_prepare(A, 1), or any earlier pull) the direction-optimising
 // engine runs (bfs_do.cu); without it -- one BFS on a fresh matrix, where building A' would cost more than the search -- the
 // top-down kernel of bfs.cu.  Both give level and minimum-id parent.  dest >= 0 stops once that vertex is reached.

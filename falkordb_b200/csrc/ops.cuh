@@ -110,6 +110,7 @@ void mxv_fp64(const DevCSR &A, bool use_values, const double *x, const unsigned 
               double init, bool accum);
 int pagerank(const DevCSR &A, const DevCSR &AT, double damping, double tol, int itermax, double *r);
 int connected_components(const DevCSR &A, u64 *d_comp);     // symmetric pattern; d_comp[v] = smallest vertex id of v's component
+int cdlp(const DevCSR &A, int itermax, u64 *d_label);         // synchronous label propagation, min label on ties; returns the rounds run
 
 void probe_pairs(const DevCSR &A, const u64 *dI, const u64 *dJ, u64 n, unsigned char *d_found, u64 *d_val);
 

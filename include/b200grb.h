@@ -275,6 +275,9 @@ int LAGraph_Cached_OutDegree(LAGraph_Graph G, char *msg);
 int LAGr_PageRank(GrB_Vector *centrality, int *iters, LAGraph_Graph G, float damping, float tol, int itermax, char *msg);
 /* algo.WCC (algo_procedures.rs:838-846; lagraph_bindings.rs:521-526): component(i) = smallest vertex id of i's component (dense) */
 int LAGr_ConnectedComponents(GrB_Vector *component, LAGraph_Graph G, char *msg);
+/* algo.labelPropagation (algo_procedures.rs:1232-1237; lagraphx_bindings.rs:218-223): label(i) after <= itermax synchronous rounds
+   of "most frequent neighbour label, smallest on ties" from label(i) = i (LDBC Graphalytics CDLP); full GrB_UINT64 vector */
+int LAGraph_cdlp(GrB_Vector *CDLP_handle, LAGraph_Graph G, int itermax, char *msg);
 
 /* ---- B200 extensions ---- */
 #define B200_LOC_HOST 0

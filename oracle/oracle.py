@@ -277,6 +277,33 @@ def wcc(A):
     return rep[lab]
 
 
+def cdlp(A, itermax=10):
+    """LAGraph_cdlp as algo.labelPropagation consumes it (algo_procedures.rs:1232-1237; LAGraph experimental/algorithm/LAGraph_cdlp.c,
+    not vendored; the algorithm is LDBC Graphalytics' CDLP): label(v) = v; each round every vertex takes the most frequent label among
+    the entries of its row, the smallest such label on ties, synchronously; a vertex with an empty row keeps its label; at most
+    `itermax` rounds, stopping early at a fixed point.  A: the symmetric pattern the reference builds.  Returns (labels, rounds)."""
+    n = A.nrows
+    L = np.arange(n, dtype=np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(A.p))
+    rounds = 0
+    if A.nnz == 0:
+        return L, 0
+    while rounds < itermax:
+        key, cnt = np.unique(rows * (n + 1) + L[A.j], return_counts=True)
+        r, lab = key // (n + 1), key % (n + 1)
+        order = np.lexsort((lab, -cnt, r))                  # by row, then count descending, then label ascending
+        first = np.ones(len(order), bool)
+        first[1:] = r[order][1:] != r[order][:-1]
+        new = L.copy()
+        new[r[order][first]] = lab[order][first]
+        rounds += 1
+        same = np.array_equal(new, L)
+        L = new
+        if same:
+            break
+    return L, rounds
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -147,6 +147,51 @@ def test_lagr_connected_components_min_id_representatives():
     L.LAGraph_Delete(C.byref(G2), None)
 
 
+@pytest.mark.parametrize("itermax", [1, 3, 10])
+def test_lagraph_cdlp_label_propagation(itermax):
+    """algo.labelPropagation's LAGraph_cdlp (algo_procedures.rs:1232-1237): synchronous "most frequent neighbour label, smallest on
+    ties" from label(v) = v, bit-exact against the oracle after 1, 3 and 10 rounds on a symmetrised RMAT graph (skewed rows, isolated
+    vertices, self-edges) joined with the reference flow test's three fully connected triples (tests/flow/test_cdlp.py:83-178)"""
+    fb.init()
+    L = lib()
+    from falkordb_b200.grb import Matrix
+    A = orc.rmat_csr(12, 6, 77)
+    n = A.nrows
+    r, c, _ = A.tuples()
+    keep = (r < n - 16) & (c < n - 16)                # the last 16 vertices belong to the triples (and stay isolated beyond them)
+    t0 = n - 12
+    tr = np.array([t0 + 3 * k + a for k in range(3) for a, b in ((0, 1), (0, 2), (1, 2))], np.uint64)
+    tc = np.array([t0 + 3 * k + b for k in range(3) for a, b in ((0, 1), (0, 2), (1, 2))], np.uint64)
+    loops = np.array([100, 200, 300], np.uint64)      # self-edges count as neighbours carrying the vertex's own label
+    rows = np.concatenate([r[keep], c[keep], tr, tc, loops]).astype(np.uint64)
+    cols = np.concatenate([c[keep], r[keep], tc, tr, loops]).astype(np.uint64)
+    S = orc.build_matrix(n, n, rows, cols)
+    want, rounds = orc.cdlp(S, itermax)
+    m = Matrix.import_csr(n, n, S.p.astype(np.uint64), S.j, None, bool)
+    G, h = P(), P(m.h.value)
+    m.h = P()
+    assert L.LAGraph_New(C.byref(G), C.byref(h), 0, None) == 0           # LAGraph_ADJACENCY_UNDIRECTED
+    out = P()
+    assert L.LAGraph_cdlp(C.byref(out), G, itermax, None) == 0
+    nv = C.c_uint64(n)
+    I, X = np.empty(n, np.uint64), np.empty(n, np.int64)
+    check(L.GrB_Vector_extractTuples_INT64(I.ctypes.data, X.ctypes.data, C.byref(nv), out))      # extract_vector_i64
+    assert nv.value == n and np.array_equal(I, np.arange(n)), "the label vector is dense"
+    assert np.array_equal(X, want), f"labels differ from the oracle after {rounds} rounds"
+    if itermax >= 3:
+        for k in range(3):
+            assert X[t0 + 3 * k] == X[t0 + 3 * k + 1] == X[t0 + 3 * k + 2] == t0 + 3 * k
+    assert X[n - 13] == n - 13, "an isolated vertex keeps its label"
+    L.GrB_Vector_free(C.byref(out))
+    L.LAGraph_Delete(C.byref(G), None)
+    d = Matrix.import_csr(n, n, A.p.astype(np.uint64), A.j, None, bool)
+    G2, h2 = P(), P(d.h.value)
+    d.h = P()
+    assert L.LAGraph_New(C.byref(G2), C.byref(h2), 1, None) == 0          # directed, symmetry unknown
+    assert L.LAGraph_cdlp(C.byref(out), G2, itermax, None) == -1005
+    L.LAGraph_Delete(C.byref(G2), None)
+
+
 def test_repack_output_batches_host_mirror():
     """batch.rs:81, 274-287: <= 1024 rows per output batch, NodeIds + u16 selection vector, order preserved"""
     run_host_test("repack_output_batches")
