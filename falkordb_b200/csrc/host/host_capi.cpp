@@ -438,6 +438,189 @@ static void t_traverse_over_tensor_operand() {
     REQUIRE(got == want, "3 fused hops over a dirty tensor snapshot");
 }
 
+// ---- the C-compatible RDB form of a Tensor (tensor.rs:1049-1204) and of a VersionedMatrix (versioned_matrix.rs:1082-1113) ----
+typedef std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> EdgeList;
+static EdgeList sorted_edges(const Tensor &t) {
+    EdgeList e = t.iter_edges();
+    std::sort(e.begin(), e.end());
+    return e;
+}
+static Matrix<uint64_t> valued(uint64_t n, const EdgeList &entries) {
+    Matrix<uint64_t> m(n, n);
+    for (auto &e : entries) m.set(std::get<0>(e), std::get<1>(e), std::get<2>(e));
+    m.wait();
+    return m;
+}
+// a stream laid out the way C FalkorDB writes a tensor: (count | MSB) in the forward matrix for a multi-edge pair, its ids as the
+// INDICES of a BOOL vector blob in the base group
+static Stream c_written_stream(uint64_t n, const EdgeList &fm, const EdgeList &dp, const std::vector<std::pair<uint64_t, uint64_t>> &dm,
+                               uint64_t total, const std::vector<std::tuple<uint64_t, uint64_t, std::vector<uint64_t>>> &base_group,
+                               const std::vector<std::tuple<uint64_t, uint64_t, std::vector<uint64_t>>> &dp_group) {
+    Stream w;
+    encode_matrix(valued(n, fm), w);
+    encode_matrix(valued(n, dp), w);
+    Matrix<bool> d(n, n);
+    for (auto &e : dm) d.set(e.first, e.second, true);
+    d.wait();
+    encode_matrix(d, w);
+    w.write_unsigned(total);
+    if (!total) return w;
+    for (auto *g : {&base_group, &dp_group}) {
+        w.write_unsigned(g->size());
+        for (auto &mp : *g) {
+            w.write_unsigned(std::get<0>(mp));
+            w.write_unsigned(std::get<1>(mp));
+            encode_id_blob(std::get<2>(mp), GrB_INDEX_MAX_, w);
+        }
+    }
+    return w;
+}
+typedef std::vector<uint64_t> Ids;
+static void t_tensor_decodes_the_c_written_form() {            // host-resident matrices only: runs without a device
+    const uint64_t MSB = Tensor::MSB_MASK, BIG = ((uint64_t)1 << 40) + 1;
+    Stream s = c_written_stream(8, {{0, 1, 5}, {0, 2, 0}, {1, 2, 3 | MSB}, {3, 3, 2 | MSB}, {7, 0, 42}}, {}, {}, 8,
+                                {{1, 2, {7, 900, BIG}}, {3, 3, {11, 12}}}, {});
+    Tensor t = Tensor::decode(s);
+    REQUIRE(s.empty(), "decode consumes the whole stream");
+    REQUIRE(t.get(0, 1) == Ids{5} && t.get(0, 2) == Ids{0} && t.get(7, 0) == Ids{42}, "single-edge pairs carry their id inline (0 included)");
+    REQUIRE((t.get(1, 2) == Ids{7, 900, BIG}) && (t.get(3, 3) == Ids{11, 12}), "multi-edge ids are the blob's indices, ascending");
+    REQUIRE(t.get(2, 2).empty() && t.get(1, 3).empty(), "absent pairs");
+    uint64_t v = 0;
+    REQUIRE(t.eff_get(1, 2, &v) && v == MULTI_EDGE, "a multi-edge pair holds the sentinel inline, not the count");
+    REQUIRE(t.has_multi_edge() && t.multi_pairs() == 2 && t.edge_count() == 8, "2 multi-edge pairs, 8 edges");
+    REQUIRE(t.matrix_t().nrows() == 0, "the backward matrix is left for rebuild_backward");
+    // and back out: same layout, deltas folded (two empty layers), ids as indices
+    Stream w;
+    t.encode(w);
+    Stream probe = w;
+    Matrix<uint64_t> fm = decode_matrix<uint64_t>(probe), fdp = decode_matrix<uint64_t>(probe);
+    Matrix<bool> fdm = decode_matrix<bool>(probe);
+    REQUIRE(fm.nrows() == 8 && fm.ncols() == 8 && fm.nvals() == 5 && fdp.nvals() == 0 && fdm.nvals() == 0, "base holds everything");
+    REQUIRE(fm.get(1, 2, &v) && v == (3 | MSB), "(count | MSB) for a multi-edge pair");
+    REQUIRE(fm.get(3, 3, &v) && v == (2 | MSB) && fm.get(0, 2, &v) && v == 0 && fm.get(7, 0, &v) && v == 42, "forward values");
+    REQUIRE(probe.read_unsigned() == 8 && probe.read_unsigned() == 2, "total edges, base group size");
+    REQUIRE(probe.read_unsigned() == 1 && probe.read_unsigned() == 2 && (decode_id_blob(probe) == Ids{7, 900, BIG}), "first pair");
+    REQUIRE(probe.read_unsigned() == 3 && probe.read_unsigned() == 3 && (decode_id_blob(probe) == Ids{11, 12}), "second pair");
+    REQUIRE(probe.read_unsigned() == 0 && probe.empty(), "empty delta-plus group ends the stream");
+    Tensor t2 = Tensor::decode(w);
+    REQUIRE(sorted_edges(t2) == sorted_edges(t) && t2.edge_count() == 8, "encode -> decode keeps every (src, dst, id)");
+    // defensive merge of on-disk deltas: (m \ dm) U dp, ids from both groups
+    Stream s2 = c_written_stream(8, {{0, 1, 5}, {7, 0, 42}, {4, 4, 9}}, {{7, 0, 43}, {6, 6, 2 | MSB}}, {{7, 0}, {0, 1}}, 4, {},
+                                 {{6, 6, {100, 101}}});
+    Tensor t3 = Tensor::decode(s2);
+    REQUIRE(t3.get(7, 0) == Ids{43} && t3.get(0, 1).empty() && t3.get(4, 4) == Ids{9} && (t3.get(6, 6) == Ids{100, 101}), "merged deltas");
+    // an empty tensor: three empty layers and a zero count
+    Tensor e(5, 5);
+    Stream we;
+    e.encode(we);
+    REQUIRE(we.items.size() == 3 * 26 + 1 && we.items.back().u == 0, "3 x (container + 5 payload vectors x 5 items) + total 0");
+    Tensor e2 = Tensor::decode(we);
+    REQUIRE(e2.edge_count() == 0 && e2.fwd_m().nrows() == 5, "empty round trip");
+    // malformed input surfaces as an error, never as a half-built tensor
+    Stream bad = c_written_stream(8, {{0, 1, 5}}, {}, {}, 1, {}, {});
+    bad.items.pop_back();
+    bool threw = false;
+    try { Tensor::decode(bad); } catch (const std::runtime_error &) { threw = true; }
+    REQUIRE(threw, "a truncated tensor section is an error");
+    Stream tiny;
+    tiny.write_buffer("abc", 3);
+    threw = false;
+    try { Tensor::decode(tiny); } catch (const std::runtime_error &ex) { threw = std::string(ex.what()).find("container buffer too small") != std::string::npos; }
+    REQUIRE(threw, "container buffer too small");
+}
+static void t_tensor_encode_decode_after_mutations() {          // device: batched inserts, a fold, bulk deletes, backward rebuild
+    Tensor t(64, 64);
+    std::map<std::pair<uint64_t, uint64_t>, std::set<uint64_t>> model;       // what the tensor must hold, kept independently
+    uint64_t next = 0;
+    std::vector<uint64_t> S, D, I;
+    auto edge = [&](uint64_t s, uint64_t d) { S.push_back(s); D.push_back(d); I.push_back(next); model[{s, d}].insert(next); next++; };
+    auto at = [&](uint64_t a, uint64_t b) -> std::set<uint64_t> & { return model[std::make_pair(a, b)]; };
+    auto commit = [&]() { t.set_all_from_slices(S, D, I); S.clear(); D.clear(); I.clear(); };
+    auto expected = [&]() {
+        EdgeList e;
+        for (auto &kv : model) for (uint64_t id : kv.second) e.push_back(std::make_tuple(kv.first.first, kv.first.second, id));
+        std::sort(e.begin(), e.end());
+        return e;
+    };
+    for (uint64_t s = 0; s < 64; s++) for (uint64_t k = 1; k <= 5; k++) edge(s, (s * 7 + k * 5) % 64);   // 320 distinct pairs, id 0 included
+    commit();
+    t.wait();
+    t.fold_oversized();                                          // 320 >= MIN_FOLD_DELTA and dominates the empty base: dp folds into m
+    REQUIRE(t.fwd_m().nvals() == 320 && t.fwd_dp().nvals() == 0, "the first batch was folded into the base");
+    edge(2, 19); edge(2, 19);                                    // (2,19) holds id 10 in the base: promoted to three edges
+    edge(50, 51); edge(50, 51);                                  // a pair born multi inside one batch
+    edge(60, 1); edge(60, 1); edge(61, 2);
+    commit();
+    REQUIRE(at(2, 19).size() == 3 && *at(2, 19).begin() == 10, "test setup: (2,19) was a base single (id 10)");
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> rm;
+    auto drop = [&](uint64_t s, uint64_t d, uint64_t id) {
+        rm.push_back(std::make_tuple(id, s, d));
+        auto it = model.find({s, d});
+        it->second.erase(id);
+        if (it->second.empty()) model.erase(it);
+    };
+    for (uint64_t s = 10; s < 20; s++) drop(s, (s * 7 + 10) % 64, s * 5 + 1);        // ten singles out of the base (k = 2)
+    drop(2, 19, *at(2, 19).rbegin());                       // one of (2,19)'s three
+    drop(60, 1, *at(60, 1).begin());                        // (60,1) down to one edge: demoted to inline
+    t.remove_all(rm);
+    t.wait();
+    EdgeList before = sorted_edges(t);
+    uint64_t count = t.edge_count();
+    REQUIRE(before == expected(), "the tensor holds what the model holds before encoding");
+    REQUIRE(count == before.size(), "edge_count agrees with the enumeration");
+    REQUIRE(t.fwd_dm().nvals() >= 10 && t.fwd_dp().nvals() > 0, "test setup: all three forward layers are populated");
+    Stream w;
+    t.encode(w);
+    REQUIRE(sorted_edges(t) == before, "encode leaves the tensor usable");
+    Stream probe = w;
+    Matrix<uint64_t> fm = decode_matrix<uint64_t>(probe), fdp = decode_matrix<uint64_t>(probe);
+    Matrix<bool> fdm = decode_matrix<bool>(probe);
+    REQUIRE(fm.nvals() == model.size() && fdp.nvals() == 0 && fdm.nvals() == 0, "deltas are folded on the way out");
+    REQUIRE(probe.read_unsigned() == count, "total edge count");
+    uint64_t v = 0;
+    REQUIRE(fm.get(2, 19, &v) && v == (2 | Tensor::MSB_MASK) && fm.get(50, 51, &v) && v == (2 | Tensor::MSB_MASK), "(count | MSB)");
+    REQUIRE(fm.get(60, 1, &v) && v == *at(60, 1).begin() && fm.get(0, 5, &v) && v == 0, "inline ids, edge id 0 included");
+    Tensor u = Tensor::decode(w);
+    u.rebuild_backward();
+    REQUIRE(sorted_edges(u) == before && u.edge_count() == count, "every (src, dst, id) survives");
+    for (auto &kv : model) {
+        Ids want(kv.second.begin(), kv.second.end());
+        REQUIRE(u.get(kv.first.first, kv.first.second) == want, "ids of (" << kv.first.first << "," << kv.first.second << ")");
+    }
+    REQUIRE(u.multi_pairs() == 2 && u.matrix_t().nvals() == model.size() && u.matrix_t().get(19, 2) && u.matrix_t().get(51, 50) &&
+            !u.matrix_t().get((10 * 7 + 10) % 64, 10), "backward = transpose of the live pattern");
+    // the decoded tensor keeps working as an edge store
+    std::vector<uint64_t> S3 = {2}, D3 = {19}, I3 = {next};
+    u.set_all_from_slices(S3, D3, I3);
+    REQUIRE(u.get(2, 19).size() == 3 && u.get(2, 19).back() == next && u.edge_count() == count + 1, "insert after decode");
+}
+static void t_versioned_matrix_encode_decode() {
+    VersionedMatrix v(40, 40);
+    for (uint64_t k = 0; k < 30; k++) v.set(k, (k * 3) % 40);
+    v.wait();
+    v.remove(3, 9);
+    v.set(39, 39);
+    std::vector<std::tuple<uint64_t, uint64_t>> want, got;
+    {
+        auto it = v.iter();
+        std::tuple<uint64_t, uint64_t> t;
+        while (it.next(t)) want.push_back(t);
+    }
+    Stream w;
+    v.encode(w);
+    REQUIRE(w.items.size() == 3 * 26, "three layers: container + 5 payload vectors each");
+    VersionedMatrix u = VersionedMatrix::decode(w);
+    REQUIRE(w.empty() && u.nvals() == v.nvals() && u.nrows() == 40, "layers in order");
+    {
+        auto it = u.iter();
+        std::tuple<uint64_t, uint64_t> t;
+        while (it.next(t)) got.push_back(t);
+    }
+    REQUIRE(got == want && got.size() == 30 && u.get(39, 39) && !u.get(3, 9), "effective content");
+    u.set(3, 9);
+    REQUIRE(u.nvals() == 31, "usable after decode");
+}
+
 struct TestEntry { const char *name; void (*fn)(); };
 static TestEntry TESTS[] = {
     {"read_path_balance_point_is_flat_in_base_size", t_read_path_balance_point_is_flat_in_base_size},
@@ -458,6 +641,9 @@ static TestEntry TESTS[] = {
     {"repack_output_batches", t_repack_output_batches},
     {"var_len_trails", t_var_len_trails},
     {"var_len_trails_logic", t_var_len_trails_logic},
+    {"tensor_decodes_the_c_written_form", t_tensor_decodes_the_c_written_form},
+    {"tensor_encode_decode_after_mutations", t_tensor_encode_decode_after_mutations},
+    {"versioned_matrix_encode_decode", t_versioned_matrix_encode_decode},
 };
 
 extern "C" {

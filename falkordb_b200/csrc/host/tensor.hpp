@@ -283,6 +283,90 @@ class Tensor {
         uint64_t shadow = fwd_dp().nvals() == 0 ? 0 : fwd_dp().intersection_nvals(fwd_m());
         return fwd_m().nvals() + fwd_dp().nvals() - fwd_dm().nvals() - shadow - multi_pairs() + me_.nvals();
     }
+    // ---- the C-compatible RDB form (tensor.rs:1049-1204) ----
+    // Forward matrix as UINT64: a single-edge pair stores its edge id (MSB clear), a multi-edge pair stores (edge count | MSB) and
+    // its id list follows in the tensor section as a BOOL vector of size GrB_INDEX_MAX whose INDICES are the ids.  Deltas are
+    // folded into the base on the way out (two empty layers follow), then total edge count, then two groups (base, delta-plus).
+    static const uint64_t MSB_MASK = (uint64_t)1 << 63;
+    void encode(Stream &w) const {                               // tensor.rs:1053-1126
+        uint64_t nrows = fwd_m().nrows(), ncols = fwd_m().ncols();
+        Matrix<uint64_t> fm(nrows, ncols), empty(nrows, ncols);
+        std::vector<std::tuple<uint64_t, uint64_t, std::vector<uint64_t>>> multi;
+        {
+            auto it = fwd_iter(0, UINT64_MAX);
+            std::tuple<uint64_t, uint64_t, uint64_t> t;
+            while (it.next(t)) {
+                uint64_t src = std::get<0>(t), dst = std::get<1>(t), inl = std::get<2>(t);
+                if (inl == MULTI_EDGE) {
+                    std::vector<uint64_t> ids;
+                    uint64_t key = compound_key(src, dst);
+                    auto mi = me_.iter(key, key);
+                    std::tuple<uint64_t, uint64_t> e;
+                    while (mi.next(e)) ids.push_back(std::get<1>(e));
+                    fm.set(src, dst, (uint64_t)ids.size() | MSB_MASK);
+                    multi.push_back(std::make_tuple(src, dst, std::move(ids)));
+                } else {
+                    fm.set(src, dst, inl);
+                }
+            }
+        }
+        // the reference collects the triples and calls build(); here they are set one by one and assembled on the host by wait():
+        // the container unload that follows needs the host form anyway, so nothing of this visits the device
+        fm.wait();
+        encode_matrix(fm, w);
+        encode_matrix(empty, w);      // delta-plus
+        encode_matrix(empty, w);      // delta-minus
+        uint64_t total = edge_count();
+        w.write_unsigned(total);
+        if (total == 0) return;
+        w.write_unsigned((uint64_t)multi.size());
+        for (auto &mp : multi) {
+            w.write_unsigned(std::get<0>(mp));
+            w.write_unsigned(std::get<1>(mp));
+            encode_id_blob(std::get<2>(mp), GrB_INDEX_MAX_, w);
+        }
+        w.write_unsigned(0);          // empty delta-plus tensor group
+    }
+    // The backward matrix is left empty: the caller rebuilds it (rebuild_backward) after decode, as in the reference.
+    static Tensor decode(Stream &r) {                            // tensor.rs:1130-1204
+        Matrix<uint64_t> fwd_m = decode_matrix<uint64_t>(r), fwd_dp = decode_matrix<uint64_t>(r);
+        Matrix<bool> fwd_dm = decode_matrix<bool>(r);
+        uint64_t nrows = fwd_m.nrows(), ncols = fwd_m.ncols();
+        Matrix<uint64_t> m(nrows, ncols);
+        VersionedMatrix me(GrB_INDEX_MAX_, GrB_INDEX_MAX_);
+        bool dm_empty = fwd_dm.nvals() == 0;
+        std::tuple<uint64_t, uint64_t, uint64_t> t;
+        {
+            auto it = fwd_m.iter(0, UINT64_MAX);
+            while (it.next(t)) {
+                uint64_t src = std::get<0>(t), dst = std::get<1>(t), value = std::get<2>(t);
+                if (!dm_empty && fwd_dm.contains(src, dst)) continue;      // deleted (a live replacement id lives in fwd_dp)
+                m.set(src, dst, (value & MSB_MASK) == 0 ? value : MULTI_EDGE);
+            }
+        }
+        {
+            auto it = fwd_dp.iter(0, UINT64_MAX);
+            while (it.next(t)) m.set(std::get<0>(t), std::get<1>(t), (std::get<2>(t) & MSB_MASK) == 0 ? std::get<2>(t) : MULTI_EDGE);
+        }
+        uint64_t total_tensor_count = r.read_unsigned();
+        if (total_tensor_count > 0) {
+            for (int group = 0; group < 2; group++) {            // base (TM), then delta-plus (TDP)
+                uint64_t count = r.read_unsigned();
+                for (uint64_t k = 0; k < count; k++) {
+                    uint64_t src = r.read_unsigned(), dst = r.read_unsigned();
+                    uint64_t key = compound_key(src, dst);
+                    for (uint64_t edge_id : decode_id_blob(r)) me.set(key, edge_id);
+                }
+            }
+        }
+        m.wait();
+        Tensor out(nrows, ncols);
+        out.m_ = Cow<Matrix<uint64_t>>(m);
+        out.mt_ = VersionedMatrix(0, 0);
+        out.me_ = me;
+        return out;
+    }
+
     // every (src, dst, edge_id): inline singles first, then the multi-edge ids (tensor.rs:921-936)
     std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> iter_edges() const {
         std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> out;

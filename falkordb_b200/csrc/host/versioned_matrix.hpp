@@ -5,6 +5,7 @@
 // Written against the same C ABI calls the Rust file makes; every GraphBLAS bulk call lands in libb200grb.so.
 #pragma once
 #include "matrix.hpp"
+#include "serial.hpp"
 #include <algorithm>
 #include <optional>
 
@@ -308,6 +309,26 @@ class VersionedMatrix {
         dp_.clear(nr, nc);
         dm_.clear(nr, nc);
         needs_flush = false;
+    }
+
+    // <VersionedMatrix<V> as Encode<19> / Decode<19>>, versioned_matrix.rs:1082-1113: the three layers in order; decoded deltas
+    // have no owning transaction (tx_nvals = 0), so the write fold policy sees the whole delta as freshly added
+    void encode(Stream &w) const {
+        encode_matrix(m(), w);
+        encode_matrix(dp(), w);
+        encode_matrix(dm(), w);
+    }
+    static VersionedMatrix decode(Stream &r) {
+        Matrix<bool> m = decode_matrix<bool>(r), dp = decode_matrix<bool>(r), dm = decode_matrix<bool>(r);
+        uint64_t base = m.nvals();
+        VersionedMatrix v;
+        v.m_ = Cow<Matrix<bool>>(m);
+        v.dp_ = DeltaBool(dp);
+        v.dm_ = DeltaBool(dm);
+        v.dp_.latch(v.dp_.fold_decision(should_fold, base));
+        v.dm_.latch(v.dm_.fold_decision(should_fold, base));
+        v.needs_flush = v.dp_.folding() || v.dm_.folding();
+        return v;
     }
 
     typedef LayerIter<bool> Iter;   // sorted 3-way merge (m \ dm) U dp

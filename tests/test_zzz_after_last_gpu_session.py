@@ -200,3 +200,9 @@ def test_repack_output_batches_host_mirror():
 def test_var_len_trails_over_a_tensor():
     """cond_var_len_traverse.rs:152-386 with the adjacency fetched from a relationship Tensor through the row iterators"""
     run_host_test("var_len_trails")
+
+
+def test_tensor_rdb_round_trip_after_device_side_mutations():
+    """tensor.rs:1049-1204: batched inserts, a delta fold, bulk deletes with a demotion, then encode -> decode -> rebuild_backward;
+    every (src, dst, edge id) is checked against a model kept beside the tensor"""
+    run_host_test("tensor_encode_decode_after_mutations")
