@@ -126,6 +126,61 @@ void build_from_device_coo(const u64 *dI, const u64 *dJ, const u64 *dX, u64 n, u
     }
 }
 
+// ---- bulk tensor build (GRAPH.BULK: src/commands/bulk_insert.rs:497 -> graph.rs:2062 -> Tensor::set_all_from_slices, -------
+// tensor.rs:333-447, applied to an EMPTY tensor) ---------------------------------------------------------------------------------
+// From n (src, dst, edge id) triples: the forward UINT64 matrix whose value is the pair's edge id, or the MULTI_EDGE sentinel
+// when the pair has more than one edge, plus the (pair key, edge id) list of every edge of every multi-edge pair (what the
+// reference stores in `me`).  Two stable radix sorts ((id), then (src << 32 | dst)) put each pair's ids in ascending order inside
+// its run; one pass marks the runs longer than one; the CSR comes out of the same sorted keys as every other build.
+static const u64 TENSOR_MULTI_EDGE = ~0ULL;        // tensor.rs:206
+__global__ void k_bulk_mark(const u64 *__restrict__ keys, const u64 *__restrict__ ids, u64 n, u64 *__restrict__ xval,
+                            u32 *__restrict__ multi) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const u64 k = keys[t];
+        const bool dup = (t > 0 && keys[t - 1] == k) || (t + 1 < n && keys[t + 1] == k);
+        xval[t] = dup ? TENSOR_MULTI_EDGE : ids[t];
+        multi[t] = dup ? 1u : 0u;
+    }
+}
+__global__ void k_bulk_compact(const u64 *__restrict__ keys, const u64 *__restrict__ ids, const u32 *__restrict__ multi,
+                               const u64 *__restrict__ pos, u64 n, u64 *__restrict__ mkeys, u64 *__restrict__ mids) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < n; t += stride)
+        if (multi[t]) { const u64 d = pos[t]; mkeys[d] = keys[t]; mids[d] = ids[t]; }
+}
+void tensor_bulk_build(const u64 *dI, const u64 *dJ, const u64 *dID, u64 n, u64 nrows, u64 ncols, DevCSR &fwd, DevBuf<u64> &mkeys,
+                       DevBuf<u64> &mids, u64 *nmulti, bool *index_error) {
+    if (nrows >= ((u64)1 << 32) || ncols >= ((u64)1 << 32))
+        throw GrbError(-8, "device build: dimensions >= 2^32 are host-only");
+    *index_error = false;
+    *nmulti = 0;
+    if (n == 0) { csr_from_sorted_keys(nullptr, 0, nrows, ncols, nullptr, nullptr, fwd); return; }
+    DevBuf<u64> keys(n), ids(n);
+    DevBuf<u32> err(1);
+    err.zero();
+    LAUNCH(k_pack_keys, grid_for(n, 256, 1 << 20), 256, 0, dI, dJ, n, nrows, ncols, keys.ptr, err.ptr);
+    if (read_scalar(err.ptr)) { *index_error = true; return; }
+    d2d(ids.ptr, dID, n);
+    sort_pairs_u64(ids.ptr, keys.ptr, n, 64);            // by edge id
+    sort_pairs_u64(keys.ptr, ids.ptr, n, 64);            // stable by pair: ids stay ascending inside a pair's run
+    DevBuf<u64> xval(n), iota(n), pos(n);
+    DevBuf<u32> multi(n);
+    LAUNCH(k_bulk_mark, grid_for(n, 256, 1 << 20), 256, 0, keys.ptr, ids.ptr, n, xval.ptr, multi.ptr);
+    LAUNCH(k_iota_u64, grid_for(n, 256, 1 << 20), 256, 0, iota.ptr, n);
+    csr_from_sorted_keys(keys.ptr, n, nrows, ncols, iota.ptr, xval.ptr, fwd);
+    exclusive_scan_u32_to_u64(multi.ptr, pos.ptr, n);
+    const u64 nm = read_scalar(pos.ptr + (n - 1)) + read_scalar(multi.ptr + (n - 1));
+    *nmulti = nm;
+    if (nm) {
+        mkeys.alloc(nm);
+        mids.alloc(nm);
+        LAUNCH(k_bulk_compact, grid_for(n, 256, 1 << 20), 256, 0, keys.ptr, ids.ptr, multi.ptr, pos.ptr, n, mkeys.ptr, mids.ptr);
+    }
+}
+
 // ---- transpose --------------------------------------------------------------------------------
 __global__ void k_transpose_keys(const u64 *__restrict__ p, const u32 *__restrict__ j, u64 nrows,
                                  u64 *__restrict__ keys) {

@@ -2146,6 +2146,52 @@ GrB_Info B200_Matrix_rmat(GrB_Matrix *A, int scale, uint64_t edge_factor, uint64
     });
 }
 
+// GRAPH.BULK's edge load into an EMPTY relationship tensor (src/commands/bulk_insert.rs:497 -> graph.rs:2062-2122 ->
+// Tensor::set_all_from_slices, tensor.rs:333-447) as one device-side build instead of n host-side probe-and-insert steps: the
+// forward UINT64 matrix (value = the pair's edge id, or MULTI_EDGE = UINT64_MAX when the pair has several edges) and the (pair key
+// = src << 32 | dst, edge id) list of every edge of every multi-edge pair, sorted by (key, id) -- the entries of the reference's
+// `me` store.  *multi_keys / *multi_ids are allocated with GxB_init's malloc (NULL when *nmulti == 0): the caller frees them.
+GrB_Info B200_Tensor_bulk_build(GrB_Matrix *fwd, GrB_Index **multi_keys, GrB_Index **multi_ids, GrB_Index *nmulti, GrB_Index nrows,
+                                GrB_Index ncols, const GrB_Index *srcs, const GrB_Index *dsts, const GrB_Index *ids, GrB_Index n) {
+    CHECK_PTR(fwd); CHECK_PTR(multi_keys); CHECK_PTR(multi_ids); CHECK_PTR(nmulti);
+    if (n) { CHECK_PTR(srcs); CHECK_PTR(dsts); CHECK_PTR(ids); }
+    if (nrows >= ((u64)1 << 32) || ncols >= ((u64)1 << 32)) { tl_error = "bulk build: dimensions must be below 2^32"; return GrB_INVALID_VALUE; }
+    return guarded([&]() {
+        GpuLock g;
+        std::unique_ptr<GB_Matrix_opaque> mh(new GB_Matrix_opaque());   // released to the caller only on success
+        GrB_Matrix m = mh.get();
+        m->type = T_UINT64; m->nrows = nrows; m->ncols = ncols;
+        *multi_keys = nullptr; *multi_ids = nullptr; *nmulti = 0;
+        if (n == 0) { *fwd = mh.release(); return GrB_SUCCESS; }
+        ensure_init();
+        DevBuf<u64> dI(n), dJ(n), dID(n), mk, mi;
+        h2d(dI.ptr, (const u64 *)srcs, n);
+        h2d(dJ.ptr, (const u64 *)dsts, n);
+        h2d(dID.ptr, (const u64 *)ids, n);
+        DevCSR out;
+        bool err = false;
+        u64 nm = 0;
+        tensor_bulk_build(dI.ptr, dJ.ptr, dID.ptr, n, nrows, ncols, out, mk, mi, &nm, &err);
+        sync_stream();
+        if (err) { tl_error = "bulk build: index out of bounds"; return GrB_INDEX_OUT_OF_BOUNDS; }
+        u64 *hk = nullptr, *hi = nullptr;
+        if (nm) {
+            hk = (u64 *)g_user_malloc(nm * sizeof(u64));
+            hi = (u64 *)g_user_malloc(nm * sizeof(u64));
+            if (!hk || !hi) { if (hk) g_user_free(hk); if (hi) g_user_free(hi); throw std::bad_alloc(); }
+            try {
+                d2h(hk, mk.ptr, nm);
+                d2h(hi, mi.ptr, nm);
+                sync_stream();
+            } catch (...) { g_user_free(hk); g_user_free(hi); throw; }
+        }
+        set_dev(m, std::move(out));
+        *multi_keys = hk; *multi_ids = hi; *nmulti = nm;
+        *fwd = mh.release();
+        return GrB_SUCCESS;
+    });
+}
+
 // ExpandInto's per-row point lookups (expand_into.rs:195-249, Tensor::get -> GrB_Matrix_extractElement) as one batched call
 GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_Index *J, GrB_Index n, uint8_t *found,
                                    uint64_t *values) {

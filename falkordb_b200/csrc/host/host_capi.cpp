@@ -594,6 +594,54 @@ static void t_tensor_encode_decode_after_mutations() {          // device: batch
     u.set_all_from_slices(S3, D3, I3);
     REQUIRE(u.get(2, 19).size() == 3 && u.get(2, 19).back() == next && u.edge_count() == count + 1, "insert after decode");
 }
+static void t_tensor_bulk_load_matches_set_all_from_slices() {  // device
+    const uint64_t n = 128;
+    std::vector<uint64_t> S, D, I;
+    uint64_t x = 12345;
+    auto rnd = [&]() { x = x * 6364136223846793005ULL + 1442695040888963407ULL; return x >> 33; };
+    const uint64_t count = 3000;
+    for (uint64_t k = 0; k < count; k++) {
+        bool hot = rnd() % 4 == 0;                               // a quarter of the edges land on 40 hot pairs: long id lists
+        S.push_back(hot ? rnd() % 5 : rnd() % n);
+        D.push_back(hot ? rnd() % 8 : rnd() % n);
+        I.push_back((k * 7919) % count);                         // a permutation of 0..count-1 (7919 is prime to 3000): ids arrive unordered, 0 included
+    }
+    std::map<std::pair<uint64_t, uint64_t>, std::set<uint64_t>> model;
+    for (uint64_t k = 0; k < count; k++) model[std::make_pair(S[k], D[k])].insert(I[k]);
+    Tensor a(n, n);
+    a.set_all_from_slices(S, D, I);
+    a.wait();
+    Tensor b = Tensor::bulk_load(n, n, S, D, I);
+    REQUIRE(sorted_edges(b) == sorted_edges(a) && sorted_edges(b).size() == count, "same (src, dst, id) set as the reference's insert loop");
+    uint64_t multi = 0, v = 0;
+    for (auto &kv : model) {
+        Ids want(kv.second.begin(), kv.second.end());
+        REQUIRE(b.get(kv.first.first, kv.first.second) == want, "ids of (" << kv.first.first << "," << kv.first.second << ")");
+        REQUIRE(b.fwd_m().get(kv.first.first, kv.first.second, &v) && v == (want.size() > 1 ? MULTI_EDGE : want[0]), "inline value");
+        multi += want.size() > 1;
+    }
+    REQUIRE(multi > 40 && b.multi_pairs() == multi && a.multi_pairs() == multi, "multi-edge pairs");
+    REQUIRE(b.edge_count() == count && a.edge_count() == count, "edge_count");
+    REQUIRE(b.fwd_m().nvals() == model.size() && b.fwd_dp().nvals() == 0 && b.fwd_dm().nvals() == 0, "everything in the base, no deltas");
+    REQUIRE(b.matrix_t().nvals() == model.size() && b.extract().nvals() == model.size(), "backward matrix and pattern");
+    {
+        auto it = b.matrix_t().iter();
+        std::tuple<uint64_t, uint64_t> t;
+        while (it.next(t)) REQUIRE(model.count(std::make_pair(std::get<1>(t), std::get<0>(t))), "backward entry without a forward pair");
+    }
+    // the loaded tensor is an ordinary tensor afterwards
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> rm;
+    auto first = model.begin();
+    for (uint64_t id : first->second) rm.push_back(std::make_tuple(id, first->first.first, first->first.second));
+    b.remove_all(rm);
+    REQUIRE(b.get(first->first.first, first->first.second).empty() && b.edge_count() == count - first->second.size(), "delete after load");
+    // corner cases
+    Tensor e = Tensor::bulk_load(n, n, {}, {}, {});
+    REQUIRE(e.edge_count() == 0 && e.fwd_m().nrows() == n, "empty load");
+    bool threw = false;
+    try { Tensor::bulk_load(n, n, {1}, {n}, {0}); } catch (const std::runtime_error &) { threw = true; }
+    REQUIRE(threw, "an endpoint outside the matrix is an error");
+}
 static void t_versioned_matrix_encode_decode() {
     VersionedMatrix v(40, 40);
     for (uint64_t k = 0; k < 30; k++) v.set(k, (k * 3) % 40);
@@ -644,6 +692,7 @@ static TestEntry TESTS[] = {
     {"tensor_decodes_the_c_written_form", t_tensor_decodes_the_c_written_form},
     {"tensor_encode_decode_after_mutations", t_tensor_encode_decode_after_mutations},
     {"versioned_matrix_encode_decode", t_versioned_matrix_encode_decode},
+    {"tensor_bulk_load_matches_set_all_from_slices", t_tensor_bulk_load_matches_set_all_from_slices},
 };
 
 extern "C" {

@@ -367,6 +367,30 @@ class Tensor {
         return out;
     }
 
+    // GRAPH.BULK's edge load into an empty tensor (bulk_insert.rs:497 -> graph.rs:2062-2135) through the device-side build
+    // B200_Tensor_bulk_build: the state Tensor::new + set_all_from_slices + the end-of-command fold would reach, in one call
+    static Tensor bulk_load(uint64_t nrows, uint64_t ncols, const std::vector<uint64_t> &srcs, const std::vector<uint64_t> &dsts,
+                            const std::vector<uint64_t> &ids) {
+        if (srcs.size() != dsts.size() || srcs.size() != ids.size()) throw std::logic_error("bulk_load: slices differ in length");
+        GrB_Matrix raw = nullptr;
+        GrB_Index *mk = nullptr, *mi = nullptr, nm = 0;
+        grb_ok(B200_Tensor_bulk_build(&raw, &mk, &mi, &nm, nrows, ncols, srcs.data(), dsts.data(), ids.data(), srcs.size()),
+               "B200_Tensor_bulk_build");
+        Tensor t(nrows, ncols);
+        t.m_ = Cow<Matrix<uint64_t>>(Matrix<uint64_t>::adopt(raw, false));
+        if (nm) {
+            std::vector<uint64_t> keys(mk, mk + nm), eids(mi, mi + nm);
+            std::free(mk);
+            std::free(mi);
+            Matrix<bool> me(GrB_INDEX_MAX_, GrB_INDEX_MAX_);
+            me.build(keys, eids);
+            me.wait();
+            t.me_ = VersionedMatrix::from_matrix(me);
+        }
+        t.rebuild_backward();
+        return t;
+    }
+
     // every (src, dst, edge_id): inline singles first, then the multi-edge ids (tensor.rs:921-936)
     std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> iter_edges() const {
         std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> out;

@@ -7,6 +7,9 @@ namespace b200 {
 // build.cu
 void build_from_device_coo(const u64 *dI, const u64 *dJ, const u64 *dX, u64 n, u64 nrows, u64 ncols, DevCSR &out,
                            bool *index_error);
+// GRAPH.BULK into an empty tensor: forward u64 CSR (edge id or the MULTI_EDGE sentinel) + the (pair key, id) list of multi-edge pairs
+void tensor_bulk_build(const u64 *dI, const u64 *dJ, const u64 *dID, u64 n, u64 nrows, u64 ncols, DevCSR &fwd, DevBuf<u64> &mkeys,
+                       DevBuf<u64> &mids, u64 *nmulti, bool *index_error);
 void transpose_csr(const DevCSR &A, DevCSR &out, bool keep_values);
 void rmat_csr(int scale, u64 edge_factor, u64 seed, DevCSR &out);
 void rmat_block_csr(int scale, u64 edge_factor, u64 seed, u64 lo, u64 hi, int by_col, DevCSR &out);

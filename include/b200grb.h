@@ -327,6 +327,14 @@ GrB_Info B200_bfs_dist_merge(const uint64_t *gathered, int nranks, uint64_t nwor
 GrB_Info B200_bfs_dist_pull(GrB_Matrix ATlocal, uint64_t row_lo, const uint64_t *frontier_bits, const uint64_t *visited,
                             uint64_t *disc, uint64_t nwords, uint64_t *scanned_out);
 GrB_Info B200_bfs_dist_parents(GrB_Matrix ATlocal, uint64_t row_lo, const int32_t *level_full, int64_t *parent_local);
+
+/* GRAPH.BULK's edge load into an EMPTY relationship tensor (src/commands/bulk_insert.rs:497 -> graph.rs:2062 ->
+ * Tensor::set_all_from_slices, tensor.rs:333-447) as one device-side build: *fwd = the forward UINT64 matrix (value = the pair's
+ * edge id, or UINT64_MAX = tensor.rs:206's MULTI_EDGE when the pair has several edges); *multi_keys / *multi_ids = (src << 32 | dst,
+ * edge id) for every edge of every multi-edge pair, sorted by (key, id) -- the entries of `me`.  The two arrays come from GxB_init's
+ * malloc (NULL when *nmulti == 0) and are the caller's to free. */
+GrB_Info B200_Tensor_bulk_build(GrB_Matrix *fwd, GrB_Index **multi_keys, GrB_Index **multi_ids, GrB_Index *nmulti, GrB_Index nrows,
+                                GrB_Index ncols, const GrB_Index *srcs, const GrB_Index *dsts, const GrB_Index *ids, GrB_Index n);
 /* Batched point lookup: found[t] = 1 (and values[t] = A(I[t],J[t]) when `values` is non-NULL) iff the entry is stored.
  * ExpandInto's per-row Tensor::get (graph/src/runtime/ops/expand_into.rs:195-249 -> GrB_Matrix_extractElement_UINT64)
  * for a whole 1024-row batch in one device call; host arrays in, host arrays out. */

@@ -12,7 +12,7 @@ import pytest
 
 import falkordb_b200 as fb
 import oracle as orc
-from falkordb_b200._lib import lib, obj, check, P
+from falkordb_b200._lib import lib, obj, check, P, U64
 from falkordb_b200.grb import Matrix, Descriptor
 from test_gpu_parity import to_dev, assert_same, bitmap_of, diag_csr
 from test_host_tensor import run as run_host_test
@@ -206,3 +206,55 @@ def test_tensor_rdb_round_trip_after_device_side_mutations():
     """tensor.rs:1049-1204: batched inserts, a delta fold, bulk deletes with a demotion, then encode -> decode -> rebuild_backward;
     every (src, dst, edge id) is checked against a model kept beside the tensor"""
     run_host_test("tensor_encode_decode_after_mutations")
+
+
+def test_tensor_bulk_load_host_mirror():
+    """GRAPH.BULK into an empty tensor (bulk_insert.rs:497 -> graph.rs:2062 -> tensor.rs:333-447): the device-side build against the
+    reference's per-edge insert loop (host mirror), every (src, dst, id), inline values, multi-edge lists, backward matrix"""
+    run_host_test("tensor_bulk_load_matches_set_all_from_slices")
+
+
+@pytest.mark.parametrize("n,count,hot", [(1 << 10, 5000, 64), (1 << 17, 400_000, 1 << 12), (300, 1, 1)])
+def test_tensor_bulk_build_against_a_numpy_model(n, count, hot):
+    """B200_Tensor_bulk_build at sizes the host mirror's insert loop would take minutes for: forward CSR (columns and values) and the
+    multi-edge (key, id) list against numpy on unordered ids"""
+    fb.init()
+    L = lib()
+    from falkordb_b200.grb import Matrix
+    rng = np.random.default_rng(count)
+    src = rng.integers(0, n, count).astype(np.uint64)
+    dst = rng.integers(0, n, count).astype(np.uint64)
+    h = rng.random(count) < 0.3                                  # 30 % of the edges fall on few pairs: long id lists
+    src[h] = rng.integers(0, hot, int(h.sum())).astype(np.uint64) % np.uint64(n)
+    dst[h] = (src[h] * np.uint64(7) + np.uint64(3)) % np.uint64(n)
+    ids = rng.permutation(count).astype(np.uint64)               # unordered, id 0 included
+    fwd, mk, mi, nm = P(), C.POINTER(U64)(), C.POINTER(U64)(), U64()
+    check(L.B200_Tensor_bulk_build(C.byref(fwd), C.byref(mk), C.byref(mi), C.byref(nm), n, n, src.ctypes.data, dst.ctypes.data,
+                                   ids.ctypes.data, count))
+    M = Matrix(0, 0, np.uint64, _handle=fwd)
+    p, j, x = M.export_csr()
+    key = (src << np.uint64(32)) | dst
+    order = np.lexsort((ids, key))
+    ks, iss = key[order], ids[order]
+    uk, first, cnt = np.unique(ks, return_index=True, return_counts=True)
+    assert M.nvals() == len(uk)
+    assert np.array_equal(np.repeat(np.arange(n, dtype=np.uint64), np.diff(p.astype(np.int64))), uk >> np.uint64(32)), "rows"
+    assert np.array_equal(j.astype(np.uint64), uk & np.uint64(0xFFFFFFFF)), "columns"
+    want_x = np.where(cnt > 1, np.uint64(0xFFFFFFFFFFFFFFFF), iss[first])
+    assert np.array_equal(x, want_x), "inline edge id, or MULTI_EDGE for a pair with several edges"
+    in_multi = np.repeat(cnt > 1, cnt)
+    assert nm.value == int(in_multi.sum())
+    if nm.value:
+        got_k = np.ctypeslib.as_array(mk, shape=(nm.value,)).copy()
+        got_i = np.ctypeslib.as_array(mi, shape=(nm.value,)).copy()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(mk); libc.free(mi)
+        assert np.array_equal(got_k, ks[in_multi]) and np.array_equal(got_i, iss[in_multi]), "the multi-edge list, sorted by (pair, id)"
+    else:
+        assert not mk and not mi
+    bad = dst.copy()
+    bad[0] = n
+    f2 = P()
+    rc = L.B200_Tensor_bulk_build(C.byref(f2), C.byref(mk), C.byref(mi), C.byref(nm), n, n, src.ctypes.data, bad.ctypes.data, ids.ctypes.data, count)
+    assert rc != 0 and not f2, "an endpoint outside the matrix is refused and nothing is handed out"
