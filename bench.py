@@ -186,6 +186,18 @@ def workload_name(a):
     return f"{a.hops}-hop mxm chain F*A^{a.hops}, RMAT scale-{a.scale} ef{a.edge_factor} seed {a.seed}"
 
 
+# wall-clock budget of the reference arm's steps + warm-up: the full 512-source batch takes ~12 s on the 128-thread host, so
+# the driver's --steps 20 --warmup 5 fits with the SAME batches as the b200 arm (about five minutes, like round 1's arm)
+REFERENCE_ARM_BUDGET_S = 360.0
+
+
+def workload_config(a, n, nnzA, sources):
+    """`config` of the JSON line: what defines the workload, identical for both arms (arm-specific settings go to `options`)"""
+    return {"workload": workload_name(a), "n": n, "nnz_A": nnzA, "sources_per_gpu_per_step": sources,
+            "l2_policy": ("inputs larger than L2 (A col_idx %.2f GB) and a fresh random source batch every step" % (4 * nnzA / 1e9))
+            if 4 * nnzA > 256e6 else "A fits in L2 at this scale (%.3f GB): a smoke configuration, not a bench size" % (4 * nnzA / 1e9)}
+
+
 def run_reference(a):
     """The reference's CPU implementation of the path.  SuiteSparse:GraphBLAS is not vendored under /root/reference and
     cannot be built here (cmake + generated code), so this arm times the oracle port (kind="port"): row-task Gustavson with
@@ -204,12 +216,13 @@ def run_reference(a):
     deg = np.diff(A.p)
     S = a.cpu_sources
     if S <= 0:
-        probe = pick_sources(deg, 2, min(64, a.sources), a.seed + 17, 0)
+        # one source per thread keeps every thread busy during the probe, so the per-source estimate is not pessimistic
+        probe = pick_sources(deg, 2, min(max(cores, 64), a.sources), a.seed + 17, 0)
         orc.chain(A, probe[0], a.hops, keep=False)                   # allocates the per-thread workspaces
         t0 = time.perf_counter()
         orc.chain(A, probe[1], a.hops, keep=False)
         per_src = (time.perf_counter() - t0) / len(probe[1])
-        budget = 240.0 / max(1, a.steps + a.warmup)
+        budget = REFERENCE_ARM_BUDGET_S / max(1, a.steps + a.warmup)
         S = a.sources if per_src * a.sources <= budget else max(cores, int(budget / per_src) // cores * cores)
         S = min(S, a.sources)
     batches = pick_sources(deg, a.steps + a.warmup, S, a.seed, 0)
@@ -228,7 +241,8 @@ def run_reference(a):
         "impl": "reference", "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": teps,
         "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n": A.nrows, "nnz_A": A.nnz, "sources_per_gpu_per_step": S},
+        "config": workload_config(a, A.nrows, A.nnz, S),
+        "options": {"threads": cores, "sources_probe_s_per_source": None if a.cpu_sources > 0 else per_src},
         "graph_build_s": round(gen_s, 1), "result_format": "CSR (sorted rows, the form the reference's iterator walks)",
         "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
                          "threads_busy_fraction": float(np.mean(busy)) if busy else None,
@@ -563,11 +577,9 @@ def run_b200(a):
         "metric": "traversed edges/sec (mxm TEPS), 3-hop ANY_PAIR mxm chain", "value": flops / (ms * 1e-3), "unit": "edges/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
-        "config": {"workload": workload_name(a),
-                   "n": n, "nnz_A": nnzA, "sources_per_gpu_per_step": a.sources, "parallelism": f"replicated A, sources sharded x{world}",
-                   "numa_node_bound": numa,
-                   "l2_policy": "inputs larger than L2 (A col_idx %.2f GB) and a fresh random source batch every step" % (4 * nnzA / 1e9),
-                   "bits_mode": a.bits_mode, "pull_mode": a.pull_mode, "setup_s": round(setup_s, 2)},
+        "config": workload_config(a, n, nnzA, a.sources),
+        "options": {"parallelism": f"replicated A, sources sharded x{world}", "numa_node_bound": numa, "bits_mode": a.bits_mode,
+                    "pull_mode": a.pull_mode, "opt": list(a.opt), "setup_s": round(setup_s, 2)},
         "flops_per_step": flops / a.steps, "nnz_out_per_step": nnz_out / a.steps,
         "e2e": {"value": e2e_flops / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": e2e_wall_ms / a.steps, "result_format": e2e_kind,
