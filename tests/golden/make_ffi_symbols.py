@@ -13,7 +13,11 @@ GB = "graph/src/graph/graphblas"
 WRAPPERS = [f"{GB}/matrix.rs", f"{GB}/vector.rs", f"{GB}/tensor.rs", f"{GB}/versioned_matrix.rs"]
 # the traversal operators and the BFS procedure reach the C API through the wrappers plus these direct call sites
 CALLERS = ["graph/src/runtime/ops/cond_traverse.rs", "graph/src/runtime/ops/expand_into.rs", "src/module_init.rs"]
-BFS_FUNCS = {"LAGraph_New", "LAGraph_Delete", "LAGr_BreadthFirstSearch_Extended", "LAGraph_Init", "LAGraph_Finalize"}
+# algo_procedures.rs: the shared helpers (create_lagraph_graph .. build_compact_adj_symmetric_from_tensors) and the four procedures
+# this backend serves -- algo.pageRank, algo.WCC, algo.BFS, algo.labelPropagation -- by line range of the frozen reference;
+# betweenness (:884-1020) and everything from MSF on (:1274-) call LAGraph kernels that stay with LAGraph
+ALGO_RANGES = [(360, 673), (689, 883), (1021, 1273)]
+ALGO_ALWAYS = {"LAGraph_Init", "LAGraph_Finalize"}
 
 
 def declared():
@@ -53,10 +57,20 @@ def main():
             elif name in st:
                 statics.setdefault(name, {"declared": st[name], "first_use": where})
     ap = "graph/src/runtime/functions/algo_procedures.rs"
-    for name, where in used(ap).items():          # algo.BFS only (the other procedures are SURVEY 8 f4)
-        if name in BFS_FUNCS and name in fn:
-            functions.setdefault(name, {"declared": fn[name], "first_use": where})
-    doc = {"generated_by": "tests/golden/make_ffi_symbols.py", "wrappers": WRAPPERS + CALLERS + [ap + " (BFS subset)"],
+    for ln, line in enumerate(open(os.path.join(REF, ap), encoding="utf-8", errors="replace"), 1):
+        if not any(lo <= ln <= hi for lo, hi in ALGO_RANGES):
+            continue
+        for m in re.finditer(r"\b((?:GrB|GxB|LAGr|LAGraph)_[A-Za-z0-9_]+)\b", line.split("//")[0]):
+            name, where = m.group(1), f"{ap}:{ln}"
+            if name in fn:
+                functions.setdefault(name, {"declared": fn[name], "first_use": where})
+            elif name in st:
+                statics.setdefault(name, {"declared": st[name], "first_use": where})
+    for name in ALGO_ALWAYS:
+        if name in fn:
+            functions.setdefault(name, {"declared": fn[name], "first_use": ap})
+    doc = {"generated_by": "tests/golden/make_ffi_symbols.py",
+           "wrappers": WRAPPERS + CALLERS + [ap + " (helpers, pageRank, WCC, BFS, labelPropagation: lines %s)" % ALGO_RANGES],
            "functions": dict(sorted(functions.items())), "statics": dict(sorted(statics.items()))}
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_ffi_symbols.json")
     with open(dst, "w") as f:
