@@ -20,7 +20,10 @@ flops_h = sum_{(i,k) in F_h} deg_A(k)  divided by the step time  (SURVEY.md 8d).
 batches.  Multi-GPU: the batch rows are independent, so ranks shard the sources with A replicated and no data-path
 collective (weak scaling: fixed sources per rank); ranks bind to their GPU's NUMA node.
 Other workloads (--workload): bfs (config 5: partitioned direction-optimising BFS over NCCL), triangles (config 4), delta
-(delta-matrix sync kernels at fold sizes), pagerank (FP64 mxv).
+(delta-matrix sync kernels at fold sizes), pagerank (FP64 mxv).  The chain line also carries configs 5 and 4 at their stated
+sizes as sub-objects `partitioned_bfs` (RMAT-26, rows of A partitioned over the N ranks, NCCL all-gather per level; levels and
+min-id parents checked against the oracle) and `masked_triangles` (RMAT-24, strong scaling), each measured by a child process per
+rank after the chain's timed regions (--side; a child that fails costs its sub-object only).
 """
 import argparse
 import ctypes as C
@@ -66,6 +69,10 @@ def parse():
                     help="row slices of a batch in the bitmap hand-off (falkordb_b200.traverse_to_host): slice k's D2H overlaps "
                          "slice k+1's hops; 0 = 128-row slices (default), 1 = whole batch, blocking export")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--side", default="bfs:26,triangles:24",
+                    help="chain workload only: BASELINE configs 5 and 4 measured next to the chain, each as a child process per rank "
+                         "(own process group), reported as sub-objects of the chain line; '' or 'none' = skip")
+    ap.add_argument("--side-timeout", type=int, default=420, help="seconds a side workload may take before its children are stopped")
     return ap.parse_args()
 
 
@@ -202,8 +209,8 @@ def run_reference(a):
     """The reference's CPU implementation of the path.  SuiteSparse:GraphBLAS is not vendored under /root/reference and
     cannot be built here (cmake + generated code), so this arm times the oracle port (kind="port"): row-task Gustavson with
     thread-persistent bitmap workspaces on every host thread (oracle/grb_oracle.c: orc_chain), the whole chain in C.
-    Each step = one batch of the b200 arm's workload -- the same --sources per step when the run then fits in ~4 minutes
-    (a 64-source probe decides), else the largest multiple of the thread count that does."""
+    Each step = one batch of the b200 arm's workload -- the same --sources per step when steps + warm-up then fit six minutes
+    (one untimed full batch decides), else the largest multiple of the thread count that does."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -214,17 +221,19 @@ def run_reference(a):
     A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
     gen_s = time.time() - t0
     deg = np.diff(A.p)
-    S = a.cpu_sources
-    if S <= 0:
-        # one source per thread keeps every thread busy during the probe, so the per-source estimate is not pessimistic
-        probe = pick_sources(deg, 2, min(max(cores, 64), a.sources), a.seed + 17, 0)
-        orc.chain(A, probe[0], a.hops, keep=False)                   # allocates the per-thread workspaces
+    S = a.cpu_sources if a.cpu_sources > 0 else a.sources
+    probe_s = None
+    if a.cpu_sources <= 0:
+        # one whole batch of the b200 arm's size decides: the same batches when steps + warm-up then fit the budget, else the
+        # largest multiple of the thread count that does (a smaller probe would be pessimistic: few rows per thread, idle threads)
+        probe = pick_sources(deg, 1, S, a.seed + 17, 0)[0]
+        orc.chain(A, probe[:cores], a.hops, keep=False)                # allocates the per-thread workspaces
         t0 = time.perf_counter()
-        orc.chain(A, probe[1], a.hops, keep=False)
-        per_src = (time.perf_counter() - t0) / len(probe[1])
-        budget = REFERENCE_ARM_BUDGET_S / max(1, a.steps + a.warmup)
-        S = a.sources if per_src * a.sources <= budget else max(cores, int(budget / per_src) // cores * cores)
-        S = min(S, a.sources)
+        orc.chain(A, probe, a.hops, keep=False)
+        probe_s = time.perf_counter() - t0
+        total = probe_s * max(1, a.steps + a.warmup)
+        if total > REFERENCE_ARM_BUDGET_S:
+            S = min(S, max(cores, int(S * REFERENCE_ARM_BUDGET_S / total) // cores * cores))
     batches = pick_sources(deg, a.steps + a.warmup, S, a.seed, 0)
     for b in batches[:a.warmup]:
         orc.chain(A, b, a.hops, keep=False)
@@ -242,13 +251,48 @@ def run_reference(a):
         "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
         "config": workload_config(a, A.nrows, A.nnz, S),
-        "options": {"threads": cores, "sources_probe_s_per_source": None if a.cpu_sources > 0 else per_src},
+        "options": {"threads": cores, "full_batch_probe_s": probe_s, "budget_s": REFERENCE_ARM_BUDGET_S},
         "graph_build_s": round(gen_s, 1), "result_format": "CSR (sorted rows, the form the reference's iterator walks)",
         "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
                          "threads_busy_fraction": float(np.mean(busy)) if busy else None,
                          "algorithm": "Gustavson, one frontier row per task (LPT order), per-thread persistent n-bit accumulators"},
         "e2e": {"value": teps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def side_workload(a, workload, scale, extra, port_offset):
+    """Run `bench.py --workload <workload>` as a child process of THIS rank -- under torchrun every rank starts one, and the children
+    form their own process group on MASTER_PORT + port_offset -- and return rank 0's JSON line (None on other ranks), or
+    {"error": ...}.  A child that crashes, hangs (stopped by PID at the timeout) or prints nothing costs its sub-object, never the
+    chain line: the multi-GPU BFS exchange and the N > 1 triangle split had not run on hardware when this was written."""
+    env = dict(os.environ)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)         # the children's rank 0 hosts its own rendezvous store
+    if "MASTER_PORT" in env:
+        env["MASTER_PORT"] = str(int(env["MASTER_PORT"]) + port_offset)
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload, "--gpus", str(a.gpus), "--scale", str(scale),
+           "--edge-factor", str(a.edge_factor), "--seed", str(a.seed)] + extra
+    t0 = time.time()
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=a.side_timeout)
+    except subprocess.TimeoutExpired:
+        return {"error": f"stopped after {a.side_timeout} s"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+    if r.returncode != 0:
+        return {"error": f"exit code {r.returncode}", "stderr_tail": r.stderr[-600:]}
+    if int(os.environ.get("RANK", "0")) != 0:
+        return None
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("{"):
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                break
+            d["child_wall_s"] = round(time.time() - t0, 1)
+            for k in ("clocks", "higher_is_better", "vs_baseline", "dtype", "data", "kernels_rank0", "row_cuts"):
+                d.pop(k, None)
+            return d
+    return {"error": "no JSON line from the child", "stderr_tail": r.stderr[-600:]}
 
 
 def reduce_over_ranks(max_vals, sum_vals, device):
@@ -475,6 +519,14 @@ def run_b200(a):
     if world > 1:
         (ms, e2e_ms, csr_ms), w = reduce_over_ranks([ms, e2e_ms, csr_ms], [flops, e2e_flops, launches, nnz_out, e2e_nnz, csr_flops], "cuda")
         flops, e2e_flops, launches, nnz_out, e2e_nnz, csr_flops = [int(x) for x in w]
+    # ---- BASELINE configs 5 and 4 next to the chain, as child processes (every rank takes part; rank 0 keeps the lines) ----
+    side = {}
+    for spec in [x for x in a.side.split(",") if x and x != "none"]:
+        name, _, sc = spec.partition(":")
+        if name == "bfs":
+            side["partitioned_bfs"] = side_workload(a, "bfs", int(sc or 26), ["--bfs-sources", "8", "--warmup", "2", "--bfs-parity", "1"], 1)
+        elif name == "triangles":
+            side["masked_triangles"] = side_workload(a, "triangles", int(sc or 24), ["--steps", "3", "--warmup", "1", "--tri-parity", "1"], 2)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -591,6 +643,7 @@ def run_b200(a):
                                 if csr_steps and csr_ms > 0 else None)},
         "gpu_launches": int(launches), "kernels": kstats, "roofline": roof, "roofline_survey_formula": survey,
         "cpu_baseline": cpu, "clocks": clk}
+    line.update(side)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
