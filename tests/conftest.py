@@ -12,8 +12,12 @@ if ROOT not in sys.path:
 SESSION_T0 = time.time()
 
 
+_CONFIG = [None]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    _CONFIG[0] = config
 
 
 def _has_gpu():
@@ -33,10 +37,28 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+# ---- running tally (what the watchdog below reports if it has to end the session) -----------------------------------------------
+_TALLY = {"passed": 0, "failed": 0, "skipped": 0, "current": ""}
+
+
+def pytest_runtest_logstart(nodeid, location):
+    _TALLY["current"] = nodeid
+
+
+def pytest_runtest_logreport(report):
+    if report.when == "call":
+        if report.passed:
+            _TALLY["passed"] += 1
+        elif report.failed:
+            _TALLY["failed"] += 1
+    if report.skipped:
+        _TALLY["skipped"] += 1
+
+
 # ---- host-memory watchdog ------------------------------------------------------------------------------------------------------
 # A test that runs away with host memory must kill ITSELF, not the machine: a box that goes down under the test suite looks like a
-# lost GPU to whoever drives it.  A daemon thread polls this process's resident set and aborts it (exit code 86, message on
-# stderr) once it passes half of the machine's RAM or comes within 16 GiB of all of it.  (Round 2 lost a test box to the oracle's
+# lost GPU to whoever drives it.  A daemon thread polls this process's resident set and ends it (exit code 1, with the summary
+# pytest would have printed) once it passes half of the machine's RAM or comes within 16 GiB of all of it.  (Round 2 lost a test box to the oracle's
 # saxpy-form masked product on RMAT-24 -- ~1e11 unmasked entries; the oracle now uses the dot form, and this is the backstop.)
 def _start_memory_watchdog():
     import threading
@@ -53,9 +75,23 @@ def _start_memory_watchdog():
         while True:
             try:
                 if me.memory_info().rss > limit:
-                    sys.stderr.write(f"\n[conftest] resident set passed {limit >> 30} GiB: aborting the test process to protect the host\n")
-                    sys.stderr.flush()
-                    os._exit(86)
+                    # the main thread is inside a C call and cannot be interrupted: end the process, but leave the summary pytest
+                    # would have printed (the running test counts as the failure), so the tests that passed stay on record
+                    msg = (f"\nFAILED {_TALLY['current']} - host memory watchdog: resident set passed {limit >> 30} GiB "
+                           f"(tests/conftest.py), the process was ended to protect the host\n"
+                           f"{_TALLY['failed'] + 1} failed, {_TALLY['passed']} passed, {_TALLY['skipped']} skipped "
+                           f"in {time.time() - SESSION_T0:.2f}s\n")
+                    try:                      # pytest holds fds 1 and 2 while a test runs: hand them back before writing
+                        capman = _CONFIG[0].pluginmanager.getplugin("capturemanager")
+                        capman.suspend_global_capture(in_=True)
+                    except Exception:
+                        pass
+                    for fd in (1, 2):
+                        try:
+                            os.write(fd, msg.encode())
+                        except OSError:
+                            pass
+                    os._exit(1)
             except Exception:
                 return
             _time.sleep(0.25)
