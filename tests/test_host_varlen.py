@@ -2,7 +2,7 @@
 graph/src/runtime/ops/cond_var_len_traverse.rs:152-386) against a brute-force enumeration of every relationship-unique path:
 outgoing / incoming / bidirectional expansion, hop windows incl. 0 and windows longer than any trail, a fixed destination, and
 the adjacency-order emission of a frame.  The DFS itself makes no GraphBLAS call, so this runs without a GPU; the same check over
-a Tensor (adjacency fetched through the row iterators of the C ABI) is tests/test_zzz_after_last_gpu_session.py."""
+a Tensor (adjacency fetched through the row iterators of the C ABI) is tests/test_zz2_after_last_gpu_session.py."""
 from test_host_tensor import run
 
 
