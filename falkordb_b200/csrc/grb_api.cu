@@ -2377,6 +2377,50 @@ GrB_Info B200_traverse_batch(const GrB_Index *sources, GrB_Index nsrc, const GrB
     return info;
 }
 
+// ---- multi-source reachability as ONE C call (the multiplicity-insensitive core of CondVarLenTraverse with
+// emit_path = false, cond_var_len_traverse.rs:196, and of AllShortestPaths' BFS phase, all_shortest_paths.rs:7-25) ----
+// Row i of *reached = every vertex reachable from sources[i] by a walk of 1..max_hops edges of A (max_hops < 0: until no row finds
+// a new vertex); with include_sources the zero-length walk (i, sources[i]) belongs to the result and is never re-discovered.
+// Each level is F<!R, replace, struct> = F*A (GrB_DESC_RSC, matrix.rs:1386) followed by R = R u F (matrix.rs:1398-1400); both stay
+// in device frontier form for <= 1024 sources.  Composed from the public entry points.  *reached is a new nsrc x n BOOL matrix.
+GrB_Info B200_reach_batch(GrB_Matrix *reached, const GrB_Index *sources, GrB_Index nsrc, GrB_Matrix A, int64_t max_hops,
+                          int include_sources, int64_t *levels_out) {
+    CHECK_PTR(reached); CHECK_MAT(A);
+    if (nsrc) CHECK_PTR(sources);
+    if (A->nrows != A->ncols) { tl_error = "reach_batch: A must be square"; return GrB_DIMENSION_MISMATCH; }
+    const u64 n = A->ncols;
+    GrB_Scalar one = nullptr;
+    GrB_Matrix F = nullptr, R = nullptr;
+    GrB_Info info = GrB_Scalar_new(&one, GrB_BOOL);
+    if (!info) info = GrB_Scalar_setElement_BOOL(one, true);
+    if (!info) info = GrB_Matrix_new(&F, GrB_BOOL, nsrc, n);
+    if (!info) info = GrB_Matrix_new(&R, GrB_BOOL, nsrc, n);
+    if (!info && nsrc) {
+        uvec<u64> rows(nsrc);
+        for (u64 i = 0; i < nsrc; i++) rows[i] = i;
+        info = GxB_Matrix_build_Scalar(F, rows.data(), sources, one, nsrc);
+        if (!info && include_sources) info = GxB_Matrix_build_Scalar(R, rows.data(), sources, one, nsrc);
+    }
+    int64_t level = 0;
+    while (!info && nsrc && (max_hops < 0 || level < max_hops)) {
+        GrB_Index rn = 0, fn = 0;
+        info = GrB_Matrix_nvals(&rn, R);
+        if (info) break;
+        info = rn ? GrB_mxm(F, R, nullptr, GxB_ANY_PAIR_BOOL, F, A, GrB_DESC_RSC)
+                  : GrB_mxm(F, nullptr, nullptr, GxB_ANY_PAIR_BOOL, F, A, nullptr);
+        if (!info) info = GrB_Matrix_nvals(&fn, F);
+        if (info || fn == 0) break;
+        info = GrB_Matrix_eWiseAdd_BinaryOp(R, nullptr, nullptr, GxB_ANY_BOOL, R, F, nullptr);
+        level++;
+    }
+    GrB_Scalar_free(&one);
+    GrB_Matrix_free(&F);
+    if (info) { GrB_Matrix_free(&R); return info; }
+    if (levels_out) *levels_out = level;
+    *reached = R;
+    return GrB_SUCCESS;
+}
+
 // returns every cached device block to the driver (the caching allocator otherwise keeps freed blocks for reuse)
 GrB_Info B200_pool_trim(void) {
     return guarded([&]() {

@@ -8,7 +8,7 @@ import enum
 
 import numpy as np
 
-from ._lib import lib, obj, check, GrbError, P, U64
+from ._lib import lib, obj, check, GrbError, P, U64, I64
 
 GxB_SPARSITY_STATUS, GxB_SPARSITY_CONTROL, GxB_HYPER_HASH, GxB_WILL_WAIT = 7034, 7036, 7048, 7076
 GrB_STORAGE_ORIENTATION_HINT = 100
@@ -427,6 +427,15 @@ def traverse_to_host(sources, A, hops, out_bitmap, sub_batches=None):
     copies overlap the next slice's hops (the result transfer, not the GPU, bounds this call).  Returns the flops."""
     del sub_batches                      # the slicing lives in the library now
     return traverse_batch(sources, [A] * hops, OUT_BITMAP, out_bitmap=out_bitmap)[0]
+
+
+def reach_batch(sources, A, max_hops=None, include_sources=False):
+    """B200_reach_batch: `multi_source_reach` below as ONE C-ABI call (what a Rust operator would bind).  Returns (R, levels)."""
+    sources = _u64arr(sources)
+    h, lv = P(), I64()
+    check(lib().B200_reach_batch(C.byref(h), sources.ctypes.data, len(sources), A.h, -1 if max_hops is None else int(max_hops),
+                                 1 if include_sources else 0, C.byref(lv)))
+    return Matrix(0, 0, bool, _handle=h), lv.value
 
 
 def multi_source_reach(sources, A, max_hops=None, include_sources=False):

@@ -349,6 +349,12 @@ GrB_Info B200_Matrix_extract_pairs(GrB_Matrix A, const GrB_Index *I, const GrB_I
 GrB_Info B200_traverse_batch(const GrB_Index *sources, GrB_Index nsrc, const GrB_Matrix *hops, int nhops, int format,
                              uint64_t *out_bits, uint64_t words_per_row, uint64_t *out_p, uint32_t *out_j, uint64_t out_j_capacity,
                              uint64_t *nvals_out, uint64_t *flops_out, int *format_out);
+/* Multi-source reachability in one call (CondVarLenTraverse with emit_path = false, cond_var_len_traverse.rs:196;
+ * AllShortestPaths' BFS phase, all_shortest_paths.rs:7-25): row i of *reached (new nsrc x n BOOL matrix) = the vertices reachable
+ * from sources[i] by 1..max_hops edges of the square matrix A (max_hops < 0: to the fixed point); include_sources adds the
+ * zero-length walk.  Levels are F<!R,replace,struct> = F*A then R = R u F, in device frontier form; *levels_out = levels run. */
+GrB_Info B200_reach_batch(GrB_Matrix *reached, const GrB_Index *sources, GrB_Index nsrc, GrB_Matrix A, int64_t max_hops,
+                          int include_sources, int64_t *levels_out);
 GrB_Info B200_sync(void);
 GrB_Info B200_pool_trim(void); /* hand the caching allocator's free device blocks back to the driver */
 void *B200_stream(void); /* the cudaStream_t every kernel of this library is launched on */

@@ -105,6 +105,35 @@ def test_lagraph_cdlp_label_propagation(itermax):
     L.LAGraph_Delete(C.byref(G2), None)
 
 
+@pytest.mark.parametrize("nsrc,max_hops,include", [(64, None, False), (200, 2, False), (300, None, True), (5, 1, False), (1, 0, True)])
+def test_reach_batch_c_entry(nsrc, max_hops, include):
+    """B200_reach_batch (the var-len reach fast path / allShortestPaths BFS phase as one C call) against the level loop on the
+    oracle, and entry for entry against the hardware-verified Python composition of the same public calls"""
+    from test_gpu_parity import from_dev
+    A = orc.rmat_csr(11, 4, 19)
+    n = A.nrows
+    rng = np.random.default_rng(nsrc)
+    src = rng.choice(n, size=nsrc, replace=False)
+    dA = to_dev(A)
+    R, levels = fb.reach_batch(src, dA, max_hops, include)
+    rows = np.arange(nsrc)
+    F = orc.build_matrix(nsrc, n, rows, src)
+    Ro = orc.build_matrix(nsrc, n, rows, src) if include else orc.build_matrix(nsrc, n, [], [])
+    lv = 0
+    while max_hops is None or lv < max_hops:
+        F = orc.mxm(F, A, Ro, mask_mode=2) if Ro.nnz else orc.mxm(F, A)
+        if F.nnz == 0:
+            break
+        Ro = orc.ewise_add(Ro, F)
+        lv += 1
+    assert levels == lv
+    R.wait()
+    assert_same(R, Ro, f"reach_batch nsrc={nsrc} max_hops={max_hops} include={include}")
+    R2, levels2 = fb.multi_source_reach(src, dA, max_hops, include)
+    R2.wait()
+    assert levels2 == levels and from_dev(R2).tuples()[1].tolist() == from_dev(R).tuples()[1].tolist()
+
+
 def test_repack_output_batches_host_mirror():
     """batch.rs:81, 274-287: <= 1024 rows per output batch, NodeIds + u16 selection vector, order preserved"""
     run_host_test("repack_output_batches")
