@@ -260,7 +260,7 @@ def run_reference(a):
         "gpu_launches": 0}))
 
 
-def side_workload(a, workload, scale, extra, port_offset):
+def side_workload(a, workload, scale, extra, port_offset, script=None):
     """Run `bench.py --workload <workload>` as a child process of THIS rank -- under torchrun every rank starts one, and the children
     form their own process group on MASTER_PORT + port_offset -- and return rank 0's JSON line (None on other ranks), or
     {"error": ...}.  A child that crashes, hangs (stopped by PID at the timeout) or prints nothing costs its sub-object, never the
@@ -269,7 +269,7 @@ def side_workload(a, workload, scale, extra, port_offset):
     env.pop("TORCHELASTIC_USE_AGENT_STORE", None)         # the children's rank 0 hosts its own rendezvous store
     if "MASTER_PORT" in env:
         env["MASTER_PORT"] = str(int(env["MASTER_PORT"]) + port_offset)
-    cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload, "--gpus", str(a.gpus), "--scale", str(scale),
+    cmd = [sys.executable, script or os.path.abspath(__file__), "--workload", workload, "--gpus", str(a.gpus), "--scale", str(scale),
            "--edge-factor", str(a.edge_factor), "--seed", str(a.seed)] + extra
     t0 = time.time()
     try:
