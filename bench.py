@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--side", default="bfs:26,triangles:24",
                     help="chain workload only: BASELINE configs 5 and 4 measured next to the chain, each as a child process per rank "
                          "(own process group), reported as sub-objects of the chain line; '' or 'none' = skip")
-    ap.add_argument("--side-timeout", type=int, default=420, help="seconds a side workload may take before its children are stopped")
+    ap.add_argument("--side-timeout", type=int, default=300, help="seconds a side workload may take before its children are stopped")
     return ap.parse_args()
 
 
