@@ -69,9 +69,10 @@ def parse():
                     help="row slices of a batch in the bitmap hand-off (falkordb_b200.traverse_to_host): slice k's D2H overlaps "
                          "slice k+1's hops; 0 = 128-row slices (default), 1 = whole batch, blocking export")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--side", default="bfs:26,triangles:24",
+    ap.add_argument("--side", default="bfs:26,triangles:24,delta:23,pagerank:22",
                     help="chain workload only: BASELINE configs 5 and 4 measured next to the chain, each as a child process per rank "
-                         "(own process group), reported as sub-objects of the chain line; '' or 'none' = skip")
+                         "(own process group), reported as sub-objects of the chain line; delta / pagerank (single-GPU kernels with "
+                         "per-kernel rooflines and parity) at N = 1 only; '' or 'none' = skip")
     ap.add_argument("--side-timeout", type=int, default=300, help="seconds a side workload may take before its children are stopped")
     return ap.parse_args()
 
@@ -527,6 +528,8 @@ def run_b200(a):
             side["partitioned_bfs"] = side_workload(a, "bfs", int(sc or 26), ["--bfs-sources", "8", "--warmup", "2", "--bfs-parity", "1"], 1)
         elif name == "triangles":
             side["masked_triangles"] = side_workload(a, "triangles", int(sc or 24), ["--steps", "3", "--warmup", "1", "--tri-parity", "1"], 2)
+        elif name in ("delta", "pagerank") and world == 1:      # single-GPU kernels: delta-matrix sync at fold sizes, FP64 mxv / PageRank
+            side["delta_sync" if name == "delta" else "pagerank_fp64"] = side_workload(a, name, int(sc or 22), ["--steps", "3", "--warmup", "1"], 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
