@@ -290,7 +290,7 @@ def side_workload(a, workload, scale, extra, port_offset, script=None):
             except ValueError:
                 break
             d["child_wall_s"] = round(time.time() - t0, 1)
-            for k in ("clocks", "higher_is_better", "vs_baseline", "dtype", "data", "kernels_rank0", "row_cuts"):
+            for k in ("clocks", "higher_is_better", "vs_baseline", "data"):
                 d.pop(k, None)
             return d
     return {"error": "no JSON line from the child", "stderr_tail": r.stderr[-600:]}
