@@ -75,3 +75,33 @@ def test_wcc_matches_union_find():
                 parent[max(ra, rb)] = min(ra, rb)
         want = np.array([find(v) for v in range(n)], np.int64)
         assert np.array_equal(orc.wcc(A), want)
+
+
+def test_masked_product_dot_form_equals_saxpy_form_then_mask():
+    """The oracle evaluates C<M> = A*B in dot form (oracle/grb_oracle.c: mxm_masked_dot; nothing outside the mask is ever formed --
+    the saxpy form materialised ~1e11 unmasked entries for config 4 at full size).  It must equal the unmasked saxpy product with
+    the mask applied afterwards, entry for entry, count the same flops (sum of deg_B(k) over A's entries: SURVEY 8d), and agree
+    with scipy -- on the triangle pattern L*L<L>, on a rectangular product with an unrelated mask, and with empty rows."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4)
+    A0 = orc.rmat_csr(12, 8, 3)
+    U = orc.ewise_add(A0, orc.transpose(A0))
+    n = U.nrows
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(U.p))
+    keep = U.j.astype(np.int64) < rows
+    L = orc.build_matrix(n, n, rows[keep], U.j[keep])
+    cases = [(L, L, L)]
+    A = orc.build_matrix(300, 500, rng.integers(0, 300, 4000), rng.integers(0, 500, 4000))
+    B = orc.build_matrix(500, 400, rng.integers(0, 500, 6000), rng.integers(0, 400, 6000))
+    M = orc.build_matrix(300, 400, rng.integers(0, 150, 9000), rng.integers(0, 400, 9000))      # rows 150.. of the mask are empty
+    cases.append((A, B, M))
+    for A_, B_, M_ in cases:
+        got, fl = orc.mxm(A_, B_, M_, 1, return_flops=True)
+        full = orc.mxm(A_, B_)
+        want = orc.mask_assign(None, full, M_, comp=False, structural=True, replace=True)
+        assert np.array_equal(got.p, want.p) and np.array_equal(got.j, want.j)
+        assert fl == int(np.diff(B_.p)[A_.j].sum())
+        S = (A_.to_scipy().astype(np.int64) @ B_.to_scipy().astype(np.int64)).multiply(M_.to_scipy().astype(np.int64)).tocsr()
+        S.eliminate_zeros()
+        S.sort_indices()
+        assert np.array_equal(got.p, S.indptr) and np.array_equal(got.j, S.indices)
