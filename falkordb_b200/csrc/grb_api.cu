@@ -2174,19 +2174,21 @@ GrB_Info B200_Tensor_bulk_build(GrB_Matrix *fwd, GrB_Index **multi_keys, GrB_Ind
         tensor_bulk_build(dI.ptr, dJ.ptr, dID.ptr, n, nrows, ncols, out, mk, mi, &nm, &err);
         sync_stream();
         if (err) { tl_error = "bulk build: index out of bounds"; return GrB_INDEX_OUT_OF_BOUNDS; }
-        u64 *hk = nullptr, *hi = nullptr;
+        struct UserBuf {                       // handed to the caller only on success
+            u64 *p = nullptr;
+            ~UserBuf() { if (p) g_user_free(p); }
+            u64 *release() { u64 *r = p; p = nullptr; return r; }
+        } hk, hi;
         if (nm) {
-            hk = (u64 *)g_user_malloc(nm * sizeof(u64));
-            hi = (u64 *)g_user_malloc(nm * sizeof(u64));
-            if (!hk || !hi) { if (hk) g_user_free(hk); if (hi) g_user_free(hi); throw std::bad_alloc(); }
-            try {
-                d2h(hk, mk.ptr, nm);
-                d2h(hi, mi.ptr, nm);
-                sync_stream();
-            } catch (...) { g_user_free(hk); g_user_free(hi); throw; }
+            hk.p = (u64 *)g_user_malloc(nm * sizeof(u64));
+            hi.p = (u64 *)g_user_malloc(nm * sizeof(u64));
+            if (!hk.p || !hi.p) throw std::bad_alloc();
+            d2h(hk.p, mk.ptr, nm);
+            d2h(hi.p, mi.ptr, nm);
+            sync_stream();
         }
         set_dev(m, std::move(out));
-        *multi_keys = hk; *multi_ids = hi; *nmulti = nm;
+        *multi_keys = hk.release(); *multi_ids = hi.release(); *nmulti = nm;
         *fwd = mh.release();
         return GrB_SUCCESS;
     });
