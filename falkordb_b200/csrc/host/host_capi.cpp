@@ -420,6 +420,70 @@ static void t_var_len_trails() {            // the same over a Tensor: adjacency
     vl_check([&](uint64_t lo, uint64_t hi, bool rev, bool bi, int64_t dest) { return VarLenIter(t, lo, hi, rev, bi, dest, true); });
 }
 
+// The reference's query-level goldens for variable-length traversals (tests/flow/test_variable_length_traversals.py), transcribed
+// at the level this mirror covers: which (from, to) pairs and path lengths the trail enumerator yields.  Host only.
+struct ListAdjacency {          // node_relationships over explicit edge lists (ids = positions): out by (dst, id), in by (src, id)
+    std::vector<uint64_t> S, D;
+    std::vector<Edge> operator()(uint64_t node, EdgeDirection dir) const {
+        std::vector<Edge> out, in;
+        for (size_t e = 0; e < S.size(); e++) {
+            if (S[e] == node) out.push_back({S[e], D[e], (uint64_t)e});
+            if (D[e] == node && !(dir == EdgeDirection::Both && S[e] == node)) in.push_back({S[e], D[e], (uint64_t)e});
+        }
+        std::sort(out.begin(), out.end(), [](const Edge &a, const Edge &b) { return a.dst != b.dst ? a.dst < b.dst : a.id < b.id; });
+        std::sort(in.begin(), in.end(), [](const Edge &a, const Edge &b) { return a.src != b.src ? a.src < b.src : a.id < b.id; });
+        std::vector<Edge> r;
+        if (dir != EdgeDirection::Incoming) r = out;
+        if (dir != EdgeDirection::Outgoing) r.insert(r.end(), in.begin(), in.end());
+        return r;
+    }
+};
+// every result of MATCH (a)-[*lo..hi]-(b) over the given start nodes: (from, to, path length)
+static std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> vl_all(const ListAdjacency &g, const std::vector<uint64_t> &starts, uint64_t lo,
+                                                                      uint64_t hi, bool rev, bool bi, int64_t dest = -1) {
+    std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> out;
+    for (uint64_t s : starts) {
+        VarLenIterT<ListAdjacency> it(g, lo, hi, rev, bi, dest, true);
+        it.begin_start_node(s);
+        VarLenResult r;
+        while (it.next(r)) out.push_back(std::make_tuple(r.from, r.to, (uint64_t)r.edges.size()));
+    }
+    std::sort(out.begin(), out.end());
+    return out;
+}
+static void t_var_len_flow_goldens() {
+    const uint64_t INF = UINT64_MAX;
+    typedef std::vector<std::tuple<uint64_t, uint64_t, uint64_t>> Rows;
+    // test_variable_length_traversals.py:16-37: A -> B -> C -> D ("A can reach 3 nodes, B can reach 2 nodes, C can reach 1 node")
+    ListAdjacency chain{{0, 1, 2}, {1, 2, 3}};
+    std::vector<uint64_t> all4{0, 1, 2, 3};
+    REQUIRE(vl_all(chain, all4, 1, INF, false, false).size() == 6, "test02: (a)-[*]->(b) has max_results = 6 rows");
+    REQUIRE(vl_all(chain, all4, 1, INF, true, false).size() == 6, "test02: (a)<-[*]-(b) has 6 rows");
+    REQUIRE(vl_all(chain, all4, 1, INF, false, true).size() == 12, "test06: the undirected traversal represents every combination twice");
+    REQUIRE(vl_all(ListAdjacency{{}, {}}, all4, 0, 1, false, false).size() == 4, "test07: a zero-length traversal always returns the source");
+    Rows fromA = vl_all(chain, {0}, 1, INF, false, false);
+    REQUIRE((fromA == Rows{{0, 1, 1}, {0, 2, 2}, {0, 3, 3}}), "A reaches B, C, D by 1, 2, 3 hops");
+    // test11_range_length_edges (:236-266): a->b, b->c, c->a, d->d; undirected patterns between a and c
+    ListAdjacency tri{{0, 1, 2, 3}, {1, 2, 0, 3}};
+    REQUIRE((vl_all(tri, {0}, 2, 2, false, true, 2) == Rows{{0, 2, 2}}), "(a)-[*2]-(c): length 2");
+    REQUIRE((vl_all(tri, {0}, 2, INF, false, true, 2) == Rows{{0, 2, 2}}), "(a)-[*2..]-(c): length 2");
+    REQUIRE((vl_all(tri, {0}, 1, INF, false, true, 2) == Rows{{0, 2, 1}, {0, 2, 2}}), "(a)-[*]-(c): lengths 1 and 2");
+    REQUIRE((vl_all(tri, {3}, 0, 0, false, true) == Rows{{3, 3, 0}}), "(d)-[*0]-(): length 0");
+    // test12_close_cycle (:268-293): a->b->c->a, a->d; (a)-[*2..]->(z) does not get stuck and yields z = a, c, d
+    ListAdjacency cyc{{0, 1, 2, 0}, {1, 2, 0, 3}};
+    Rows z = vl_all(cyc, {0}, 2, INF, false, false);
+    REQUIRE((z == Rows{{0, 0, 3}, {0, 2, 2}, {0, 3, 4}}), "three results: a (3 hops), c (2), d (4)");
+    // test13_fanout (:295-330): a tree with fanout 3 and depth 2; (root)-[*0..]->(n) returns all 13 nodes
+    ListAdjacency tree;
+    for (uint64_t a = 1; a <= 3; a++) { tree.S.push_back(0); tree.D.push_back(a); }
+    for (uint64_t a = 1; a <= 3; a++) for (uint64_t k = 0; k < 3; k++) { tree.S.push_back(a); tree.D.push_back(4 + (a - 1) * 3 + k); }
+    Rows t13 = vl_all(tree, {0}, 0, INF, false, false);
+    REQUIRE(t13.size() == 13 && std::get<1>(t13[0]) == 0 && std::get<2>(t13[0]) == 0, "13 rows, the root first");
+    std::set<uint64_t> reached;
+    for (auto &r : t13) reached.insert(std::get<1>(r));
+    REQUIRE(reached.size() == 13, "every node exactly once");
+}
+
 static void t_traverse_over_tensor_operand() {
     uint64_t n = 64;
     Tensor t(n, n);
@@ -689,6 +753,7 @@ static TestEntry TESTS[] = {
     {"repack_output_batches", t_repack_output_batches},
     {"var_len_trails", t_var_len_trails},
     {"var_len_trails_logic", t_var_len_trails_logic},
+    {"var_len_flow_goldens", t_var_len_flow_goldens},
     {"tensor_decodes_the_c_written_form", t_tensor_decodes_the_c_written_form},
     {"tensor_encode_decode_after_mutations", t_tensor_encode_decode_after_mutations},
     {"versioned_matrix_encode_decode", t_versioned_matrix_encode_decode},

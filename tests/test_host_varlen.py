@@ -8,3 +8,8 @@ from test_host_tensor import run
 
 def test_var_len_trail_enumeration_logic_host_only():
     run("var_len_trails_logic")
+
+
+def test_var_len_reference_flow_test_goldens_host_only():
+    """tests/flow/test_variable_length_traversals.py test02 / 06 / 07 / 11 / 12 / 13: row counts, (from, to) pairs and path lengths"""
+    run("var_len_flow_goldens")
