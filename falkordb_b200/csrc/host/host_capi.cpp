@@ -15,6 +15,8 @@ using namespace fdb;
 static thread_local std::string g_msg;
 #define REQUIRE(cond, text) do { if (!(cond)) { std::ostringstream os; os << "line " << __LINE__ << ": " << text; throw std::runtime_error(os.str()); } } while (0)
 
+typedef std::vector<uint64_t> Ids;
+
 // ---- versioned_matrix.rs:1265-1330 : fold-policy arithmetic (pure host) ----
 static uint64_t threshold(uint64_t k, uint64_t tx) { uint64_t target = k * tx; for (uint64_t d = 1;; d++) if (d * d >= target) return d; }
 static const uint64_t HUGE_BASE = UINT64_MAX / 4;
@@ -484,6 +486,37 @@ static void t_var_len_flow_goldens() {
     REQUIRE(reached.size() == 13, "every node exactly once");
 }
 
+// tests/flow/test_multiple_edges.py:11-96 at the tensor level: two nodes, edges created and deleted one at a time on the same pair;
+// edge counts, edge ids and the variable-length count the queries return
+static void t_multiple_edges_flow() {
+    Tensor t(16, 16);
+    const uint64_t a = 0, b = 1;
+    auto trails = [&]() {                                  // MATCH (a)-[:R*]->(b) RETURN count(b)
+        t.wait();
+        t.rebuild_backward();
+        VarLenIter it(t, 1, UINT64_MAX, false, false, (int64_t)b, false);
+        it.begin_start_node(a);
+        VarLenResult r;
+        uint64_t k = 0;
+        while (it.next(r)) k++;
+        return k;
+    };
+    REQUIRE(t.get(a, b).empty() && t.edge_count() == 0, "no connections yet (:16-21)");
+    t.set_all_from_slices({a}, {b}, {0});
+    REQUIRE((t.get(a, b) == Ids{0}) && t.edge_count() == 1, "a single edge, ID(e) = 0 (:24-36)");
+    t.set_all_from_slices({a}, {b}, {1});
+    REQUIRE((t.get(a, b) == Ids{0, 1}) && t.edge_count() == 2, "two connections (:39-47)");
+    REQUIRE(trails() == 2, "the variable-length pattern sees both edges (:50-53)");
+    auto gone = t.remove_all({std::make_tuple(0ULL, a, b)});
+    REQUIRE(gone.empty() && (t.get(a, b) == Ids{1}) && t.edge_count() == 1, "first connection removed: ID(e) = 1 remains (:56-67)");
+    gone = t.remove_all({std::make_tuple(1ULL, a, b)});
+    REQUIRE(gone.size() == 1 && t.get(a, b).empty() && t.edge_count() == 0, "second connection removed: the pair is empty (:70-79)");
+    REQUIRE(trails() == 0, "nothing left to traverse");
+    t.set_all_from_slices({a}, {b}, {2});
+    REQUIRE((t.get(a, b) == Ids{2}) && t.edge_count() == 1, "the connection can be re-formed (:87-95)");
+    REQUIRE(trails() == 1, "one trail again");
+}
+
 static void t_traverse_over_tensor_operand() {
     uint64_t n = 64;
     Tensor t(n, n);
@@ -539,7 +572,6 @@ static Stream c_written_stream(uint64_t n, const EdgeList &fm, const EdgeList &d
     }
     return w;
 }
-typedef std::vector<uint64_t> Ids;
 static void t_tensor_decodes_the_c_written_form() {            // host-resident matrices only: runs without a device
     const uint64_t MSB = Tensor::MSB_MASK, BIG = ((uint64_t)1 << 40) + 1;
     Stream s = c_written_stream(8, {{0, 1, 5}, {0, 2, 0}, {1, 2, 3 | MSB}, {3, 3, 2 | MSB}, {7, 0, 42}}, {}, {}, 8,
@@ -754,6 +786,7 @@ static TestEntry TESTS[] = {
     {"var_len_trails", t_var_len_trails},
     {"var_len_trails_logic", t_var_len_trails_logic},
     {"var_len_flow_goldens", t_var_len_flow_goldens},
+    {"multiple_edges_flow", t_multiple_edges_flow},
     {"tensor_decodes_the_c_written_form", t_tensor_decodes_the_c_written_form},
     {"tensor_encode_decode_after_mutations", t_tensor_encode_decode_after_mutations},
     {"versioned_matrix_encode_decode", t_versioned_matrix_encode_decode},

@@ -139,6 +139,11 @@ def test_repack_output_batches_host_mirror():
     run_host_test("repack_output_batches")
 
 
+def test_multiple_edges_flow_test_at_the_tensor_level():
+    """tests/flow/test_multiple_edges.py:11-96: edges created and deleted one at a time on one pair -- counts, ids, var-len count"""
+    run_host_test("multiple_edges_flow")
+
+
 def test_var_len_trails_over_a_tensor():
     """cond_var_len_traverse.rs:152-386 with the adjacency fetched from a relationship Tensor through the row iterators"""
     run_host_test("var_len_trails")
