@@ -782,6 +782,25 @@ def run_bfs(a):
         dist.destroy_process_group()
 
 
+def triangle_row_cuts(lp, lj, world):
+    """Row blocks of L with equal WORK for C<L> = L*L, not equal rows (tril(L) of an RMAT graph is heavily skewed: equal-row blocks
+    gave 43 % strong-scaling efficiency at N = 4).  What a pair (i, k) of L costs the kernel: the shorter of L(k,:) and L(i,:) drives
+    the intersection (ewise.cu: k_masked_pairs), plus a fixed part.  Every rank derives the same cuts from the replicated L.
+    Returns (cuts[world + 1], work per block)."""
+    n = len(lp) - 1
+    degL = np.diff(lp)
+    rows_of = np.repeat(np.arange(n, dtype=np.int64), degL)
+    work = np.minimum(degL[lj], degL[rows_of]) + 8
+    del rows_of
+    csum = np.concatenate([[0], np.cumsum(work, dtype=np.int64)])
+    rowwork_cum = csum[lp]                                     # work of rows [0, i)
+    total_w = int(rowwork_cum[-1])
+    cuts = [int(np.searchsorted(rowwork_cum, total_w * g // world, side="left")) for g in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    per_block = [int(rowwork_cum[cuts[g + 1]] - rowwork_cum[cuts[g]]) for g in range(world)]
+    return cuts, per_block
+
+
 def run_triangles(a):
     """BASELINE config 4: masked ExpandInto SpGEMM, C<L,struct,replace> = L*L over ANY_PAIR with L = tril(A u A') of the
     RMAT graph: which edges close at least one wedge.  Row blocks of the OUTPUT are independent (mask and left operand
@@ -811,18 +830,9 @@ def run_triangles(a):
     # (equal-row blocks gave 43 % strong-scaling efficiency at N = 4); every rank derives the same split from the replicated L
     lp, lj, _ = Lfull.export_csr()
     lp = lp.astype(np.int64)
-    degL = np.diff(lp)
-    # what a pair (i,k) costs the kernel: the shorter of B(k,:) and M(i,:) drives (ewise.cu: k_masked_pairs), plus a fixed part
-    rows_of = np.repeat(np.arange(n, dtype=np.int64), degL)
-    work = np.minimum(degL[lj], degL[rows_of]) + 8
-    del rows_of
-    csum = np.concatenate([[0], np.cumsum(work, dtype=np.int64)])
-    rowwork_cum = csum[lp]                                     # work of rows [0, i)
-    total_w = int(rowwork_cum[-1])
-    cuts = [int(np.searchsorted(rowwork_cum, total_w * g // world, side="left")) for g in range(world + 1)]
-    cuts[0], cuts[-1] = 0, n
+    cuts, _ = triangle_row_cuts(lp, lj, world)
     lo, hi = cuts[rank], cuts[rank + 1]
-    del lj, csum, work
+    del lj
     if world > 1:
         hb = P()
         check(L_.B200_Matrix_rmat_block(C.byref(hb), a.scale, a.edge_factor, a.seed, lo, hi, 2))

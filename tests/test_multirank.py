@@ -58,3 +58,39 @@ def test_sharded_sources_and_whole_job_reduction():
     Fb, _ = bench.cpu_chain(orc, A, np.array(b1[0], dtype=np.uint64), 2)
     assert np.array_equal(F.j, np.concatenate([Fa.j, Fb.j]))
     assert np.array_equal(F.p, np.concatenate([Fa.p, Fb.p[1:] + Fa.p[-1]]))
+
+
+def test_triangle_row_blocks_balance_the_intersection_work():
+    """BASELINE config 4 at N > 1 (bench.py: run_triangles): row blocks of L = tril(A u A') with equal intersection work, every rank
+    computing the same cuts from the replicated L.  The cuts must tile the rows, balance the kernel's work model to a few percent
+    where equal-row blocks are off by integer factors, and -- rows of the masked product being independent -- the per-block results
+    must concatenate to the whole product."""
+    import bench
+    import oracle as orc
+    A = orc.rmat_csr(14, 16, 1)
+    U = orc.ewise_add(A, orc.transpose(A))
+    n = U.nrows
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(U.p))
+    keep = U.j.astype(np.int64) < rows
+    L = orc.build_matrix(n, n, rows[keep], U.j[keep])
+    full = orc.mxm(L, L, L, 1)
+    for world in (2, 4, 8):
+        cuts, work = bench.triangle_row_cuts(L.p, L.j, world)
+        assert cuts[0] == 0 and cuts[-1] == n and all(a <= b for a, b in zip(cuts, cuts[1:])) and len(cuts) == world + 1
+        mean = sum(work) / world
+        assert max(work) <= 1.05 * mean, (world, work)
+        # the same work model over equal-row blocks: what round 1 did
+        eq = [n * g // world for g in range(world + 1)]
+        deg = np.diff(L.p)
+        w_entry = np.minimum(deg[L.j], deg[np.repeat(np.arange(n), deg)]) + 8
+        csum = np.concatenate([[0], np.cumsum(w_entry)])
+        eq_work = [int(csum[L.p[eq[g + 1]]] - csum[L.p[eq[g]]]) for g in range(world)]
+        assert max(eq_work) > 1.5 * (sum(eq_work) / world) > 0, "equal-row blocks of tril(L) are badly skewed (the reason for the cuts)"
+        parts_p, parts_j = [np.zeros(1, np.int64)], []
+        for g in range(world):
+            lo, hi = cuts[g], cuts[g + 1]
+            Lb = orc.CSR(hi - lo, n, L.p[lo:hi + 1] - L.p[lo], L.j[L.p[lo]:L.p[hi]])
+            Cb = orc.mxm(Lb, L, Lb, 1)
+            parts_p.append(Cb.p[1:] + parts_p[-1][-1])
+            parts_j.append(Cb.j)
+        assert np.array_equal(np.concatenate(parts_p), full.p) and np.array_equal(np.concatenate(parts_j), full.j)
