@@ -38,11 +38,16 @@ def pytest_collection_modifyitems(config, items):
 
 
 # ---- running tally (what the watchdog below reports if it has to end the session) -----------------------------------------------
-_TALLY = {"passed": 0, "failed": 0, "skipped": 0, "current": ""}
+_TALLY = {"passed": 0, "failed": 0, "skipped": 0, "current": "", "started": 0.0}
 
 
 def pytest_runtest_logstart(nodeid, location):
     _TALLY["current"] = nodeid
+    _TALLY["started"] = time.time()
+
+
+def pytest_runtest_logfinish(nodeid, location):
+    _TALLY["current"] = ""
 
 
 def pytest_runtest_logreport(report):
@@ -55,48 +60,62 @@ def pytest_runtest_logreport(report):
         _TALLY["skipped"] += 1
 
 
-# ---- host-memory watchdog ------------------------------------------------------------------------------------------------------
-# A test that runs away with host memory must kill ITSELF, not the machine: a box that goes down under the test suite looks like a
-# lost GPU to whoever drives it.  A daemon thread polls this process's resident set and ends it (exit code 1, with the summary
-# pytest would have printed) once it passes half of the machine's RAM or comes within 16 GiB of all of it.  (Round 2 lost a test box to the oracle's
-# saxpy-form masked product on RMAT-24 -- ~1e11 unmasked entries; the oracle now uses the dot form, and this is the backstop.)
-def _start_memory_watchdog():
+# ---- watchdog: host memory, a hung test, the session's wall-clock limit ----------------------------------------------------------
+# A test that runs away with host memory must end ITSELF, not the machine: a box that goes down under the test suite looks like a
+# lost GPU to whoever drives it (round 2 lost a test box to the oracle's saxpy-form masked product on RMAT-24 -- ~1e11 unmasked
+# entries; the oracle now uses the dot form, and this is the backstop).  Likewise a test stuck inside a device synchronisation
+# cannot be interrupted from Python (signal handlers wait for the C call to return), and a session that overruns the driver's limit
+# is killed without a summary -- every earlier pass would be lost with it.  A daemon thread polls
+#   * this process's resident set: past half of the machine's RAM, or within 16 GiB of all of it,
+#   * the running test's age: B200_TEST_LIMIT_S (default 600 s),
+#   * the session's age: B200_SESSION_LIMIT_S (default 1140 s; the GPU suite is driven with a 1200 s limit),
+# and when one trips ends the process with exit code 1 AFTER writing the summary pytest would have printed (the running test
+# counts as the failure), so the tests that passed stay on record.
+TEST_LIMIT_S = float(os.environ.get("B200_TEST_LIMIT_S", "600"))
+SESSION_LIMIT_S = float(os.environ.get("B200_SESSION_LIMIT_S", "1140"))
+
+
+def _start_watchdog():
     import threading
-    import time as _time
     try:
         import psutil
+        total = psutil.virtual_memory().total
+        limit = min(total // 2, max(total - (16 << 30), total // 4))
+        me = psutil.Process()
     except Exception:
-        return
-    total = psutil.virtual_memory().total
-    limit = min(total // 2, max(total - (16 << 30), total // 4))
-    me = psutil.Process()
+        psutil, limit, me = None, 0, None
+
+    def end(reason):
+        msg = (f"\nFAILED {_TALLY['current']} - {reason} (tests/conftest.py watchdog)\n"
+               f"{_TALLY['failed'] + 1} failed, {_TALLY['passed']} passed, {_TALLY['skipped']} skipped "
+               f"in {time.time() - SESSION_T0:.2f}s\n")
+        try:                                  # pytest holds fds 1 and 2 while a test runs: hand them back before writing
+            capman = _CONFIG[0].pluginmanager.getplugin("capturemanager")
+            capman.suspend_global_capture(in_=True)
+        except Exception:
+            pass
+        for fd in (1, 2):
+            try:
+                os.write(fd, msg.encode())
+            except OSError:
+                pass
+        os._exit(1)
 
     def watch():
         while True:
             try:
-                if me.memory_info().rss > limit:
-                    # the main thread is inside a C call and cannot be interrupted: end the process, but leave the summary pytest
-                    # would have printed (the running test counts as the failure), so the tests that passed stay on record
-                    msg = (f"\nFAILED {_TALLY['current']} - host memory watchdog: resident set passed {limit >> 30} GiB "
-                           f"(tests/conftest.py), the process was ended to protect the host\n"
-                           f"{_TALLY['failed'] + 1} failed, {_TALLY['passed']} passed, {_TALLY['skipped']} skipped "
-                           f"in {time.time() - SESSION_T0:.2f}s\n")
-                    try:                      # pytest holds fds 1 and 2 while a test runs: hand them back before writing
-                        capman = _CONFIG[0].pluginmanager.getplugin("capturemanager")
-                        capman.suspend_global_capture(in_=True)
-                    except Exception:
-                        pass
-                    for fd in (1, 2):
-                        try:
-                            os.write(fd, msg.encode())
-                        except OSError:
-                            pass
-                    os._exit(1)
+                now = time.time()
+                if me is not None and me.memory_info().rss > limit:
+                    end(f"resident set passed {limit >> 30} GiB: the process was ended to protect the host")
+                if _TALLY["current"] and now - _TALLY["started"] > TEST_LIMIT_S:
+                    end(f"the test ran for more than {TEST_LIMIT_S:.0f} s (hung?)")
+                if _TALLY["current"] and now - SESSION_T0 > SESSION_LIMIT_S:
+                    end(f"the session passed {SESSION_LIMIT_S:.0f} s: ended here so that the summary is on record")
             except Exception:
                 return
-            _time.sleep(0.25)
+            time.sleep(0.25)
 
     threading.Thread(target=watch, daemon=True, name="rss-watchdog").start()
 
 
-_start_memory_watchdog()
+_start_watchdog()
