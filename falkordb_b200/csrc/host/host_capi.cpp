@@ -341,6 +341,24 @@ static void t_repack_output_batches() {
     REQUIRE(repack(ExpandResult{}).empty(), "nothing in, nothing out");
 }
 
+static void t_repack_logic() {                  // host only: the re-pack itself makes no GraphBLAS call
+    ExpandResult r;
+    for (uint64_t row : {0ULL, 3ULL, 1023ULL})
+        for (uint64_t d = 0; d < (row == 3 ? 1500ULL : 700ULL); d++) { r.row_idx.push_back(row); r.dest.push_back(row * 100000 + d); }
+    std::vector<OutBatch> b = repack(r);
+    REQUIRE(b.size() == 3 && b[0].node_ids.size() == 1024 && b[1].node_ids.size() == 1024 && b[2].node_ids.size() == 2900 - 2048, "2900 pairs -> 1024 + 1024 + 852");
+    size_t k = 0;
+    for (const OutBatch &ob : b)
+        for (size_t t = 0; t < ob.node_ids.size(); t++, k++)
+            REQUIRE(ob.node_ids[t] == r.dest[k] && ob.selection[t] == r.row_idx[k], "order and parent rows preserved at pair " << k);
+    REQUIRE(k == 2900 && b[0].selection[699] == 0 && b[0].selection[700] == 3 && b[2].selection.back() == 1023, "parents 0, 3 and 1023 (the largest u16 row of a batch)");
+    REQUIRE(repack(r, 4096).size() == 1 && repack(ExpandResult{}).empty(), "one batch when it fits; nothing in, nothing out");
+    r.row_idx[5] = BATCH_SIZE;                       // a parent row outside any input batch
+    bool threw = false;
+    try { repack(r); } catch (const std::runtime_error &) { threw = true; }
+    REQUIRE(threw, "a parent row >= BATCH_SIZE is an error, not a truncated u16");
+}
+
 // CondVarLenTraverse's trail enumerator (cond_var_len_traverse.rs:152-386) against a brute-force enumeration of every trail:
 // a small multigraph with a cycle, a multi-edge pair, a self-loop and a dead end; outgoing, incoming and bidirectional expansion,
 // min/max hop windows, a fixed destination, and the emission order inside one frame (adjacency order).  Run twice: over a plain
@@ -783,6 +801,7 @@ static TestEntry TESTS[] = {
     {"batch_can_demote_and_then_empty_the_same_pair", t_batch_can_demote_and_then_empty_the_same_pair},
     {"traverse_over_tensor_operand", t_traverse_over_tensor_operand},
     {"repack_output_batches", t_repack_output_batches},
+    {"repack_logic", t_repack_logic},
     {"var_len_trails", t_var_len_trails},
     {"var_len_trails_logic", t_var_len_trails_logic},
     {"var_len_flow_goldens", t_var_len_flow_goldens},

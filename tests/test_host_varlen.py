@@ -13,3 +13,8 @@ def test_var_len_trail_enumeration_logic_host_only():
 def test_var_len_reference_flow_test_goldens_host_only():
     """tests/flow/test_variable_length_traversals.py test02 / 06 / 07 / 11 / 12 / 13: row counts, (from, to) pairs and path lengths"""
     run("var_len_flow_goldens")
+
+
+def test_output_batch_repack_logic_host_only():
+    """batch.rs:81, 274-287: <= 1024 rows per output batch, NodeIds + u16 selection vector, order preserved (cond_traverse.hpp: repack)"""
+    run("repack_logic")
