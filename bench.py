@@ -199,6 +199,29 @@ def workload_name(a):
 REFERENCE_ARM_BUDGET_S = 360.0
 
 
+def calibrate_cpu_threads(orc, A, deg, a, all_threads):
+    """The CPU arm's team size, measured rather than assumed: all the host threads, half and a quarter of them each run the same
+    256-source mini-batch (two rows per thread at the full team), and the fastest wins -- hyper-threads sharing a core's cache, a far
+    NUMA node or a CPU quota below the thread count can all make fewer threads faster for this cache-bound kernel.  Returns
+    (threads chosen, {threads: seconds})."""
+    cand = sorted({t for t in (all_threads, all_threads // 2, all_threads // 4) if t >= 8} | ({all_threads} if all_threads < 8 else set()), reverse=True)
+    if len(cand) < 2:
+        return all_threads, {}
+    probe = pick_sources(deg, 1, min(a.sources, 256), a.seed + 23, 0)[0]
+    times = {}
+    for t in cand:
+        orc.lib().orc_set_num_threads(t)
+        orc.chain(A, probe[:t], a.hops, keep=False)                  # workspaces of this team
+        t0 = time.perf_counter()
+        orc.chain(A, probe, a.hops, keep=False)
+        times[t] = time.perf_counter() - t0
+    best = min(cand, key=lambda t: times[t])
+    if times[all_threads] <= 1.05 * times[best]:                     # within noise: keep every thread
+        best = all_threads
+    orc.lib().orc_set_num_threads(best)
+    return best, {str(k): round(v, 3) for k, v in times.items()}
+
+
 def workload_config(a, n, nnzA, sources):
     """`config` of the JSON line: what defines the workload, identical for both arms (arm-specific settings go to `options`)"""
     return {"workload": workload_name(a), "n": n, "nnz_A": nnzA, "sources_per_gpu_per_step": sources,
@@ -222,6 +245,8 @@ def run_reference(a):
     A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
     gen_s = time.time() - t0
     deg = np.diff(A.p)
+    all_threads = cores
+    cores, team_probe = calibrate_cpu_threads(orc, A, deg, a, all_threads)
     S = a.cpu_sources if a.cpu_sources > 0 else a.sources
     probe_s = None
     if a.cpu_sources <= 0:
@@ -252,7 +277,8 @@ def run_reference(a):
         "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/u32 index", "data": "synthetic",
         "config": workload_config(a, A.nrows, A.nnz, S),
-        "options": {"threads": cores, "full_batch_probe_s": probe_s, "budget_s": REFERENCE_ARM_BUDGET_S},
+        "options": {"threads": cores, "host_threads": all_threads, "team_size_probe_s": team_probe, "full_batch_probe_s": probe_s,
+                    "budget_s": REFERENCE_ARM_BUDGET_S},
         "graph_build_s": round(gen_s, 1), "result_format": "CSR (sorted rows, the form the reference's iterator walks)",
         "cpu_baseline": {"value": teps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
                          "threads_busy_fraction": float(np.mean(busy)) if busy else None,
@@ -600,11 +626,12 @@ def run_b200(a):
             import oracle as orc
             from oracle import CSR
             os.sched_setaffinity(0, all_cpus)
-            cores = host_threads()
-            orc.lib().orc_set_num_threads(cores)
+            all_threads = host_threads()
+            orc.lib().orc_set_num_threads(all_threads)
             pj = np.empty(nnzA, np.uint32)
             fb.check(L.B200_Matrix_export_CSR(A.h, p.ctypes.data, pj.ctypes.data, None, 0))
             Ao = CSR(n, n, p.astype(np.int64), pj)
+            cores, team_probe = calibrate_cpu_threads(orc, Ao, deg, a, all_threads)
             ncpu = a.cpu_sources if a.cpu_sources > 0 else a.sources
             b = batches[a.warmup][:ncpu]
             orc.chain(Ao, b[: min(len(b), cores)], a.hops, keep=False)          # untimed: allocates the per-thread workspaces
@@ -620,7 +647,7 @@ def run_b200(a):
             del G
             cpu = {"value": cfl / ct, "unit": "edges/s", "cores": cores, "kind": "port",
                    "sample": f"{a.hops}-hop chain for the {len(b)} sources of the first timed batch ({cfl} flops, {ct:.1f} s)",
-                   "threads_busy_fraction": busy,
+                   "threads_busy_fraction": busy, "host_threads": all_threads, "team_size_probe_s": team_probe,
                    "algorithm": "Gustavson, one frontier row per task (LPT order), per-thread persistent n-bit accumulators",
                    "full_size_parity_bit_exact": parity, "parity_rows": len(b), "result_digest": [int(x) for x in cdg]}
         except Exception as ex:  # the baseline must never take the bench line down
