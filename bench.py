@@ -244,6 +244,7 @@ def run_reference(a):
     t0 = time.time()
     A = orc.rmat_csr(a.scale, a.edge_factor, a.seed)
     gen_s = time.time() - t0
+    A = orc.spread(A)                          # pages interleaved over the sockets by first touch (oracle.py: spread)
     deg = np.diff(A.p)
     all_threads = cores
     cores, team_probe = calibrate_cpu_threads(orc, A, deg, a, all_threads)
@@ -630,7 +631,8 @@ def run_b200(a):
             orc.lib().orc_set_num_threads(all_threads)
             pj = np.empty(nnzA, np.uint32)
             fb.check(L.B200_Matrix_export_CSR(A.h, p.ctypes.data, pj.ctypes.data, None, 0))
-            Ao = CSR(n, n, p.astype(np.int64), pj)
+            Ao = orc.spread(CSR(n, n, p.astype(np.int64), pj))       # pages interleaved over the sockets by first touch
+            del pj
             cores, team_probe = calibrate_cpu_threads(orc, Ao, deg, a, all_threads)
             ncpu = a.cpu_sources if a.cpu_sources > 0 else a.sources
             b = batches[a.warmup][:ncpu]

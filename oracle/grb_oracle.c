@@ -265,6 +265,20 @@ static orc_ws *ws_get(int t, int64_t ncols) {       /* thread t's workspace, gro
     if (!w->list) w->list = xmalloc(sizeof(uint32_t) * ORC_LIST_CAP);
     return w;
 }
+/* dst <- src with the destination's pages FIRST TOUCHED by the whole team, 2 MB pieces dealt round-robin: on a multi-socket host
+ * the copy ends up interleaved over the memory controllers instead of sitting on the node of the thread that built the graph, where
+ * every thread's random row fetches would queue on one socket's DRAM.  dst must be freshly allocated (untouched) memory. */
+void orc_parallel_copy(void *dst, const void *src, int64_t bytes) {
+    const int64_t piece = (int64_t)2 << 20, npieces = (bytes + piece - 1) / piece;
+    const int team = orc_num_threads();
+    (void)team;
+#pragma omp parallel for schedule(static, 1) num_threads(team)
+    for (int64_t c = 0; c < npieces; c++) {
+        const int64_t off = c * piece, len = bytes - off < piece ? bytes - off : piece;
+        memcpy((char *)dst + off, (const char *)src + off, (size_t)len);
+    }
+}
+
 /* how well the last product used the host: busy thread-seconds / (team size * wall seconds) */
 double orc_last_busy_fraction(void) { return (g_wall_s > 0 && g_team > 0) ? g_busy_s / (g_wall_s * g_team) : 0.0; }
 int orc_last_busy_threads(void) { return g_busy_threads; }

@@ -53,6 +53,7 @@ def lib():
         L.orc_last_busy_threads.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_parallel_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         _LIB = L
     return _LIB
 
@@ -306,6 +307,19 @@ def cdlp(A, itermax=10):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def spread(A):
+    """A copy of A whose arrays were first touched by every thread of the team (2 MB pieces, round-robin): on a multi-socket host
+    the graph is then interleaved over the memory controllers rather than resident on the node of the thread that built it."""
+    def cp(a):
+        if a is None:
+            return None
+        out = np.empty_like(a)                       # fresh, untouched pages
+        if a.nbytes:
+            lib().orc_parallel_copy(out.ctypes.data, a.ctypes.data, a.nbytes)
+        return out
+    return CSR(A.nrows, A.ncols, cp(A.p), cp(A.j), cp(A.x))
 
 
 # ---- wrapper-level algebra the reference documents in-tree, composed from the primitives ----
